@@ -1,0 +1,149 @@
+"""ctypes binding of libfdgraph.so -- the same stub a Julia `ccall` wrapper makes."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import _build
+
+FDG_OK = 0
+ERR_NAMES = {1: "BAD_ARG", 2: "BAD_GRAPH", 3: "UNSUPPORTED", 4: "CUDA", 5: "NCCL", 6: "NO_DEVICE", 7: "CAPACITY"}
+FDG_F64, FDG_C128 = 0, 1
+
+
+class FdgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libfdgraph: {ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class GraphDesc(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_int64), ("n_edges", C.c_int64),
+        ("node_id", C.POINTER(C.c_int64)), ("node_op", C.POINTER(C.c_int32)), ("node_pow", C.POINTER(C.c_int32)),
+        ("child_ptr", C.POINTER(C.c_int64)), ("child_node", C.POINTER(C.c_int32)),
+        ("child_factor", C.POINTER(C.c_double)),
+        ("n_graphs", C.c_int64), ("graphs", C.POINTER(C.c_int32)),
+        ("n_roots", C.c_int64), ("root_id", C.POINTER(C.c_int64)),
+    ]
+
+
+class Options(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("max_slots", C.c_int32), ("prefetch", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in (
+        "n_leaves", "n_inner", "n_roots", "n_operands", "n_packets", "n_slots", "n_scratch", "leaf_loads",
+        "flops_add", "flops_mul", "bytes_in", "bytes_out", "max_depth")] + [("reserved", C.c_int64 * 3)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved"}
+
+
+# every symbol include/fdgraph.h declares; tests check that the library exports each one
+EXPORTS = [
+    "fdg_abi_version", "fdg_last_error", "fdg_compile", "fdg_destroy", "fdg_stats", "fdg_leafmap", "fdg_last_root",
+    "fdg_program_words", "fdg_eval", "fdg_eval_accumulate", "fdg_eval_host", "fdg_set_launch", "fdg_launch_count",
+    "fdg_comm_unique_id", "fdg_comm_init", "fdg_comm_destroy", "fdg_allreduce",
+]
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Loads libfdgraph.so (building it in-tree if a compiler is there).  Fails loudly otherwise."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        path = _build.build()
+    L = C.CDLL(path)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    L.fdg_abi_version.restype = C.c_int
+    L.fdg_last_error.restype = C.c_char_p
+    L.fdg_compile.argtypes = [C.POINTER(GraphDesc), C.POINTER(Options), C.POINTER(vp)]
+    L.fdg_destroy.argtypes = [vp]
+    L.fdg_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.fdg_leafmap.argtypes = [vp, C.POINTER(i32)]
+    L.fdg_last_root.argtypes = [vp, C.POINTER(i32)]
+    L.fdg_program_words.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(i64)]
+    L.fdg_eval.argtypes = [vp, vp, i64, vp, i64, i64, vp]
+    L.fdg_eval_accumulate.argtypes = [vp, vp, i64, i64, vp, vp]
+    L.fdg_eval_host.argtypes = [vp, vp, i64, vp, i64, i64]
+    L.fdg_set_launch.argtypes = [vp, i32, i32, i32]
+    L.fdg_launch_count.argtypes = [vp, C.POINTER(i64)]
+    L.fdg_comm_unique_id.argtypes = [vp]
+    L.fdg_comm_init.argtypes = [C.POINTER(vp), i32, i32, vp]
+    L.fdg_comm_destroy.argtypes = [vp]
+    L.fdg_allreduce.argtypes = [vp, vp, i64, vp]
+    for name in EXPORTS:
+        if name not in ("fdg_abi_version", "fdg_last_error"):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != FDG_OK:
+        raise FdgError(rc, lib().fdg_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a: np.ndarray, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def compile_raw(raw, dtype: int = FDG_F64, max_slots: int = 0, prefetch: int = 0) -> C.c_void_p:
+    """fdg_compile on a RawGraph; returns the opaque handle."""
+    L = lib()
+    raw.validate_dtypes()
+    d = GraphDesc()
+    d.n_nodes, d.n_edges = raw.n_nodes, raw.n_edges
+    d.node_id = _ptr(raw.node_id, C.c_int64)
+    d.node_op = _ptr(raw.node_op, C.c_int32)
+    d.node_pow = _ptr(raw.node_pow, C.c_int32)
+    d.child_ptr = _ptr(raw.child_ptr, C.c_int64)
+    d.child_node = _ptr(raw.child_node, C.c_int32)
+    d.child_factor = _ptr(raw.child_factor, C.c_double)
+    d.n_graphs, d.graphs = int(raw.graphs.shape[0]), _ptr(raw.graphs, C.c_int32)
+    d.n_roots, d.root_id = int(raw.root_id.shape[0]), _ptr(raw.root_id, C.c_int64)
+    o = Options()
+    o.dtype, o.max_slots, o.prefetch = int(dtype), int(max_slots), int(prefetch)
+    h = C.c_void_p()
+    check(L.fdg_compile(C.byref(d), C.byref(o), C.byref(h)))
+    return h
+
+
+def stats(h) -> dict:
+    s = Stats()
+    check(lib().fdg_stats(h, C.byref(s)))
+    return s.as_dict()
+
+
+def leafmap(h, n_leaves: int) -> np.ndarray:
+    out = np.empty(max(n_leaves, 1), np.int32)
+    check(lib().fdg_leafmap(h, _ptr(out, C.c_int32)))
+    return out[:n_leaves]
+
+
+def last_root(h) -> int:
+    v = C.c_int32()
+    check(lib().fdg_last_root(h, C.byref(v)))
+    return int(v.value)
+
+
+def program_words(h) -> np.ndarray:
+    p = C.POINTER(C.c_uint32)()
+    n = C.c_int64()
+    check(lib().fdg_program_words(h, C.byref(p), C.byref(n)))
+    return np.ctypeslib.as_array(p, shape=(int(n.value),)).copy()
+
+
+def launch_count(h) -> int:
+    v = C.c_int64()
+    check(lib().fdg_launch_count(h, C.byref(v)))
+    return int(v.value)

@@ -1,0 +1,468 @@
+// fdg_capi.cu -- C ABI of libfdgraph.so (include/fdgraph.h): handles, launches, host pipeline, NCCL.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/fdgraph.h"
+#include "fdg_lower.h"
+#include "fdg_vm.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    // a missing driver / device is its own status: there is no CPU fallback behind this library
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError)
+        return fail(FDG_ERR_NO_DEVICE, std::string(what) + ": " + cudaGetErrorString(e) +
+                                           " (libfdgraph has no CPU fallback; a CUDA device is required)");
+    return fail(FDG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CUDA_TRY(x)                                    \
+    do {                                               \
+        cudaError_t e_ = (x);                          \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #x); \
+    } while (0)
+
+struct DeviceState {
+    uint4 *d_prog = nullptr;
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    double *partial = nullptr;
+    size_t partial_bytes = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    // host pipeline (fdg_eval_host)
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    void *d_leaf[2] = {nullptr, nullptr};
+    void *d_root[2] = {nullptr, nullptr};
+    size_t d_leaf_bytes = 0, d_root_bytes = 0;
+};
+
+}  // namespace
+
+struct fdg_program {
+    fdg::Lowered low;
+    int threads = 128;
+    int spt = 0;  // samples per thread: 0 auto
+    int blocks_per_sm = 0;
+    std::map<int, DeviceState> dev;
+    long long launches = 0;
+    std::mutex mu;
+};
+
+struct fdg_comm {
+    void *nccl_comm = nullptr;
+};
+
+namespace {
+
+template <class V, bool ACC>
+int launch_variant(fdg_program *h, DeviceState &ds, fdg::VmArgs &args, long long batch, cudaStream_t stream) {
+    const fdg::Lowered &low = h->low;
+    constexpr int S = V::kSamples;
+    constexpr int W = V::kWidth;
+    auto kern = fdg::fdg_vm_kernel<V, ACC>;
+    int T = h->threads;
+    auto smem_for = [&](int t) -> size_t {
+        size_t b = (size_t)low.n_slots * t * sizeof(V);
+        if (ACC) b += (size_t)(t / 32) * low.R * W * sizeof(double);
+        return b;
+    };
+    while (T > 32 && smem_for(T) > (size_t)ds.max_smem_optin) T /= 2;
+    const size_t smem = smem_for(T);
+    if (smem > (size_t)ds.max_smem_optin)
+        return fail(FDG_ERR_CAPACITY, "slot file does not fit shared memory: " + std::to_string(smem) + " bytes");
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
+    if (occ < 1) return fail(FDG_ERR_CAPACITY, "kernel cannot be resident with this slot file");
+    if (h->blocks_per_sm > 0) occ = std::min(occ, h->blocks_per_sm);
+    const long long per_tile = (long long)T * S;
+    const long long n_tiles = (batch + per_tile - 1) / per_tile;
+    const long long grid = std::min<long long>(n_tiles, (long long)ds.sm_count * occ);
+    args.n_tiles = n_tiles;
+    args.n_roots = (int)low.R;
+    args.n_slots = low.n_slots;
+    if (low.n_scratch > 0) {
+        const size_t need = (size_t)low.n_scratch * grid * T * sizeof(V);
+        if (need > ds.scratch_bytes) {
+            if (ds.scratch) CUDA_TRY(cudaFree(ds.scratch));
+            ds.scratch = nullptr;
+            ds.scratch_bytes = 0;
+            CUDA_TRY(cudaMalloc(&ds.scratch, need));
+            ds.scratch_bytes = need;
+        }
+        args.scratch = ds.scratch;
+    }
+    long long rows = 0;
+    if (ACC) {
+        rows = grid * (T / 32);
+        const size_t need = (size_t)rows * low.R * W * sizeof(double);
+        if (need > ds.partial_bytes) {
+            if (ds.partial) CUDA_TRY(cudaFree(ds.partial));
+            ds.partial = nullptr;
+            ds.partial_bytes = 0;
+            CUDA_TRY(cudaMalloc((void **)&ds.partial, std::max<size_t>(need, 256)));
+            ds.partial_bytes = std::max<size_t>(need, 256);
+        }
+        args.partial = ds.partial;
+    }
+    kern<<<(unsigned)grid, T, smem, stream>>>(args);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    if (ACC) {
+        const int rw = (int)low.R * W;
+        if (rw > 0) {
+            fdg::fdg_reduce_partials<<<(rw + 127) / 128, 128, 0, stream>>>(ds.partial, rows, rw,
+                                                                          static_cast<double *>(args.root));
+            CUDA_TRY(cudaGetLastError());
+            h->launches++;
+        }
+    }
+    return FDG_OK;
+}
+
+int get_device_state(fdg_program *h, DeviceState **out) {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    auto it = h->dev.find(dev);
+    if (it == h->dev.end()) {
+        DeviceState ds;
+        CUDA_TRY(cudaDeviceGetAttribute(&ds.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&ds.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        // the program, padded with one extra END packet (the kernel prefetches one packet ahead)
+        std::vector<uint32_t> w = h->low.words;
+        w.insert(w.end(), {FDG_HDR(FDG_OP_END, 0, 0), 0u, 0u, 0u});
+        CUDA_TRY(cudaMalloc((void **)&ds.d_prog, w.size() * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpy(ds.d_prog, w.data(), w.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        it = h->dev.emplace(dev, ds).first;
+    }
+    *out = &it->second;
+    return FDG_OK;
+}
+
+int do_eval(fdg_program *h, const void *leaf, int64_t ld_leaf, void *root, int64_t ld_root, int64_t batch,
+            void *stream, bool accumulate) {
+    if (!h) return fail(FDG_ERR_BAD_ARG, "null handle");
+    if (batch < 0) return fail(FDG_ERR_BAD_ARG, "negative batch");
+    if (batch == 0) return FDG_OK;
+    const fdg::Lowered &low = h->low;
+    if (low.L > 0 && !leaf) return fail(FDG_ERR_BAD_ARG, "null leaf pointer");
+    if (low.R > 0 && !root) return fail(FDG_ERR_BAD_ARG, "null root pointer");
+    if (low.L > 0 && ld_leaf < batch) return fail(FDG_ERR_BAD_ARG, "ld_leaf < batch");
+    if (!accumulate && low.R > 0 && ld_root < batch) return fail(FDG_ERR_BAD_ARG, "ld_root < batch");
+    const bool cplx = low.dtype == FDG_C128;
+    const size_t esize = cplx ? 16 : 8;
+    if (((uintptr_t)leaf % esize) || ((uintptr_t)root % 8) || (!accumulate && (uintptr_t)root % esize))
+        return fail(FDG_ERR_BAD_ARG, "leaf/root pointer not aligned to the element size");
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceState *ds = nullptr;
+    int rc = get_device_state(h, &ds);
+    if (rc != FDG_OK) return rc;
+    fdg::VmArgs args{};
+    args.prog = ds->d_prog;
+    args.leaf = leaf;
+    args.ld_leaf = ld_leaf;
+    args.root = root;
+    args.ld_root = ld_root;
+    args.batch = batch;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cplx) {
+        return accumulate ? launch_variant<fdg::VCplx, true>(h, *ds, args, batch, st)
+                          : launch_variant<fdg::VCplx, false>(h, *ds, args, batch, st);
+    }
+    // two samples per thread need 16-byte aligned sample pairs that stay inside the allocation
+    bool two = h->spt != 1;
+    if (two) {
+        const bool leaf_ok = low.L == 0 || (((uintptr_t)leaf % 16 == 0) && (ld_leaf % 2 == 0) &&
+                                            (batch % 2 == 0 || ld_leaf > batch));
+        const bool root_ok = accumulate || low.R == 0 || (((uintptr_t)root % 16 == 0) && (ld_root % 2 == 0));
+        two = leaf_ok && root_ok;
+        if (!two && h->spt == 2)
+            return fail(FDG_ERR_BAD_ARG, "two samples per thread need 16-byte aligned buffers and even leading dimensions");
+    }
+    if (two)
+        return accumulate ? launch_variant<fdg::VReal<2>, true>(h, *ds, args, batch, st)
+                          : launch_variant<fdg::VReal<2>, false>(h, *ds, args, batch, st);
+    return accumulate ? launch_variant<fdg::VReal<1>, true>(h, *ds, args, batch, st)
+                      : launch_variant<fdg::VReal<1>, false>(h, *ds, args, batch, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fdg_abi_version(void) { return FDG_ABI_VERSION; }
+const char *fdg_last_error(void) { return g_err.c_str(); }
+
+int fdg_compile(const fdg_graph_desc *graph, const fdg_options *opts, fdg_handle *out) {
+    if (!graph || !out) return fail(FDG_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    fdg_options o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts) o = *opts;
+    for (int i = 0; i < 5; ++i)
+        if (o.reserved[i] != 0) return fail(FDG_ERR_BAD_ARG, "fdg_options.reserved must be zero");
+    fdg_program *p = new (std::nothrow) fdg_program();
+    if (!p) return fail(FDG_ERR_BAD_ARG, "out of memory");
+    std::string err;
+    int rc;
+    try {
+        rc = fdg::lower(*graph, o, p->low, err);
+    } catch (const std::exception &e) {
+        rc = FDG_ERR_BAD_ARG;
+        err = std::string("lowering failed: ") + e.what();
+    }
+    if (rc != FDG_OK) {
+        delete p;
+        return fail(rc, err);
+    }
+    *out = p;
+    return FDG_OK;
+}
+
+int fdg_destroy(fdg_handle h) {
+    if (!h) return FDG_OK;
+    for (auto &kv : h->dev) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) break;
+        cudaSetDevice(kv.first);
+        DeviceState &ds = kv.second;
+        cudaFree(ds.d_prog);
+        cudaFree(ds.scratch);
+        cudaFree(ds.partial);
+        for (int i = 0; i < 2; ++i) {
+            if (ds.streams[i]) cudaStreamDestroy(ds.streams[i]);
+            cudaFree(ds.d_leaf[i]);
+            cudaFree(ds.d_root[i]);
+        }
+        cudaSetDevice(cur);
+    }
+    delete h;
+    return FDG_OK;
+}
+
+int fdg_stats(fdg_handle h, fdg_stats_t *out) {
+    if (!h || !out) return fail(FDG_ERR_BAD_ARG, "null argument");
+    std::memset(out, 0, sizeof(*out));
+    const fdg::Lowered &l = h->low;
+    const bool c = l.dtype == FDG_C128;
+    out->n_leaves = l.L;
+    out->n_inner = l.N;
+    out->n_roots = l.R;
+    out->n_operands = l.n_operands;
+    out->n_packets = (int64_t)l.words.size() / 4;
+    out->n_slots = l.n_slots;
+    out->n_scratch = l.n_scratch;
+    out->leaf_loads = l.leaf_loads;
+    // complex*complex = 4 mul + 2 add, complex*real = 2 mul, complex+complex = 2 add
+    out->flops_mul = c ? 4 * (l.muls_vv + l.pow_muls) + 2 * l.muls_vf : l.muls_vv + l.pow_muls + l.muls_vf;
+    out->flops_add = c ? 2 * (l.muls_vv + l.pow_muls) + 2 * l.adds_vv : l.adds_vv;
+    out->bytes_in = (c ? 16 : 8) * l.L;
+    out->bytes_out = (c ? 16 : 8) * l.R;
+    out->max_depth = l.max_depth;
+    return FDG_OK;
+}
+
+int fdg_leafmap(fdg_handle h, int32_t *leaf_node) {
+    if (!h || (!leaf_node && h->low.L > 0)) return fail(FDG_ERR_BAD_ARG, "null argument");
+    std::copy(h->low.leaf_node.begin(), h->low.leaf_node.end(), leaf_node);
+    return FDG_OK;
+}
+
+int fdg_last_root(fdg_handle h, int32_t *out) {
+    if (!h || !out) return fail(FDG_ERR_BAD_ARG, "null argument");
+    *out = h->low.last_root;
+    return FDG_OK;
+}
+
+int fdg_program_words(fdg_handle h, const uint32_t **words, int64_t *n_words) {
+    if (!h || !words || !n_words) return fail(FDG_ERR_BAD_ARG, "null argument");
+    *words = h->low.words.data();
+    *n_words = (int64_t)h->low.words.size();
+    return FDG_OK;
+}
+
+int fdg_eval(fdg_handle h, const void *leaf, int64_t ld_leaf, void *root, int64_t ld_root, int64_t batch,
+             void *stream) {
+    return do_eval(h, leaf, ld_leaf, root, ld_root, batch, stream, false);
+}
+
+int fdg_eval_accumulate(fdg_handle h, const void *leaf, int64_t ld_leaf, int64_t batch, double *acc, void *stream) {
+    return do_eval(h, leaf, ld_leaf, acc, 0, batch, stream, true);
+}
+
+int fdg_eval_host(fdg_handle h, const void *leaf_host, int64_t ld_leaf, void *root_host, int64_t ld_root,
+                  int64_t batch) {
+    if (!h) return fail(FDG_ERR_BAD_ARG, "null handle");
+    if (batch < 0) return fail(FDG_ERR_BAD_ARG, "negative batch");
+    if (batch == 0) return FDG_OK;
+    const fdg::Lowered &low = h->low;
+    if ((low.L > 0 && !leaf_host) || (low.R > 0 && !root_host)) return fail(FDG_ERR_BAD_ARG, "null host buffer");
+    if ((low.L > 0 && ld_leaf < batch) || (low.R > 0 && ld_root < batch))
+        return fail(FDG_ERR_BAD_ARG, "leading dimension < batch");
+    const size_t es = low.dtype == FDG_C128 ? 16 : 8;
+    DeviceState *ds = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        int rc = get_device_state(h, &ds);
+        if (rc != FDG_OK) return rc;
+    }
+    // chunk so that one chunk of leaves is about 64 MiB; an even number of samples keeps pairs aligned
+    const size_t row = std::max<size_t>((size_t)std::max<int64_t>(low.L, 1) * es, 1);
+    int64_t chunk = (int64_t)((64ull << 20) / row);
+    chunk = std::max<int64_t>(1024, chunk) & ~(int64_t)1023;
+    chunk = std::min<int64_t>(chunk, (batch + 1) & ~(int64_t)1);
+    const size_t need_leaf = (size_t)chunk * std::max<int64_t>(low.L, 1) * es;
+    const size_t need_root = (size_t)chunk * std::max<int64_t>(low.R, 1) * es;
+    for (int i = 0; i < 2; ++i) {
+        if (!ds->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&ds->streams[i], cudaStreamNonBlocking));
+    }
+    if (need_leaf > ds->d_leaf_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (ds->d_leaf[i]) CUDA_TRY(cudaFree(ds->d_leaf[i]));
+            ds->d_leaf[i] = nullptr;
+            CUDA_TRY(cudaMalloc(&ds->d_leaf[i], need_leaf));
+        }
+        ds->d_leaf_bytes = need_leaf;
+    }
+    if (need_root > ds->d_root_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (ds->d_root[i]) CUDA_TRY(cudaFree(ds->d_root[i]));
+            ds->d_root[i] = nullptr;
+            CUDA_TRY(cudaMalloc(&ds->d_root[i], need_root));
+        }
+        ds->d_root_bytes = need_root;
+    }
+    int k = 0;
+    for (int64_t c0 = 0; c0 < batch; c0 += chunk, k ^= 1) {
+        const int64_t nb = std::min<int64_t>(chunk, batch - c0);
+        cudaStream_t st = ds->streams[k];
+        if (low.L > 0)
+            CUDA_TRY(cudaMemcpy2DAsync(ds->d_leaf[k], (size_t)chunk * es,
+                                       static_cast<const char *>(leaf_host) + (size_t)c0 * es, (size_t)ld_leaf * es,
+                                       (size_t)nb * es, (size_t)low.L, cudaMemcpyHostToDevice, st));
+        int rc = do_eval(h, ds->d_leaf[k], chunk, ds->d_root[k], chunk, nb, st, false);
+        if (rc != FDG_OK) return rc;
+        if (low.R > 0)
+            CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(root_host) + (size_t)c0 * es, (size_t)ld_root * es,
+                                       ds->d_root[k], (size_t)chunk * es, (size_t)nb * es, (size_t)low.R,
+                                       cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ds->streams[0]));
+    CUDA_TRY(cudaStreamSynchronize(ds->streams[1]));
+    return FDG_OK;
+}
+
+int fdg_set_launch(fdg_handle h, int32_t threads, int32_t samples_per_thread, int32_t blocks_per_sm) {
+    if (!h) return fail(FDG_ERR_BAD_ARG, "null handle");
+    if (threads != 0 && (threads < 32 || threads > 256 || (threads & (threads - 1))))
+        return fail(FDG_ERR_BAD_ARG, "threads must be 32, 64, 128 or 256");
+    if (samples_per_thread < 0 || samples_per_thread > 2) return fail(FDG_ERR_BAD_ARG, "samples_per_thread must be 0, 1 or 2");
+    if (blocks_per_sm < 0) return fail(FDG_ERR_BAD_ARG, "blocks_per_sm must be >= 0");
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (threads) h->threads = threads;
+    h->spt = samples_per_thread;
+    h->blocks_per_sm = blocks_per_sm;
+    return FDG_OK;
+}
+
+int fdg_launch_count(fdg_handle h, int64_t *out) {
+    if (!h || !out) return fail(FDG_ERR_BAD_ARG, "null argument");
+    *out = h->launches;
+    return FDG_OK;
+}
+
+// ---- NCCL, resolved at run time so that single-GPU users need no NCCL at all ---------------------------
+namespace {
+struct Id128 {  // ncclUniqueId is passed by value: 128 bytes
+    char b[128];
+};
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, Id128, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+int load_nccl() {
+    std::call_once(g_nccl_once, [] {
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.lib) break;
+        }
+        if (!g_nccl.lib) return;
+        g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(g_nccl.lib, "ncclGetUniqueId"));
+        g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(g_nccl.lib, "ncclCommInitRank"));
+        g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(g_nccl.lib, "ncclCommDestroy"));
+        g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(g_nccl.lib, "ncclAllReduce"));
+        g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(g_nccl.lib, "ncclGetErrorString"));
+    });
+    if (!g_nccl.lib || !g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
+        return fail(FDG_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    return FDG_OK;
+}
+int nccl_fail(int rc, const char *what) {
+    return fail(FDG_ERR_NCCL, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "nccl error"));
+}
+}  // namespace
+
+int fdg_comm_unique_id(void *id128) {
+    if (!id128) return fail(FDG_ERR_BAD_ARG, "null argument");
+    int rc = load_nccl();
+    if (rc != FDG_OK) return rc;
+    int n = g_nccl.GetUniqueId(id128);
+    return n == 0 ? FDG_OK : nccl_fail(n, "ncclGetUniqueId");
+}
+
+int fdg_comm_init(fdg_comm_t *out, int32_t nranks, int32_t rank, const void *id128) {
+    if (!out || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(FDG_ERR_BAD_ARG, "bad argument");
+    int rc = load_nccl();
+    if (rc != FDG_OK) return rc;
+    Id128 id;
+    std::memcpy(id.b, id128, 128);
+    fdg_comm *c = new (std::nothrow) fdg_comm();
+    if (!c) return fail(FDG_ERR_BAD_ARG, "out of memory");
+    int n = g_nccl.CommInitRank(&c->nccl_comm, nranks, id, rank);
+    if (n != 0) {
+        delete c;
+        return nccl_fail(n, "ncclCommInitRank");
+    }
+    *out = c;
+    return FDG_OK;
+}
+
+int fdg_comm_destroy(fdg_comm_t c) {
+    if (!c) return FDG_OK;
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    delete c;
+    return FDG_OK;
+}
+
+int fdg_allreduce(fdg_comm_t c, double *acc, int64_t n, void *stream) {
+    if (!c || !c->nccl_comm || (!acc && n > 0) || n < 0) return fail(FDG_ERR_BAD_ARG, "bad argument");
+    if (n == 0) return FDG_OK;
+    // ncclFloat64 = 8, ncclSum = 0 (nccl.h)
+    int rc = g_nccl.AllReduce(acc, acc, (size_t)n, 8, 0, c->nccl_comm, static_cast<cudaStream_t>(stream));
+    return rc == 0 ? FDG_OK : nccl_fail(rc, "ncclAllReduce");
+}
+
+}  // extern "C"

@@ -1,0 +1,682 @@
+// fdg_lower.cpp -- lowering of the reference's Graph DAG to the VM program (host only, no CUDA).
+//
+// Stage A reproduces the reference emitter's statement order and leaf numbering
+//   (src/backend/static.jl:98-133: post-order DFS over `graphs`, children in stored order,
+//    first visit of an id wins, leaf k = k-th distinct leaf id, `root[r] = g` right after the
+//    statement of a node whose id is in `root`, r = first position of that id).
+// Stage B decides which values live where: single-use inner nodes are folded straight into their
+//   parent's accumulator (acc_d registers), multi-use nodes and roots are materialised in the
+//   shared-memory slot file, leaves are staged into slots by asynchronous loads.
+// Stage C allocates slots (Belady eviction, spills to global scratch when a program does not fit),
+//   hoists leaf loads ahead of their first use (software prefetch) and packs packets.
+//
+// None of this changes any arithmetic: every fold keeps the stored operand order, so the packet
+// program computes exactly the values of the emitted function (bit for bit, see fdg_isa.h).
+#include "fdg_lower.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <unordered_map>
+
+#include "fdg_isa.h"
+
+namespace fdg {
+namespace {
+
+struct Operand {
+    int32_t val;
+    double f;
+};
+
+struct Stmt {          // one value of the emitted function, in emitter order
+    int8_t op = -1;    // -1 leaf, else FDG_OP_SUM / PROD / POWER
+    int32_t pow_n = 0;
+    int64_t first = 0;  // operands[first .. first+count)
+    int32_t count = 0;
+    int32_t root = -1;  // root position assigned right after this statement
+    int32_t uses = 0;   // operand references from live statements
+    bool live = false;
+    int32_t leaf = -1;  // leaf index k for leaves
+};
+
+// symbolic (pre-allocation) VM operation
+struct Sym {
+    uint8_t base;  // FDG_R_*
+    uint8_t d;
+    int32_t val;  // value read (MOV..XMULF) or defined (ST); -1 otherwise
+    int32_t arg;  // POW exponent / ROOT position
+    double f;
+};
+
+inline bool reads_value(uint8_t b) {
+    return b == FDG_R_MOV || b == FDG_R_MUL || b == FDG_R_ADD || b == FDG_R_MOVF || b == FDG_R_MULF ||
+           b == FDG_R_ADDF || b == FDG_R_XADDF || b == FDG_R_XMULF;
+}
+inline bool has_factor(uint8_t b) {
+    return b == FDG_R_MOVF || b == FDG_R_MULF || b == FDG_R_ADDF || b == FDG_R_SCALE || b == FDG_R_RADDF ||
+           b == FDG_R_RMULF || b == FDG_R_XADDF || b == FDG_R_XMULF;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage A: emitter order
+// ------------------------------------------------------------------------------------------------
+int build_statements(const fdg_graph_desc &g, std::vector<Stmt> &st, std::vector<Operand> &ops, Lowered &out,
+                     std::string &err) {
+    const int64_t n = g.n_nodes;
+    if (n < 0 || g.n_edges < 0 || g.n_graphs < 0 || g.n_roots < 0) {
+        err = "negative size in graph description";
+        return FDG_ERR_BAD_ARG;
+    }
+    if (n > 0 && (!g.node_id || !g.node_op || !g.node_pow || !g.child_ptr)) {
+        err = "null node array";
+        return FDG_ERR_BAD_ARG;
+    }
+    if (g.n_edges > 0 && (!g.child_node || !g.child_factor)) {
+        err = "null edge array";
+        return FDG_ERR_BAD_ARG;
+    }
+    if ((g.n_graphs > 0 && !g.graphs) || (g.n_roots > 0 && !g.root_id)) {
+        err = "null graphs/root array";
+        return FDG_ERR_BAD_ARG;
+    }
+    if (n > 0 && (g.child_ptr[0] != 0 || g.child_ptr[n] != g.n_edges)) {
+        err = "child_ptr does not span [0, n_edges]";
+        return FDG_ERR_BAD_GRAPH;
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t a = g.child_ptr[i], b = g.child_ptr[i + 1];
+        if (b < a) {
+            err = "child_ptr not monotone";
+            return FDG_ERR_BAD_GRAPH;
+        }
+        const int32_t op = g.node_op[i];
+        if (op < FDG_OP_UNITARY || op > FDG_OP_POWER) {
+            // static.jl:6-11: "Static representation ... with operator X not yet implemented"
+            err = "unknown operator code " + std::to_string(op) + " at node " + std::to_string(i);
+            return FDG_ERR_BAD_GRAPH;
+        }
+        const int64_t nc = b - a;
+        if (op == FDG_OP_UNITARY && nc != 0) {
+            err = "Unitary node with subgraphs";
+            return FDG_ERR_BAD_GRAPH;
+        }
+        if (op == FDG_OP_POWER && nc != 0) {
+            if (nc != 1) {
+                err = "Power node must have exactly one subgraph";
+                return FDG_ERR_BAD_GRAPH;
+            }
+            if (g.node_pow[i] < 2) {
+                err = "Power{N} with N < 2 is not supported (N=" + std::to_string(g.node_pow[i]) + ")";
+                return FDG_ERR_BAD_GRAPH;
+            }
+            if (g.node_pow[i] >= FDG_MAX_ARG) {
+                err = "Power exponent too large";
+                return FDG_ERR_UNSUPPORTED;
+            }
+        }
+        for (int64_t e = a; e < b; ++e) {
+            const int32_t c = g.child_node[e];
+            if (c < 0 || c >= n) {
+                err = "child index out of range";
+                return FDG_ERR_BAD_GRAPH;
+            }
+        }
+    }
+    for (int64_t i = 0; i < g.n_graphs; ++i)
+        if (g.graphs[i] < 0 || g.graphs[i] >= n) {
+            err = "graphs[] index out of range";
+            return FDG_ERR_BAD_GRAPH;
+        }
+
+    // `findfirst(x -> x == g_id, root)`: the first position of an id is the one written (static.jl:112)
+    std::unordered_map<int64_t, int32_t> root_pos;
+    root_pos.reserve((size_t)g.n_roots * 2 + 1);
+    for (int64_t r = 0; r < g.n_roots; ++r) root_pos.emplace(g.root_id[r], (int32_t)r);
+    out.R = g.n_roots;
+    out.root_set.assign((size_t)g.n_roots, 0);
+    out.last_root = -1;
+
+    std::unordered_map<int64_t, int32_t> val_of_id;
+    val_of_id.reserve((size_t)n * 2 + 1);
+    std::vector<uint8_t> color((size_t)n, 0);  // 0 new, 1 on the DFS stack, 2 done
+    struct Fr {
+        int32_t node;
+        int64_t e;
+    };
+    std::vector<Fr> stack;
+    for (int64_t gi = 0; gi < g.n_graphs; ++gi) {
+        if (color[g.graphs[gi]] == 2) continue;  // the whole object sub-DAG was walked already
+        stack.push_back({g.graphs[gi], g.child_ptr[g.graphs[gi]]});
+        color[g.graphs[gi]] = 1;
+        while (!stack.empty()) {
+            Fr &fr = stack.back();
+            const int32_t u = fr.node;
+            if (fr.e < g.child_ptr[u + 1]) {
+                const int32_t c = g.child_node[fr.e++];
+                if (color[c] == 1) {
+                    err = "graph has a cycle through node " + std::to_string(c);
+                    return FDG_ERR_BAD_GRAPH;
+                }
+                if (color[c] == 0) {
+                    color[c] = 1;
+                    stack.push_back({c, g.child_ptr[c]});
+                }
+                continue;
+            }
+            // post-visit of object u
+            stack.pop_back();
+            color[u] = 2;
+            const int64_t uid = g.node_id[u];
+            if (val_of_id.count(uid)) continue;  // `g_id in inds_visited... && continue`
+            Stmt s;
+            const int64_t a = g.child_ptr[u], b = g.child_ptr[u + 1];
+            if (a == b) {  // leaf: isempty(subgraphs(g)), whatever the operator tag (static.jl:115)
+                s.op = -1;
+                s.leaf = (int32_t)out.L++;
+                out.leaf_node.push_back(u);
+            } else {
+                s.op = (int8_t)g.node_op[u];
+                s.pow_n = g.node_pow[u];
+                s.first = (int64_t)ops.size();
+                s.count = (int32_t)(b - a);
+                for (int64_t e = a; e < b; ++e) {
+                    auto it = val_of_id.find(g.node_id[g.child_node[e]]);
+                    if (it == val_of_id.end()) {
+                        err = "internal: child statement missing";
+                        return FDG_ERR_BAD_GRAPH;
+                    }
+                    ops.push_back({it->second, g.child_factor[e]});
+                }
+                out.N++;
+            }
+            auto rp = root_pos.find(uid);
+            if (rp != root_pos.end()) {
+                s.root = rp->second;
+                out.root_set[(size_t)rp->second] = 1;
+                out.last_root = rp->second;
+            }
+            val_of_id.emplace(uid, (int32_t)st.size());
+            st.push_back(s);
+        }
+    }
+    if (out.L >= FDG_MAX_LEAVES) {
+        err = "too many leaves for the packet encoding";
+        return FDG_ERR_UNSUPPORTED;
+    }
+    if (out.R >= FDG_MAX_ARG) {
+        err = "too many roots for the packet encoding";
+        return FDG_ERR_UNSUPPORTED;
+    }
+    // liveness and use counts (operands always precede their users)
+    for (int64_t v = (int64_t)st.size() - 1; v >= 0; --v) {
+        Stmt &s = st[(size_t)v];
+        if (s.root >= 0) s.live = true;
+        if (!s.live || s.op < 0) continue;
+        for (int32_t i = 0; i < s.count; ++i) {
+            Stmt &c = st[(size_t)ops[(size_t)(s.first + i)].val];
+            c.live = true;
+            c.uses++;
+        }
+    }
+    return FDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage B: symbolic code generation
+// ------------------------------------------------------------------------------------------------
+struct CodeGen {
+    const std::vector<Stmt> &st;
+    const std::vector<Operand> &ops;
+    std::vector<Sym> code;
+    int32_t n_values;  // statements + temporaries
+    int32_t max_depth = 0;
+    Lowered &out;
+
+    CodeGen(const std::vector<Stmt> &s, const std::vector<Operand> &o, Lowered &l)
+        : st(s), ops(o), n_values((int32_t)s.size()), out(l) {}
+
+    bool materialised(const Stmt &s) const { return s.op < 0 || s.root >= 0 || s.uses >= 2; }
+
+    void emit(uint8_t base, int d, int32_t val = -1, int32_t arg = 0, double f = 1.0) {
+        code.push_back({base, (uint8_t)d, val, arg, f});
+    }
+
+    struct Frame {
+        int32_t v;
+        int8_t d;
+        int32_t i;
+        int8_t mode;  // pending combine once the child returns: 0 none, 1 first operand, 2 register, 3 spilled
+        double f;
+        int32_t tmp;
+    };
+
+    // computes statement `unit` into acc0
+    void gen_unit(int32_t unit) {
+        std::vector<Frame> stack;
+        stack.push_back({unit, 0, 0, 0, 1.0, -1});
+        while (!stack.empty()) {
+            Frame &fr = stack.back();
+            const Stmt &s = st[(size_t)fr.v];
+            const int d = fr.d;
+            max_depth = std::max<int32_t>(max_depth, (int32_t)stack.size());
+            if (fr.mode != 0) {
+                // a child computed inline has just returned: fold it into this node's accumulator
+                const bool sum = s.op == FDG_OP_SUM;
+                if (fr.mode == 1) {
+                    if (fr.f != 1.0 && s.op != FDG_OP_POWER) {
+                        emit(FDG_R_SCALE, d, -1, 0, fr.f);
+                        out.muls_vf++;
+                    }
+                } else if (fr.mode == 2) {
+                    emit(sum ? FDG_R_RADDF : FDG_R_RMULF, d + 1, -1, 0, fr.f);
+                    count_combine(sum, fr.f);
+                } else {
+                    emit(sum ? FDG_R_XADDF : FDG_R_XMULF, d, fr.tmp, 0, fr.f);
+                    count_combine(sum, fr.f);
+                }
+                fr.mode = 0;
+                fr.i++;
+                continue;
+            }
+            if (fr.i == s.count) {
+                if (s.op == FDG_OP_POWER) {
+                    emit(FDG_R_POW, d, -1, s.pow_n, 1.0);
+                    out.pow_muls += s.pow_n - 1;
+                    const double f = ops[(size_t)s.first].f;
+                    if (f != 1.0) {
+                        emit(FDG_R_SCALE, d, -1, 0, f);
+                        out.muls_vf++;
+                    }
+                }
+                stack.pop_back();
+                continue;
+            }
+            const Operand &o = ops[(size_t)(s.first + fr.i)];
+            const Stmt &c = st[(size_t)o.val];
+            out.n_operands++;
+            if (materialised(c)) {
+                // operand comes from the slot file
+                if (s.op == FDG_OP_POWER) {
+                    emit(FDG_R_MOV, d, o.val);
+                } else if (fr.i == 0) {
+                    if (o.f == 1.0) {
+                        emit(FDG_R_MOV, d, o.val);
+                    } else {
+                        emit(FDG_R_MOVF, d, o.val, 0, o.f);
+                        out.muls_vf++;
+                    }
+                } else if (s.op == FDG_OP_SUM) {
+                    if (o.f == 1.0) {
+                        emit(FDG_R_ADD, d, o.val);
+                    } else {
+                        emit(FDG_R_ADDF, d, o.val, 0, o.f);
+                        out.muls_vf++;
+                    }
+                    out.adds_vv++;
+                } else {
+                    if (o.f == 1.0) {
+                        emit(FDG_R_MUL, d, o.val);
+                    } else {
+                        emit(FDG_R_MULF, d, o.val, 0, o.f);
+                        out.muls_vf++;
+                    }
+                    out.muls_vv++;
+                }
+                fr.i++;
+                continue;
+            }
+            // single-use inner node: evaluate it right here
+            fr.f = o.f;
+            if (fr.i == 0) {
+                fr.mode = 1;
+                const int32_t child = o.val;
+                stack.push_back({child, (int8_t)d, 0, 0, 1.0, -1});  // NB: invalidates fr
+            } else if (d + 1 < FDG_NREG) {
+                fr.mode = 2;
+                const int32_t child = o.val;
+                stack.push_back({child, (int8_t)(d + 1), 0, 0, 1.0, -1});
+            } else {
+                fr.mode = 3;
+                fr.tmp = n_values++;
+                emit(FDG_R_ST, d, fr.tmp);
+                const int32_t child = o.val;
+                stack.push_back({child, (int8_t)d, 0, 0, 1.0, -1});
+            }
+        }
+    }
+
+    void count_combine(bool sum, double f) {
+        // RADDF/RMULF/XADDF/XMULF always multiply by f; only f != 1 is an operation of the
+        // reference function, the f == 1 multiply is an exact identity.
+        if (f != 1.0) out.muls_vf++;
+        if (sum)
+            out.adds_vv++;
+        else
+            out.muls_vv++;
+    }
+
+    void run() {
+        for (int32_t v = 0; v < (int32_t)st.size(); ++v) {
+            const Stmt &s = st[(size_t)v];
+            if (!s.live) continue;
+            if (s.op < 0) {
+                if (s.root >= 0) {  // a leaf that is itself a root: root[r] = leafVal[k]
+                    emit(FDG_R_MOV, 0, v);
+                    emit(FDG_R_ROOT, 0, -1, s.root);
+                }
+                continue;
+            }
+            if (!(s.root >= 0 || s.uses >= 2)) continue;  // folded into its single parent
+            gen_unit(v);
+            if (s.root >= 0) emit(FDG_R_ROOT, 0, -1, s.root);
+            if (s.uses >= 1) emit(FDG_R_ST, 0, v);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Stage C: slots, prefetch, packets
+// ------------------------------------------------------------------------------------------------
+struct Op2 {  // post-allocation, non-LDL operation
+    uint8_t kind;  // 0 register op, 1 SPILL, 2 FILL
+    Sym s;
+    int32_t slot;     // slot read / written
+    int32_t scratch;  // SPILL / FILL
+};
+struct Ldl {
+    int32_t slot, leaf;
+    int64_t anchor;    // index into ops2 before which the load originally sits
+    int64_t earliest;  // smallest legal anchor (after the last access of the slot's previous content)
+};
+
+struct Allocator {
+    const std::vector<Stmt> &st;
+    const std::vector<Sym> &code;
+    int32_t n_values, max_slots;
+    std::vector<Op2> ops2;
+    std::vector<Ldl> ldls;
+    std::vector<std::vector<int64_t>> use_pos;  // per value: positions in `code` that read it
+    std::vector<int32_t> use_ptr, val_slot, val_scratch;
+    std::vector<int32_t> slot_val;
+    std::vector<int64_t> slot_last;  // index in ops2 of the last op touching the slot, -1 if none
+    std::vector<int32_t> free_slots;
+    int32_t n_slots = 0, n_scratch = 0;
+    int64_t leaf_loads = 0;
+
+    Allocator(const std::vector<Stmt> &s, const std::vector<Sym> &c, int32_t nv, int32_t ms)
+        : st(s), code(c), n_values(nv), max_slots(ms) {}
+
+    int64_t next_use(int32_t v) const {
+        const auto &u = use_pos[(size_t)v];
+        const int32_t p = use_ptr[(size_t)v];
+        return p < (int32_t)u.size() ? u[(size_t)p] : INT64_MAX;
+    }
+    bool is_leaf(int32_t v) const { return v < (int32_t)st.size() && st[(size_t)v].op < 0; }
+
+    int32_t alloc_slot() {
+        if (!free_slots.empty()) {
+            // take the free slot that has been idle the longest: most room to hoist a load into it
+            size_t best = 0;
+            for (size_t i = 1; i < free_slots.size(); ++i)
+                if (slot_last[(size_t)free_slots[i]] < slot_last[(size_t)free_slots[best]]) best = i;
+            const int32_t s = free_slots[best];
+            free_slots[best] = free_slots.back();
+            free_slots.pop_back();
+            return s;
+        }
+        if (n_slots < max_slots) {
+            slot_val.push_back(-1);
+            slot_last.push_back(-1);
+            return n_slots++;
+        }
+        // evict the resident value whose next use is farthest away (Belady)
+        int32_t victim = -1;
+        int64_t far = -1;
+        for (int32_t s = 0; s < n_slots; ++s) {
+            const int32_t v = slot_val[(size_t)s];
+            if (v < 0) continue;
+            const int64_t nu = next_use(v);
+            if (nu > far) {
+                far = nu;
+                victim = s;
+            }
+        }
+        const int32_t v = slot_val[(size_t)victim];
+        if (!is_leaf(v) && next_use(v) != INT64_MAX && val_scratch[(size_t)v] < 0) {
+            val_scratch[(size_t)v] = n_scratch++;
+            Op2 o{};
+            o.kind = 1;
+            o.slot = victim;
+            o.scratch = val_scratch[(size_t)v];
+            slot_last[(size_t)victim] = (int64_t)ops2.size();
+            ops2.push_back(o);
+        }
+        val_slot[(size_t)v] = -1;
+        slot_val[(size_t)victim] = -1;
+        return victim;
+    }
+
+    void release_if_dead(int32_t v) {
+        if (next_use(v) != INT64_MAX) return;
+        const int32_t s = val_slot[(size_t)v];
+        if (s < 0) return;
+        val_slot[(size_t)v] = -1;
+        slot_val[(size_t)s] = -1;
+        free_slots.push_back(s);
+    }
+
+    void run() {
+        use_pos.assign((size_t)n_values, {});
+        for (size_t p = 0; p < code.size(); ++p)
+            if (reads_value(code[p].base)) use_pos[(size_t)code[p].val].push_back((int64_t)p);
+        use_ptr.assign((size_t)n_values, 0);
+        val_slot.assign((size_t)n_values, -1);
+        val_scratch.assign((size_t)n_values, -1);
+        for (size_t p = 0; p < code.size(); ++p) {
+            const Sym &s = code[p];
+            Op2 o{};
+            o.kind = 0;
+            o.s = s;
+            o.slot = -1;
+            if (reads_value(s.base)) {
+                const int32_t v = s.val;
+                if (val_slot[(size_t)v] < 0) {
+                    const int32_t sl = alloc_slot();
+                    if (is_leaf(v)) {
+                        ldls.push_back({sl, st[(size_t)v].leaf, (int64_t)ops2.size(), slot_last[(size_t)sl] + 1});
+                        leaf_loads++;
+                    } else {
+                        Op2 f{};
+                        f.kind = 2;
+                        f.slot = sl;
+                        f.scratch = val_scratch[(size_t)v];
+                        slot_last[(size_t)sl] = (int64_t)ops2.size();
+                        ops2.push_back(f);
+                    }
+                    val_slot[(size_t)v] = sl;
+                    slot_val[(size_t)sl] = v;
+                }
+                o.slot = val_slot[(size_t)v];
+                use_ptr[(size_t)v]++;
+                slot_last[(size_t)o.slot] = (int64_t)ops2.size();
+                ops2.push_back(o);
+                release_if_dead(v);
+            } else if (s.base == FDG_R_ST) {
+                const int32_t v = s.val;
+                if (use_pos[(size_t)v].empty()) continue;  // never read: nothing to keep
+                const int32_t sl = alloc_slot();
+                val_slot[(size_t)v] = sl;
+                slot_val[(size_t)sl] = v;
+                o.slot = sl;
+                slot_last[(size_t)sl] = (int64_t)ops2.size();
+                ops2.push_back(o);
+            } else {
+                ops2.push_back(o);
+            }
+        }
+    }
+};
+
+struct Packer {
+    const Allocator &al;
+    std::vector<uint32_t> &words;
+    int32_t dist;
+    int64_t committed = 0, completed = 0;  // cp.async groups
+    std::vector<int64_t> slot_group;       // group that fills the slot, -1 when filled synchronously
+
+    Packer(const Allocator &a, std::vector<uint32_t> &w, int32_t d) : al(a), words(w), dist(d) {}
+
+    void packet(uint32_t w0, uint32_t w1 = 0, uint32_t w2 = 0, uint32_t w3 = 0) {
+        words.push_back(w0);
+        words.push_back(w1);
+        words.push_back(w2);
+        words.push_back(w3);
+    }
+    void need(int32_t slot) {
+        const int64_t g = slot_group[(size_t)slot];
+        if (g < 0 || g < completed) return;
+        // allow `pend` newer groups to stay in flight
+        int64_t pend = committed - (g + 1);
+        if (pend > FDG_MAX_WAIT) pend = FDG_MAX_WAIT;
+        packet(FDG_HDR(FDG_OP_WAIT, 0, (uint32_t)pend));
+        completed = committed - pend;
+    }
+    static void split(double f, uint32_t &lo, uint32_t &hi) {
+        uint64_t u;
+        std::memcpy(&u, &f, 8);
+        lo = (uint32_t)u;
+        hi = (uint32_t)(u >> 32);
+    }
+
+    void run() {
+        const auto &ops2 = al.ops2;
+        const int64_t M = (int64_t)ops2.size();
+        slot_group.assign((size_t)std::max(al.n_slots, 1), -1);
+        // bucket the loads by their hoisted anchor
+        std::vector<std::vector<int32_t>> at((size_t)M + 1);
+        for (size_t i = 0; i < al.ldls.size(); ++i) {
+            const Ldl &l = al.ldls[i];
+            int64_t t = l.anchor - dist;
+            if (t < l.earliest) t = l.earliest;
+            if (t > l.anchor) t = l.anchor;
+            at[(size_t)t].push_back((int32_t)i);
+        }
+        int64_t j = 0;
+        while (j <= M) {
+            // loads anchored before op j, three per packet, one cp.async group per packet
+            const auto &lst = at[(size_t)j];
+            for (size_t k = 0; k < lst.size(); k += 3) {
+                const size_t n = std::min<size_t>(3, lst.size() - k);
+                uint32_t w[3] = {0, 0, 0};
+                for (size_t q = 0; q < n; ++q) {
+                    const Ldl &l = al.ldls[(size_t)lst[k + q]];
+                    w[q] = FDG_LDL_WORD(l.slot, l.leaf);
+                    slot_group[(size_t)l.slot] = committed;
+                }
+                packet(FDG_HDR(FDG_OP_LDL, n, 0), w[0], w[1], w[2]);
+                committed++;
+            }
+            if (j == M) break;
+            const Op2 &o = ops2[(size_t)j];
+            if (o.kind == 1) {  // SPILL
+                need(o.slot);
+                packet(FDG_HDR(FDG_OP_SPILL, 0, (uint32_t)o.scratch), (uint32_t)o.slot);
+                ++j;
+                continue;
+            }
+            if (o.kind == 2) {  // FILL
+                slot_group[(size_t)o.slot] = -1;
+                packet(FDG_HDR(FDG_OP_FILL, 0, (uint32_t)o.scratch), (uint32_t)o.slot);
+                ++j;
+                continue;
+            }
+            const Sym &s = o.s;
+            const uint32_t opc = FDG_REGOP(s.base, s.d);
+            if (s.base == FDG_R_MOV || s.base == FDG_R_MUL || s.base == FDG_R_ADD) {
+                // pack a run of the same fold: MOV a [MUL b [MUL c]] / MUL a b c / ADD a b c
+                const uint8_t follow = s.base == FDG_R_ADD ? FDG_R_ADD : FDG_R_MUL;
+                uint32_t w[3] = {(uint32_t)o.slot, 0, 0};
+                int n = 1;
+                while (n < 3 && j + n < M && at[(size_t)(j + n)].empty()) {
+                    const Op2 &o2 = ops2[(size_t)(j + n)];
+                    if (o2.kind != 0 || o2.s.base != follow || o2.s.d != s.d) break;
+                    w[n] = (uint32_t)o2.slot;
+                    ++n;
+                }
+                for (int q = 0; q < n; ++q) need((int32_t)w[q]);
+                packet(FDG_HDR(opc, n, 0), w[0], w[1], w[2]);
+                j += n;
+                continue;
+            }
+            uint32_t lo = 0, hi = 0;
+            if (has_factor(s.base)) split(s.f, lo, hi);
+            switch (s.base) {
+                case FDG_R_MOVF:
+                case FDG_R_MULF:
+                case FDG_R_ADDF:
+                case FDG_R_XADDF:
+                case FDG_R_XMULF:
+                    need(o.slot);
+                    packet(FDG_HDR(opc, 1, 0), (uint32_t)o.slot, lo, hi);
+                    break;
+                case FDG_R_SCALE:
+                case FDG_R_RADDF:
+                case FDG_R_RMULF:
+                    packet(FDG_HDR(opc, 0, 0), 0, lo, hi);
+                    break;
+                case FDG_R_POW:
+                case FDG_R_ROOT:
+                    packet(FDG_HDR(opc, 0, (uint32_t)s.arg));
+                    break;
+                case FDG_R_ST:
+                    slot_group[(size_t)o.slot] = -1;
+                    packet(FDG_HDR(opc, 0, (uint32_t)o.slot));
+                    break;
+                default:
+                    break;
+            }
+            ++j;
+        }
+        packet(FDG_HDR(FDG_OP_END, 0, 0));
+    }
+};
+
+}  // namespace
+
+int lower(const fdg_graph_desc &g, const fdg_options &opt, Lowered &out, std::string &err) {
+    if (opt.dtype != FDG_F64 && opt.dtype != FDG_C128) {
+        err = "unsupported dtype (only FDG_F64 and FDG_C128)";  // static.jl:151 "Unsupported type"
+        return FDG_ERR_UNSUPPORTED;
+    }
+    out = Lowered();
+    out.dtype = opt.dtype;
+    std::vector<Stmt> st;
+    std::vector<Operand> ops;
+    int rc = build_statements(g, st, ops, out, err);
+    if (rc != FDG_OK) return rc;
+
+    CodeGen cg(st, ops, out);
+    cg.run();
+    out.max_depth = cg.max_depth;
+
+    int32_t max_slots = opt.max_slots > 0 ? opt.max_slots : 96;
+    if (max_slots < 4) max_slots = 4;
+    if (max_slots > FDG_MAX_SLOTS) max_slots = FDG_MAX_SLOTS;
+    Allocator al(st, cg.code, cg.n_values, max_slots);
+    al.run();
+    if (al.n_scratch >= FDG_MAX_ARG) {
+        err = "program needs too many scratch values";
+        return FDG_ERR_CAPACITY;
+    }
+    out.n_slots = std::max(al.n_slots, 1);
+    out.n_scratch = al.n_scratch;
+    out.leaf_loads = al.leaf_loads;
+
+    int32_t dist = opt.prefetch == 0 ? 24 : (opt.prefetch < 0 ? 0 : opt.prefetch);
+    Packer pk(al, out.words, dist);
+    pk.run();
+    return FDG_OK;
+}
+
+}  // namespace fdg

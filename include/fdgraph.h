@@ -1,0 +1,155 @@
+/*
+ * fdgraph.h -- C ABI of libfdgraph.so, the B200 (sm_100a) back end for FeynmanDiagram.jl's
+ * computational-graph evaluator.
+ *
+ * This is the drop-in boundary for the ONE hot path this project accelerates:
+ *
+ *   reference                                                    replaced by
+ *   ---------------------------------------------------------   ---------------------------------
+ *   Compilers.compile(graphs; root)   src/backend/static.jl:221-227      fdg_compile + fdg_leafmap
+ *   to_julia_str / to_Cstr / to_python_str (emit + leaf numbering)
+ *        static.jl:98-133, :155-197, compiler_python.jl:9-52             fdg_compile (lowering)
+ *   generated eval_graph!(root, leafVal)   static.jl:100,117,123,127,131 fdg_eval (batch of samples)
+ *   batched torch form  eval_graph(leafVal[B,L]) -> root[B,R]
+ *        compiler_python.jl:23,28,43-49                                  fdg_eval / fdg_eval_host
+ *   (no counterpart: MC accumulation over samples, multi-GPU)            fdg_eval_accumulate,
+ *                                                                        fdg_comm_* / fdg_allreduce
+ *
+ * Conventions
+ *   - plain C types only; every function returns an int status (FDG_OK == 0) and never throws.
+ *     fdg_last_error() returns a thread-local message for the last non-zero status.
+ *   - the caller owns every data buffer and the CUDA stream; a handle owns the lowered program
+ *     and its device copy (one per device, uploaded lazily on first evaluation).
+ *   - data layout is batch-major ("one column per leaf / root", the layout of a Julia B x L
+ *     matrix and of the reference's torch emitter): leaf value l of sample b lives at
+ *     leaf[l * ld_leaf + b], root r of sample b at root[r * ld_root + b].  Element type is
+ *     double (FDG_F64) or interleaved (re, im) doubles (FDG_C128, Julia ComplexF64).
+ *   - leaf numbering is the reference's: leaf k (0-based here, k+1 in Julia) is the k-th distinct
+ *     leaf (by Graph id) met by the post-order DFS over `graphs` (static.jl:106-120).
+ *   - arithmetic is the reference's: n-ary Sum / Prod are left folds in stored subgraph order,
+ *     a `* factor` exists only where the factor != 1, no FMA contraction.  Results are
+ *     bit-identical to the emitted Julia / C function for Sum, Prod and Power{2,3}.
+ */
+#ifndef FDGRAPH_H
+#define FDGRAPH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDG_ABI_VERSION 1
+
+/* status codes */
+enum {
+    FDG_OK = 0,
+    FDG_ERR_BAD_ARG = 1,      /* null pointer, negative size, misaligned buffer ...          */
+    FDG_ERR_BAD_GRAPH = 2,    /* cycle, child index out of range, unknown operator, Power N<2,
+                                 Power with != 1 subgraph (static.jl:6-11 `error(...)`)      */
+    FDG_ERR_UNSUPPORTED = 3,  /* dtype / option not supported (static.jl:151)                 */
+    FDG_ERR_CUDA = 4,         /* CUDA runtime error (message has cudaGetErrorString)          */
+    FDG_ERR_NCCL = 5,         /* NCCL missing or failing                                      */
+    FDG_ERR_NO_DEVICE = 6,    /* no CUDA device: there is NO CPU fallback                     */
+    FDG_ERR_CAPACITY = 7      /* program does not fit the on-chip slot file even with spills  */
+};
+
+/* node operators: abstractgraph.jl:3-12.  A node with no subgraphs is a LEAF for the back end
+ * whatever its operator tag (static.jl:115). */
+enum { FDG_OP_UNITARY = 0, FDG_OP_SUM = 1, FDG_OP_PROD = 2, FDG_OP_POWER = 3 };
+
+/* element types of leafVal / root (julia_to_C_typestr, static.jl:135-153) */
+enum { FDG_F64 = 0, FDG_C128 = 1 };
+
+/* The DAG as the Julia/Python side flattens it: one entry per node OBJECT, in any order.
+ * Replaces walking Graph{F,W} / FeynmanGraph{F,W} (graph.jl:28-40, feynmangraph.jl:72-82)
+ * through id/operator/subgraphs/subgraph_factors. */
+typedef struct fdg_graph_desc {
+    int64_t n_nodes;
+    int64_t n_edges;
+    const int64_t *node_id;      /* [n_nodes] Graph.id -- the emitter dedupes by id, first visit wins */
+    const int32_t *node_op;      /* [n_nodes] FDG_OP_*                                        */
+    const int32_t *node_pow;     /* [n_nodes] N of Power{N} (ignored otherwise)               */
+    const int64_t *child_ptr;    /* [n_nodes+1] CSR offsets into child_node / child_factor    */
+    const int32_t *child_node;   /* [n_edges] node index of each subgraph, stored order       */
+    const double *child_factor;  /* [n_edges] subgraph_factors                                */
+    int64_t n_graphs;
+    const int32_t *graphs;       /* [n_graphs] node index of each element of `graphs`         */
+    int64_t n_roots;
+    const int64_t *root_id;      /* [n_roots] the `root` kwarg: ids, default id.(graphs)      */
+} fdg_graph_desc;
+
+typedef struct fdg_options {
+    int32_t dtype;        /* FDG_F64 (default) or FDG_C128                                     */
+    int32_t max_slots;    /* cap on on-chip value slots per sample (0 = choose automatically)  */
+    int32_t prefetch;     /* leaf prefetch distance in packets (0 = default, <0 = demand only) */
+    int32_t reserved[5];  /* must be zero                                                      */
+} fdg_options;
+
+typedef struct fdg_program *fdg_handle;
+
+/* counters describing a lowered program (fdg_stats) */
+typedef struct fdg_stats_t {
+    int64_t n_leaves;       /* L: distinct leaves = columns of leafVal                         */
+    int64_t n_inner;        /* N: distinct inner nodes (statements of the emitted function)    */
+    int64_t n_roots;        /* R: columns of root                                              */
+    int64_t n_operands;     /* operand references (edges after dedupe)                         */
+    int64_t n_packets;      /* 16-byte VM packets                                              */
+    int64_t n_slots;        /* on-chip slots per sample the program uses                       */
+    int64_t n_scratch;      /* spilled values per sample kept in global scratch                */
+    int64_t leaf_loads;     /* leaf fetches per sample issued by the program (>= L)            */
+    int64_t flops_add;      /* real additions per sample (complex: x2)                         */
+    int64_t flops_mul;      /* real multiplications per sample                                 */
+    int64_t bytes_in;       /* algorithmic input bytes per sample  = sizeof(W) * L             */
+    int64_t bytes_out;      /* algorithmic output bytes per sample = sizeof(W) * R (eval mode) */
+    int64_t max_depth;      /* accumulator nesting depth of the program                        */
+    int64_t reserved[3];
+} fdg_stats_t;
+
+int fdg_abi_version(void);
+const char *fdg_last_error(void);
+
+/* --- compile: host-only, needs no GPU ---------------------------------------------------------- */
+int fdg_compile(const fdg_graph_desc *graph, const fdg_options *opts /* may be NULL */, fdg_handle *out);
+int fdg_destroy(fdg_handle h);
+int fdg_stats(fdg_handle h, fdg_stats_t *out);
+/* leafmap: node index (into the desc arrays) of leaf k, k = 0..L-1 -- same numbering as the
+ * reference's `leafmap::Dict{Int,Graph}` (static.jl:118-119), 0-based. */
+int fdg_leafmap(fdg_handle h, int32_t *leaf_node /* [L] */);
+/* position in `root` (0-based) written last -- eval_graph! returns that value (static.jl:127,131);
+ * -1 if no root statement exists. */
+int fdg_last_root(fdg_handle h, int32_t *out);
+/* the lowered VM program (for inspection / tests): n_packets * 4 uint32 words */
+int fdg_program_words(fdg_handle h, const uint32_t **words, int64_t *n_words);
+
+/* --- evaluate: device pointers, asynchronous on `stream` (a cudaStream_t, may be NULL) ---------- */
+/* root[r*ld_root + b] = graph r at sample b, b < batch.  Columns of `root` whose id was never met
+ * are left untouched, like the reference. */
+int fdg_eval(fdg_handle h, const void *leaf, int64_t ld_leaf, void *root, int64_t ld_root,
+             int64_t batch, void *stream);
+/* acc[r] += sum_b root_r(b): deterministic fixed-order reduction on device (no atomics).
+ * acc has R doubles (2R for FDG_C128) in device memory. */
+int fdg_eval_accumulate(fdg_handle h, const void *leaf, int64_t ld_leaf, int64_t batch, double *acc,
+                        void *stream);
+/* host-buffer convenience (the reference-facing call: leafVal / root are ordinary host arrays):
+ * chunked H2D -> fdg_eval -> D2H through pinned staging on two streams; synchronous. */
+int fdg_eval_host(fdg_handle h, const void *leaf_host, int64_t ld_leaf, void *root_host, int64_t ld_root,
+                  int64_t batch);
+/* choose launch shape: threads per block, samples per thread (1 or 2), blocks per SM (0 = auto). */
+int fdg_set_launch(fdg_handle h, int32_t threads, int32_t samples_per_thread, int32_t blocks_per_sm);
+/* number of kernel launches issued by this handle so far (bench's gpu_launches) */
+int fdg_launch_count(fdg_handle h, int64_t *out);
+
+/* --- multi-GPU: one process per GPU; the only exchange is the sum of the per-root accumulators ---- */
+typedef struct fdg_comm *fdg_comm_t;
+int fdg_comm_unique_id(void *id128 /* 128 bytes out */);
+int fdg_comm_init(fdg_comm_t *out, int32_t nranks, int32_t rank, const void *id128);
+int fdg_comm_destroy(fdg_comm_t c);
+/* in-place sum over ranks of n doubles in device memory (ncclAllReduce, ncclSum) */
+int fdg_allreduce(fdg_comm_t c, double *acc, int64_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDGRAPH_H */
