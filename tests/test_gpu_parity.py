@@ -1,0 +1,195 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes / torch pointers), against the CPU
+oracle on the same seeded inputs.  Bar: BIT-EXACT for Float64 and ComplexF64 (Sum, Prod, Power{2,3}; Power{N>=4}
+uses the same compensated algorithm on both sides and is compared bit-exactly as well)."""
+import numpy as np
+import pytest
+
+import fdgraph_b200 as fd
+import graphgen
+from fdgraph_b200 import _capi
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _dev_eval(ev, leaf_host: np.ndarray, batch: int, spt: int = 0, threads: int = 0, fill=-3.0):
+    """leaf_host (L, ld) -> root (R, batch) through fdg_eval with device buffers."""
+    ev.set_launch(threads, spt, 0)
+    dt = torch.float64 if leaf_host.dtype == np.float64 else torch.complex128
+    leaf = torch.from_numpy(leaf_host).cuda()
+    ld = leaf_host.shape[1]
+    root = torch.full((max(ev.n_roots, 1), ld), fill, dtype=dt, device="cuda")
+    ev.eval_device(leaf.data_ptr(), ld, root.data_ptr(), ld, batch, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return root.cpu().numpy()[: ev.n_roots, :batch]
+
+
+def _parity(roots, dtype=np.float64, batch=1000, ld=0, spt=0, threads=0, max_slots=0, prefetch=0, signed=True, root=None):
+    raw, _ = fd.flatten(roots, root)
+    ev = fd.compile_raw(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch)
+    orc = O.Oracle(raw)
+    leaf = graphgen.leaf_values(5, max(ev.n_leaves, 1), batch, dtype=dtype, signed=signed, ld=ld)
+    want = orc.eval(np.ascontiguousarray(leaf[:, :batch]), "emitter", root=np.full((orc.n_roots, batch), -3.0, dtype))
+    got = _dev_eval(ev, leaf, batch, spt, threads)
+    assert got.tobytes() == want.tobytes()
+    return ev
+
+
+def test_known_answers_through_the_public_call():
+    # reference test/compiler.jl:18-31 (4.5) and test/computational_graph.jl:874-887 (26, 27, 702)
+    v1, v2 = fd.FeynmanGraph([]), fd.FeynmanGraph([])
+    g = fd.FeynmanGraph([v1, v2], factor=1.5)
+    eval_graph, leafmap = fd.Compilers.compile([g])
+    root = np.array([0.0])
+    leaf = np.array([1.0, 2.0])
+    assert eval_graph(root, leaf) == 4.5 == (leaf[0] + leaf[1]) * 1.5
+    assert root[0] == 4.5 and leafmap[0] is v1 and leafmap[1] is v2
+    g1, g2 = fd.Graph([]), fd.Graph([], factor=2)
+    g3 = 2 * (3 * g1 + 5 * g2)
+    g4 = g1 + 2 * (3 * g1 + 5 * g2)
+    g5 = g4 * g3
+    f, _ = fd.compile([g3, g4, g5])
+    root = np.zeros(3)
+    assert f(root, np.ones(2)) == 702.0
+    assert list(root) == [26.0, 27.0, 702.0]
+
+
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("spt", [1, 2])
+def test_random_dag_f64(seed, spt):
+    _parity(graphgen.random_dag(seed, n_leaves=6 + seed, n_inner=40 + 10 * seed, n_roots=3), spt=spt, batch=1536 + 2 * seed)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_dag_c128(seed):
+    _parity(graphgen.random_dag(200 + seed, n_leaves=7, n_inner=60, n_roots=3, max_pow=5), dtype=np.complex128, batch=777)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_tree_nesting(seed):
+    _parity(graphgen.random_tree(300 + seed, depth=8), max_slots=6 + seed, batch=515, ld=516)
+
+
+def test_power_ge_4():
+    _parity(graphgen.random_dag(7, n_leaves=4, n_inner=30, n_roots=2, p_power=0.4, max_pow=7), signed=False)
+
+
+@pytest.mark.parametrize("max_slots,prefetch", [(4, -1), (5, 8), (8, 64), (16, 1), (64, 24)])
+def test_spills_and_prefetch(max_slots, prefetch):
+    roots = graphgen.random_dag(42, n_leaves=20, n_inner=120, n_roots=4)
+    ev = _parity(roots, max_slots=max_slots, prefetch=prefetch, batch=4100, ld=4102)
+    if max_slots <= 5:
+        assert ev.stats["n_scratch"] > 0
+
+
+@pytest.mark.parametrize("batch,ld", [(1, 1), (1, 2), (2, 2), (3, 3), (3, 4), (31, 32), (33, 40), (255, 256), (257, 257), (1025, 1026)])
+def test_ragged_batches(batch, ld):
+    # odd / tiny batches, padded leading dimensions, the one- and two-samples-per-thread kernels
+    _parity(graphgen.random_dag(9, n_leaves=9, n_inner=50, n_roots=3), batch=batch, ld=ld)
+
+
+@pytest.mark.parametrize("threads", [32, 64, 128, 256])
+def test_block_shapes(threads):
+    _parity(graphgen.sum_of_products(5, n_leaves=40, n_terms=300, term_len=6, n_roots=2), threads=threads, batch=5000,
+            max_slots=24, prefetch=16)
+
+
+def test_roots_unset_columns_are_left_untouched():
+    a, b = fd.Graph([]), fd.Graph([])
+    s = fd.Graph([a, b], operator=fd.Sum())
+    p = fd.Graph([s, s, a], operator=fd.Prod())
+    _parity([p, s, a], root=[a.id, 999, p.id, s.id, a.id], batch=100)
+
+
+def test_empty_batch_and_empty_program():
+    a, b = fd.Graph([]), fd.Graph([])
+    ev, _ = fd.compile([a + b])
+    ev.eval_device(0, 0, 0, 0, 0)  # batch 0: no launch, no error
+    ev0 = fd.compile_raw(fd.flatten([])[0])
+    ev0.eval_device(0, 8, 0, 8, 8)
+    torch.cuda.synchronize()
+
+
+def test_bad_arguments_are_reported_not_executed():
+    a, b = fd.Graph([]), fd.Graph([])
+    ev, _ = fd.compile([a + b])
+    x = torch.zeros(64, dtype=torch.float64, device="cuda")
+    with pytest.raises(_capi.FdgError) as e:
+        ev.eval_device(x.data_ptr(), 4, x.data_ptr(), 8, 8)  # ld_leaf < batch
+    assert e.value.code == 1
+    with pytest.raises(_capi.FdgError):
+        ev.eval_device(0, 8, x.data_ptr(), 8, 8)  # null leaf
+
+
+def test_accumulate_is_the_sum_of_eval_and_deterministic():
+    roots = graphgen.random_dag(21, n_leaves=10, n_inner=60, n_roots=4)
+    raw, _ = fd.flatten(roots)
+    for dtype, w in ((np.float64, 1), (np.complex128, 2)):
+        ev = fd.compile_raw(raw, dtype=dtype)
+        batch = 100_003
+        leaf_h = graphgen.leaf_values(3, ev.n_leaves, batch, dtype=dtype, signed=True, ld=batch + 1)
+        per_sample = _dev_eval(ev, leaf_h, batch)
+        leaf = torch.from_numpy(leaf_h).cuda()
+        accs = []
+        for _ in range(2):
+            acc = torch.zeros(ev.n_roots * w, dtype=torch.float64, device="cuda")
+            ev.accumulate(leaf.T[:batch], acc)
+            ev.accumulate(leaf.T[:batch], acc)  # accumulates on top
+            torch.cuda.synchronize()
+            accs.append(acc.cpu().numpy())
+        assert accs[0].tobytes() == accs[1].tobytes()  # fixed-order reduction: run-to-run identical
+        want = 2 * per_sample.sum(axis=1)
+        scale = 2 * np.abs(per_sample).sum(axis=1)
+        got = accs[0].view(dtype) if w == 2 else accs[0]
+        assert (np.abs(got - want) <= 1e-12 * scale).all()
+
+
+def test_host_buffers_through_eval_graph_call():
+    # the reference-facing call with ordinary host arrays: (B, L) in, (B, R) out, batch-major or not
+    roots = graphgen.random_dag(31, n_leaves=12, n_inner=70, n_roots=3)
+    f, leafmap = fd.compile(roots)
+    orc = O.Oracle(f.raw)
+    B = 70_001
+    leafT = graphgen.leaf_values(8, f.n_leaves, B)
+    want = orc.eval(leafT).T
+    for order in ("F", "C"):
+        leafVal = np.asarray(leafT.T, order=order)
+        root = np.zeros((B, f.n_roots), order=order)
+        ret = f(root, leafVal)
+        assert root.tobytes(order="C") == want.tobytes(order="C")
+        assert (ret == want[:, f.last_root]).all()
+
+
+def test_torch_tensors_batch_major():
+    roots = graphgen.random_dag(32, n_leaves=12, n_inner=70, n_roots=3)
+    f, _ = fd.compile(roots)
+    orc = O.Oracle(f.raw)
+    B = 4097
+    leafT = graphgen.leaf_values(8, f.n_leaves, B)
+    leafVal = torch.from_numpy(leafT).cuda().T  # (B, L) with strides (1, B)
+    root = torch.empty(f.n_roots, B, dtype=torch.float64, device="cuda").T
+    f(root, leafVal)
+    torch.cuda.synchronize()
+    assert root.T.contiguous().cpu().numpy().tobytes() == orc.eval(leafT).tobytes()
+    with pytest.raises(ValueError):
+        f(torch.empty(B, f.n_roots, dtype=torch.float64, device="cuda"), leafVal.contiguous())
+
+
+def test_large_batch_properties():
+    """Full-size style checks that do not need the oracle on every sample: linearity in the root factors and
+    agreement of a strided subsample with the oracle."""
+    roots = graphgen.sum_of_products(77, n_leaves=32, n_terms=60, term_len=4, n_roots=2)
+    scaled = [fd.Graph([r], operator=fd.Prod(), subgraph_factors=[2.0]) for r in roots]  # exact: *2
+    f, _ = fd.compile(roots + scaled)
+    B = 1 << 22
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    leaf = (torch.rand(f.n_leaves, B, dtype=torch.float64, device="cuda", generator=g) + 0.5)
+    root = torch.empty(f.n_roots, B, dtype=torch.float64, device="cuda")
+    f(root.T, leaf.T)
+    torch.cuda.synchronize()
+    assert torch.equal(root[2], 2 * root[0]) and torch.equal(root[3], 2 * root[1])
+    idx = torch.arange(0, B, 4099, device="cuda")
+    sub = leaf[:, idx].cpu().numpy()
+    want = O.Oracle(f.raw).eval(np.ascontiguousarray(sub))
+    assert root[:, idx].cpu().numpy().tobytes() == want.tobytes()

@@ -1,0 +1,186 @@
+"""CPU-only checks of the native lowering (fdg_compile): the packet program, run by the ISA emulator,
+must reproduce the oracle's emitter-order values bit for bit, whatever the slot budget / prefetch distance."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import fdgraph_b200 as fd
+import graphgen
+import vm_emulator as E
+from fdgraph_b200 import _capi
+from oracle import oracle as O
+
+
+def _check(roots, dtype=np.float64, max_slots=0, prefetch=0, batch=7, signed=True, root=None):
+    raw, nodes = fd.flatten(roots, root)
+    ev = fd.compile_raw(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch)
+    orc = O.Oracle(raw)
+    assert ev.n_leaves == orc.n_leaves and (ev.leaf_nodes == orc.leaf_nodes).all()
+    assert ev.last_root == orc.last_root
+    leaf = graphgen.leaf_values(11, max(ev.n_leaves, 1), batch, dtype=dtype, signed=signed)
+    want = orc.eval(leaf, "emitter", root=np.full((orc.n_roots, batch), -3.0, dtype))
+    got, mask, cnt = E.run(ev.program_words(), leaf, ev.n_roots)
+    got[~mask] = -3.0
+    assert got.tobytes() == want.tobytes(), E.disassemble(ev.program_words())
+    assert cnt["max_slot"] + 1 <= ev.stats["n_slots"]
+    assert cnt["ldl"] == ev.stats["leaf_loads"]
+    return ev, cnt
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_dag_f64(seed):
+    _check(graphgen.random_dag(seed, n_leaves=6 + seed, n_inner=30 + 5 * seed, n_roots=3))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_dag_deep(seed):
+    # deep nesting exercises the accumulator registers and the spilled-accumulator (XADDF/XMULF) path
+    _check(graphgen.random_dag(100 + seed, n_leaves=5, n_inner=80, n_roots=2, max_fan=3, deep=True))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_tree_nesting(seed):
+    ev, _ = _check(graphgen.random_tree(300 + seed, depth=8), max_slots=6 + seed)
+    assert ev.stats["max_depth"] >= 6
+    words = ev.program_words().reshape(-1, 4)
+    bases = {int((w & 0xFF) - 8) // 4 for w in words[:, 0] if (w & 0xFF) >= 8}
+    assert {E.R_RADDF, E.R_XADDF} <= bases  # both the register and the spilled combine paths are used
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_dag_c128(seed):
+    _check(graphgen.random_dag(200 + seed, n_leaves=7, n_inner=40, n_roots=3, max_pow=5), dtype=np.complex128)
+
+
+def test_power_ge_4_f64():
+    _check(graphgen.random_dag(7, n_leaves=4, n_inner=30, n_roots=2, p_power=0.4, max_pow=7), signed=False)
+
+
+@pytest.mark.parametrize("max_slots", [4, 5, 8, 16])
+@pytest.mark.parametrize("prefetch", [-1, 1, 8, 64])
+def test_small_slot_file_spills_and_prefetch(max_slots, prefetch):
+    roots = graphgen.random_dag(42, n_leaves=20, n_inner=120, n_roots=4)
+    ev, cnt = _check(roots, max_slots=max_slots, prefetch=prefetch)
+    assert ev.stats["n_slots"] <= max_slots
+    if max_slots <= 8:
+        assert ev.stats["n_scratch"] > 0 or ev.stats["leaf_loads"] > ev.n_leaves
+
+
+def test_sum_of_products_shape():
+    roots = graphgen.sum_of_products(5, n_leaves=40, n_terms=300, term_len=6, n_roots=2)
+    ev, cnt = _check(roots, max_slots=24, prefetch=16)
+    st = ev.stats
+    # single-use products are folded into the accumulators: no slot traffic for them
+    assert st["n_scratch"] == 0
+    assert st["flops_mul"] >= 300 * 5 and st["flops_add"] == 2 * 299
+
+
+def test_stats_counts_match_reference_operation_count():
+    # count_operation (tree_properties.jl:165-185): sum (fan_in - 1) adds, prod (fan_in - 1) muls; + 1 mul per factor != 1
+    a, b, c = fd.Graph([]), fd.Graph([]), fd.Graph([])
+    s = fd.Graph([a, b, c], operator=fd.Sum(), subgraph_factors=[1.0, 2.0, 1.0])
+    p = fd.Graph([s, a, b], operator=fd.Prod(), subgraph_factors=[1.0, 1.0, -1.0])
+    ev, _ = _check([p])
+    assert ev.stats["flops_add"] == 2 and ev.stats["flops_mul"] == 2 + 1 + 1
+    assert ev.stats["bytes_in"] == 24 and ev.stats["bytes_out"] == 8
+    evc = fd.compile_raw(ev.raw, dtype=np.complex128)
+    assert evc.stats["bytes_in"] == 48 and evc.stats["flops_mul"] == 4 * 2 + 2 * 2
+
+
+def test_roots_leaf_shared_and_unset():
+    a, b = fd.Graph([]), fd.Graph([])
+    s = fd.Graph([a, b], operator=fd.Sum())
+    p = fd.Graph([s, s, a], operator=fd.Prod())
+    _check([p, s, a], root=[a.id, 999, p.id, s.id, a.id])
+
+
+def test_unary_chains_and_dead_nodes():
+    a = fd.Graph([])
+    chain = a
+    for f in (2.0, 1.0, -3.0, 1.0):
+        chain = fd.Graph([chain], operator=fd.Prod() if f != 1.0 else fd.Sum(), subgraph_factors=[f])
+    dead = fd.Graph([a, a], operator=fd.Prod())  # computed by the emitter, never observable
+    top = fd.Graph([chain, dead], operator=fd.Sum())
+    _check([top, chain], root=[chain.id])
+
+
+def test_long_left_deep_chain_is_not_recursive():
+    g = fd.Graph([])
+    acc = g
+    for i in range(20000):
+        acc = fd.Graph([acc, g], operator=fd.Sum(), subgraph_factors=[1.0, 0.5])
+    raw, _ = fd.flatten([acc])
+    ev = fd.compile_raw(raw)
+    assert ev.stats["n_inner"] == 20000
+    orc = O.Oracle(raw)
+    leaf = np.array([[1.0, 2.0]])
+    got, _, _ = E.run(ev.program_words(), leaf, 1)
+    assert got.tobytes() == orc.eval(leaf).tobytes()
+
+
+def test_empty_and_trivial():
+    ev = fd.compile_raw(fd.flatten([])[0])
+    assert ev.stats["n_leaves"] == 0 and ev.stats["n_packets"] == 1
+    a = fd.Graph([])
+    _check([a])  # a leaf that is itself the root
+
+
+def _desc_err(raw):
+    with pytest.raises(_capi.FdgError) as e:
+        fd.compile_raw(raw)
+    return e.value
+
+
+def test_error_codes():
+    a, b = fd.Graph([]), fd.Graph([])
+    s = fd.Graph([a, b], operator=fd.Sum())
+    raw, _ = fd.flatten([s])
+    bad = fd.RawGraph(**{k: getattr(raw, k).copy() for k in raw.__dataclass_fields__})
+    bad.child_node[0] = 77
+    assert _desc_err(bad).code == 2  # FDG_ERR_BAD_GRAPH
+    bad = fd.RawGraph(**{k: getattr(raw, k).copy() for k in raw.__dataclass_fields__})
+    bad.node_op[-1] = 9  # unknown operator: static.jl:6-11 error(...)
+    assert _desc_err(bad).code == 2
+    # a cycle
+    bad = fd.RawGraph(**{k: getattr(raw, k).copy() for k in raw.__dataclass_fields__})
+    bad.child_node[0] = len(bad.node_id) - 1
+    assert _desc_err(bad).code == 2
+    # Power{N<2}
+    p = fd.Graph([a], operator=fd.Power(2))
+    rawp, _ = fd.flatten([p])
+    rawp.node_pow[:] = -1
+    assert _desc_err(rawp).code == 2
+    with pytest.raises(TypeError):
+        fd.compile_raw(raw, dtype=np.float32)  # static.jl:151 "Unsupported type"
+    with pytest.raises(NotImplementedError):
+        class Weird(fd.graph.Operator):
+            pass
+        fd.flatten([fd.Graph([a], operator=Weird())])
+
+
+def test_library_exports_every_declared_symbol():
+    import os
+    import re
+
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(here, "include", "fdgraph.h")).read()
+    declared = set(re.findall(r"\b(fdg_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"fdg_graph_desc", "fdg_options"}
+    L = _capi.lib()
+    assert declared == set(_capi.EXPORTS)
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert L.fdg_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    a, b = fd.Graph([]), fd.Graph([])
+    ev, _ = fd.compile([a + b])
+    with pytest.raises(_capi.FdgError) as e:
+        ev(np.zeros(1), np.array([1.0, 2.0]))
+    assert e.value.code in (6, 4)  # FDG_ERR_NO_DEVICE (or a CUDA error): never a silent CPU result

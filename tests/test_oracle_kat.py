@@ -1,0 +1,118 @@
+"""Pins the CPU oracle (and the host Graph mirror) against the reference's own known-answer tests."""
+import numpy as np
+import pytest
+
+import fdgraph_b200 as fd
+from oracle import oracle as O
+
+
+def _emit(graphs, leaf, root=None):
+    raw, nodes = fd.flatten(graphs, root)
+    orc = O.Oracle(raw)
+    out = orc.eval(np.asarray(leaf, np.float64).reshape(-1, 1), mode="emitter")
+    return orc, out[:, 0], nodes
+
+
+def test_compile_directly_4p5():
+    # reference test/compiler.jl:2-16: FeynmanGraph([ext_vertex, ext_vertex]; factor=1.5), leaf=[1,2] -> 4.5
+    v1, v2 = fd.FeynmanGraph([]), fd.FeynmanGraph([])
+    g = fd.FeynmanGraph([v1, v2], factor=1.5)
+    orc, out, nodes = _emit([g], [1.0, 2.0])
+    assert out[0] == 4.5 == (1.0 + 2.0) * 1.5
+    # leaf numbering: first visited leaf is column 0 (static.jl:117-119); return value = last root (static.jl:127)
+    assert [nodes[i] for i in orc.leaf_nodes] == [v1, v2]
+    assert orc.last_root == 0
+    # the interpreter agrees (eval.jl)
+    assert O.eval_interp_py(g, {v1.id: 0, v2.id: 1}, [1.0, 2.0]) == 4.5
+
+
+def test_eval_26_27_702():
+    # reference test/computational_graph.jl:874-887
+    g1 = fd.Graph([])
+    g2 = fd.Graph([], factor=2)
+    g3 = 2 * (3 * g1 + 5 * g2)
+    g4 = g1 + 2 * (3 * g1 + 5 * g2)
+    g5 = g4 * g3
+    assert O.eval_interp_py(g3) == 26
+    assert O.eval_interp_py(g4) == 27
+    assert O.eval_interp_py(g5) == 27 * 26
+    orc, out, _ = _emit([g3, g4, g5], [1.0, 1.0])
+    assert list(out) == [26.0, 27.0, 702.0]
+    for mode in ("emitter", "interp"):
+        r = orc.eval(np.ones((2, 5)), mode=mode)
+        assert (r == np.array([[26.0], [27.0], [702.0]])).all()
+
+
+def test_graph_constructor_conventions():
+    # graph.jl:69-73 factor wrapping, :136-147 scalar product merges trivial unary chains
+    g1 = fd.Graph([])
+    w = fd.Graph([], factor=2)
+    assert isinstance(w.operator, fd.Prod) and w.subgraph_factors == [2.0] and w.subgraphs[0].isleaf()
+    h = 5 * w
+    assert h.subgraphs[0] is w.subgraphs[0] and h.subgraph_factors == [10.0]
+    s = g1 + g1  # linear_combination merges equal ids (graph.jl:199-201)
+    assert len(s.subgraphs) == 1 and s.subgraph_factors == [2.0]
+    p = g1 * g1  # multi_product -> Power(2) (graph.jl:318-319)
+    assert isinstance(p.operator, fd.Power) and p.operator.N == 2
+    with pytest.raises(AssertionError):
+        fd.Power(1)
+    lc = fd.linear_combination([g1, w, g1], [2, 1, 3])  # vector form merges duplicates, unwraps w
+    assert [x.id for x in lc.subgraphs] == [g1.id, w.subgraphs[0].id] and lc.subgraph_factors == [5.0, 2.0]
+    mp = fd.multi_product([g1, g1, w])
+    assert isinstance(mp.operator, fd.Prod) and isinstance(mp.subgraphs[0].operator, fd.Power)
+
+
+def test_root_semantics():
+    # static.jl:111-114,126-128: only ids in `root` are written, at the first position of the id;
+    # the return value is the last root assigned.
+    a, b = fd.Graph([]), fd.Graph([])
+    s = fd.Graph([a, b], operator=fd.Sum(), subgraph_factors=[2.0, 3.0])
+    p = fd.Graph([s, a], operator=fd.Prod())
+    raw, _ = fd.flatten([p], root=[s.id, 12345, p.id, s.id])
+    orc = O.Oracle(raw)
+    out = orc.eval(np.array([[2.0], [5.0]]), root=np.full((4, 1), -7.0))
+    assert list(out[:, 0]) == [19.0, -7.0, 38.0, -7.0]
+    assert orc.last_root == 2
+
+
+def test_dedupe_by_id_first_visit_wins():
+    # two distinct leaf objects with the same id are one variable g<ID> (static.jl:116,122)
+    a = fd.Graph([])
+    a2 = fd.Graph([])
+    a2.id = a.id
+    s = fd.Graph([a, a2], operator=fd.Sum())
+    raw, nodes = fd.flatten([s])
+    orc = O.Oracle(raw)
+    assert orc.n_leaves == 1
+    assert orc.eval(np.array([[3.0]]))[0, 0] == 6.0
+
+
+def test_emitter_vs_interpreter_rounding_differs_for_prod():
+    # eval! computes prod(g_i*f_i), the emitter ((g1*f1)*g2)*f2: same value, maybe different bits
+    rng = np.random.default_rng(0)
+    a, b, c = fd.Graph([]), fd.Graph([]), fd.Graph([])
+    p = fd.Graph([a, b, c], operator=fd.Prod(), subgraph_factors=[1.0 / 3.0, 0.7, 1.1])
+    raw, _ = fd.flatten([p])
+    orc = O.Oracle(raw)
+    leaf = 0.5 + rng.random((3, 4096))
+    e, i = orc.eval(leaf, "emitter"), orc.eval(leaf, "interp")
+    assert np.allclose(e, i, rtol=1e-14)
+    assert (e != i).any()
+    l0 = leaf[:, 0]
+    assert e[0, 0] == ((l0[0] * (1.0 / 3.0)) * l0[1]) * 0.7 * l0[2] * 1.1
+    assert i[0, 0] == (l0[0] * (1.0 / 3.0)) * (l0[1] * 0.7) * (l0[2] * 1.1)
+
+
+def test_exact_rational_agrees():
+    import graphgen
+
+    roots = graphgen.random_dag(3, n_leaves=5, n_inner=25, n_roots=3)
+    raw, _ = fd.flatten(roots)
+    orc = O.Oracle(raw)
+    leaf = graphgen.leaf_values(1, orc.n_leaves, 4, signed=True)
+    out = orc.eval(leaf)
+    for b in range(4):
+        exact = O.eval_exact(orc, leaf[:, b])
+        bound = O.eval_abs_bound(orc, leaf[:, b])
+        for r in range(orc.n_roots):
+            assert abs(out[r, b] - float(exact[r])) <= 64 * 2.3e-16 * bound[r] * orc.n_stmts

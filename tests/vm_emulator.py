@@ -144,6 +144,7 @@ def run(words: np.ndarray, leaf: np.ndarray, n_roots: int, strict: bool = True):
         return slots[s]
 
     ended = False
+    np.seterr(all="ignore")  # overflow / nan are legitimate values here; they must match bit for bit too
     for pc in range(w.shape[0]):
         w0, w1, w2, w3 = (int(x) for x in w[pc])
         op, n, arg = w0 & 0xFF, (w0 >> 8) & 3, w0 >> 10
