@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- MC-sample graph-evals/sec of the graph-evaluation hot path (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--samples S]
+
+One "step" = the compiled graph set evaluated at S Monte-Carlo sample points per GPU with the per-root sums
+accumulated on device (fdg_eval_accumulate) and, for N > 1, one NCCL all-reduce of the R accumulators
+(fdg_allreduce).  S defaults to 2^26 (BASELINE.json).  The leaf matrix of S samples does not fit HBM for the
+order-4 graphs (2^26 x 1514 x 8 B = 813 GB), so a resident batch (<= --resident-gb of HBM, >> L2) is generated
+on device before timing and a step is ceil(S / resident) passes over it: every pass streams the whole resident
+batch from HBM (inputs larger than L2, no cache flush needed).
+
+`value`   graph-evals/s = samples/s x R roots, whole job over all ranks, inputs resident in HBM.
+`e2e`     same metric through the reference-facing call eval_graph(root, leafVal) with HOST buffers (pinned):
+          H2D of the leaves and D2H of the roots inside the timed region.
+`--impl reference` times the CPU restatement of the reference's generated function (oracle/, "port": no julia
+binary exists in this image) on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gv_ver4_o4")
+    ap.add_argument("--samples", type=int, default=1 << 26, help="samples per step per GPU")
+    ap.add_argument("--resident-gb", type=float, default=48.0)
+    ap.add_argument("--e2e-samples", type=int, default=0, help="samples per e2e step (0 = about 2 GiB of leaves)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline leg")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "c128"])
+    ap.add_argument("--max-slots", type=int, default=0)
+    ap.add_argument("--prefetch", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--spt", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def load_workload(name):
+    import fdgraph_b200 as fd
+
+    path = os.path.join(ROOT, "workloads", name + ".npz")
+    if not os.path.exists(path):
+        raise SystemExit(f"unknown workload {name!r}: {path} not found")
+    return fd.RawGraph.load(path)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(raw, dtype, target_seconds, nthreads=0):
+    """Times the CPU port of the reference's generated function (oracle/fdg_oracle.c, emitter semantics, one
+    contiguous leafVal per sample, OpenMP over samples).  Returns (samples/s, threads, samples, seconds)."""
+    from oracle import oracle as O
+
+    orc = O.Oracle(raw)
+    cores = O.lib().oracle_max_threads() if nthreads <= 0 else nthreads
+    rng = np.random.default_rng(1234)
+    npdt = np.float64 if dtype == "f64" else np.complex128
+
+    def run(n):
+        leaf = (0.5 + rng.random((n, max(orc.n_leaves, 1)))).astype(npdt)
+        root = np.zeros((n, orc.n_roots), npdt)
+        t = time.perf_counter()
+        orc.eval(leaf, mode="emitter", layout="sample", nthreads=cores, root=root)
+        return time.perf_counter() - t
+
+    n = max(cores * 4, 64)
+    run(n)  # warm
+    t = run(n)
+    n2 = int(min(max(n, n * target_seconds / max(t, 1e-6)), 1 << 24))
+    n2 = max(cores, (n2 // cores) * cores)
+    t2 = run(n2)
+    return n2 / t2, cores, n2, t2
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    raw = load_workload(a.workload)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import oracle as O
+
+        orc = O.Oracle(raw)
+        R = orc.n_roots
+        per_step = a.cpu_seconds / max(a.steps + a.warmup, 1)
+        rate0, cores, _, _ = cpu_reference(raw, a.dtype, 1.0)
+        n = int(max(cores, rate0 * per_step))
+        npdt = np.float64 if a.dtype == "f64" else np.complex128
+        rng = np.random.default_rng(1234)
+        leaf = (0.5 + rng.random((n, max(orc.n_leaves, 1)))).astype(npdt)
+        root = np.zeros((n, R), npdt)
+        for _ in range(a.warmup):
+            orc.eval(leaf, mode="emitter", layout="sample", nthreads=cores, root=root)
+        t = time.perf_counter()
+        for _ in range(a.steps):
+            orc.eval(leaf, mode="emitter", layout="sample", nthreads=cores, root=root)
+        dt = time.perf_counter() - t
+        val = n * a.steps * R / dt
+        sample = f"{n} samples/step x {a.steps} steps of {a.workload}, sample-major leaves, emitter-order C port, OpenMP"
+        print(json.dumps({
+            "impl": "reference", "metric": "MC-sample graph-evals/sec", "value": val, "unit": "graph-evals/s",
+            "samples_per_s": val / R, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": a.workload, "samples_per_step": n, "roots": R, "leaves": orc.n_leaves},
+            "cpu_baseline": {"value": val, "unit": "graph-evals/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "graph-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import torch
+
+    import fdgraph_b200 as fd
+    from fdgraph_b200 import _capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # our own communicator for the C-ABI all-reduce; torch.distributed is only the rendezvous
+        import ctypes
+
+        ident = [None]
+        if rank == 0:
+            buf = (ctypes.c_ubyte * 128)()
+            _capi.check(_capi.lib().fdg_comm_unique_id(buf))
+            ident = [bytes(buf)]
+        dist.broadcast_object_list(ident, src=0)
+        comm = ctypes.c_void_p()
+        idbuf = (ctypes.c_ubyte * 128).from_buffer_copy(ident[0])
+        _capi.check(_capi.lib().fdg_comm_init(ctypes.byref(comm), world, rank, idbuf))
+
+    npdt = np.float64 if a.dtype == "f64" else np.complex128
+    tdt = torch.float64 if a.dtype == "f64" else torch.complex128
+    es = 8 if a.dtype == "f64" else 16
+    f = fd.compile_raw(raw, dtype=npdt, max_slots=a.max_slots, prefetch=a.prefetch)
+    f.set_launch(a.threads, a.spt, 0)
+    st = f.stats
+    L, R, W = st["n_leaves"], st["n_roots"], (1 if a.dtype == "f64" else 2)
+
+    # ---- resident batch, generated on device (untimed) ---------------------------------------------------------
+    budget = int(a.resident_gb * 2 ** 30)
+    res = min(a.samples, max(1024, budget // max(L * es, 1)))
+    res = 1 << int(math.floor(math.log2(res)))
+    passes = max(1, -(-a.samples // res))
+    samples_step = passes * res
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    leaf = torch.empty(max(L, 1), res, dtype=tdt, device="cuda")
+    chunk = max(1, (1 << 28) // max(res, 1))
+    for l0 in range(0, max(L, 1), chunk):
+        rows = leaf[l0:l0 + chunk]
+        if a.dtype == "f64":
+            rows.copy_(torch.rand(rows.shape, dtype=torch.float64, device="cuda", generator=gen) + 0.5)
+        else:
+            rr = torch.view_as_real(rows)
+            rr.copy_(torch.rand(rr.shape, dtype=torch.float64, device="cuda", generator=gen) + 0.5)
+    acc = torch.zeros(max(R * W, 1), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(events=None):
+        for _ in range(passes):
+            if events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            f.accumulate_device(leaf.data_ptr(), res, res, acc.data_ptr(), stream)
+            if events is not None:
+                e1.record()
+                events.append((e0, e1))
+        if comm is not None:
+            _capi.check(_capi.lib().fdg_allreduce(comm, acc.data_ptr(), R * W, stream))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 0)):
+        acc.zero_()
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = f.launches
+    events = []
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for _ in range(a.steps):
+        step(events)
+    t1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = t0.elapsed_time(t1)
+    launches = f.launches - launches0
+    kern_ms = [e0.elapsed_time(e1) for e0, e1 in events]
+    if dist is not None:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    samples_total = samples_step * a.steps * world
+    sps = samples_total / (ms * 1e-3)
+    value = sps * R
+
+    # ---- roofline of the dominant kernel (the VM kernel; the partial-sum reduce kernel is ~microseconds) ---------
+    peak, peak_src = peaks()
+    avg_launch_s = 1e-3 * float(np.mean(kern_ms)) if kern_ms else float("nan")
+    bytes_launch = st["bytes_in"] * res  # accumulate mode: sizeof(W) * L per sample
+    achieved = bytes_launch / avg_launch_s / 1e9
+    flops_launch = (st["flops_add"] + st["flops_mul"]) * res
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp)).get(a.workload)
+        if tj and tj.get("resident_samples"):
+            traffic = tj["dram_bytes_per_launch"] * res / tj["resident_samples"]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "fdg_vm_kernel",
+                "avg_launch_ms": 1e3 * avg_launch_s, "algorithmic_bytes_per_sample": st["bytes_in"],
+                "fp64_gflops_achieved": flops_launch / avg_launch_s / 1e9, "flops_per_sample": st["flops_add"] + st["flops_mul"],
+                "flop_per_byte": (st["flops_add"] + st["flops_mul"]) / max(st["bytes_in"], 1)}
+
+    out = {
+        "metric": "MC-sample graph-evals/sec", "value": value, "unit": "graph-evals/s", "samples_per_s": sps,
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": a.workload, "mode": "accumulate (per-root sums on device" + (", NCCL all-reduce)" if world > 1 else ")"),
+                   "samples_per_step_per_gpu": samples_step, "resident_samples": res, "passes_per_step": passes,
+                   "leaves": L, "statements": st["n_inner"], "roots": R, "packets": st["n_packets"], "slots": st["n_slots"],
+                   "scratch_values": st["n_scratch"], "leaf_loads_per_sample": st["leaf_loads"],
+                   "l2": f"resident inputs {L * es * res / 2 ** 30:.1f} GiB per GPU >> 126 MB L2, no flush needed",
+                   "leaf_values": "0.5 + U[0,1), seed 1234 + rank"},
+        "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+    # ---- e2e: the reference-facing call with host buffers ------------------------------------------------------
+    if not a.no_e2e:
+        be = a.e2e_samples or max(1024, min(a.samples, (2 << 30) // max(L * es, 1)))
+        be = 1 << int(math.floor(math.log2(be)))
+        hl = torch.empty(max(L, 1), be, dtype=tdt).pin_memory()
+        hr = torch.empty(max(R, 1), be, dtype=tdt).pin_memory()
+        hl_np, hr_np = hl.numpy(), hr.numpy()
+        hl_np[...] = 0.5 + np.random.default_rng(99 + rank).random(hl_np.shape)
+        for _ in range(2):
+            f(hr_np.T, hl_np.T)
+        barrier()
+        k_e2e = max(2, min(a.steps, 5))
+        t = time.perf_counter()
+        for _ in range(k_e2e):
+            f(hr_np.T, hl_np.T)  # eval_graph(root, leafVal): H2D, kernel, D2H, synchronous
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        if dist is not None:
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        out["e2e"] = {"value": be * k_e2e * world * R / dt, "unit": "graph-evals/s", "h2d_bytes_per_step": L * es * be,
+                      "d2h_bytes_per_step": R * es * be, "samples_per_step_per_gpu": be, "steps": k_e2e,
+                      "api": "Compilers.compile(graphs) -> eval_graph(root, leafVal) on pinned host arrays (fdg_eval_host)"}
+        del hl, hr
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------------
+    if rank == 0 and world == 1 and not a.no_cpu:
+        rate, cores, n, secs = cpu_reference(raw, a.dtype, a.cpu_seconds)
+        out["cpu_baseline"] = {"value": rate * R, "unit": "graph-evals/s", "cores": cores, "kind": "port",
+                               "sample": f"{n} samples of {a.workload} in {secs:.1f} s, emitter-order C port of the generated "
+                                         f"function (oracle/fdg_oracle.c), sample-major leaves, OpenMP over samples"}
+    if rank == 0:
+        print(json.dumps(out))
+    if comm is not None:
+        _capi.lib().fdg_comm_destroy(comm)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,65 @@
+"""Generates the workload graphs under workloads/ from the reference's own data files.
+
+Run in the build container (needs /root/reference for the GV `.diag` files); the GPU box only reads the
+committed .npz files.  Each file is a flattened graph (the arrays of fdg_graph_desc, include/fdgraph.h) produced by
+the restated front end + optimize! (oracle/frontend/), i.e. what `Compilers.compile(diags)` receives in
+example/benchmark_GV.jl:23-39 / example/benchmark.jl:23-39.  workloads/MANIFEST.json records provenance, sizes and
+the all-leaves-one value of every root (an exact integer-valued checksum of the diagram content).
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+import fdgraph_b200 as fd  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from oracle.frontend import gv, optimize as opt  # noqa: E402
+
+OUT = os.path.join(ROOT, "workloads")
+
+
+def emit(name, builder, source, manifest):
+    t = time.time()
+    fd.uidreset()
+    graphs = builder()
+    opt.optimize(graphs)
+    raw, _ = fd.flatten(graphs)
+    raw.save(os.path.join(OUT, name + ".npz"))
+    orc = O.Oracle(raw)
+    ones = orc.eval(np.ones((max(orc.n_leaves, 1), 1)))[:, 0]
+    ev = fd.compile_raw(raw)
+    manifest[name] = {
+        "source": source, "n_leaves": orc.n_leaves, "n_statements": orc.n_stmts, "n_roots": orc.n_roots,
+        "n_nodes": raw.n_nodes, "n_edges": raw.n_edges, "flops_add": ev.stats["flops_add"], "flops_mul": ev.stats["flops_mul"],
+        "all_leaves_one": [float(x) for x in ones],
+    }
+    print(f"{name}: L={orc.n_leaves} stmts={orc.n_stmts} R={orc.n_roots} edges={raw.n_edges}  ({time.time() - t:.1f}s)")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    manifest = {}
+    for order in (2, 3, 4, 5, 6):
+        emit(f"gv_sigma_o{order}", lambda o=order: gv.diagsGV("sigma", o),
+             f"GV.diagsGV(:sigma, {order}) + optimize!  (src/frontend/GV_diagrams/groups_sigma/Sigma{order}_0_0.diag)", manifest)
+    for order in (1, 2, 3, 4):
+        emit(f"gv_ver4_o{order}", lambda o=order: gv.diagsGV_ver4(o),
+             f"GV.diagsGV_ver4({order}) + optimize!  (groups_vertex4/Vertex4{order}_0_0.diag; example/benchmark_GV.jl:23-25)",
+             manifest)
+    for order in (3, 4):
+        emit(f"gv_ver4I_o{order}", lambda o=order: gv.diagsGV_ver4(o, channels=[gv.Alli]),
+             f"GV.diagsGV_ver4({order}, channels=[Alli]) + optimize!  (groups_vertex4/Vertex4I{order}_0_0.diag)", manifest)
+    extra = os.path.join(OUT, "MANIFEST.extra.json")  # entries written by other generators (Parquet, Taylor)
+    if os.path.exists(extra):
+        manifest.update(json.load(open(extra)))
+    with open(os.path.join(OUT, "MANIFEST.json"), "w") as fh:
+        json.dump(manifest, fh, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
