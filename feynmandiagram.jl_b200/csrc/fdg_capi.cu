@@ -78,6 +78,7 @@ int launch_variant(fdg_program *h, DeviceState &ds, fdg::VmArgs &args, long long
     int T = h->threads;
     auto smem_for = [&](int t) -> size_t {
         size_t b = (size_t)low.n_slots * t * sizeof(V);
+        b += (size_t)(t / 32) * 2 * FDG_CHUNK * 16;  // per-warp program buffers
         if (ACC) b += (size_t)(t / 32) * low.R * W * sizeof(double);
         return b;
     };
@@ -144,9 +145,10 @@ int get_device_state(fdg_program *h, DeviceState **out) {
         DeviceState ds;
         CUDA_TRY(cudaDeviceGetAttribute(&ds.sm_count, cudaDevAttrMultiProcessorCount, dev));
         CUDA_TRY(cudaDeviceGetAttribute(&ds.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        // the program, padded with one extra END packet (the kernel prefetches one packet ahead)
+        // the program, padded with END packets to whole chunks plus two (the kernel prefetches two chunks ahead)
         std::vector<uint32_t> w = h->low.words;
-        w.insert(w.end(), {FDG_HDR(FDG_OP_END, 0, 0), 0u, 0u, 0u});
+        const size_t chunk_words = 4 * FDG_CHUNK;
+        w.resize(((w.size() + chunk_words - 1) / chunk_words + 2) * chunk_words, 0u);
         CUDA_TRY(cudaMalloc((void **)&ds.d_prog, w.size() * sizeof(uint32_t)));
         CUDA_TRY(cudaMemcpy(ds.d_prog, w.data(), w.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         it = h->dev.emplace(dev, ds).first;

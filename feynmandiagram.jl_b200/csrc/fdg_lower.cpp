@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <unordered_map>
 
 #include "fdg_isa.h"
@@ -42,20 +43,25 @@ struct Stmt {          // one value of the emitted function, in emitter order
 
 // symbolic (pre-allocation) VM operation
 struct Sym {
-    uint8_t base;  // FDG_R_*
-    uint8_t d;
-    int32_t val;  // value read (MOV..XMULF) or defined (ST); -1 otherwise
-    int32_t arg;  // POW exponent / ROOT position
+    uint8_t op;  // FDG_OP_*
+    uint8_t k;   // operand count (TERM / MOV / MUL / ADD)
+    uint8_t push, first;
+    int32_t vals[FDG_TERM_MAX];  // values read; vals[0] is also the value defined by ST
+    int32_t arg;                 // POW exponent / ROOT position
     double f;
 };
 
-inline bool reads_value(uint8_t b) {
-    return b == FDG_R_MOV || b == FDG_R_MUL || b == FDG_R_ADD || b == FDG_R_MOVF || b == FDG_R_MULF ||
-           b == FDG_R_ADDF || b == FDG_R_XADDF || b == FDG_R_XMULF;
-}
-inline bool has_factor(uint8_t b) {
-    return b == FDG_R_MOVF || b == FDG_R_MULF || b == FDG_R_ADDF || b == FDG_R_SCALE || b == FDG_R_RADDF ||
-           b == FDG_R_RMULF || b == FDG_R_XADDF || b == FDG_R_XMULF;
+inline int reads_count(const Sym &s) {
+    switch (s.op) {
+        case FDG_OP_TERM:
+        case FDG_OP_MOV:
+        case FDG_OP_MUL:
+        case FDG_OP_ADD: return s.k;
+        case FDG_OP_MULF:
+        case FDG_OP_XADDF:
+        case FDG_OP_XMULF: return 1;
+        default: return 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -110,7 +116,7 @@ int build_statements(const fdg_graph_desc &g, std::vector<Stmt> &st, std::vector
                 err = "Power{N} with N < 2 is not supported (N=" + std::to_string(g.node_pow[i]) + ")";
                 return FDG_ERR_BAD_GRAPH;
             }
-            if (g.node_pow[i] >= FDG_MAX_ARG) {
+            if (g.node_pow[i] >= (1 << 30)) {
                 err = "Power exponent too large";
                 return FDG_ERR_UNSUPPORTED;
             }
@@ -204,7 +210,7 @@ int build_statements(const fdg_graph_desc &g, std::vector<Stmt> &st, std::vector
         err = "too many leaves for the packet encoding";
         return FDG_ERR_UNSUPPORTED;
     }
-    if (out.R >= FDG_MAX_ARG) {
+    if (out.R >= (1 << 30)) {
         err = "too many roots for the packet encoding";
         return FDG_ERR_UNSUPPORTED;
     }
@@ -223,57 +229,97 @@ int build_statements(const fdg_graph_desc &g, std::vector<Stmt> &st, std::vector
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage B: symbolic code generation
+// Stage B: symbolic code generation (stack machine: A on top of R1..R3)
 // ------------------------------------------------------------------------------------------------
 struct CodeGen {
     const std::vector<Stmt> &st;
     const std::vector<Operand> &ops;
+    const std::vector<uint8_t> &remat;  // multi-use statements that are recomputed at every use instead of kept
+    std::vector<uint8_t> computed;      // materialised statements whose value already sits in the slot file
     std::vector<Sym> code;
     int32_t n_values;  // statements + temporaries
     int32_t max_depth = 0;
-    Lowered &out;
+    bool pending_push = false;
 
-    CodeGen(const std::vector<Stmt> &s, const std::vector<Operand> &o, Lowered &l)
-        : st(s), ops(o), n_values((int32_t)s.size()), out(l) {}
+    CodeGen(const std::vector<Stmt> &s, const std::vector<Operand> &o, const std::vector<uint8_t> &r)
+        : st(s), ops(o), remat(r), computed(s.size(), 0), n_values((int32_t)s.size()) {}
 
-    bool materialised(const Stmt &s) const { return s.op < 0 || s.root >= 0 || s.uses >= 2; }
+    bool is_leaf(int32_t v) const { return st[(size_t)v].op < 0; }
+    // kept in the slot file once computed: roots and multi-use nodes (unless rematerialised)
+    bool materialised(int32_t v) const {
+        const Stmt &s = st[(size_t)v];
+        return s.op >= 0 && (s.root >= 0 || (s.uses >= 2 && !remat[(size_t)v]));
+    }
+    // readable from the slot file right now
+    bool available(int32_t v) const { return is_leaf(v) || (materialised(v) && computed[(size_t)v]); }
 
-    void emit(uint8_t base, int d, int32_t val = -1, int32_t arg = 0, double f = 1.0) {
-        code.push_back({base, (uint8_t)d, val, arg, f});
+    Sym &emit(uint8_t op, int32_t val = -1, int32_t arg = 0, double f = 1.0) {
+        Sym s{};
+        s.op = op;
+        s.k = val >= 0 ? 1 : 0;
+        s.vals[0] = val;
+        s.arg = arg;
+        s.f = f;
+        if (op == FDG_OP_MOV) {  // a MOV always starts a fold: it is the packet that pushes
+            s.push = pending_push;
+            pending_push = false;
+        }
+        code.push_back(s);
+        return code.back();
+    }
+    void emit_term(bool first, const int32_t *vals, int k, double f) {
+        Sym s{};
+        s.op = FDG_OP_TERM;
+        s.k = (uint8_t)k;
+        s.first = first;
+        for (int i = 0; i < k; ++i) s.vals[i] = vals[i];
+        s.f = f;
+        if (first) {
+            s.push = pending_push;
+            pending_push = false;
+        }
+        code.push_back(s);
+    }
+
+    // a Sum operand that is an unmaterialised product of slot values with unit factors: one TERM packet
+    bool termable(int32_t v) const {
+        const Stmt &c = st[(size_t)v];
+        if (c.op != FDG_OP_PROD || materialised(v) || c.count > FDG_TERM_MAX) return false;
+        for (int32_t i = 0; i < c.count; ++i) {
+            const Operand &o = ops[(size_t)(c.first + i)];
+            if (o.f != 1.0 || !available(o.val)) return false;
+        }
+        return true;
     }
 
     struct Frame {
         int32_t v;
-        int8_t d;
         int32_t i;
-        int8_t mode;  // pending combine once the child returns: 0 none, 1 first operand, 2 register, 3 spilled
+        int8_t mode;  // pending combine once the child returns: 0 none, 1 first operand, 2 stack, 3 parked in a slot
         double f;
         int32_t tmp;
     };
 
-    // computes statement `unit` into acc0
+    // computes statement `unit` into A with an empty stack; materialised nodes met on the way are computed at
+    // their first use, stored, and read from the slot file afterwards
     void gen_unit(int32_t unit) {
         std::vector<Frame> stack;
-        stack.push_back({unit, 0, 0, 0, 1.0, -1});
+        int depth = 0;  // stack registers holding partial folds of enclosing nodes
+        stack.push_back({unit, 0, 0, 1.0, -1});
         while (!stack.empty()) {
             Frame &fr = stack.back();
             const Stmt &s = st[(size_t)fr.v];
-            const int d = fr.d;
             max_depth = std::max<int32_t>(max_depth, (int32_t)stack.size());
+            const bool sum = s.op == FDG_OP_SUM;
             if (fr.mode != 0) {
-                // a child computed inline has just returned: fold it into this node's accumulator
-                const bool sum = s.op == FDG_OP_SUM;
+                // a child computed inline has just returned in A: fold it into this node
                 if (fr.mode == 1) {
-                    if (fr.f != 1.0 && s.op != FDG_OP_POWER) {
-                        emit(FDG_R_SCALE, d, -1, 0, fr.f);
-                        out.muls_vf++;
-                    }
+                    if (fr.f != 1.0 && s.op != FDG_OP_POWER) emit(FDG_OP_SCALE, -1, 0, fr.f);
                 } else if (fr.mode == 2) {
-                    emit(sum ? FDG_R_RADDF : FDG_R_RMULF, d + 1, -1, 0, fr.f);
-                    count_combine(sum, fr.f);
+                    emit(sum ? FDG_OP_RADDF : FDG_OP_RMULF, -1, 0, fr.f);
+                    --depth;
                 } else {
-                    emit(sum ? FDG_R_XADDF : FDG_R_XMULF, d, fr.tmp, 0, fr.f);
-                    count_combine(sum, fr.f);
+                    emit(sum ? FDG_OP_XADDF : FDG_OP_XMULF, fr.tmp, 0, fr.f);
                 }
                 fr.mode = 0;
                 fr.i++;
@@ -281,96 +327,81 @@ struct CodeGen {
             }
             if (fr.i == s.count) {
                 if (s.op == FDG_OP_POWER) {
-                    emit(FDG_R_POW, d, -1, s.pow_n, 1.0);
-                    out.pow_muls += s.pow_n - 1;
+                    emit(FDG_OP_POW, -1, s.pow_n, 1.0);
                     const double f = ops[(size_t)s.first].f;
-                    if (f != 1.0) {
-                        emit(FDG_R_SCALE, d, -1, 0, f);
-                        out.muls_vf++;
-                    }
+                    if (f != 1.0) emit(FDG_OP_SCALE, -1, 0, f);
+                }
+                if (materialised(fr.v)) {
+                    if (s.root >= 0) emit(FDG_OP_ROOT, -1, s.root);
+                    if (s.uses >= 1) emit(FDG_OP_ST, fr.v);
+                    computed[(size_t)fr.v] = 1;
                 }
                 stack.pop_back();
                 continue;
             }
             const Operand &o = ops[(size_t)(s.first + fr.i)];
-            const Stmt &c = st[(size_t)o.val];
-            out.n_operands++;
-            if (materialised(c)) {
+            const bool first = fr.i == 0;
+            if (available(o.val)) {
                 // operand comes from the slot file
                 if (s.op == FDG_OP_POWER) {
-                    emit(FDG_R_MOV, d, o.val);
-                } else if (fr.i == 0) {
-                    if (o.f == 1.0) {
-                        emit(FDG_R_MOV, d, o.val);
-                    } else {
-                        emit(FDG_R_MOVF, d, o.val, 0, o.f);
-                        out.muls_vf++;
-                    }
-                } else if (s.op == FDG_OP_SUM) {
-                    if (o.f == 1.0) {
-                        emit(FDG_R_ADD, d, o.val);
-                    } else {
-                        emit(FDG_R_ADDF, d, o.val, 0, o.f);
-                        out.muls_vf++;
-                    }
-                    out.adds_vv++;
+                    emit(FDG_OP_MOV, o.val);
+                } else if (first) {
+                    if (o.f == 1.0)
+                        emit(FDG_OP_MOV, o.val);
+                    else
+                        emit_term(true, &o.val, 1, o.f);  // A = v * f
+                } else if (sum) {
+                    if (o.f == 1.0)
+                        emit(FDG_OP_ADD, o.val);
+                    else
+                        emit_term(false, &o.val, 1, o.f);  // A = A + v * f
                 } else {
-                    if (o.f == 1.0) {
-                        emit(FDG_R_MUL, d, o.val);
-                    } else {
-                        emit(FDG_R_MULF, d, o.val, 0, o.f);
-                        out.muls_vf++;
-                    }
-                    out.muls_vv++;
+                    if (o.f == 1.0)
+                        emit(FDG_OP_MUL, o.val);
+                    else
+                        emit(FDG_OP_MULF, o.val, 0, o.f);
                 }
                 fr.i++;
                 continue;
             }
-            // single-use inner node: evaluate it right here
-            fr.f = o.f;
-            if (fr.i == 0) {
-                fr.mode = 1;
-                const int32_t child = o.val;
-                stack.push_back({child, (int8_t)d, 0, 0, 1.0, -1});  // NB: invalidates fr
-            } else if (d + 1 < FDG_NREG) {
-                fr.mode = 2;
-                const int32_t child = o.val;
-                stack.push_back({child, (int8_t)(d + 1), 0, 0, 1.0, -1});
-            } else {
-                fr.mode = 3;
-                fr.tmp = n_values++;
-                emit(FDG_R_ST, d, fr.tmp);
-                const int32_t child = o.val;
-                stack.push_back({child, (int8_t)d, 0, 0, 1.0, -1});
+            if (sum && termable(o.val)) {
+                // A (+)= (v1 * v2 * ... * vk) * f in one packet, no stack traffic
+                const Stmt &c = st[(size_t)o.val];
+                int32_t vals[FDG_TERM_MAX];
+                for (int32_t q = 0; q < c.count; ++q) vals[q] = ops[(size_t)(c.first + q)].val;
+                emit_term(first, vals, c.count, o.f);
+                fr.i++;
+                continue;
             }
+            // an inner node that is not in the slot file: evaluate it right here
+            fr.f = o.f;
+            const int32_t child = o.val;
+            if (first) {
+                fr.mode = 1;  // A is free: the child's fold simply starts in A
+            } else if (depth < FDG_STACK_REGS) {
+                fr.mode = 2;  // the child's first packet pushes this node's partial fold
+                pending_push = true;
+                ++depth;
+            } else {
+                fr.mode = 3;  // stack full: park the partial fold in a slot
+                fr.tmp = n_values++;
+                emit(FDG_OP_ST, fr.tmp);
+            }
+            stack.push_back({child, 0, 0, 1.0, -1});  // NB: invalidates fr
         }
     }
 
-    void count_combine(bool sum, double f) {
-        // RADDF/RMULF/XADDF/XMULF always multiply by f; only f != 1 is an operation of the
-        // reference function, the f == 1 multiply is an exact identity.
-        if (f != 1.0) out.muls_vf++;
-        if (sum)
-            out.adds_vv++;
-        else
-            out.muls_vv++;
-    }
-
     void run() {
+        // roots in the order the emitted function assigns them; everything else on demand
         for (int32_t v = 0; v < (int32_t)st.size(); ++v) {
             const Stmt &s = st[(size_t)v];
-            if (!s.live) continue;
-            if (s.op < 0) {
-                if (s.root >= 0) {  // a leaf that is itself a root: root[r] = leafVal[k]
-                    emit(FDG_R_MOV, 0, v);
-                    emit(FDG_R_ROOT, 0, -1, s.root);
-                }
+            if (s.root < 0) continue;
+            if (s.op < 0) {  // a leaf that is itself a root: root[r] = leafVal[k]
+                emit(FDG_OP_MOV, v);
+                emit(FDG_OP_ROOT, -1, s.root);
                 continue;
             }
-            if (!(s.root >= 0 || s.uses >= 2)) continue;  // folded into its single parent
-            gen_unit(v);
-            if (s.root >= 0) emit(FDG_R_ROOT, 0, -1, s.root);
-            if (s.uses >= 1) emit(FDG_R_ST, 0, v);
+            if (!computed[(size_t)v]) gen_unit(v);
         }
     }
 };
@@ -379,10 +410,10 @@ struct CodeGen {
 // Stage C: slots, prefetch, packets
 // ------------------------------------------------------------------------------------------------
 struct Op2 {  // post-allocation, non-LDL operation
-    uint8_t kind;  // 0 register op, 1 SPILL, 2 FILL
+    uint8_t kind;  // 0 VM op, 1 SPILL, 2 FILL
     Sym s;
-    int32_t slot;     // slot read / written
-    int32_t scratch;  // SPILL / FILL
+    int32_t slots[FDG_TERM_MAX];  // slots read (kind 0) / slots[0] = slot written by ST, SPILL source, FILL target
+    int32_t scratch;              // SPILL / FILL
 };
 struct Ldl {
     int32_t slot, leaf;
@@ -400,6 +431,7 @@ struct Allocator {
     std::vector<int32_t> use_ptr, val_slot, val_scratch;
     std::vector<int32_t> slot_val;
     std::vector<int64_t> slot_last;  // index in ops2 of the last op touching the slot, -1 if none
+    std::vector<uint8_t> slot_pinned;
     std::vector<int32_t> free_slots;
     int32_t n_slots = 0, n_scratch = 0;
     int64_t leaf_loads = 0;
@@ -428,14 +460,15 @@ struct Allocator {
         if (n_slots < max_slots) {
             slot_val.push_back(-1);
             slot_last.push_back(-1);
+            slot_pinned.push_back(0);
             return n_slots++;
         }
-        // evict the resident value whose next use is farthest away (Belady)
+        // evict the resident value whose next use is farthest away (Belady); never an operand of this packet
         int32_t victim = -1;
         int64_t far = -1;
         for (int32_t s = 0; s < n_slots; ++s) {
             const int32_t v = slot_val[(size_t)s];
-            if (v < 0) continue;
+            if (v < 0 || slot_pinned[(size_t)s]) continue;
             const int64_t nu = next_use(v);
             if (nu > far) {
                 far = nu;
@@ -447,7 +480,7 @@ struct Allocator {
             val_scratch[(size_t)v] = n_scratch++;
             Op2 o{};
             o.kind = 1;
-            o.slot = victim;
+            o.slots[0] = victim;
             o.scratch = val_scratch[(size_t)v];
             slot_last[(size_t)victim] = (int64_t)ops2.size();
             ops2.push_back(o);
@@ -468,8 +501,13 @@ struct Allocator {
 
     void run() {
         use_pos.assign((size_t)n_values, {});
-        for (size_t p = 0; p < code.size(); ++p)
-            if (reads_value(code[p].base)) use_pos[(size_t)code[p].val].push_back((int64_t)p);
+        for (size_t p = 0; p < code.size(); ++p) {
+            const int k = reads_count(code[p]);
+            for (int q = 0; q < k; ++q) {
+                auto &u = use_pos[(size_t)code[p].vals[q]];
+                if (u.empty() || u.back() != (int64_t)p) u.push_back((int64_t)p);
+            }
+        }
         use_ptr.assign((size_t)n_values, 0);
         val_slot.assign((size_t)n_values, -1);
         val_scratch.assign((size_t)n_values, -1);
@@ -478,37 +516,49 @@ struct Allocator {
             Op2 o{};
             o.kind = 0;
             o.s = s;
-            o.slot = -1;
-            if (reads_value(s.base)) {
-                const int32_t v = s.val;
-                if (val_slot[(size_t)v] < 0) {
-                    const int32_t sl = alloc_slot();
-                    if (is_leaf(v)) {
-                        ldls.push_back({sl, st[(size_t)v].leaf, (int64_t)ops2.size(), slot_last[(size_t)sl] + 1});
-                        leaf_loads++;
-                    } else {
-                        Op2 f{};
-                        f.kind = 2;
-                        f.slot = sl;
-                        f.scratch = val_scratch[(size_t)v];
-                        slot_last[(size_t)sl] = (int64_t)ops2.size();
-                        ops2.push_back(f);
-                    }
-                    val_slot[(size_t)v] = sl;
-                    slot_val[(size_t)sl] = v;
+            const int k = reads_count(s);
+            if (k > 0) {
+                // bring every operand in, pinning the ones already placed for this packet
+                for (int q = 0; q < k; ++q) {
+                    const int32_t v = s.vals[q];
+                    if (val_slot[(size_t)v] >= 0) slot_pinned[(size_t)val_slot[(size_t)v]] = 1;
                 }
-                o.slot = val_slot[(size_t)v];
-                use_ptr[(size_t)v]++;
-                slot_last[(size_t)o.slot] = (int64_t)ops2.size();
+                for (int q = 0; q < k; ++q) {
+                    const int32_t v = s.vals[q];
+                    if (val_slot[(size_t)v] < 0) {
+                        const int32_t sl = alloc_slot();
+                        if (is_leaf(v)) {
+                            ldls.push_back({sl, st[(size_t)v].leaf, (int64_t)ops2.size(), slot_last[(size_t)sl] + 1});
+                            leaf_loads++;
+                        } else {
+                            Op2 f{};
+                            f.kind = 2;
+                            f.slots[0] = sl;
+                            f.scratch = val_scratch[(size_t)v];
+                            slot_last[(size_t)sl] = (int64_t)ops2.size();
+                            ops2.push_back(f);
+                        }
+                        val_slot[(size_t)v] = sl;
+                        slot_val[(size_t)sl] = v;
+                        slot_pinned[(size_t)sl] = 1;
+                    }
+                    o.slots[q] = val_slot[(size_t)v];
+                }
+                for (int q = 0; q < k; ++q) {
+                    const int32_t v = s.vals[q];
+                    slot_pinned[(size_t)o.slots[q]] = 0;
+                    slot_last[(size_t)o.slots[q]] = (int64_t)ops2.size();
+                    if (next_use(v) == (int64_t)p) use_ptr[(size_t)v]++;
+                }
                 ops2.push_back(o);
-                release_if_dead(v);
-            } else if (s.base == FDG_R_ST) {
-                const int32_t v = s.val;
+                for (int q = 0; q < k; ++q) release_if_dead(s.vals[q]);
+            } else if (s.op == FDG_OP_ST) {
+                const int32_t v = s.vals[0];
                 if (use_pos[(size_t)v].empty()) continue;  // never read: nothing to keep
                 const int32_t sl = alloc_slot();
                 val_slot[(size_t)v] = sl;
                 slot_val[(size_t)sl] = v;
-                o.slot = sl;
+                o.slots[0] = sl;
                 slot_last[(size_t)sl] = (int64_t)ops2.size();
                 ops2.push_back(o);
             } else {
@@ -524,6 +574,7 @@ struct Packer {
     int32_t dist;
     int64_t committed = 0, completed = 0;  // cp.async groups
     std::vector<int64_t> slot_group;       // group that fills the slot, -1 when filled synchronously
+    uint32_t wait_field = 0;               // header wait field of the packet being assembled
 
     Packer(const Allocator &a, std::vector<uint32_t> &w, int32_t d) : al(a), words(w), dist(d) {}
 
@@ -533,14 +584,20 @@ struct Packer {
         words.push_back(w2);
         words.push_back(w3);
     }
+    int64_t n_packets() const { return (int64_t)words.size() / 4; }
+    // the packet about to be emitted reads `slot`: make sure its cp.async group has landed
     void need(int32_t slot) {
         const int64_t g = slot_group[(size_t)slot];
         if (g < 0 || g < completed) return;
-        // allow `pend` newer groups to stay in flight
-        int64_t pend = committed - (g + 1);
+        int64_t pend = committed - (g + 1);  // newer groups may stay in flight
         if (pend > FDG_MAX_WAIT) pend = FDG_MAX_WAIT;
-        packet(FDG_HDR(FDG_OP_WAIT, 0, (uint32_t)pend));
-        completed = committed - pend;
+        if (wait_field == 0 || (uint32_t)(pend + 1) < wait_field) wait_field = (uint32_t)(pend + 1);
+        completed = std::max(completed, committed - pend);
+    }
+    uint32_t take_wait() {
+        const uint32_t w = wait_field;
+        wait_field = 0;
+        return w;
     }
     static void split(double f, uint32_t &lo, uint32_t &hi) {
         uint64_t u;
@@ -553,11 +610,12 @@ struct Packer {
         const auto &ops2 = al.ops2;
         const int64_t M = (int64_t)ops2.size();
         slot_group.assign((size_t)std::max(al.n_slots, 1), -1);
-        // bucket the loads by their hoisted anchor
+        // bucket the loads by their hoisted anchor (quantised so that neighbours share a packet)
         std::vector<std::vector<int32_t>> at((size_t)M + 1);
         for (size_t i = 0; i < al.ldls.size(); ++i) {
             const Ldl &l = al.ldls[i];
             int64_t t = l.anchor - dist;
+            if (dist > 0) t &= ~(int64_t)3;
             if (t < l.earliest) t = l.earliest;
             if (t > l.anchor) t = l.anchor;
             at[(size_t)t].push_back((int32_t)i);
@@ -574,71 +632,84 @@ struct Packer {
                     w[q] = FDG_LDL_WORD(l.slot, l.leaf);
                     slot_group[(size_t)l.slot] = committed;
                 }
-                packet(FDG_HDR(FDG_OP_LDL, n, 0), w[0], w[1], w[2]);
+                packet(FDG_HDR(FDG_OP_LDL, n, 0, 0, 0, 0), w[0], w[1], w[2]);
                 committed++;
             }
             if (j == M) break;
             const Op2 &o = ops2[(size_t)j];
             if (o.kind == 1) {  // SPILL
-                need(o.slot);
-                packet(FDG_HDR(FDG_OP_SPILL, 0, (uint32_t)o.scratch), (uint32_t)o.slot);
+                need(o.slots[0]);
+                packet(FDG_HDR(FDG_OP_SPILL, 0, take_wait(), 0, 0, 0), (uint32_t)o.slots[0], (uint32_t)o.scratch);
                 ++j;
                 continue;
             }
             if (o.kind == 2) {  // FILL
-                slot_group[(size_t)o.slot] = -1;
-                packet(FDG_HDR(FDG_OP_FILL, 0, (uint32_t)o.scratch), (uint32_t)o.slot);
+                slot_group[(size_t)o.slots[0]] = -1;
+                packet(FDG_HDR(FDG_OP_FILL, 0, 0, 0, 0, 0), (uint32_t)o.slots[0], (uint32_t)o.scratch);
                 ++j;
                 continue;
             }
             const Sym &s = o.s;
-            const uint32_t opc = FDG_REGOP(s.base, s.d);
-            if (s.base == FDG_R_MOV || s.base == FDG_R_MUL || s.base == FDG_R_ADD) {
-                // pack a run of the same fold: MOV a [MUL b [MUL c]] / MUL a b c / ADD a b c
-                const uint8_t follow = s.base == FDG_R_ADD ? FDG_R_ADD : FDG_R_MUL;
-                uint32_t w[3] = {(uint32_t)o.slot, 0, 0};
-                int n = 1;
-                while (n < 3 && j + n < M && at[(size_t)(j + n)].empty()) {
-                    const Op2 &o2 = ops2[(size_t)(j + n)];
-                    if (o2.kind != 0 || o2.s.base != follow || o2.s.d != s.d) break;
-                    w[n] = (uint32_t)o2.slot;
-                    ++n;
-                }
-                for (int q = 0; q < n; ++q) need((int32_t)w[q]);
-                packet(FDG_HDR(opc, n, 0), w[0], w[1], w[2]);
-                j += n;
-                continue;
-            }
             uint32_t lo = 0, hi = 0;
-            if (has_factor(s.base)) split(s.f, lo, hi);
-            switch (s.base) {
-                case FDG_R_MOVF:
-                case FDG_R_MULF:
-                case FDG_R_ADDF:
-                case FDG_R_XADDF:
-                case FDG_R_XMULF:
-                    need(o.slot);
-                    packet(FDG_HDR(opc, 1, 0), (uint32_t)o.slot, lo, hi);
+            split(s.f, lo, hi);
+            switch (s.op) {
+                case FDG_OP_MOV:
+                case FDG_OP_MUL:
+                case FDG_OP_ADD: {
+                    // pack a run of the same fold: MOV a [MUL b [MUL c]] / MUL a b c / ADD a b c
+                    const uint8_t follow = s.op == FDG_OP_ADD ? FDG_OP_ADD : FDG_OP_MUL;
+                    uint32_t w[3] = {(uint32_t)o.slots[0], 0, 0};
+                    int n = 1;
+                    while (n < 3 && j + n < M && at[(size_t)(j + n)].empty()) {
+                        const Op2 &o2 = ops2[(size_t)(j + n)];
+                        if (o2.kind != 0 || o2.s.op != follow) break;
+                        w[n] = (uint32_t)o2.slots[0];
+                        ++n;
+                    }
+                    for (int q = 0; q < n; ++q) need((int32_t)w[q]);
+                    packet(FDG_HDR(s.op, n, take_wait(), s.push, 0, 0), w[0], w[1], w[2]);
+                    j += n;
+                    continue;
+                }
+                case FDG_OP_TERM: {
+                    const int k = s.k;
+                    for (int q = 0; q < k; ++q) need(o.slots[q]);
+                    if (k > 3 && (n_packets() % FDG_CHUNK) == FDG_CHUNK - 1)
+                        packet(FDG_HDR(FDG_OP_NOP, 0, 0, 0, 0, 0));  // keep the pair inside one chunk
+                    const uint32_t s1 = k > 1 ? (uint32_t)o.slots[1] : 0, s2 = k > 2 ? (uint32_t)o.slots[2] : 0;
+                    packet(FDG_HDR(FDG_OP_TERM, k, take_wait(), s.push, s.first, (uint32_t)o.slots[0]), s1 | (s2 << 16), lo, hi);
+                    if (k > 3) {
+                        uint32_t e[4] = {0, 0, 0, 0};
+                        for (int q = 3; q < k; ++q) e[(q - 3) >> 1] |= (uint32_t)o.slots[q] << (16 * ((q - 3) & 1));
+                        packet(e[0], e[1], e[2], e[3]);
+                    }
                     break;
-                case FDG_R_SCALE:
-                case FDG_R_RADDF:
-                case FDG_R_RMULF:
-                    packet(FDG_HDR(opc, 0, 0), 0, lo, hi);
+                }
+                case FDG_OP_MULF:
+                case FDG_OP_XADDF:
+                case FDG_OP_XMULF:
+                    need(o.slots[0]);
+                    packet(FDG_HDR(s.op, 1, take_wait(), 0, 0, 0), (uint32_t)o.slots[0], lo, hi);
                     break;
-                case FDG_R_POW:
-                case FDG_R_ROOT:
-                    packet(FDG_HDR(opc, 0, (uint32_t)s.arg));
+                case FDG_OP_SCALE:
+                case FDG_OP_RADDF:
+                case FDG_OP_RMULF:
+                    packet(FDG_HDR(s.op, 0, 0, 0, 0, 0), 0, lo, hi);
                     break;
-                case FDG_R_ST:
-                    slot_group[(size_t)o.slot] = -1;
-                    packet(FDG_HDR(opc, 0, (uint32_t)o.slot));
+                case FDG_OP_POW:
+                case FDG_OP_ROOT:
+                    packet(FDG_HDR(s.op, 0, 0, 0, 0, 0), (uint32_t)s.arg);
+                    break;
+                case FDG_OP_ST:
+                    slot_group[(size_t)o.slots[0]] = -1;
+                    packet(FDG_HDR(s.op, 0, 0, 0, 0, 0), (uint32_t)o.slots[0]);
                     break;
                 default:
                     break;
             }
             ++j;
         }
-        packet(FDG_HDR(FDG_OP_END, 0, 0));
+        packet(FDG_HDR(FDG_OP_END, 0, 0, 0, 0, 0));
     }
 };
 
@@ -656,16 +727,62 @@ int lower(const fdg_graph_desc &g, const fdg_options &opt, Lowered &out, std::st
     int rc = build_statements(g, st, ops, out, err);
     if (rc != FDG_OK) return rc;
 
-    CodeGen cg(st, ops, out);
-    cg.run();
-    out.max_depth = cg.max_depth;
+    // algorithmic operation counts of the reference function (count_operation, tree_properties.jl:165-185,
+    // plus one multiply per factor != 1 and N-1 multiplies per Power{N}); independent of how the VM evaluates it
+    for (const Stmt &s : st) {
+        if (!s.live || s.op < 0) continue;
+        out.n_operands += s.count;
+        for (int32_t i = 0; i < s.count; ++i)
+            if (ops[(size_t)(s.first + i)].f != 1.0) out.muls_vf++;
+        if (s.op == FDG_OP_SUM) out.adds_vv += s.count - 1;
+        if (s.op == FDG_OP_PROD) out.muls_vv += s.count - 1;
+        if (s.op == FDG_OP_POWER) out.pow_muls += s.pow_n - 1;
+    }
 
-    int32_t max_slots = opt.max_slots > 0 ? opt.max_slots : 96;
-    if (max_slots < 4) max_slots = 4;
+    int32_t max_slots = opt.max_slots > 0 ? opt.max_slots : 48;
+    if (max_slots < FDG_TERM_MAX + 1) max_slots = FDG_TERM_MAX + 1;  // every operand of a TERM must be resident
     if (max_slots > FDG_MAX_SLOTS) max_slots = FDG_MAX_SLOTS;
-    Allocator al(st, cg.code, cg.n_values, max_slots);
-    al.run();
-    if (al.n_scratch >= FDG_MAX_ARG) {
+
+    // cost of recomputing a statement from leaves (capped): cheap multi-use values that the allocator had to
+    // spill to global scratch are rematerialised instead (recomputing gives the same bits)
+    const int32_t kCheap = 16;
+    std::vector<int32_t> cost(st.size(), 0);
+    for (size_t v = 0; v < st.size(); ++v) {
+        const Stmt &s = st[v];
+        if (s.op < 0) {
+            cost[v] = 1;
+            continue;
+        }
+        int64_t c = 0;
+        for (int32_t i = 0; i < s.count; ++i) c += cost[(size_t)ops[(size_t)(s.first + i)].val];
+        cost[v] = (int32_t)std::min<int64_t>(c, 1 << 20);
+    }
+    std::vector<uint8_t> remat(st.size(), 0);
+    std::vector<Sym> code;
+    int32_t n_values = 0;
+    Allocator *al_ptr = nullptr;
+    std::unique_ptr<Allocator> al_owner;
+    for (int iter = 0; iter < 4; ++iter) {
+        CodeGen cg(st, ops, remat);
+        cg.run();
+        out.max_depth = cg.max_depth;
+        code.swap(cg.code);
+        n_values = cg.n_values;
+        al_owner.reset(new Allocator(st, code, n_values, max_slots));
+        al_owner->run();
+        al_ptr = al_owner.get();
+        if (al_ptr->n_scratch == 0 || iter == 3) break;
+        bool changed = false;
+        for (size_t v = 0; v < st.size(); ++v) {
+            if (al_ptr->val_scratch[v] >= 0 && !remat[v] && st[v].root < 0 && cost[v] <= kCheap) {
+                remat[v] = 1;
+                changed = true;
+            }
+        }
+        if (!changed) break;
+    }
+    Allocator &al = *al_ptr;
+    if (al.n_scratch >= (1 << 30)) {
         err = "program needs too many scratch values";
         return FDG_ERR_CAPACITY;
     }

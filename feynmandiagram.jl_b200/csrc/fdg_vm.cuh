@@ -166,6 +166,12 @@ struct alignas(sizeof(V)) Packed {
 
 // ---- the kernel --------------------------------------------------------------------------------------
 // V: VReal<1>, VReal<2> or VCplx.  ACC: false = write root per sample, true = per-warp running sums.
+//
+// Dynamic shared memory:  [ slot file: n_slots x T values | per-warp program buffers: 2 x 32 packets |
+//                           accumulate mode: per-warp running sums racc[warp][root * W] ]
+// Program fetch: the 32 lanes of a warp fetch the NEXT chunk of 32 packets with one coalesced 16-byte load
+// each while the current chunk executes out of shared memory (broadcast LDS.128 per packet), so the global
+// latency of the instruction stream is hidden behind a whole chunk of work.
 template <class V, bool ACC>
 __global__ void __launch_bounds__(256) fdg_vm_kernel(const VmArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -173,21 +179,24 @@ __global__ void __launch_bounds__(256) fdg_vm_kernel(const VmArgs a) {
     constexpr int W = V::kWidth;
     const int T = blockDim.x;
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
     const uint32_t stride = (uint32_t)T * (uint32_t)sizeof(V);
     unsigned char *const my = smem + (size_t)tid * sizeof(V);
     const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
     const long long gthread = (long long)blockIdx.x * T + tid;
     const long long gstride = (long long)gridDim.x * T;
-    double *racc = nullptr;
-    const int RW = a.n_roots * W;
-    // dynamic smem: [slot file: n_slots * T values | accumulate mode: per-warp running sums racc[warp][root * W]]
     const uint32_t slot_file_bytes = (uint32_t)a.n_slots * stride;
+    uint4 *const wbuf = reinterpret_cast<uint4 *>(smem + slot_file_bytes) + warp * (2 * FDG_CHUNK);
+    const int RW = a.n_roots * W;
+    double *racc = nullptr;
     if constexpr (ACC) {
-        racc = reinterpret_cast<double *>(smem + slot_file_bytes) + (size_t)(tid >> 5) * RW;
-        for (int r = (tid & 31); r < RW; r += 32) racc[r] = 0.0;
+        racc = reinterpret_cast<double *>(smem + slot_file_bytes + (size_t)(T >> 5) * 2 * FDG_CHUNK * sizeof(uint4)) +
+               (size_t)warp * RW;
+        for (int r = lane; r < RW; r += 32) racc[r] = 0.0;
         __syncwarp();
     }
-    auto slot_ptr = [&](uint32_t s) -> V * { return reinterpret_cast<V *>(my + s * stride); };
+    auto slot_ptr = [&](uint32_t s) -> Packed<V> * { return reinterpret_cast<Packed<V> *>(my + s * stride); };
     auto ld = [&](uint32_t s) -> V { return reinterpret_cast<const Packed<V> *>(my + s * stride)->v; };
 
     for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -199,148 +208,196 @@ __global__ void __launch_bounds__(256) fdg_vm_kernel(const VmArgs a) {
         const unsigned char *const leaf_b = static_cast<const unsigned char *>(a.leaf) + (size_t)bl * (8 * W);
         const size_t leaf_stride = (size_t)a.ld_leaf * (8 * W);
 
-        V acc0, acc1, acc2, acc3;
+        V A, R1, R2, R3;
 #pragma unroll
-        for (int i = 0; i < S * W; ++i) acc0.x[i] = acc1.x[i] = acc2.x[i] = acc3.x[i] = 0.0;
+        for (int i = 0; i < S * W; ++i) A.x[i] = R1.x[i] = R2.x[i] = R3.x[i] = 0.0;
 
-        const uint4 *pc = a.prog;
-        uint4 pk = __ldg(pc);
-        for (;;) {
-            const uint4 nx = __ldg(pc + 1);  // the program is padded with a trailing END packet
-            ++pc;
-            const uint32_t hdr = pk.x;
-            const uint32_t op = FDG_HDR_OP(hdr);
-            const uint32_t n = FDG_HDR_N(hdr);
-            const uint32_t arg = FDG_HDR_ARG(hdr);
-            const double f = __hiloint2double((int)pk.w, (int)pk.z);
-            if (op == FDG_OP_END) break;
-            switch (op) {
-                case FDG_OP_LDL: {
+        // prime the program buffers: chunk 0 into buffer 0, chunk 1 in flight (the program is padded on upload)
+        const uint4 *gp = a.prog;
+        __syncwarp();
+        wbuf[lane] = __ldg(gp + lane);
+        uint4 nxt = __ldg(gp + FDG_CHUNK + lane);
+        __syncwarp();
+        int cur = 0;
+        bool done = false;
+        while (!done) {
+            const uint4 *pb = wbuf + cur * FDG_CHUNK;
+            uint4 pk = pb[0];
+#pragma unroll 1
+            for (int i = 0; i < FDG_CHUNK; ++i) {
+                uint4 pn = pb[(i + 1) & (FDG_CHUNK - 1)];  // next packet (wraps harmlessly on the last one)
+                const uint32_t hdr = pk.x;
+                const uint32_t op = FDG_HDR_OP(hdr);
+                const uint32_t k = FDG_HDR_K(hdr);
+                if (hdr & (7u << 10)) cp_async_wait(FDG_HDR_WAIT(hdr) - 1u);
+                if (op == FDG_OP_TERM) {
+                    const double f = __hiloint2double((int)pk.w, (int)pk.z);
+                    V t = ld(hdr >> 20);
+                    if (k > 1) {
+                        const V u = ld(pk.y & 0xffffu);
+                        if (k > 2) {
+                            const V w = ld(pk.y >> 16);
+                            t = vmul(vmul(t, u), w);
+                            if (k > 3) {
+                                const uint4 e = pn;  // extension packet: s3..s10
+                                ++i;
+                                pn = pb[(i + 1) & (FDG_CHUNK - 1)];
+                                t = vmul(t, ld(e.x & 0xffffu));
+                                if (k > 4) {
+                                    t = vmul(t, ld(e.x >> 16));
+                                    if (k > 5) {
+                                        t = vmul(t, ld(e.y & 0xffffu));
+                                        if (k > 6) t = vmul(t, ld(e.y >> 16));
+                                        if (k > 7) t = vmul(t, ld(e.z & 0xffffu));
+                                        if (k > 8) t = vmul(t, ld(e.z >> 16));
+                                        if (k > 9) t = vmul(t, ld(e.w & 0xffffu));
+                                        if (k > 10) t = vmul(t, ld(e.w >> 16));
+                                    }
+                                }
+                            }
+                        } else {
+                            t = vmul(t, u);
+                        }
+                    }
+                    t = vscale(t, f);
+                    if (hdr & (1u << 14)) {  // first term of a fold
+                        if (hdr & (1u << 13)) {
+                            R3 = R2;
+                            R2 = R1;
+                            R1 = A;
+                        }
+                        A = t;
+                    } else {
+                        A = vadd(A, t);
+                    }
+                } else if (op == FDG_OP_MUL) {
+                    if (k == 1) {
+                        A = vmul(A, ld(pk.y));
+                    } else if (k == 2) {
+                        const V v1 = ld(pk.y), v2 = ld(pk.z);
+                        A = vmul(vmul(A, v1), v2);
+                    } else {
+                        const V v1 = ld(pk.y), v2 = ld(pk.z), v3 = ld(pk.w);
+                        A = vmul(vmul(vmul(A, v1), v2), v3);
+                    }
+                } else if (op == FDG_OP_MOV) {
+                    if (hdr & (1u << 13)) {
+                        R3 = R2;
+                        R2 = R1;
+                        R1 = A;
+                    }
+                    if (k == 1) {
+                        A = ld(pk.y);
+                    } else if (k == 2) {
+                        const V v1 = ld(pk.y), v2 = ld(pk.z);
+                        A = vmul(v1, v2);
+                    } else {
+                        const V v1 = ld(pk.y), v2 = ld(pk.z), v3 = ld(pk.w);
+                        A = vmul(vmul(v1, v2), v3);
+                    }
+                } else if (op == FDG_OP_LDL) {
                     const uint32_t w[3] = {pk.y, pk.z, pk.w};
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        if (i < (int)n) {
-                            const uint32_t s = w[i] & (FDG_MAX_SLOTS - 1);
-                            const uint32_t l = w[i] >> FDG_LDL_SLOT_BITS;
+                    for (int q = 0; q < 3; ++q) {
+                        if (q < (int)k) {
+                            const uint32_t s = w[q] & (FDG_MAX_SLOTS - 1);
+                            const uint32_t l = w[q] >> FDG_LDL_SLOT_BITS;
                             cp_async<sizeof(V)>(my_s + s * stride, leaf_b + (size_t)l * leaf_stride);
                         }
                     }
                     cp_async_commit();
-                } break;
-                case FDG_OP_WAIT: cp_async_wait(arg); break;
-                case FDG_OP_SPILL: {
-                    V *g = static_cast<V *>(a.scratch) + ((size_t)arg * gstride + gthread);
-                    *reinterpret_cast<Packed<V> *>(g) = *reinterpret_cast<const Packed<V> *>(slot_ptr(pk.y));
-                } break;
-                case FDG_OP_FILL: {
-                    const V *g = static_cast<const V *>(a.scratch) + ((size_t)arg * gstride + gthread);
-                    *reinterpret_cast<Packed<V> *>(slot_ptr(pk.y)) = *reinterpret_cast<const Packed<V> *>(g);
-                } break;
-
-#define FDG_CASE(BASE, D, A, P, ...)     \
-    case FDG_REGOP(BASE, D): {           \
-        V &A_ = A;                       \
-        V &P_ = P;                       \
-        (void)P_;                        \
-        __VA_ARGS__                      \
-    } break;
-#define FDG_CASE4(BASE, ...)                    \
-    FDG_CASE(BASE, 0, acc0, acc0, __VA_ARGS__)  \
-    FDG_CASE(BASE, 1, acc1, acc0, __VA_ARGS__)  \
-    FDG_CASE(BASE, 2, acc2, acc1, __VA_ARGS__)  \
-    FDG_CASE(BASE, 3, acc3, acc2, __VA_ARGS__)
-
-                    FDG_CASE4(FDG_R_MOV, {
-                        if (n == 1) {
-                            A_ = ld(pk.y);
-                        } else if (n == 2) {
-                            const V v1 = ld(pk.y), v2 = ld(pk.z);
-                            A_ = vmul(v1, v2);
-                        } else {
-                            const V v1 = ld(pk.y), v2 = ld(pk.z), v3 = ld(pk.w);
-                            A_ = vmul(vmul(v1, v2), v3);
-                        }
-                    })
-                    FDG_CASE4(FDG_R_MUL, {
-                        if (n == 1) {
-                            A_ = vmul(A_, ld(pk.y));
-                        } else if (n == 2) {
-                            const V v1 = ld(pk.y), v2 = ld(pk.z);
-                            A_ = vmul(vmul(A_, v1), v2);
-                        } else {
-                            const V v1 = ld(pk.y), v2 = ld(pk.z), v3 = ld(pk.w);
-                            A_ = vmul(vmul(vmul(A_, v1), v2), v3);
-                        }
-                    })
-                    FDG_CASE4(FDG_R_ADD, {
-                        if (n == 1) {
-                            A_ = vadd(A_, ld(pk.y));
-                        } else if (n == 2) {
-                            const V v1 = ld(pk.y), v2 = ld(pk.z);
-                            A_ = vadd(vadd(A_, v1), v2);
-                        } else {
-                            const V v1 = ld(pk.y), v2 = ld(pk.z), v3 = ld(pk.w);
-                            A_ = vadd(vadd(vadd(A_, v1), v2), v3);
-                        }
-                    })
-                    FDG_CASE4(FDG_R_MOVF, { A_ = vscale(ld(pk.y), f); })
-                    FDG_CASE4(FDG_R_MULF, { A_ = vscale(vmul(A_, ld(pk.y)), f); })
-                    FDG_CASE4(FDG_R_ADDF, { A_ = vadd(A_, vscale(ld(pk.y), f)); })
-                    FDG_CASE4(FDG_R_SCALE, { A_ = vscale(A_, f); })
-                    FDG_CASE4(FDG_R_RADDF, { P_ = vadd(P_, vscale(A_, f)); })
-                    FDG_CASE4(FDG_R_RMULF, { P_ = vscale(vmul(P_, A_), f); })
-                    FDG_CASE4(FDG_R_XADDF, { A_ = vadd(ld(pk.y), vscale(A_, f)); })
-                    FDG_CASE4(FDG_R_XMULF, { A_ = vscale(vmul(ld(pk.y), A_), f); })
-                    FDG_CASE4(FDG_R_POW, { A_ = vpow(A_, arg); })
-                    FDG_CASE4(FDG_R_ST, { *reinterpret_cast<Packed<V> *>(slot_ptr(arg)) = *reinterpret_cast<Packed<V> *>(&A_); })
-                    FDG_CASE4(FDG_R_ROOT, {
-                        if constexpr (!ACC) {
-                            if (active) {
-                                double *o = static_cast<double *>(a.root) + ((size_t)arg * a.ld_root + b0) * W;
-                                if constexpr (S == 2) {
-                                    if (b0 + 1 < a.batch)
-                                        *reinterpret_cast<double2 *>(o) = make_double2(A_.x[0], A_.x[1]);
-                                    else
-                                        o[0] = A_.x[0];
-                                } else if constexpr (W == 2) {
-                                    *reinterpret_cast<double2 *>(o) = make_double2(A_.x[0], A_.x[1]);
-                                } else {
-                                    o[0] = A_.x[0];
+                } else if (op == FDG_OP_RADDF) {
+                    const double f = __hiloint2double((int)pk.w, (int)pk.z);
+                    A = vadd(R1, vscale(A, f));
+                    R1 = R2;
+                    R2 = R3;
+                } else if (op == FDG_OP_RMULF) {
+                    const double f = __hiloint2double((int)pk.w, (int)pk.z);
+                    A = vscale(vmul(R1, A), f);
+                    R1 = R2;
+                    R2 = R3;
+                } else if (op == FDG_OP_ST) {
+                    *slot_ptr(pk.y) = *reinterpret_cast<Packed<V> *>(&A);
+                } else {
+                    const double f = __hiloint2double((int)pk.w, (int)pk.z);
+                    switch (op) {
+                        case FDG_OP_END: done = true; break;
+                        case FDG_OP_ADD:
+                            if (k == 1) {
+                                A = vadd(A, ld(pk.y));
+                            } else if (k == 2) {
+                                const V v1 = ld(pk.y), v2 = ld(pk.z);
+                                A = vadd(vadd(A, v1), v2);
+                            } else {
+                                const V v1 = ld(pk.y), v2 = ld(pk.z), v3 = ld(pk.w);
+                                A = vadd(vadd(vadd(A, v1), v2), v3);
+                            }
+                            break;
+                        case FDG_OP_MULF: A = vscale(vmul(A, ld(pk.y)), f); break;
+                        case FDG_OP_SCALE: A = vscale(A, f); break;
+                        case FDG_OP_XADDF: A = vadd(ld(pk.y), vscale(A, f)); break;
+                        case FDG_OP_XMULF: A = vscale(vmul(ld(pk.y), A), f); break;
+                        case FDG_OP_POW: A = vpow(A, pk.y); break;
+                        case FDG_OP_SPILL: {
+                            V *g = static_cast<V *>(a.scratch) + ((size_t)pk.z * gstride + gthread);
+                            *reinterpret_cast<Packed<V> *>(g) = *slot_ptr(pk.y);
+                        } break;
+                        case FDG_OP_FILL: {
+                            const V *g = static_cast<const V *>(a.scratch) + ((size_t)pk.z * gstride + gthread);
+                            *slot_ptr(pk.y) = *reinterpret_cast<const Packed<V> *>(g);
+                        } break;
+                        case FDG_OP_ROOT: {
+                            const uint32_t r = pk.y;
+                            if constexpr (!ACC) {
+                                if (active) {
+                                    double *o = static_cast<double *>(a.root) + ((size_t)r * a.ld_root + b0) * W;
+                                    if constexpr (S == 2) {
+                                        if (b0 + 1 < a.batch)
+                                            *reinterpret_cast<double2 *>(o) = make_double2(A.x[0], A.x[1]);
+                                        else
+                                            o[0] = A.x[0];
+                                    } else if constexpr (W == 2) {
+                                        *reinterpret_cast<double2 *>(o) = make_double2(A.x[0], A.x[1]);
+                                    } else {
+                                        o[0] = A.x[0];
+                                    }
+                                }
+                            } else {
+                                // fixed-shape reduction: samples of the thread, then the xor tree over lanes
+                                double s0 = active ? A.x[0] : 0.0, s1 = 0.0;
+                                if constexpr (W == 2) s1 = active ? A.x[1] : 0.0;
+                                if constexpr (S == 2) s0 = __dadd_rn(s0, (b0 + 1 < a.batch) ? A.x[1] : 0.0);
+#pragma unroll
+                                for (int m = 16; m >= 1; m >>= 1) {
+                                    s0 = __dadd_rn(s0, __shfl_xor_sync(0xffffffffu, s0, m));
+                                    if constexpr (W == 2) s1 = __dadd_rn(s1, __shfl_xor_sync(0xffffffffu, s1, m));
+                                }
+                                if (lane == 0) {
+                                    racc[r * W] = __dadd_rn(racc[r * W], s0);
+                                    if constexpr (W == 2) racc[r * W + 1] = __dadd_rn(racc[r * W + 1], s1);
                                 }
                             }
-                        } else {
-                            // fixed-shape reduction: samples of the thread, then the xor tree over lanes
-                            double s[W];
-                            if constexpr (W == 2) {
-                                s[0] = active ? A_.x[0] : 0.0;
-                                s[1] = active ? A_.x[1] : 0.0;
-                            } else {
-                                s[0] = active ? A_.x[0] : 0.0;
-                                if constexpr (S == 2) s[0] = __dadd_rn(s[0], (b0 + 1 < a.batch) ? A_.x[1] : 0.0);
-                            }
-#pragma unroll
-                            for (int k = 0; k < W; ++k) {
-#pragma unroll
-                                for (int m = 16; m >= 1; m >>= 1) s[k] = __dadd_rn(s[k], __shfl_xor_sync(0xffffffffu, s[k], m));
-                            }
-                            if ((tid & 31) == 0) {
-#pragma unroll
-                                for (int k = 0; k < W; ++k) racc[arg * W + k] = __dadd_rn(racc[arg * W + k], s[k]);
-                            }
-                        }
-                    })
-#undef FDG_CASE4
-#undef FDG_CASE
-                default: break;
+                        } break;
+                        default: break;  // NOP
+                    }
+                    if (done) break;
+                }
+                pk = pn;
             }
-            pk = nx;
+            if (done) break;
+            // hand over to the prefetched chunk and start fetching the one after it
+            cur ^= 1;
+            wbuf[cur * FDG_CHUNK + lane] = nxt;
+            gp += FDG_CHUNK;
+            nxt = __ldg(gp + FDG_CHUNK + lane);
+            __syncwarp();
         }
         cp_async_wait(0);
     }
     if constexpr (ACC) {
         __syncwarp();
-        const long long warp_row = (long long)blockIdx.x * (T >> 5) + (tid >> 5);
-        for (int r = (tid & 31); r < RW; r += 32) a.partial[warp_row * RW + r] = racc[r];
+        const long long warp_row = (long long)blockIdx.x * (T >> 5) + warp;
+        for (int r = lane; r < RW; r += 32) a.partial[warp_row * RW + r] = racc[r];
     }
 }
 

@@ -13,13 +13,26 @@ from fractions import Fraction
 
 import numpy as np
 
-NREG = 4
-FIRST_REG_OP = 8
-OP_END, OP_LDL, OP_WAIT, OP_SPILL, OP_FILL = 0, 1, 2, 3, 4
-(R_MOV, R_MUL, R_ADD, R_MOVF, R_MULF, R_ADDF, R_SCALE, R_RADDF, R_RMULF, R_XADDF, R_XMULF, R_POW, R_ST,
- R_ROOT) = range(14)
-NAMES = ["MOV", "MUL", "ADD", "MOVF", "MULF", "ADDF", "SCALE", "RADDF", "RMULF", "XADDF", "XMULF", "POW", "ST", "ROOT"]
+CHUNK = 32
+TERM_MAX = 11
+(OP_END, OP_NOP, OP_LDL, OP_SPILL, OP_FILL, OP_TERM, OP_MOV, OP_MUL, OP_ADD, OP_MULF, OP_SCALE, OP_RADDF, OP_RMULF,
+ OP_XADDF, OP_XMULF, OP_POW, OP_ST, OP_ROOT) = range(18)
+NAMES = ["END", "NOP", "LDL", "SPILL", "FILL", "TERM", "MOV", "MUL", "ADD", "MULF", "SCALE", "RADDF", "RMULF", "XADDF",
+         "XMULF", "POW", "ST", "ROOT"]
 SLOT_BITS = 12
+
+
+def _hdr(w0):
+    return dict(op=w0 & 63, k=(w0 >> 6) & 15, wait=(w0 >> 10) & 7, push=(w0 >> 13) & 1, first=(w0 >> 14) & 1, slot0=w0 >> 20)
+
+
+def _term_slots(w, pc, k, slot0):
+    slots = [slot0, w[pc][1] & 0xFFFF, w[pc][1] >> 16][:k]
+    if k > 3:
+        e = w[pc + 1]
+        for q in range(3, k):
+            slots.append((int(e[(q - 3) >> 1]) >> (16 * ((q - 3) & 1))) & 0xFFFF)
+    return [int(x) for x in slots]
 
 
 def _fma(x, y, z):
@@ -88,38 +101,44 @@ def _vpow(a: np.ndarray, n: int, cplx: bool):
 
 
 def disassemble(words: np.ndarray):
+    w = np.asarray(words, np.uint32).reshape(-1, 4).tolist()
     out = []
-    for i, (w0, w1, w2, w3) in enumerate(np.asarray(words, np.uint32).reshape(-1, 4).tolist()):
-        op, n, arg = w0 & 0xFF, (w0 >> 8) & 3, w0 >> 10
+    pc = 0
+    while pc < len(w):
+        w0, w1, w2, w3 = w[pc]
+        h = _hdr(w0)
+        op, k = h["op"], h["k"]
         f = np.array([w2, w3], np.uint32).view(np.float64)[0]
-        if op == OP_END:
-            out.append(f"{i:5d} END")
-        elif op == OP_LDL:
-            parts = [f"v[{w & 0xFFF}]<-leaf{w >> SLOT_BITS}" for w in (w1, w2, w3)[:n]]
-            out.append(f"{i:5d} LDL " + ", ".join(parts))
-        elif op == OP_WAIT:
-            out.append(f"{i:5d} WAIT {arg}")
-        elif op == OP_SPILL:
-            out.append(f"{i:5d} SPILL scratch[{arg}] <- v[{w1}]")
-        elif op == OP_FILL:
-            out.append(f"{i:5d} FILL v[{w1}] <- scratch[{arg}]")
+        pre = f"{pc:5d} " + (f"[wait {h['wait'] - 1}] " if h["wait"] else "") + ("[push] " if h["push"] else "")
+        name = NAMES[op] if op < len(NAMES) else f"?{op}"
+        if op == OP_LDL:
+            out.append(pre + "LDL " + ", ".join(f"v[{x & 0xFFF}]<-leaf{x >> SLOT_BITS}" for x in (w1, w2, w3)[:k]))
+        elif op in (OP_SPILL, OP_FILL):
+            out.append(pre + f"{name} v[{w1}] scratch[{w2}]")
+        elif op == OP_TERM:
+            sl = _term_slots(w, pc, k, h["slot0"])
+            out.append(pre + ("A = " if h["first"] else "A += ") + " * ".join(f"v[{x}]" for x in sl) + f" * {float(f)!r}")
+            if k > 3:
+                pc += 1
+        elif op in (OP_MOV, OP_MUL, OP_ADD):
+            out.append(pre + f"{name}{k} " + " ".join(f"v[{x}]" for x in (w1, w2, w3)[:k]))
+        elif op in (OP_MULF, OP_XADDF, OP_XMULF):
+            out.append(pre + f"{name} v[{w1}] f={float(f)!r}")
+        elif op in (OP_SCALE, OP_RADDF, OP_RMULF):
+            out.append(pre + f"{name} f={float(f)!r}")
+        elif op in (OP_POW, OP_ST, OP_ROOT):
+            out.append(pre + f"{name} {w1}")
         else:
-            base, d = divmod(op - FIRST_REG_OP, NREG)
-            name = NAMES[base] if base < len(NAMES) else f"?{base}"
-            if base in (R_MOV, R_MUL, R_ADD):
-                out.append(f"{i:5d} {name}{n} a{d} " + " ".join(f"v[{w}]" for w in (w1, w2, w3)[:n]))
-            elif base in (R_MOVF, R_MULF, R_ADDF, R_XADDF, R_XMULF):
-                out.append(f"{i:5d} {name} a{d} v[{w1}] f={f!r}")
-            elif base in (R_SCALE, R_RADDF, R_RMULF):
-                out.append(f"{i:5d} {name} a{d} f={f!r}")
-            else:
-                out.append(f"{i:5d} {name} a{d} arg={arg}")
+            out.append(pre + name)
+        if op == OP_END:
+            break
+        pc += 1
     return "\n".join(out)
 
 
 def run(words: np.ndarray, leaf: np.ndarray, n_roots: int, strict: bool = True):
     """leaf: (L, B) float64 or complex128.  Returns (root (R, B), set-mask (R,), counters)."""
-    w = np.asarray(words, np.uint32).reshape(-1, 4)
+    w = np.asarray(words, np.uint32).reshape(-1, 4).tolist()
     cplx = leaf.dtype == np.complex128
     B = leaf.shape[1]
     mul = _cmul if cplx else (lambda x, y: x * y)
@@ -129,9 +148,11 @@ def run(words: np.ndarray, leaf: np.ndarray, n_roots: int, strict: bool = True):
     slots = {}
     slot_group = {}
     scratch = {}
-    acc = [np.zeros(B, leaf.dtype) for _ in range(NREG)]
+    zero = np.zeros(B, leaf.dtype)
+    A, R1, R2, R3 = zero, zero, zero, zero
+    depth = 0
     committed = completed = 0
-    cnt = {"packets": 0, "ldl": 0, "wait": 0, "slot_reads": 0, "max_slot": -1}
+    cnt = {"packets": 0, "ldl": 0, "wait": 0, "slot_reads": 0, "max_slot": -1, "max_depth": 0}
 
     def rd(s):
         cnt["slot_reads"] += 1
@@ -145,83 +166,97 @@ def run(words: np.ndarray, leaf: np.ndarray, n_roots: int, strict: bool = True):
 
     ended = False
     np.seterr(all="ignore")  # overflow / nan are legitimate values here; they must match bit for bit too
-    for pc in range(w.shape[0]):
-        w0, w1, w2, w3 = (int(x) for x in w[pc])
-        op, n, arg = w0 & 0xFF, (w0 >> 8) & 3, w0 >> 10
+    pc = 0
+    while pc < len(w):
+        w0, w1, w2, w3 = w[pc]
+        h = _hdr(w0)
+        op, k = h["op"], h["k"]
         f = float(np.array([w2, w3], np.uint32).view(np.float64)[0])
         cnt["packets"] += 1
+        if h["wait"]:
+            assert h["wait"] - 1 <= 6
+            completed = max(completed, committed - (h["wait"] - 1))
+            cnt["wait"] += 1
+        if h["push"]:
+            assert op == OP_MOV or (op == OP_TERM and h["first"]), "push on a packet that does not start a fold"
+            R3, R2, R1 = R2, R1, A
+            depth += 1
+            assert depth <= 3, "accumulator stack overflow"
+            cnt["max_depth"] = max(cnt["max_depth"], depth)
         if op == OP_END:
             ended = True
             break
-        if op == OP_LDL:
-            assert 1 <= n <= 3
-            for ww in (w1, w2, w3)[:n]:
+        elif op == OP_NOP:
+            pass
+        elif op == OP_LDL:
+            assert 1 <= k <= 3
+            for ww in (w1, w2, w3)[:k]:
                 s, l = ww & ((1 << SLOT_BITS) - 1), ww >> SLOT_BITS
                 slots[s] = leaf[l].copy()
                 slot_group[s] = committed
                 cnt["ldl"] += 1
                 cnt["max_slot"] = max(cnt["max_slot"], s)
             committed += 1
-            continue
-        if op == OP_WAIT:
-            assert arg <= 7
-            completed = max(completed, committed - arg)
-            cnt["wait"] += 1
-            continue
-        if op == OP_SPILL:
-            scratch[arg] = rd(w1).copy()
-            continue
-        if op == OP_FILL:
-            slots[w1] = scratch[arg].copy()
+        elif op == OP_SPILL:
+            scratch[w2] = rd(w1).copy()
+        elif op == OP_FILL:
+            slots[w1] = scratch[w2].copy()
             slot_group[w1] = -1
             cnt["max_slot"] = max(cnt["max_slot"], w1)
-            continue
-        assert op >= FIRST_REG_OP, f"bad opcode {op}"
-        base, d = divmod(op - FIRST_REG_OP, NREG)
-        A = acc[d]
-        if base == R_MOV:
+        elif op == OP_TERM:
+            assert 1 <= k <= TERM_MAX
+            sl = _term_slots(w, pc, k, h["slot0"])
+            if k > 3:
+                assert pc // CHUNK == (pc + 1) // CHUNK, "TERM extension packet crosses a chunk boundary"
+                pc += 1
+                cnt["packets"] += 1
+            t = rd(sl[0])
+            for x in sl[1:]:
+                t = mul(t, rd(x))
+            t = scale(t, f)
+            A = t.copy() if h["first"] else A + t
+        elif op == OP_MOV:
             v = rd(w1)
-            if n >= 2:
+            if k >= 2:
                 v = mul(v, rd(w2))
-            if n >= 3:
+            if k >= 3:
                 v = mul(v, rd(w3))
-            acc[d] = v.copy()
-        elif base == R_MUL:
-            for ww in (w1, w2, w3)[:n]:
+            A = v.copy()
+        elif op == OP_MUL:
+            for ww in (w1, w2, w3)[:k]:
                 A = mul(A, rd(ww))
-            acc[d] = A
-        elif base == R_ADD:
-            for ww in (w1, w2, w3)[:n]:
+        elif op == OP_ADD:
+            for ww in (w1, w2, w3)[:k]:
                 A = A + rd(ww)
-            acc[d] = A
-        elif base == R_MOVF:
-            acc[d] = scale(rd(w1), f)
-        elif base == R_MULF:
-            acc[d] = scale(mul(A, rd(w1)), f)
-        elif base == R_ADDF:
-            acc[d] = A + scale(rd(w1), f)
-        elif base == R_SCALE:
-            acc[d] = scale(A, f)
-        elif base == R_RADDF:
-            assert d >= 1
-            acc[d - 1] = acc[d - 1] + scale(A, f)
-        elif base == R_RMULF:
-            assert d >= 1
-            acc[d - 1] = scale(mul(acc[d - 1], A), f)
-        elif base == R_XADDF:
-            acc[d] = rd(w1) + scale(A, f)
-        elif base == R_XMULF:
-            acc[d] = scale(mul(rd(w1), A), f)
-        elif base == R_POW:
-            acc[d] = _vpow(A, arg, cplx)
-        elif base == R_ST:
-            slots[arg] = A.copy()
-            slot_group[arg] = -1
-            cnt["max_slot"] = max(cnt["max_slot"], arg)
-        elif base == R_ROOT:
-            root[arg] = A
-            root_set[arg] = True
+        elif op == OP_MULF:
+            A = scale(mul(A, rd(w1)), f)
+        elif op == OP_SCALE:
+            A = scale(A, f)
+        elif op == OP_RADDF:
+            assert depth >= 1, "pop from an empty accumulator stack"
+            A = R1 + scale(A, f)
+            R1, R2 = R2, R3
+            depth -= 1
+        elif op == OP_RMULF:
+            assert depth >= 1, "pop from an empty accumulator stack"
+            A = scale(mul(R1, A), f)
+            R1, R2 = R2, R3
+            depth -= 1
+        elif op == OP_XADDF:
+            A = rd(w1) + scale(A, f)
+        elif op == OP_XMULF:
+            A = scale(mul(rd(w1), A), f)
+        elif op == OP_POW:
+            A = _vpow(A, w1, cplx)
+        elif op == OP_ST:
+            slots[w1] = A.copy()
+            slot_group[w1] = -1
+            cnt["max_slot"] = max(cnt["max_slot"], w1)
+        elif op == OP_ROOT:
+            root[w1] = A
+            root_set[w1] = True
         else:
-            raise AssertionError(f"bad register op {base}")
+            raise AssertionError(f"bad opcode {op}")
+        pc += 1
     assert ended, "program has no END packet"
     return root, root_set, cnt
