@@ -187,17 +187,23 @@ int do_eval(fdg_program *h, const void *leaf, int64_t ld_leaf, void *root, int64
         return accumulate ? launch_variant<fdg::VCplx, true>(h, *ds, args, batch, st)
                           : launch_variant<fdg::VCplx, false>(h, *ds, args, batch, st);
     }
-    // two samples per thread need 16-byte aligned sample pairs that stay inside the allocation
-    bool two = h->spt != 1;
-    if (two) {
-        const bool leaf_ok = low.L == 0 || (((uintptr_t)leaf % 16 == 0) && (ld_leaf % 2 == 0) &&
-                                            (batch % 2 == 0 || ld_leaf > batch));
+    // S samples per thread need 16-byte aligned sample groups that stay inside the allocation:
+    // even leading dimensions and the rounded-up batch within ld_leaf
+    auto fits = [&](int64_t s) {
+        const int64_t padded = (batch + s - 1) / s * s;
+        const bool leaf_ok = low.L == 0 || (((uintptr_t)leaf % 16 == 0) && (ld_leaf % 2 == 0) && padded <= ld_leaf);
         const bool root_ok = accumulate || low.R == 0 || (((uintptr_t)root % 16 == 0) && (ld_root % 2 == 0));
-        two = leaf_ok && root_ok;
-        if (!two && h->spt == 2)
-            return fail(FDG_ERR_BAD_ARG, "two samples per thread need 16-byte aligned buffers and even leading dimensions");
-    }
-    if (two)
+        return leaf_ok && root_ok;
+    };
+    int spt = h->spt;
+    if (spt == 0) spt = (batch >= (1 << 16) && fits(4)) ? 4 : (fits(2) ? 2 : 1);  // auto: widest that fits
+    if (spt > 1 && !fits(spt))
+        return fail(FDG_ERR_BAD_ARG, "several samples per thread need 16-byte aligned buffers, even leading dimensions "
+                                     "and the batch rounded up to the group size within ld_leaf");
+    if (spt == 4)
+        return accumulate ? launch_variant<fdg::VReal<4>, true>(h, *ds, args, batch, st)
+                          : launch_variant<fdg::VReal<4>, false>(h, *ds, args, batch, st);
+    if (spt == 2)
         return accumulate ? launch_variant<fdg::VReal<2>, true>(h, *ds, args, batch, st)
                           : launch_variant<fdg::VReal<2>, false>(h, *ds, args, batch, st);
     return accumulate ? launch_variant<fdg::VReal<1>, true>(h, *ds, args, batch, st)
@@ -374,7 +380,8 @@ int fdg_set_launch(fdg_handle h, int32_t threads, int32_t samples_per_thread, in
     if (!h) return fail(FDG_ERR_BAD_ARG, "null handle");
     if (threads != 0 && (threads < 32 || threads > 256 || (threads & (threads - 1))))
         return fail(FDG_ERR_BAD_ARG, "threads must be 32, 64, 128 or 256");
-    if (samples_per_thread < 0 || samples_per_thread > 2) return fail(FDG_ERR_BAD_ARG, "samples_per_thread must be 0, 1 or 2");
+    if (samples_per_thread < 0 || samples_per_thread > 4 || samples_per_thread == 3)
+        return fail(FDG_ERR_BAD_ARG, "samples_per_thread must be 0 (auto), 1, 2 or 4");
     if (blocks_per_sm < 0) return fail(FDG_ERR_BAD_ARG, "blocks_per_sm must be >= 0");
     std::lock_guard<std::mutex> lock(h->mu);
     if (threads) h->threads = threads;

@@ -22,17 +22,22 @@
 
 #define FDG_STACK_REGS 3     /* R1..R3 below the accumulator A */
 #define FDG_MAX_WAIT 6       /* largest cp.async.wait_group immediate used (header field is wait+1 <= 7) */
-#define FDG_TERM_MAX 11      /* operands of one TERM packet pair */
+#define FDG_TERM_MAX 11      /* operands of one TERM record */
+#define FDG_LDL_MAX 7        /* loads of one LDL packet pair */
 #define FDG_CHUNK 32         /* packets per program chunk (one per lane of the fetching warp) */
 
 enum {
     FDG_OP_END = 0,    // end of program
     FDG_OP_NOP = 1,    // padding (keeps a TERM and its extension packet inside one chunk)
-    FDG_OP_LDL = 2,    // k leaf loads, async (cp.async, one commit group): w[1..k] = slot | leaf << 12
+    FDG_OP_LDL = 2,    // k <= 7 leaf loads, async (cp.async, one commit group): slot | leaf << 12 in w1..w3 and, for
+                       //   k > 3, in the four words of the NEXT packet
     FDG_OP_SPILL = 3,  // scratch[w2] = v[w1]
     FDG_OP_FILL = 4,   // v[w1] = scratch[w2]                      (synchronous)
-    FDG_OP_TERM = 5,   // t = v[s0] * v[s1] * ... * v[s(k-1)];  A = first ? t*f : A + t*f      f = (w2, w3)
-                       //   s0 = hdr >> 20, s1 | s2 << 16 = w1; k > 3: the NEXT packet holds s3..s10, 16 bits each
+    FDG_OP_TERM = 5,   // a BLOCK of w1 terms with k operands each, run by a dispatch-free inner loop:
+                       //     for each record: t = v[s0] * v[s1] * ... * v[s(k-1)];  A = A + t * f
+                       //   (`first`: the first record sets A = t * f instead).  Records follow the header packet:
+                       //     {s0 | s1 << 16, s2 | s3 << 16, f_lo, f_hi} and, for k > 4, {s4 | s5 << 16, ..., s10}.
+                       //   header and records never straddle a chunk boundary.
     FDG_OP_MOV = 6,    // A = v[w1]; then *= v[w2], *= v[w3] for k = 2, 3                        (start of a fold)
     FDG_OP_MUL = 7,    // A = ((A * v[w1]) * v[w2]) * v[w3]                                     (k = 1..3)
     FDG_OP_ADD = 8,    // A = ((A + v[w1]) + v[w2]) + v[w3]

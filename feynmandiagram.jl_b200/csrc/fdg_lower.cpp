@@ -364,8 +364,9 @@ struct CodeGen {
                 fr.i++;
                 continue;
             }
-            if (sum && termable(o.val)) {
-                // A (+)= (v1 * v2 * ... * vk) * f in one packet, no stack traffic
+            if ((sum || first) && s.op != FDG_OP_POWER && termable(o.val)) {
+                // A (+)= (v1 * v2 * ... * vk) * f as one term record, no stack traffic.  As the first operand of a
+                // Prod this is A = (v1 * ... * vk) * f, the same left fold the MOV/MUL/SCALE sequence would compute.
                 const Stmt &c = st[(size_t)o.val];
                 int32_t vals[FDG_TERM_MAX];
                 for (int32_t q = 0; q < c.count; ++q) vals[q] = ops[(size_t)(c.first + q)].val;
@@ -606,11 +607,26 @@ struct Packer {
         hi = (uint32_t)(u >> 32);
     }
 
+    void pad_to_chunk() {
+        while (n_packets() % FDG_CHUNK) packet(FDG_HDR(FDG_OP_NOP, 0, 0, 0, 0, 0));
+    }
+    int64_t room() const { return FDG_CHUNK - n_packets() % FDG_CHUNK; }  // packets left in the current chunk
+
     void run() {
         const auto &ops2 = al.ops2;
         const int64_t M = (int64_t)ops2.size();
         slot_group.assign((size_t)std::max(al.n_slots, 1), -1);
-        // bucket the loads by their hoisted anchor (quantised so that neighbours share a packet)
+        // maximal runs of TERM ops that one block could cover: run_start[j] = first op of the run containing j
+        std::vector<int64_t> run_start((size_t)M + 1);
+        for (int64_t j = 0; j < M; ++j) {
+            const Op2 &o = ops2[(size_t)j];
+            const bool cont = j > 0 && o.kind == 0 && o.s.op == FDG_OP_TERM && !o.s.first && ops2[(size_t)(j - 1)].kind == 0 &&
+                              ops2[(size_t)(j - 1)].s.op == FDG_OP_TERM && ops2[(size_t)(j - 1)].s.k == o.s.k;
+            run_start[(size_t)j] = cont ? run_start[(size_t)(j - 1)] : j;
+        }
+        run_start[(size_t)M] = M;
+        // bucket the loads by their hoisted anchor; a load that would land inside a run of terms moves to the start
+        // of the run when that is legal (so the run stays one block), anchors are quantised so neighbours share packets
         std::vector<std::vector<int32_t>> at((size_t)M + 1);
         for (size_t i = 0; i < al.ldls.size(); ++i) {
             const Ldl &l = al.ldls[i];
@@ -618,22 +634,26 @@ struct Packer {
             if (dist > 0) t &= ~(int64_t)3;
             if (t < l.earliest) t = l.earliest;
             if (t > l.anchor) t = l.anchor;
+            if (run_start[(size_t)t] >= l.earliest) t = run_start[(size_t)t];
             at[(size_t)t].push_back((int32_t)i);
         }
         int64_t j = 0;
         while (j <= M) {
-            // loads anchored before op j, three per packet, one cp.async group per packet
+            // loads anchored before op j, up to seven per packet pair, one cp.async group each
             const auto &lst = at[(size_t)j];
-            for (size_t k = 0; k < lst.size(); k += 3) {
-                const size_t n = std::min<size_t>(3, lst.size() - k);
-                uint32_t w[3] = {0, 0, 0};
+            for (size_t k = 0; k < lst.size();) {
+                size_t n = std::min<size_t>(FDG_LDL_MAX, lst.size() - k);
+                if (n > 3 && room() < 2) n = 3;
+                uint32_t w[FDG_LDL_MAX] = {0, 0, 0, 0, 0, 0, 0};
                 for (size_t q = 0; q < n; ++q) {
                     const Ldl &l = al.ldls[(size_t)lst[k + q]];
                     w[q] = FDG_LDL_WORD(l.slot, l.leaf);
                     slot_group[(size_t)l.slot] = committed;
                 }
                 packet(FDG_HDR(FDG_OP_LDL, n, 0, 0, 0, 0), w[0], w[1], w[2]);
+                if (n > 3) packet(w[3], w[4], w[5], w[6]);
                 committed++;
+                k += n;
             }
             if (j == M) break;
             const Op2 &o = ops2[(size_t)j];
@@ -672,18 +692,29 @@ struct Packer {
                     continue;
                 }
                 case FDG_OP_TERM: {
+                    // one block: this term and the following terms of the same fold with the same operand count,
+                    // as far as no load is anchored in between and the records fit the current chunk
                     const int k = s.k;
-                    for (int q = 0; q < k; ++q) need(o.slots[q]);
-                    if (k > 3 && (n_packets() % FDG_CHUNK) == FDG_CHUNK - 1)
-                        packet(FDG_HDR(FDG_OP_NOP, 0, 0, 0, 0, 0));  // keep the pair inside one chunk
-                    const uint32_t s1 = k > 1 ? (uint32_t)o.slots[1] : 0, s2 = k > 2 ? (uint32_t)o.slots[2] : 0;
-                    packet(FDG_HDR(FDG_OP_TERM, k, take_wait(), s.push, s.first, (uint32_t)o.slots[0]), s1 | (s2 << 16), lo, hi);
-                    if (k > 3) {
-                        uint32_t e[4] = {0, 0, 0, 0};
-                        for (int q = 3; q < k; ++q) e[(q - 3) >> 1] |= (uint32_t)o.slots[q] << (16 * ((q - 3) & 1));
-                        packet(e[0], e[1], e[2], e[3]);
+                    const int rec = k > 4 ? 2 : 1;
+                    if (room() < 1 + rec) pad_to_chunk();
+                    int64_t n = 1;
+                    while (j + n < M && run_start[(size_t)(j + n)] == run_start[(size_t)j] && at[(size_t)(j + n)].empty() &&
+                           1 + (n + 1) * rec <= room())
+                        ++n;
+                    for (int64_t t = 0; t < n; ++t)
+                        for (int q = 0; q < k; ++q) need(ops2[(size_t)(j + t)].slots[q]);
+                    packet(FDG_HDR(FDG_OP_TERM, k, take_wait(), s.push, s.first, 0), (uint32_t)n);
+                    for (int64_t t = 0; t < n; ++t) {
+                        const Op2 &ot = ops2[(size_t)(j + t)];
+                        uint32_t e[6] = {0, 0, 0, 0, 0, 0};
+                        for (int q = 0; q < k; ++q) e[q >> 1] |= (uint32_t)ot.slots[q] << (16 * (q & 1));
+                        uint32_t flo, fhi;
+                        split(ot.s.f, flo, fhi);
+                        packet(e[0], e[1], flo, fhi);
+                        if (rec == 2) packet(e[2], e[3], e[4], e[5]);
                     }
-                    break;
+                    j += n;
+                    continue;
                 }
                 case FDG_OP_MULF:
                 case FDG_OP_XADDF:

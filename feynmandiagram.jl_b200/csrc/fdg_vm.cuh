@@ -159,13 +159,68 @@ __device__ __forceinline__ void cp_async_wait(unsigned n) {
     }
 }
 
+// ---- shared-memory access by 32-bit shared address ------------------------------------------------------
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
 template <class V>
-struct alignas(sizeof(V)) Packed {
+__device__ __forceinline__ V lds_val(uint32_t addr) {
     V v;
-};
+    constexpr int N = sizeof(V) / 8;
+    if constexpr (N == 1) {
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v.x[0]) : "r"(addr));
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i += 2)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x[i]), "=d"(v.x[i + 1]) : "r"(addr + 8 * i));
+    }
+    return v;
+}
+template <class V>
+__device__ __forceinline__ void sts_val(uint32_t addr, const V &v) {
+    constexpr int N = sizeof(V) / 8;
+    if constexpr (N == 1) {
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v.x[0]) : "memory");
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i += 2)
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr + 8 * i), "d"(v.x[i]), "d"(v.x[i + 1]) : "memory");
+    }
+}
+
+// One block of `n` term records with K operands each (FDG_OP_TERM): the dispatch-free inner loop.
+//   A = A + (v[s0] * v[s1] * ... * v[s(K-1)]) * f     for every record, in order.
+template <class V, int K>
+__device__ __forceinline__ void term_block(uint32_t &pp, uint32_t n, bool first, V &A, const uint32_t my_s, const uint32_t stride) {
+    constexpr uint32_t REC = K > 4 ? 32 : 16;
+#pragma unroll 1
+    for (uint32_t j = 0; j < n; ++j) {
+        const uint4 r = lds_u4(pp);
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if constexpr (K > 4) e = lds_u4(pp + 16);
+        pp += REC;
+        const uint32_t s[12] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16, e.x & 0xffffu, e.x >> 16,
+                                e.y & 0xffffu, e.y >> 16, e.z & 0xffffu, e.z >> 16, e.w & 0xffffu, e.w >> 16};
+        V v[K];
+#pragma unroll
+        for (int q = 0; q < K; ++q) v[q] = lds_val<V>(my_s + s[q] * stride);
+        V t = v[0];
+#pragma unroll
+        for (int q = 1; q < K; ++q) t = vmul(t, v[q]);
+        t = vscale(t, __hiloint2double((int)r.w, (int)r.z));
+        if (first) {
+            A = t;
+            first = false;
+        } else {
+            A = vadd(A, t);
+        }
+    }
+}
 
 // ---- the kernel --------------------------------------------------------------------------------------
-// V: VReal<1>, VReal<2> or VCplx.  ACC: false = write root per sample, true = per-warp running sums.
+// V: VReal<1>, VReal<2>, VReal<4> or VCplx.  ACC: false = write root per sample, true = per-warp running sums.
 //
 // Dynamic shared memory:  [ slot file: n_slots x T values | per-warp program buffers: 2 x 32 packets |
 //                           accumulate mode: per-warp running sums racc[warp][root * W] ]
@@ -182,11 +237,12 @@ __global__ void __launch_bounds__(256) fdg_vm_kernel(const VmArgs a) {
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const uint32_t stride = (uint32_t)T * (uint32_t)sizeof(V);
-    unsigned char *const my = smem + (size_t)tid * sizeof(V);
-    const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
+    const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t my_s = smem_s + (uint32_t)tid * (uint32_t)sizeof(V);
     const long long gthread = (long long)blockIdx.x * T + tid;
     const long long gstride = (long long)gridDim.x * T;
     const uint32_t slot_file_bytes = (uint32_t)a.n_slots * stride;
+    const uint32_t wbuf_s = smem_s + slot_file_bytes + (uint32_t)warp * (2 * FDG_CHUNK * 16);
     uint4 *const wbuf = reinterpret_cast<uint4 *>(smem + slot_file_bytes) + warp * (2 * FDG_CHUNK);
     const int RW = a.n_roots * W;
     double *racc = nullptr;
@@ -196,15 +252,13 @@ __global__ void __launch_bounds__(256) fdg_vm_kernel(const VmArgs a) {
         for (int r = lane; r < RW; r += 32) racc[r] = 0.0;
         __syncwarp();
     }
-    auto slot_ptr = [&](uint32_t s) -> Packed<V> * { return reinterpret_cast<Packed<V> *>(my + s * stride); };
-    auto ld = [&](uint32_t s) -> V { return reinterpret_cast<const Packed<V> *>(my + s * stride)->v; };
 
     for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const long long b0 = (tile * T + tid) * S;
         const bool active = b0 < a.batch;
-        // inactive threads re-read a valid (aligned) sample so that every address stays in bounds
+        // inactive threads re-read a valid (aligned) sample group so that every address stays in bounds
         long long bl = b0;
-        if (!active) bl = S == 2 ? ((a.batch - 1) & ~1LL) : (a.batch - 1);
+        if (!active) bl = (a.batch - 1) & ~(long long)(S - 1);
         const unsigned char *const leaf_b = static_cast<const unsigned char *>(a.leaf) + (size_t)bl * (8 * W);
         const size_t leaf_stride = (size_t)a.ld_leaf * (8 * W);
 
@@ -218,180 +272,183 @@ __global__ void __launch_bounds__(256) fdg_vm_kernel(const VmArgs a) {
         wbuf[lane] = __ldg(gp + lane);
         uint4 nxt = __ldg(gp + FDG_CHUNK + lane);
         __syncwarp();
-        int cur = 0;
-        bool done = false;
-        while (!done) {
-            const uint4 *pb = wbuf + cur * FDG_CHUNK;
-            uint4 pk = pb[0];
-#pragma unroll 1
-            for (int i = 0; i < FDG_CHUNK; ++i) {
-                uint4 pn = pb[(i + 1) & (FDG_CHUNK - 1)];  // next packet (wraps harmlessly on the last one)
-                const uint32_t hdr = pk.x;
-                const uint32_t op = FDG_HDR_OP(hdr);
-                const uint32_t k = FDG_HDR_K(hdr);
-                if (hdr & (7u << 10)) cp_async_wait(FDG_HDR_WAIT(hdr) - 1u);
-                if (op == FDG_OP_TERM) {
-                    const double f = __hiloint2double((int)pk.w, (int)pk.z);
-                    V t = ld(hdr >> 20);
-                    if (k > 1) {
-                        const V u = ld(pk.y & 0xffffu);
-                        if (k > 2) {
-                            const V w = ld(pk.y >> 16);
-                            t = vmul(vmul(t, u), w);
-                            if (k > 3) {
-                                const uint4 e = pn;  // extension packet: s3..s10
-                                ++i;
-                                pn = pb[(i + 1) & (FDG_CHUNK - 1)];
-                                t = vmul(t, ld(e.x & 0xffffu));
-                                if (k > 4) {
-                                    t = vmul(t, ld(e.x >> 16));
-                                    if (k > 5) {
-                                        t = vmul(t, ld(e.y & 0xffffu));
-                                        if (k > 6) t = vmul(t, ld(e.y >> 16));
-                                        if (k > 7) t = vmul(t, ld(e.z & 0xffffu));
-                                        if (k > 8) t = vmul(t, ld(e.z >> 16));
-                                        if (k > 9) t = vmul(t, ld(e.w & 0xffffu));
-                                        if (k > 10) t = vmul(t, ld(e.w >> 16));
-                                    }
-                                }
-                            }
-                        } else {
-                            t = vmul(t, u);
-                        }
+        uint32_t cur = 0;
+        uint32_t pp = wbuf_s;                    // shared address of the next packet
+        uint32_t pend = wbuf_s + FDG_CHUNK * 16;  // end of the current chunk
+        for (;;) {
+            if (pp == pend) {
+                // hand over to the prefetched chunk and start fetching the one after it
+                cur ^= 1u;
+                wbuf[cur * FDG_CHUNK + lane] = nxt;
+                gp += FDG_CHUNK;
+                nxt = __ldg(gp + FDG_CHUNK + lane);
+                __syncwarp();
+                pp = wbuf_s + cur * (FDG_CHUNK * 16);
+                pend = pp + FDG_CHUNK * 16;
+            }
+            const uint4 pk = lds_u4(pp);
+            pp += 16;
+            const uint32_t hdr = pk.x;
+            const uint32_t op = FDG_HDR_OP(hdr);
+            const uint32_t k = FDG_HDR_K(hdr);
+            if (hdr & (7u << 10)) cp_async_wait(FDG_HDR_WAIT(hdr) - 1u);
+            if (hdr & (1u << 13)) {  // push: this packet starts a nested fold
+                R3 = R2;
+                R2 = R1;
+                R1 = A;
+            }
+            if (op == FDG_OP_TERM) {
+                const bool first = (hdr >> 14) & 1u;
+                const uint32_t n = pk.y;
+                switch (k) {
+                    case 1: term_block<V, 1>(pp, n, first, A, my_s, stride); break;
+                    case 2: term_block<V, 2>(pp, n, first, A, my_s, stride); break;
+                    case 3: term_block<V, 3>(pp, n, first, A, my_s, stride); break;
+                    case 4: term_block<V, 4>(pp, n, first, A, my_s, stride); break;
+                    case 5: term_block<V, 5>(pp, n, first, A, my_s, stride); break;
+                    case 6: term_block<V, 6>(pp, n, first, A, my_s, stride); break;
+                    case 7: term_block<V, 7>(pp, n, first, A, my_s, stride); break;
+                    case 8: term_block<V, 8>(pp, n, first, A, my_s, stride); break;
+                    case 9: term_block<V, 9>(pp, n, first, A, my_s, stride); break;
+                    case 10: term_block<V, 10>(pp, n, first, A, my_s, stride); break;
+                    default: term_block<V, 11>(pp, n, first, A, my_s, stride); break;
+                }
+                continue;
+            }
+            const double f = __hiloint2double((int)pk.w, (int)pk.z);
+            switch (op) {
+                case FDG_OP_END: goto program_done;
+                case FDG_OP_LDL: {
+                    uint4 e = make_uint4(0, 0, 0, 0);
+                    if (k > 3) {
+                        e = lds_u4(pp);
+                        pp += 16;
                     }
-                    t = vscale(t, f);
-                    if (hdr & (1u << 14)) {  // first term of a fold
-                        if (hdr & (1u << 13)) {
-                            R3 = R2;
-                            R2 = R1;
-                            R1 = A;
-                        }
-                        A = t;
-                    } else {
-                        A = vadd(A, t);
-                    }
-                } else if (op == FDG_OP_MUL) {
-                    if (k == 1) {
-                        A = vmul(A, ld(pk.y));
-                    } else if (k == 2) {
-                        const V v1 = ld(pk.y), v2 = ld(pk.z);
-                        A = vmul(vmul(A, v1), v2);
-                    } else {
-                        const V v1 = ld(pk.y), v2 = ld(pk.z), v3 = ld(pk.w);
-                        A = vmul(vmul(vmul(A, v1), v2), v3);
-                    }
-                } else if (op == FDG_OP_MOV) {
-                    if (hdr & (1u << 13)) {
-                        R3 = R2;
-                        R2 = R1;
-                        R1 = A;
-                    }
-                    if (k == 1) {
-                        A = ld(pk.y);
-                    } else if (k == 2) {
-                        const V v1 = ld(pk.y), v2 = ld(pk.z);
-                        A = vmul(v1, v2);
-                    } else {
-                        const V v1 = ld(pk.y), v2 = ld(pk.z), v3 = ld(pk.w);
-                        A = vmul(vmul(v1, v2), v3);
-                    }
-                } else if (op == FDG_OP_LDL) {
-                    const uint32_t w[3] = {pk.y, pk.z, pk.w};
+                    const uint32_t w[7] = {pk.y, pk.z, pk.w, e.x, e.y, e.z, e.w};
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) {
+                    for (int q = 0; q < 7; ++q) {
                         if (q < (int)k) {
                             const uint32_t s = w[q] & (FDG_MAX_SLOTS - 1);
                             const uint32_t l = w[q] >> FDG_LDL_SLOT_BITS;
-                            cp_async<sizeof(V)>(my_s + s * stride, leaf_b + (size_t)l * leaf_stride);
+                            const unsigned char *src = leaf_b + (size_t)l * leaf_stride;
+                            if constexpr (sizeof(V) == 32) {
+                                cp_async<16>(my_s + s * stride, src);
+                                cp_async<16>(my_s + s * stride + 16, src + 16);
+                            } else {
+                                cp_async<sizeof(V)>(my_s + s * stride, src);
+                            }
                         }
                     }
                     cp_async_commit();
-                } else if (op == FDG_OP_RADDF) {
-                    const double f = __hiloint2double((int)pk.w, (int)pk.z);
+                } break;
+                case FDG_OP_MOV:
+                    if (k == 1) {
+                        A = lds_val<V>(my_s + pk.y * stride);
+                    } else if (k == 2) {
+                        const V v1 = lds_val<V>(my_s + pk.y * stride), v2 = lds_val<V>(my_s + pk.z * stride);
+                        A = vmul(v1, v2);
+                    } else {
+                        const V v1 = lds_val<V>(my_s + pk.y * stride), v2 = lds_val<V>(my_s + pk.z * stride),
+                                v3 = lds_val<V>(my_s + pk.w * stride);
+                        A = vmul(vmul(v1, v2), v3);
+                    }
+                    break;
+                case FDG_OP_MUL:
+                    if (k == 1) {
+                        A = vmul(A, lds_val<V>(my_s + pk.y * stride));
+                    } else if (k == 2) {
+                        const V v1 = lds_val<V>(my_s + pk.y * stride), v2 = lds_val<V>(my_s + pk.z * stride);
+                        A = vmul(vmul(A, v1), v2);
+                    } else {
+                        const V v1 = lds_val<V>(my_s + pk.y * stride), v2 = lds_val<V>(my_s + pk.z * stride),
+                                v3 = lds_val<V>(my_s + pk.w * stride);
+                        A = vmul(vmul(vmul(A, v1), v2), v3);
+                    }
+                    break;
+                case FDG_OP_ADD:
+                    if (k == 1) {
+                        A = vadd(A, lds_val<V>(my_s + pk.y * stride));
+                    } else if (k == 2) {
+                        const V v1 = lds_val<V>(my_s + pk.y * stride), v2 = lds_val<V>(my_s + pk.z * stride);
+                        A = vadd(vadd(A, v1), v2);
+                    } else {
+                        const V v1 = lds_val<V>(my_s + pk.y * stride), v2 = lds_val<V>(my_s + pk.z * stride),
+                                v3 = lds_val<V>(my_s + pk.w * stride);
+                        A = vadd(vadd(vadd(A, v1), v2), v3);
+                    }
+                    break;
+                case FDG_OP_RADDF:
                     A = vadd(R1, vscale(A, f));
                     R1 = R2;
                     R2 = R3;
-                } else if (op == FDG_OP_RMULF) {
-                    const double f = __hiloint2double((int)pk.w, (int)pk.z);
+                    break;
+                case FDG_OP_RMULF:
                     A = vscale(vmul(R1, A), f);
                     R1 = R2;
                     R2 = R3;
-                } else if (op == FDG_OP_ST) {
-                    *slot_ptr(pk.y) = *reinterpret_cast<Packed<V> *>(&A);
-                } else {
-                    const double f = __hiloint2double((int)pk.w, (int)pk.z);
-                    switch (op) {
-                        case FDG_OP_END: done = true; break;
-                        case FDG_OP_ADD:
-                            if (k == 1) {
-                                A = vadd(A, ld(pk.y));
-                            } else if (k == 2) {
-                                const V v1 = ld(pk.y), v2 = ld(pk.z);
-                                A = vadd(vadd(A, v1), v2);
-                            } else {
-                                const V v1 = ld(pk.y), v2 = ld(pk.z), v3 = ld(pk.w);
-                                A = vadd(vadd(vadd(A, v1), v2), v3);
-                            }
-                            break;
-                        case FDG_OP_MULF: A = vscale(vmul(A, ld(pk.y)), f); break;
-                        case FDG_OP_SCALE: A = vscale(A, f); break;
-                        case FDG_OP_XADDF: A = vadd(ld(pk.y), vscale(A, f)); break;
-                        case FDG_OP_XMULF: A = vscale(vmul(ld(pk.y), A), f); break;
-                        case FDG_OP_POW: A = vpow(A, pk.y); break;
-                        case FDG_OP_SPILL: {
-                            V *g = static_cast<V *>(a.scratch) + ((size_t)pk.z * gstride + gthread);
-                            *reinterpret_cast<Packed<V> *>(g) = *slot_ptr(pk.y);
-                        } break;
-                        case FDG_OP_FILL: {
-                            const V *g = static_cast<const V *>(a.scratch) + ((size_t)pk.z * gstride + gthread);
-                            *slot_ptr(pk.y) = *reinterpret_cast<const Packed<V> *>(g);
-                        } break;
-                        case FDG_OP_ROOT: {
-                            const uint32_t r = pk.y;
-                            if constexpr (!ACC) {
-                                if (active) {
-                                    double *o = static_cast<double *>(a.root) + ((size_t)r * a.ld_root + b0) * W;
-                                    if constexpr (S == 2) {
-                                        if (b0 + 1 < a.batch)
-                                            *reinterpret_cast<double2 *>(o) = make_double2(A.x[0], A.x[1]);
-                                        else
-                                            o[0] = A.x[0];
-                                    } else if constexpr (W == 2) {
-                                        *reinterpret_cast<double2 *>(o) = make_double2(A.x[0], A.x[1]);
-                                    } else {
-                                        o[0] = A.x[0];
-                                    }
-                                }
-                            } else {
-                                // fixed-shape reduction: samples of the thread, then the xor tree over lanes
-                                double s0 = active ? A.x[0] : 0.0, s1 = 0.0;
-                                if constexpr (W == 2) s1 = active ? A.x[1] : 0.0;
-                                if constexpr (S == 2) s0 = __dadd_rn(s0, (b0 + 1 < a.batch) ? A.x[1] : 0.0);
+                    break;
+                case FDG_OP_ST: sts_val<V>(my_s + pk.y * stride, A); break;
+                case FDG_OP_MULF: A = vscale(vmul(A, lds_val<V>(my_s + pk.y * stride)), f); break;
+                case FDG_OP_SCALE: A = vscale(A, f); break;
+                case FDG_OP_XADDF: A = vadd(lds_val<V>(my_s + pk.y * stride), vscale(A, f)); break;
+                case FDG_OP_XMULF: A = vscale(vmul(lds_val<V>(my_s + pk.y * stride), A), f); break;
+                case FDG_OP_POW: A = vpow(A, pk.y); break;
+                case FDG_OP_SPILL: {
+                    V *g = static_cast<V *>(a.scratch) + ((size_t)pk.z * gstride + gthread);
+                    const V v = lds_val<V>(my_s + pk.y * stride);
 #pragma unroll
-                                for (int m = 16; m >= 1; m >>= 1) {
-                                    s0 = __dadd_rn(s0, __shfl_xor_sync(0xffffffffu, s0, m));
-                                    if constexpr (W == 2) s1 = __dadd_rn(s1, __shfl_xor_sync(0xffffffffu, s1, m));
-                                }
-                                if (lane == 0) {
-                                    racc[r * W] = __dadd_rn(racc[r * W], s0);
-                                    if constexpr (W == 2) racc[r * W + 1] = __dadd_rn(racc[r * W + 1], s1);
-                                }
+                    for (int i = 0; i < S * W; ++i) g->x[i] = v.x[i];
+                } break;
+                case FDG_OP_FILL: {
+                    const V *g = static_cast<const V *>(a.scratch) + ((size_t)pk.z * gstride + gthread);
+                    V v;
+#pragma unroll
+                    for (int i = 0; i < S * W; ++i) v.x[i] = g->x[i];
+                    sts_val<V>(my_s + pk.y * stride, v);
+                } break;
+                case FDG_OP_ROOT: {
+                    const uint32_t r = pk.y;
+                    if constexpr (!ACC) {
+                        if (active) {
+                            double *o = static_cast<double *>(a.root) + ((size_t)r * a.ld_root + b0) * W;
+                            if constexpr (W == 2) {
+                                *reinterpret_cast<double2 *>(o) = make_double2(A.x[0], A.x[1]);
+                            } else if (b0 + S <= a.batch) {
+                                if constexpr (S == 1) o[0] = A.x[0];
+                                if constexpr (S >= 2) *reinterpret_cast<double2 *>(o) = make_double2(A.x[0], A.x[1]);
+                                if constexpr (S == 4) *reinterpret_cast<double2 *>(o + 2) = make_double2(A.x[2], A.x[3]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < S; ++i)
+                                    if (b0 + i < a.batch) o[i] = A.x[i];
                             }
-                        } break;
-                        default: break;  // NOP
+                        }
+                    } else {
+                        // fixed-shape reduction: samples of the thread in order, then the xor tree over lanes
+                        double s0 = 0.0, s1 = 0.0;
+                        if constexpr (W == 2) {
+                            s0 = active ? A.x[0] : 0.0;
+                            s1 = active ? A.x[1] : 0.0;
+                        } else {
+                            s0 = active ? A.x[0] : 0.0;
+#pragma unroll
+                            for (int i = 1; i < S; ++i) s0 = __dadd_rn(s0, (b0 + i < a.batch) ? A.x[i] : 0.0);
+                        }
+#pragma unroll
+                        for (int m = 16; m >= 1; m >>= 1) {
+                            s0 = __dadd_rn(s0, __shfl_xor_sync(0xffffffffu, s0, m));
+                            if constexpr (W == 2) s1 = __dadd_rn(s1, __shfl_xor_sync(0xffffffffu, s1, m));
+                        }
+                        if (lane == 0) {
+                            racc[r * W] = __dadd_rn(racc[r * W], s0);
+                            if constexpr (W == 2) racc[r * W + 1] = __dadd_rn(racc[r * W + 1], s1);
+                        }
                     }
-                    if (done) break;
-                }
-                pk = pn;
+                } break;
+                default: break;  // NOP
             }
-            if (done) break;
-            // hand over to the prefetched chunk and start fetching the one after it
-            cur ^= 1;
-            wbuf[cur * FDG_CHUNK + lane] = nxt;
-            gp += FDG_CHUNK;
-            nxt = __ldg(gp + FDG_CHUNK + lane);
-            __syncwarp();
         }
+    program_done:
         cp_async_wait(0);
     }
     if constexpr (ACC) {

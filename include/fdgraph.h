@@ -136,7 +136,7 @@ int fdg_eval_accumulate(fdg_handle h, const void *leaf, int64_t ld_leaf, int64_t
  * chunked H2D -> fdg_eval -> D2H through pinned staging on two streams; synchronous. */
 int fdg_eval_host(fdg_handle h, const void *leaf_host, int64_t ld_leaf, void *root_host, int64_t ld_root,
                   int64_t batch);
-/* choose launch shape: threads per block, samples per thread (1 or 2), blocks per SM (0 = auto). */
+/* choose launch shape: threads per block, samples per thread (1, 2 or 4), blocks per SM (0 = auto). */
 int fdg_set_launch(fdg_handle h, int32_t threads, int32_t samples_per_thread, int32_t blocks_per_sm);
 /* number of kernel launches issued by this handle so far (bench's gpu_launches) */
 int fdg_launch_count(fdg_handle h, int64_t *out);

@@ -56,9 +56,9 @@ def test_known_answers_through_the_public_call():
 
 
 @pytest.mark.parametrize("seed", range(8))
-@pytest.mark.parametrize("spt", [1, 2])
+@pytest.mark.parametrize("spt", [1, 2, 4])
 def test_random_dag_f64(seed, spt):
-    _parity(graphgen.random_dag(seed, n_leaves=6 + seed, n_inner=40 + 10 * seed, n_roots=3), spt=spt, batch=1536 + 2 * seed)
+    _parity(graphgen.random_dag(seed, n_leaves=6 + seed, n_inner=40 + 10 * seed, n_roots=3), spt=spt, batch=1536 + 4 * seed)
 
 
 @pytest.mark.parametrize("seed", range(4))
@@ -90,9 +90,29 @@ def test_ragged_batches(batch, ld):
 
 
 @pytest.mark.parametrize("threads", [32, 64, 128, 256])
-def test_block_shapes(threads):
-    _parity(graphgen.sum_of_products(5, n_leaves=40, n_terms=300, term_len=6, n_roots=2), threads=threads, batch=5000,
-            max_slots=24, prefetch=16)
+@pytest.mark.parametrize("spt", [1, 2, 4])
+def test_block_shapes(threads, spt):
+    _parity(graphgen.sum_of_products(5, n_leaves=40, n_terms=300, term_len=6, n_roots=2), threads=threads, spt=spt,
+            batch=5000, max_slots=24, prefetch=16)
+
+
+@pytest.mark.parametrize("term_len", [1, 2, 3, 4, 5, 7, 8, 11, 13])
+def test_term_blocks_every_operand_count(term_len):
+    _parity(graphgen.sum_of_products(6, n_leaves=30, n_terms=70, term_len=term_len, n_roots=2), batch=2050, ld=2052)
+
+
+@pytest.mark.parametrize("name", ["gv_sigma_o3", "gv_ver4_o2", "gv_ver4_o3", "gv_sigma_o5"])
+@pytest.mark.parametrize("spt", [2, 4])
+def test_real_workload_graphs(name, spt):
+    import os
+
+    raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", name + ".npz"))
+    ev = fd.compile_raw(raw)
+    orc = O.Oracle(raw)
+    batch = 4096
+    leaf = graphgen.leaf_values(5, ev.n_leaves, batch, signed=True)
+    got = _dev_eval(ev, leaf, batch, spt)
+    assert got.tobytes() == orc.eval(leaf).tobytes()
 
 
 def test_roots_unset_columns_are_left_untouched():

@@ -74,6 +74,31 @@ def test_sum_of_products_shape():
     assert st["flops_mul"] >= 300 * 5 and st["flops_add"] == 2 * 299
 
 
+@pytest.mark.parametrize("term_len", [1, 2, 3, 4, 5, 7, 8, 11, 13])
+def test_term_blocks_every_operand_count(term_len):
+    ev, cnt = _check(graphgen.sum_of_products(6, n_leaves=30, n_terms=70, term_len=term_len, n_roots=2), max_slots=20)
+    if term_len <= 11:
+        assert cnt["terms"] == 2 * 70
+
+
+@pytest.mark.parametrize("name", ["gv_sigma_o2", "gv_sigma_o3", "gv_sigma_o4", "gv_ver4_o1", "gv_ver4_o2", "gv_ver4_o3", "gv_ver4I_o3"])
+def test_real_workload_graphs(name):
+    import json
+    import os
+
+    wl = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads")
+    raw = fd.RawGraph.load(os.path.join(wl, name + ".npz"))
+    ev = fd.compile_raw(raw)
+    orc = O.Oracle(raw)
+    leaf = graphgen.leaf_values(5, ev.n_leaves, 3, signed=True)
+    got, _, _ = E.run(ev.program_words(), leaf, ev.n_roots)
+    assert got.tobytes() == orc.eval(leaf).tobytes()
+    # all-leaves-one checksum recorded when the workload was generated from the reference's .diag files
+    man = json.load(open(os.path.join(wl, "MANIFEST.json")))[name]
+    ones, _, _ = E.run(ev.program_words(), np.ones((ev.n_leaves, 1)), ev.n_roots)
+    assert list(ones[:, 0]) == man["all_leaves_one"] and ev.n_leaves == man["n_leaves"]
+
+
 def test_stats_counts_match_reference_operation_count():
     # count_operation (tree_properties.jl:165-185): sum (fan_in - 1) adds, prod (fan_in - 1) muls; + 1 mul per factor != 1
     a, b, c = fd.Graph([]), fd.Graph([]), fd.Graph([])

@@ -26,13 +26,25 @@ def _hdr(w0):
     return dict(op=w0 & 63, k=(w0 >> 6) & 15, wait=(w0 >> 10) & 7, push=(w0 >> 13) & 1, first=(w0 >> 14) & 1, slot0=w0 >> 20)
 
 
-def _term_slots(w, pc, k, slot0):
-    slots = [slot0, w[pc][1] & 0xFFFF, w[pc][1] >> 16][:k]
+def _term_records(w, pc, k, n):
+    """records of a TERM block whose header is packet pc -> ([(slots, f)], packets consumed after the header)"""
+    rec = 2 if k > 4 else 1
+    out = []
+    for t in range(n):
+        r = w[pc + 1 + t * rec]
+        e = w[pc + 2 + t * rec] if rec == 2 else [0, 0, 0, 0]
+        words = [r[0], r[1], e[0], e[1], e[2], e[3]]
+        slots = [(int(words[q >> 1]) >> (16 * (q & 1))) & 0xFFFF for q in range(k)]
+        f = float(np.array([r[2], r[3]], np.uint32).view(np.float64)[0])
+        out.append((slots, f))
+    return out, n * rec
+
+
+def _ldl_words(w, pc, k):
+    ws = list(w[pc][1:4])
     if k > 3:
-        e = w[pc + 1]
-        for q in range(3, k):
-            slots.append((int(e[(q - 3) >> 1]) >> (16 * ((q - 3) & 1))) & 0xFFFF)
-    return [int(x) for x in slots]
+        ws += list(w[pc + 1])
+    return [int(x) for x in ws[:k]], (1 if k > 3 else 0)
 
 
 def _fma(x, y, z):
@@ -112,14 +124,17 @@ def disassemble(words: np.ndarray):
         pre = f"{pc:5d} " + (f"[wait {h['wait'] - 1}] " if h["wait"] else "") + ("[push] " if h["push"] else "")
         name = NAMES[op] if op < len(NAMES) else f"?{op}"
         if op == OP_LDL:
-            out.append(pre + "LDL " + ", ".join(f"v[{x & 0xFFF}]<-leaf{x >> SLOT_BITS}" for x in (w1, w2, w3)[:k]))
+            ws, extra = _ldl_words(w, pc, k)
+            out.append(pre + "LDL " + ", ".join(f"v[{x & 0xFFF}]<-leaf{x >> SLOT_BITS}" for x in ws))
+            pc += extra
         elif op in (OP_SPILL, OP_FILL):
             out.append(pre + f"{name} v[{w1}] scratch[{w2}]")
         elif op == OP_TERM:
-            sl = _term_slots(w, pc, k, h["slot0"])
-            out.append(pre + ("A = " if h["first"] else "A += ") + " * ".join(f"v[{x}]" for x in sl) + f" * {float(f)!r}")
-            if k > 3:
-                pc += 1
+            recs, extra = _term_records(w, pc, k, w1)
+            for t, (sl, ff) in enumerate(recs):
+                lead = pre if t == 0 else " " * len(pre)
+                out.append(lead + ("A  = " if h["first"] and t == 0 else "A += ") + " * ".join(f"v[{x}]" for x in sl) + f" * {ff!r}")
+            pc += extra
         elif op in (OP_MOV, OP_MUL, OP_ADD):
             out.append(pre + f"{name}{k} " + " ".join(f"v[{x}]" for x in (w1, w2, w3)[:k]))
         elif op in (OP_MULF, OP_XADDF, OP_XMULF):
@@ -189,8 +204,12 @@ def run(words: np.ndarray, leaf: np.ndarray, n_roots: int, strict: bool = True):
         elif op == OP_NOP:
             pass
         elif op == OP_LDL:
-            assert 1 <= k <= 3
-            for ww in (w1, w2, w3)[:k]:
+            assert 1 <= k <= 7
+            ws, extra = _ldl_words(w, pc, k)
+            assert pc // CHUNK == (pc + extra) // CHUNK, "LDL extension packet crosses a chunk boundary"
+            pc += extra
+            cnt["packets"] += extra
+            for ww in ws:
                 s, l = ww & ((1 << SLOT_BITS) - 1), ww >> SLOT_BITS
                 slots[s] = leaf[l].copy()
                 slot_group[s] = committed
@@ -204,17 +223,18 @@ def run(words: np.ndarray, leaf: np.ndarray, n_roots: int, strict: bool = True):
             slot_group[w1] = -1
             cnt["max_slot"] = max(cnt["max_slot"], w1)
         elif op == OP_TERM:
-            assert 1 <= k <= TERM_MAX
-            sl = _term_slots(w, pc, k, h["slot0"])
-            if k > 3:
-                assert pc // CHUNK == (pc + 1) // CHUNK, "TERM extension packet crosses a chunk boundary"
-                pc += 1
-                cnt["packets"] += 1
-            t = rd(sl[0])
-            for x in sl[1:]:
-                t = mul(t, rd(x))
-            t = scale(t, f)
-            A = t.copy() if h["first"] else A + t
+            assert 1 <= k <= TERM_MAX and w1 >= 1
+            recs, extra = _term_records(w, pc, k, w1)
+            assert pc // CHUNK == (pc + extra) // CHUNK, "TERM block crosses a chunk boundary"
+            pc += extra
+            cnt["packets"] += extra
+            cnt["terms"] = cnt.get("terms", 0) + len(recs)
+            for t_i, (sl, ff) in enumerate(recs):
+                t = rd(sl[0])
+                for x in sl[1:]:
+                    t = mul(t, rd(x))
+                t = scale(t, ff)
+                A = t.copy() if (h["first"] and t_i == 0) else A + t
         elif op == OP_MOV:
             v = rd(w1)
             if k >= 2:

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--gb", type=float, default=8.0)
     ap.add_argument("--slots", default="32,48,64,96")
     ap.add_argument("--threads", default="64,128,256")
-    ap.add_argument("--spt", default="1,2")
+    ap.add_argument("--spt", default="2,4")
     ap.add_argument("--prefetch", default="-1,8,24,64")
     ap.add_argument("--mode", default="acc")
     ap.add_argument("--reps", type=int, default=3)
