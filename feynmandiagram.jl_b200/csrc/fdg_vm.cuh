@@ -165,35 +165,43 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
     return r;
 }
+// A value of 4 samples is stored as two 16-byte halves `plane` bytes apart ([slot][half][thread]) so that each
+// LDS.128 / STS.128 of a warp covers 512 contiguous bytes (conflict free); smaller values are contiguous.
 template <class V>
-__device__ __forceinline__ V lds_val(uint32_t addr) {
+__device__ __forceinline__ V lds_val(uint32_t addr, uint32_t plane) {
     V v;
     constexpr int N = sizeof(V) / 8;
     if constexpr (N == 1) {
         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v.x[0]) : "r"(addr));
     } else {
-#pragma unroll
-        for (int i = 0; i < N; i += 2)
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x[i]), "=d"(v.x[i + 1]) : "r"(addr + 8 * i));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x[0]), "=d"(v.x[1]) : "r"(addr));
+        if constexpr (N == 4)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x[2]), "=d"(v.x[3]) : "r"(addr + plane));
     }
     return v;
 }
 template <class V>
-__device__ __forceinline__ void sts_val(uint32_t addr, const V &v) {
+__device__ __forceinline__ void sts_val(uint32_t addr, uint32_t plane, const V &v) {
     constexpr int N = sizeof(V) / 8;
     if constexpr (N == 1) {
         asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v.x[0]) : "memory");
     } else {
-#pragma unroll
-        for (int i = 0; i < N; i += 2)
-            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr + 8 * i), "d"(v.x[i]), "d"(v.x[i + 1]) : "memory");
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x[0]), "d"(v.x[1]) : "memory");
+        if constexpr (N == 4)
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr + plane), "d"(v.x[2]), "d"(v.x[3]) : "memory");
     }
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
 }
 
 // One block of `n` term records with K operands each (FDG_OP_TERM): the dispatch-free inner loop.
 //   A = A + (v[s0] * v[s1] * ... * v[s(K-1)]) * f     for every record, in order.
 template <class V, int K>
-__device__ __forceinline__ void term_block(uint32_t &pp, uint32_t n, bool first, V &A, const uint32_t my_s, const uint32_t stride) {
+__device__ __forceinline__ void term_block(uint32_t &pp, uint32_t n, bool first, V &A, const uint32_t my_s, const uint32_t stride,
+                                           const uint32_t plane) {
     constexpr uint32_t REC = K > 4 ? 32 : 16;
 #pragma unroll 1
     for (uint32_t j = 0; j < n; ++j) {
@@ -205,7 +213,7 @@ __device__ __forceinline__ void term_block(uint32_t &pp, uint32_t n, bool first,
                                 e.y & 0xffffu, e.y >> 16, e.z & 0xffffu, e.z >> 16, e.w & 0xffffu, e.w >> 16};
         V v[K];
 #pragma unroll
-        for (int q = 0; q < K; ++q) v[q] = lds_val<V>(my_s + s[q] * stride);
+        for (int q = 0; q < K; ++q) v[q] = lds_val<V>(my_s + s[q] * stride, plane);
         V t = v[0];
 #pragma unroll
         for (int q = 1; q < K; ++q) t = vmul(t, v[q]);
@@ -228,7 +236,7 @@ __device__ __forceinline__ void term_block(uint32_t &pp, uint32_t n, bool first,
 // each while the current chunk executes out of shared memory (broadcast LDS.128 per packet), so the global
 // latency of the instruction stream is hidden behind a whole chunk of work.
 template <class V, bool ACC>
-__global__ void __launch_bounds__(256) fdg_vm_kernel(const VmArgs a) {
+__global__ void __launch_bounds__(256, 2) fdg_vm_kernel(const VmArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int S = V::kSamples;
     constexpr int W = V::kWidth;
@@ -238,7 +246,9 @@ __global__ void __launch_bounds__(256) fdg_vm_kernel(const VmArgs a) {
     const int warp = tid >> 5;
     const uint32_t stride = (uint32_t)T * (uint32_t)sizeof(V);
     const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t my_s = smem_s + (uint32_t)tid * (uint32_t)sizeof(V);
+    // 4 samples/thread: [slot][half][thread] planes of T * 16 bytes; otherwise [slot][thread]
+    const uint32_t plane = (uint32_t)T * 16u;
+    const uint32_t my_s = smem_s + (uint32_t)tid * (sizeof(V) == 32 ? 16u : (uint32_t)sizeof(V));
     const long long gthread = (long long)blockIdx.x * T + tid;
     const long long gstride = (long long)gridDim.x * T;
     const uint32_t slot_file_bytes = (uint32_t)a.n_slots * stride;
@@ -292,7 +302,8 @@ __global__ void __launch_bounds__(256) fdg_vm_kernel(const VmArgs a) {
             const uint32_t op = FDG_HDR_OP(hdr);
             const uint32_t k = FDG_HDR_K(hdr);
             if (hdr & (7u << 10)) cp_async_wait(FDG_HDR_WAIT(hdr) - 1u);
-            if (hdr & (1u << 13)) {  // push: this packet starts a nested fold
+            if (hdr & (1u << 13)) {  // push: this packet starts a nested fold (rare: keep it a real branch)
+                asm volatile("" ::: "memory");
                 R3 = R2;
                 R2 = R1;
                 R1 = A;
@@ -301,17 +312,17 @@ __global__ void __launch_bounds__(256) fdg_vm_kernel(const VmArgs a) {
                 const bool first = (hdr >> 14) & 1u;
                 const uint32_t n = pk.y;
                 switch (k) {
-                    case 1: term_block<V, 1>(pp, n, first, A, my_s, stride); break;
-                    case 2: term_block<V, 2>(pp, n, first, A, my_s, stride); break;
-                    case 3: term_block<V, 3>(pp, n, first, A, my_s, stride); break;
-                    case 4: term_block<V, 4>(pp, n, first, A, my_s, stride); break;
-                    case 5: term_block<V, 5>(pp, n, first, A, my_s, stride); break;
-                    case 6: term_block<V, 6>(pp, n, first, A, my_s, stride); break;
-                    case 7: term_block<V, 7>(pp, n, first, A, my_s, stride); break;
-                    case 8: term_block<V, 8>(pp, n, first, A, my_s, stride); break;
-                    case 9: term_block<V, 9>(pp, n, first, A, my_s, stride); break;
-                    case 10: term_block<V, 10>(pp, n, first, A, my_s, stride); break;
-                    default: term_block<V, 11>(pp, n, first, A, my_s, stride); break;
+                    case 1: term_block<V, 1>(pp, n, first, A, my_s, stride, plane); break;
+                    case 2: term_block<V, 2>(pp, n, first, A, my_s, stride, plane); break;
+                    case 3: term_block<V, 3>(pp, n, first, A, my_s, stride, plane); break;
+                    case 4: term_block<V, 4>(pp, n, first, A, my_s, stride, plane); break;
+                    case 5: term_block<V, 5>(pp, n, first, A, my_s, stride, plane); break;
+                    case 6: term_block<V, 6>(pp, n, first, A, my_s, stride, plane); break;
+                    case 7: term_block<V, 7>(pp, n, first, A, my_s, stride, plane); break;
+                    case 8: term_block<V, 8>(pp, n, first, A, my_s, stride, plane); break;
+                    case 9: term_block<V, 9>(pp, n, first, A, my_s, stride, plane); break;
+                    case 10: term_block<V, 10>(pp, n, first, A, my_s, stride, plane); break;
+                    default: term_block<V, 11>(pp, n, first, A, my_s, stride, plane); break;
                 }
                 continue;
             }
@@ -319,61 +330,57 @@ __global__ void __launch_bounds__(256) fdg_vm_kernel(const VmArgs a) {
             switch (op) {
                 case FDG_OP_END: goto program_done;
                 case FDG_OP_LDL: {
-                    uint4 e = make_uint4(0, 0, 0, 0);
-                    if (k > 3) {
-                        e = lds_u4(pp);
-                        pp += 16;
-                    }
-                    const uint32_t w[7] = {pk.y, pk.z, pk.w, e.x, e.y, e.z, e.w};
-#pragma unroll
-                    for (int q = 0; q < 7; ++q) {
-                        if (q < (int)k) {
-                            const uint32_t s = w[q] & (FDG_MAX_SLOTS - 1);
-                            const uint32_t l = w[q] >> FDG_LDL_SLOT_BITS;
-                            const unsigned char *src = leaf_b + (size_t)l * leaf_stride;
-                            if constexpr (sizeof(V) == 32) {
-                                cp_async<16>(my_s + s * stride, src);
-                                cp_async<16>(my_s + s * stride + 16, src + 16);
-                            } else {
-                                cp_async<sizeof(V)>(my_s + s * stride, src);
-                            }
+                    // the k load words sit right behind the header word (w1..w3, then the next packet)
+                    uint32_t wp = pp - 12;
+#pragma unroll 1
+                    for (uint32_t q = 0; q < k; ++q, wp += 4) {
+                        const uint32_t w = lds_u32(wp);
+                        const uint32_t s = w & (FDG_MAX_SLOTS - 1);
+                        const uint32_t l = w >> FDG_LDL_SLOT_BITS;
+                        const unsigned char *src = leaf_b + (size_t)l * leaf_stride;
+                        if constexpr (sizeof(V) == 32) {
+                            cp_async<16>(my_s + s * stride, src);
+                            cp_async<16>(my_s + s * stride + plane, src + 16);
+                        } else {
+                            cp_async<sizeof(V)>(my_s + s * stride, src);
                         }
                     }
+                    if (k > 3) pp += 16;
                     cp_async_commit();
                 } break;
                 case FDG_OP_MOV:
                     if (k == 1) {
-                        A = lds_val<V>(my_s + pk.y * stride);
+                        A = lds_val<V>(my_s + pk.y * stride, plane);
                     } else if (k == 2) {
-                        const V v1 = lds_val<V>(my_s + pk.y * stride), v2 = lds_val<V>(my_s + pk.z * stride);
+                        const V v1 = lds_val<V>(my_s + pk.y * stride, plane), v2 = lds_val<V>(my_s + pk.z * stride, plane);
                         A = vmul(v1, v2);
                     } else {
-                        const V v1 = lds_val<V>(my_s + pk.y * stride), v2 = lds_val<V>(my_s + pk.z * stride),
-                                v3 = lds_val<V>(my_s + pk.w * stride);
+                        const V v1 = lds_val<V>(my_s + pk.y * stride, plane), v2 = lds_val<V>(my_s + pk.z * stride, plane),
+                                v3 = lds_val<V>(my_s + pk.w * stride, plane);
                         A = vmul(vmul(v1, v2), v3);
                     }
                     break;
                 case FDG_OP_MUL:
                     if (k == 1) {
-                        A = vmul(A, lds_val<V>(my_s + pk.y * stride));
+                        A = vmul(A, lds_val<V>(my_s + pk.y * stride, plane));
                     } else if (k == 2) {
-                        const V v1 = lds_val<V>(my_s + pk.y * stride), v2 = lds_val<V>(my_s + pk.z * stride);
+                        const V v1 = lds_val<V>(my_s + pk.y * stride, plane), v2 = lds_val<V>(my_s + pk.z * stride, plane);
                         A = vmul(vmul(A, v1), v2);
                     } else {
-                        const V v1 = lds_val<V>(my_s + pk.y * stride), v2 = lds_val<V>(my_s + pk.z * stride),
-                                v3 = lds_val<V>(my_s + pk.w * stride);
+                        const V v1 = lds_val<V>(my_s + pk.y * stride, plane), v2 = lds_val<V>(my_s + pk.z * stride, plane),
+                                v3 = lds_val<V>(my_s + pk.w * stride, plane);
                         A = vmul(vmul(vmul(A, v1), v2), v3);
                     }
                     break;
                 case FDG_OP_ADD:
                     if (k == 1) {
-                        A = vadd(A, lds_val<V>(my_s + pk.y * stride));
+                        A = vadd(A, lds_val<V>(my_s + pk.y * stride, plane));
                     } else if (k == 2) {
-                        const V v1 = lds_val<V>(my_s + pk.y * stride), v2 = lds_val<V>(my_s + pk.z * stride);
+                        const V v1 = lds_val<V>(my_s + pk.y * stride, plane), v2 = lds_val<V>(my_s + pk.z * stride, plane);
                         A = vadd(vadd(A, v1), v2);
                     } else {
-                        const V v1 = lds_val<V>(my_s + pk.y * stride), v2 = lds_val<V>(my_s + pk.z * stride),
-                                v3 = lds_val<V>(my_s + pk.w * stride);
+                        const V v1 = lds_val<V>(my_s + pk.y * stride, plane), v2 = lds_val<V>(my_s + pk.z * stride, plane),
+                                v3 = lds_val<V>(my_s + pk.w * stride, plane);
                         A = vadd(vadd(vadd(A, v1), v2), v3);
                     }
                     break;
@@ -387,15 +394,15 @@ __global__ void __launch_bounds__(256) fdg_vm_kernel(const VmArgs a) {
                     R1 = R2;
                     R2 = R3;
                     break;
-                case FDG_OP_ST: sts_val<V>(my_s + pk.y * stride, A); break;
-                case FDG_OP_MULF: A = vscale(vmul(A, lds_val<V>(my_s + pk.y * stride)), f); break;
+                case FDG_OP_ST: sts_val<V>(my_s + pk.y * stride, plane, A); break;
+                case FDG_OP_MULF: A = vscale(vmul(A, lds_val<V>(my_s + pk.y * stride, plane)), f); break;
                 case FDG_OP_SCALE: A = vscale(A, f); break;
-                case FDG_OP_XADDF: A = vadd(lds_val<V>(my_s + pk.y * stride), vscale(A, f)); break;
-                case FDG_OP_XMULF: A = vscale(vmul(lds_val<V>(my_s + pk.y * stride), A), f); break;
+                case FDG_OP_XADDF: A = vadd(lds_val<V>(my_s + pk.y * stride, plane), vscale(A, f)); break;
+                case FDG_OP_XMULF: A = vscale(vmul(lds_val<V>(my_s + pk.y * stride, plane), A), f); break;
                 case FDG_OP_POW: A = vpow(A, pk.y); break;
                 case FDG_OP_SPILL: {
                     V *g = static_cast<V *>(a.scratch) + ((size_t)pk.z * gstride + gthread);
-                    const V v = lds_val<V>(my_s + pk.y * stride);
+                    const V v = lds_val<V>(my_s + pk.y * stride, plane);
 #pragma unroll
                     for (int i = 0; i < S * W; ++i) g->x[i] = v.x[i];
                 } break;
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__(256) fdg_vm_kernel(const VmArgs a) {
                     V v;
 #pragma unroll
                     for (int i = 0; i < S * W; ++i) v.x[i] = g->x[i];
-                    sts_val<V>(my_s + pk.y * stride, v);
+                    sts_val<V>(my_s + pk.y * stride, plane, v);
                 } break;
                 case FDG_OP_ROOT: {
                     const uint32_t r = pk.y;
