@@ -8,8 +8,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfdgraph.so")
-SOURCES = ["fdg_capi.cu", "fdg_lower.cpp"]
-HEADERS = ["fdg_vm.cuh", "fdg_isa.h", "fdg_lower.h", os.path.join("..", "..", "include", "fdgraph.h")]
+SOURCES = ["fdg_capi.cu", "fdg_lower.cpp", "fdg_jit.cpp"]
+HEADERS = ["fdg_vm.cuh", "fdg_isa.h", "fdg_lower.h", "fdg_jit.h", os.path.join("..", "..", "include", "fdgraph.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -40,7 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into feynmandiagram.jl_b200/libfdgraph.so; returns the path."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-ldl"]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-lnvptxcompiler_static", "-ldl", "-lpthread"]
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)

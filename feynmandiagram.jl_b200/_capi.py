@@ -32,7 +32,8 @@ class GraphDesc(C.Structure):
 
 
 class Options(C.Structure):
-    _fields_ = [("dtype", C.c_int32), ("max_slots", C.c_int32), ("prefetch", C.c_int32), ("reserved", C.c_int32 * 5)]
+    _fields_ = [("dtype", C.c_int32), ("max_slots", C.c_int32), ("prefetch", C.c_int32), ("schedule", C.c_int32),
+                ("backend", C.c_int32), ("jit_segment", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class Stats(C.Structure):
@@ -48,8 +49,9 @@ class Stats(C.Structure):
 EXPORTS = [
     "fdg_abi_version", "fdg_last_error", "fdg_compile", "fdg_destroy", "fdg_stats", "fdg_leafmap", "fdg_last_root",
     "fdg_program_words", "fdg_eval", "fdg_eval_accumulate", "fdg_eval_host", "fdg_set_launch", "fdg_launch_count",
-    "fdg_comm_unique_id", "fdg_comm_init", "fdg_comm_destroy", "fdg_allreduce",
+    "fdg_comm_unique_id", "fdg_comm_init", "fdg_comm_destroy", "fdg_allreduce", "fdg_jit_prepare", "fdg_jit_ptx",
 ]
+BACKEND_AUTO, BACKEND_VM, BACKEND_JIT = 0, 1, 2
 
 _lib: Optional[C.CDLL] = None
 
@@ -81,6 +83,8 @@ def lib() -> C.CDLL:
     L.fdg_comm_init.argtypes = [C.POINTER(vp), i32, i32, vp]
     L.fdg_comm_destroy.argtypes = [vp]
     L.fdg_allreduce.argtypes = [vp, vp, i64, vp]
+    L.fdg_jit_prepare.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
+    L.fdg_jit_ptx.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
     for name in EXPORTS:
         if name not in ("fdg_abi_version", "fdg_last_error"):
             getattr(L, name).restype = C.c_int
@@ -97,7 +101,8 @@ def _ptr(a: np.ndarray, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))
 
 
-def compile_raw(raw, dtype: int = FDG_F64, max_slots: int = 0, prefetch: int = 0) -> C.c_void_p:
+def compile_raw(raw, dtype: int = FDG_F64, max_slots: int = 0, prefetch: int = 0, schedule: int = 0, backend: int = 0,
+                jit_segment: int = 0) -> C.c_void_p:
     """fdg_compile on a RawGraph; returns the opaque handle."""
     L = lib()
     raw.validate_dtypes()
@@ -112,7 +117,8 @@ def compile_raw(raw, dtype: int = FDG_F64, max_slots: int = 0, prefetch: int = 0
     d.n_graphs, d.graphs = int(raw.graphs.shape[0]), _ptr(raw.graphs, C.c_int32)
     d.n_roots, d.root_id = int(raw.root_id.shape[0]), _ptr(raw.root_id, C.c_int64)
     o = Options()
-    o.dtype, o.max_slots, o.prefetch = int(dtype), int(max_slots), int(prefetch)
+    o.dtype, o.max_slots, o.prefetch, o.schedule = int(dtype), int(max_slots), int(prefetch), int(schedule)
+    o.backend, o.jit_segment = int(backend), int(jit_segment)
     h = C.c_void_p()
     check(L.fdg_compile(C.byref(d), C.byref(o), C.byref(h)))
     return h
@@ -147,3 +153,15 @@ def launch_count(h) -> int:
     v = C.c_int64()
     check(lib().fdg_launch_count(h, C.byref(v)))
     return int(v.value)
+
+
+def jit_prepare(h, samples_per_thread: int = 2, accumulate: bool = False) -> dict:
+    nk, nc, nb = C.c_int32(), C.c_int32(), C.c_int64()
+    check(lib().fdg_jit_prepare(h, samples_per_thread, int(accumulate), C.byref(nk), C.byref(nc), C.byref(nb)))
+    return {"kernels": int(nk.value), "cross_values": int(nc.value), "cubin_bytes": int(nb.value)}
+
+
+def jit_ptx(h, samples_per_thread: int, accumulate: bool, index: int):
+    p, log = C.c_char_p(), C.c_char_p()
+    check(lib().fdg_jit_ptx(h, samples_per_thread, int(accumulate), index, C.byref(p), C.byref(log)))
+    return p.value.decode(), (log.value or b"").decode()

@@ -50,13 +50,14 @@ def _batch_major(a2: np.ndarray):
 class Evaluator:
     """The callable returned by :func:`compile` -- stands in for the generated ``eval_graph!``."""
 
-    def __init__(self, raw: RawGraph, dtype=np.float64, max_slots: int = 0, prefetch: int = 0):
+    def __init__(self, raw: RawGraph, dtype=np.float64, max_slots: int = 0, prefetch: int = 0, schedule: int = 0,
+                 backend: int = 0, jit_segment: int = 0):
         self.dtype = np.dtype(dtype)
         if self.dtype not in _DTYPES:
             # static.jl:151  error("Unsupported type")
             raise TypeError(f"Unsupported type {self.dtype}: libfdgraph evaluates float64 or complex128 weights")
         self.raw = raw
-        self._h = _capi.compile_raw(raw, _DTYPES[self.dtype], max_slots, prefetch)
+        self._h = _capi.compile_raw(raw, _DTYPES[self.dtype], max_slots, prefetch, schedule, backend, jit_segment)
         self.stats = _capi.stats(self._h)
         self.n_leaves = self.stats["n_leaves"]
         self.n_roots = self.stats["n_roots"]
@@ -81,6 +82,13 @@ class Evaluator:
 
     def program_words(self) -> np.ndarray:
         return _capi.program_words(self._h)
+
+    def jit_prepare(self, samples_per_thread: int = 2, accumulate: bool = False) -> dict:
+        """Generate + assemble the specialised kernels now (host only)."""
+        return _capi.jit_prepare(self._h, samples_per_thread, accumulate)
+
+    def jit_ptx(self, samples_per_thread: int = 2, accumulate: bool = False, index: int = 0):
+        return _capi.jit_ptx(self._h, samples_per_thread, accumulate, index)
 
     def set_launch(self, threads: int = 0, samples_per_thread: int = 0, blocks_per_sm: int = 0) -> None:
         _capi.check(_capi.lib().fdg_set_launch(self._h, threads, samples_per_thread, blocks_per_sm))
@@ -173,18 +181,22 @@ class Evaluator:
 
 
 def compile(graphs: Sequence[Graph], root: Optional[Sequence[int]] = None, *, dtype=np.float64,
-            max_slots: int = 0, prefetch: int = 0) -> Tuple[Evaluator, Dict[int, Graph]]:
+            max_slots: int = 0, prefetch: int = 0, schedule: int = 0, backend: int = 0,
+            jit_segment: int = 0) -> Tuple[Evaluator, Dict[int, Graph]]:
     """``Compilers.compile(graphs; root)`` (static.jl:221-227) -> ``(eval_graph, leafmap)``.
 
     ``leafmap[k]`` is the leaf Graph whose value is read from column ``k`` of ``leafVal`` (0-based
     here; the reference's Dict is 1-based, static.jl:117-119).
     """
     raw, nodes = flatten(graphs, root)
-    ev = Evaluator(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch)
+    ev = Evaluator(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch, schedule=schedule, backend=backend,
+                   jit_segment=jit_segment)
     leafmap = {k: nodes[int(i)] for k, i in enumerate(ev.leaf_nodes)}
     return ev, leafmap
 
 
-def compile_raw(raw: RawGraph, *, dtype=np.float64, max_slots: int = 0, prefetch: int = 0) -> Evaluator:
+def compile_raw(raw: RawGraph, *, dtype=np.float64, max_slots: int = 0, prefetch: int = 0, schedule: int = 0,
+                backend: int = 0, jit_segment: int = 0) -> Evaluator:
     """Compile an already flattened graph (e.g. a workload file written by another host)."""
-    return Evaluator(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch)
+    return Evaluator(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch, schedule=schedule, backend=backend,
+                     jit_segment=jit_segment)

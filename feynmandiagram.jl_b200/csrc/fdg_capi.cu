@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/fdgraph.h"
+#include "fdg_jit.h"
 #include "fdg_lower.h"
 #include "fdg_vm.cuh"
 
@@ -49,12 +50,25 @@ struct DeviceState {
     void *d_leaf[2] = {nullptr, nullptr};
     void *d_root[2] = {nullptr, nullptr};
     size_t d_leaf_bytes = 0, d_root_bytes = 0;
+    void *cross = nullptr;  // specialised back end: values crossing kernel boundaries, [n_cross][threads * spt]
+    size_t cross_bytes = 0;
 };
 
 }  // namespace
 
+struct JitVariant {
+    fdg::JitPlan plan;
+    bool compiled = false;
+    std::map<int, std::vector<cudaKernel_t>> kernels;  // per device
+    std::map<int, cudaLibrary_t> libs_first;           // (libraries are kept alive with the handle)
+    std::map<int, std::vector<cudaLibrary_t>> libs;
+};
+
 struct fdg_program {
     fdg::Lowered low;
+    int backend = FDG_BACKEND_AUTO;
+    int jit_segment = 0;
+    std::map<int, JitVariant> jit;  // key = spt * 2 + accumulate
     int threads = 128;
     int spt = 0;  // samples per thread: 0 auto
     int blocks_per_sm = 0;
@@ -157,6 +171,97 @@ int get_device_state(fdg_program *h, DeviceState **out) {
     return FDG_OK;
 }
 
+// ---- specialised back end ----------------------------------------------------------------------------------------
+int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out) {
+    JitVariant &v = h->jit[spt * 2 + (acc ? 1 : 0)];
+    if (!v.compiled) {
+        std::string err;
+        int rc = fdg::jit_plan(h->low, spt, acc, h->jit_segment, v.plan, err);
+        if (rc == FDG_OK) rc = fdg::jit_compile(v.plan, err);
+        if (rc != FDG_OK) {
+            h->jit.erase(spt * 2 + (acc ? 1 : 0));
+            return fail(rc, err);
+        }
+        v.compiled = true;
+    }
+    *out = &v;
+    return FDG_OK;
+}
+
+int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, const void *leaf, int64_t ld_leaf, void *root,
+               int64_t ld_root, int64_t batch, cudaStream_t stream) {
+    JitVariant *v = nullptr;
+    int rc = jit_get(h, spt, acc, &v);
+    if (rc != FDG_OK) return rc;
+    auto &kern = v->kernels[dev];
+    if (kern.empty()) {
+        for (auto &sg : v->plan.seg) {
+            cudaLibrary_t lib;
+            CUDA_TRY(cudaLibraryLoadData(&lib, sg.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+            v->libs[dev].push_back(lib);
+            cudaKernel_t k;
+            CUDA_TRY(cudaLibraryGetKernel(&k, lib, sg.name.c_str()));
+            kern.push_back(k);
+        }
+    }
+    const fdg::Lowered &low = h->low;
+    const int T = 128;
+    const int64_t per_block = (int64_t)T * spt;
+    // sub-batches keep the cross buffer bounded (about 1 GiB)
+    int64_t sub = batch;
+    if (v->plan.n_cross > 0) {
+        const int64_t cap = std::max<int64_t>(per_block * ds.sm_count * 4, ((int64_t)1 << 30) / (8 * (int64_t)v->plan.n_cross));
+        sub = std::min<int64_t>(batch, cap / per_block * per_block);
+    }
+    const int64_t max_grid = (sub + per_block - 1) / per_block;
+    const int64_t ld_cross = max_grid * per_block;
+    if (v->plan.n_cross > 0) {
+        const size_t need = (size_t)v->plan.n_cross * ld_cross * sizeof(double);
+        if (need > ds.cross_bytes) {
+            if (ds.cross) CUDA_TRY(cudaFree(ds.cross));
+            ds.cross = nullptr;
+            ds.cross_bytes = 0;
+            CUDA_TRY(cudaMalloc(&ds.cross, need));
+            ds.cross_bytes = need;
+        }
+    }
+    long long rows = 0;
+    void *out = root;
+    if (acc) {
+        rows = max_grid * (T / 32);
+        const size_t need = std::max<size_t>((size_t)rows * low.R * sizeof(double), 256);
+        if (need > ds.partial_bytes) {
+            if (ds.partial) CUDA_TRY(cudaFree(ds.partial));
+            ds.partial = nullptr;
+            ds.partial_bytes = 0;
+            CUDA_TRY(cudaMalloc((void **)&ds.partial, need));
+            ds.partial_bytes = need;
+        }
+        CUDA_TRY(cudaMemsetAsync(ds.partial, 0, (size_t)rows * low.R * sizeof(double), stream));
+        out = ds.partial;
+    }
+    for (int64_t b0 = 0; b0 < batch; b0 += sub) {
+        const int64_t nb = std::min<int64_t>(sub, batch - b0);
+        const unsigned grid = (unsigned)((nb + per_block - 1) / per_block);
+        const void *p_leaf = static_cast<const char *>(leaf) + (size_t)b0 * 8;
+        void *p_out = acc ? out : static_cast<void *>(static_cast<char *>(root) + (size_t)b0 * 8);
+        void *p_cross = ds.cross;
+        long long a_ld_leaf = ld_leaf, a_ld_cross = ld_cross, a_ld_root = ld_root, a_batch = nb, a_nroots = low.R;
+        void *args[] = {(void *)&p_leaf, &a_ld_leaf, &p_cross, &a_ld_cross, &p_out, &a_ld_root, &a_batch, &a_nroots};
+        for (size_t sg = 0; sg < kern.size(); ++sg) {
+            CUDA_TRY(cudaLaunchKernel((const void *)kern[sg], dim3(grid), dim3(T), args, 0, stream));
+            h->launches++;
+        }
+    }
+    if (acc && low.R > 0) {
+        fdg::fdg_reduce_partials<<<((int)low.R + 127) / 128, 128, 0, stream>>>(ds.partial, rows, (int)low.R,
+                                                                              static_cast<double *>(root));
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+    }
+    return FDG_OK;
+}
+
 int do_eval(fdg_program *h, const void *leaf, int64_t ld_leaf, void *root, int64_t ld_root, int64_t batch,
             void *stream, bool accumulate) {
     if (!h) return fail(FDG_ERR_BAD_ARG, "null handle");
@@ -184,6 +289,7 @@ int do_eval(fdg_program *h, const void *leaf, int64_t ld_leaf, void *root, int64
     args.batch = batch;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (cplx) {
+        if (h->backend == FDG_BACKEND_JIT) return fail(FDG_ERR_UNSUPPORTED, "the specialised back end is Float64 only");
         return accumulate ? launch_variant<fdg::VCplx, true>(h, *ds, args, batch, st)
                           : launch_variant<fdg::VCplx, false>(h, *ds, args, batch, st);
     }
@@ -195,6 +301,16 @@ int do_eval(fdg_program *h, const void *leaf, int64_t ld_leaf, void *root, int64
         const bool root_ok = accumulate || low.R == 0 || (((uintptr_t)root % 16 == 0) && (ld_root % 2 == 0));
         return leaf_ok && root_ok;
     };
+    int backend = h->backend;
+    if (const char *e = getenv("FDG_BACKEND")) backend = atoi(e);
+    if (backend != FDG_BACKEND_VM && low.N + low.R > 0) {
+        const int jspt = (h->spt == 1 || !fits(2)) ? 1 : 2;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        rc = jit_launch(h, *ds, dev, jspt, accumulate, leaf, ld_leaf, root, ld_root, batch, st);
+        if (rc == FDG_OK || backend == FDG_BACKEND_JIT) return rc;
+        // AUTO: the specialised path did not build (e.g. PTX compiler unavailable) -> the VM runs the program
+    }
     int spt = h->spt;
     if (spt == 0) spt = (batch >= (1 << 16) && fits(4)) ? 4 : (fits(2) ? 2 : 1);  // auto: widest that fits
     if (spt > 1 && !fits(spt))
@@ -223,8 +339,9 @@ int fdg_compile(const fdg_graph_desc *graph, const fdg_options *opts, fdg_handle
     fdg_options o;
     std::memset(&o, 0, sizeof(o));
     if (opts) o = *opts;
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 2; ++i)
         if (o.reserved[i] != 0) return fail(FDG_ERR_BAD_ARG, "fdg_options.reserved must be zero");
+    if (o.backend < FDG_BACKEND_AUTO || o.backend > FDG_BACKEND_JIT) return fail(FDG_ERR_BAD_ARG, "unknown backend");
     fdg_program *p = new (std::nothrow) fdg_program();
     if (!p) return fail(FDG_ERR_BAD_ARG, "out of memory");
     std::string err;
@@ -239,7 +356,38 @@ int fdg_compile(const fdg_graph_desc *graph, const fdg_options *opts, fdg_handle
         delete p;
         return fail(rc, err);
     }
+    p->backend = o.backend;
+    p->jit_segment = o.jit_segment;
     *out = p;
+    return FDG_OK;
+}
+
+int fdg_jit_prepare(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t *n_kernels, int32_t *n_cross,
+                    int64_t *cubin_bytes) {
+    if (!h) return fail(FDG_ERR_BAD_ARG, "null handle");
+    if (samples_per_thread != 1 && samples_per_thread != 2) return fail(FDG_ERR_BAD_ARG, "samples_per_thread must be 1 or 2");
+    std::lock_guard<std::mutex> lock(h->mu);
+    JitVariant *v = nullptr;
+    int rc = jit_get(h, samples_per_thread, accumulate != 0, &v);
+    if (rc != FDG_OK) return rc;
+    if (n_kernels) *n_kernels = (int32_t)v->plan.seg.size();
+    if (n_cross) *n_cross = v->plan.n_cross;
+    if (cubin_bytes) {
+        *cubin_bytes = 0;
+        for (auto &s : v->plan.seg) *cubin_bytes += (int64_t)s.cubin.size();
+    }
+    return FDG_OK;
+}
+
+int fdg_jit_ptx(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t index, const char **ptx,
+                const char **ptxas_log) {
+    if (!h || !ptx) return fail(FDG_ERR_BAD_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto it = h->jit.find(samples_per_thread * 2 + (accumulate ? 1 : 0));
+    if (it == h->jit.end() || !it->second.compiled) return fail(FDG_ERR_BAD_ARG, "variant not prepared");
+    if (index < 0 || index >= (int32_t)it->second.plan.seg.size()) return fail(FDG_ERR_BAD_ARG, "kernel index out of range");
+    *ptx = it->second.plan.seg[(size_t)index].ptx.c_str();
+    if (ptxas_log) *ptxas_log = it->second.plan.seg[(size_t)index].info.c_str();
     return FDG_OK;
 }
 
@@ -253,6 +401,12 @@ int fdg_destroy(fdg_handle h) {
         cudaFree(ds.d_prog);
         cudaFree(ds.scratch);
         cudaFree(ds.partial);
+        cudaFree(ds.cross);
+        for (auto &kv2 : h->jit) {
+            auto it = kv2.second.libs.find(kv.first);
+            if (it != kv2.second.libs.end())
+                for (auto lib : it->second) cudaLibraryUnload(lib);
+        }
         for (int i = 0; i < 2; ++i) {
             if (ds.streams[i]) cudaStreamDestroy(ds.streams[i]);
             cudaFree(ds.d_leaf[i]);

@@ -1,0 +1,442 @@
+// fdg_jit.cpp -- the specialised back end: the emitted function as hand-scheduled-by-ptxas straight-line sm_100a code.
+//
+// Where the VM (fdg_vm.cuh) interprets packets, this back end writes the statements of the reference's emitted
+// function (src/backend/static.jl:98-133, one `g<ID> = ...` per node) directly as PTX -- `mul.rn.f64` / `add.rn.f64`
+// only, in the emitter's left-fold order, never fused -- and assembles it for sm_100a with the PTX compiler
+// library shipped in the CUDA toolkit (libnvptxcompiler_static).  It is the direct analogue of the reference's
+// emit-source design (to_julia_str -> RuntimeGeneratedFunction), with the sample index as the thread index:
+//   * every value of a segment lives in a register (ptxas allocates; 255 registers per thread, spills go to
+//     L1-cached local memory), leaves are read with 16-byte non-coherent loads straight from the batch-major
+//     leaf matrix, nothing is decoded at run time;
+//   * big programs are cut into SEGMENTS of consecutive statements (bounded ptxas time, compiled in parallel);
+//     a value defined in one segment and read in a later one travels through a per-launch "cross" buffer
+//     laid out [value][thread] (coalesced);
+//   * roots are stored per sample (eval) or shuffle-reduced per warp into per-warp partial sums (accumulate).
+#include "fdg_jit.h"
+
+#include <nvPTXCompiler.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <climits>
+#include <sstream>
+#include <thread>
+#include <unordered_map>
+
+namespace fdg {
+namespace {
+
+std::string dimm(double f) {  // exact double immediate
+    uint64_t u;
+    std::memcpy(&u, &f, 8);
+    char buf[32];
+    std::snprintf(buf, sizeof(buf), "0d%016llX", (unsigned long long)u);
+    return buf;
+}
+
+struct Emitter {
+    const Lowered &low;
+    const int S;      // samples per thread: 1 or 2
+    const bool acc;   // accumulate mode
+    std::ostringstream os;
+    int nfd = 0, nrd = 16, np = 8, nr = 16;
+    Emitter(const Lowered &l, int s, bool a) : low(l), S(s), acc(a) {}
+
+    int new_val() {
+        const int r = nfd;
+        nfd += S;
+        return r;
+    }
+    std::string fd(int r, int i) const { return "%fd" + std::to_string(r + i); }
+
+    void binop(const char *op, int dst, int a, int b) {
+        for (int i = 0; i < S; ++i) os << "\t" << op << ".rn.f64 " << fd(dst, i) << ", " << fd(a, i) << ", " << fd(b, i) << ";\n";
+    }
+    void scale(int dst, int a, double f) {
+        for (int i = 0; i < S; ++i) os << "\tmul.rn.f64 " << fd(dst, i) << ", " << fd(a, i) << ", " << dimm(f) << ";\n";
+    }
+    // value = load from  base + index * stride  (two f64 for S == 2)
+    int load(const char *space, const std::string &base, const std::string &stride, int64_t index) {
+        const int a = nrd++;
+        os << "\tmad.lo.u64 %rd" << a << ", " << stride << ", " << index << ", " << base << ";\n";
+        const int r = new_val();
+        if (S == 2)
+            os << "\t" << space << ".v2.f64 {" << fd(r, 0) << ", " << fd(r, 1) << "}, [%rd" << a << "];\n";
+        else
+            os << "\t" << space << ".f64 " << fd(r, 0) << ", [%rd" << a << "];\n";
+        return r;
+    }
+
+    // x^n, n >= 4: Julia >= 1.9 pow_body (base/math.jl), unrolled for the known exponent
+    int pow_body(int x0, int n) {
+        int x = x0;
+        int y = new_val(), xnlo = new_val(), ynlo = new_val();
+        for (int i = 0; i < S; ++i) {
+            os << "\tmov.f64 " << fd(y, i) << ", 0d3FF0000000000000;\n";
+            os << "\tmov.f64 " << fd(xnlo, i) << ", 0d0000000000000000;\n";
+            os << "\tmov.f64 " << fd(ynlo, i) << ", 0d0000000000000000;\n";
+        }
+        auto fma = [&](int d, int a, int b, int c) {
+            for (int i = 0; i < S; ++i)
+                os << "\tfma.rn.f64 " << fd(d, i) << ", " << fd(a, i) << ", " << fd(b, i) << ", " << fd(c, i) << ";\n";
+        };
+        auto neg = [&](int d, int a) {
+            for (int i = 0; i < S; ++i) os << "\tneg.f64 " << fd(d, i) << ", " << fd(a, i) << ";\n";
+        };
+        while (n > 1) {
+            if (n & 1) {
+                const int t = new_val(), err = new_val(), p = new_val(), np_ = new_val(), lo = new_val(), yl = new_val();
+                binop("mul", t, x, ynlo);
+                fma(err, y, xnlo, t);
+                binop("mul", p, x, y);
+                neg(np_, p);
+                fma(lo, x, y, np_);
+                binop("add", yl, lo, err);
+                y = p;
+                ynlo = yl;
+            }
+            const int t2 = new_val(), err = new_val(), p = new_val(), np_ = new_val(), lo = new_val(), xl = new_val();
+            scale(t2, x, 2.0);
+            binop("mul", err, t2, xnlo);
+            binop("mul", p, x, x);
+            neg(np_, p);
+            fma(lo, x, x, np_);
+            binop("add", xl, lo, err);
+            x = p;
+            xnlo = xl;
+            n >>= 1;
+        }
+        const int t = new_val(), err = new_val(), r1 = new_val(), r2 = new_val(), res = new_val();
+        binop("mul", t, x, ynlo);
+        fma(err, y, xnlo, t);
+        fma(r1, x, y, err);
+        binop("mul", r2, x, y);
+        for (int i = 0; i < S; ++i) {
+            const int p1 = np++, p2 = np++;
+            os << "\ttestp.finite.f64 %p" << p1 << ", " << fd(x, i) << ";\n";
+            os << "\ttestp.finite.f64 %p" << p2 << ", " << fd(err, i) << ";\n";
+            os << "\tand.pred %p" << p1 << ", %p" << p1 << ", %p" << p2 << ";\n";
+            os << "\tselp.f64 " << fd(res, i) << ", " << fd(r1, i) << ", " << fd(r2, i) << ", %p" << p1 << ";\n";
+        }
+        return res;
+    }
+
+    void root_out(int r, int32_t root) {
+        if (!acc) {
+            const int a = nrd++;
+            os << "\tmad.lo.u64 %rd" << a << ", %rd5, " << root << ", %rd6;\n";  // rootbase + root * ld_root_bytes
+            if (S == 2) {
+                os << "\t@%p1 st.global.v2.f64 [%rd" << a << "], {" << fd(r, 0) << ", " << fd(r, 1) << "};\n";
+                os << "\t@%p2 st.global.f64 [%rd" << a << "], " << fd(r, 0) << ";\n";  // odd tail: first sample only
+            } else {
+                os << "\t@%p0 st.global.f64 [%rd" << a << "], " << fd(r, 0) << ";\n";
+            }
+            return;
+        }
+        // masked sum of the thread's samples, xor-tree over the warp, lane 0 adds into the warp's partial row
+        const int s = nfd++, t = nfd++;
+        os << "\tselp.f64 %fd" << s << ", " << fd(r, 0) << ", 0d0000000000000000, %p0;\n";
+        if (S == 2) {
+            os << "\tselp.f64 %fd" << t << ", " << fd(r, 1) << ", 0d0000000000000000, %p1;\n";
+            os << "\tadd.rn.f64 %fd" << s << ", %fd" << s << ", %fd" << t << ";\n";
+        }
+        for (int m = 16; m >= 1; m >>= 1) {
+            os << "\tmov.b64 {%r8, %r9}, %fd" << s << ";\n";
+            os << "\tshfl.sync.bfly.b32 %r10, %r8, " << m << ", 31, 0xffffffff;\n";
+            os << "\tshfl.sync.bfly.b32 %r11, %r9, " << m << ", 31, 0xffffffff;\n";
+            os << "\tmov.b64 %fd" << t << ", {%r10, %r11};\n";
+            os << "\tadd.rn.f64 %fd" << s << ", %fd" << s << ", %fd" << t << ";\n";
+        }
+        os << "\t@%p3 ld.global.f64 %fd" << t << ", [%rd7+" << (int64_t)root * 8 << "];\n";
+        os << "\t@%p3 add.rn.f64 %fd" << t << ", %fd" << t << ", %fd" << s << ";\n";
+        os << "\t@%p3 st.global.f64 [%rd7+" << (int64_t)root * 8 << "], %fd" << t << ";\n";
+    }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// planning + PTX
+// ---------------------------------------------------------------------------------------------------------------------
+// Linear SSA form of the emitted function in FOLD order: a single-use node is evaluated at the point of use inside
+// its parent's left fold (so at most one partial accumulator per nesting level is live), a multi-use node or root is
+// evaluated at its first use and its value id remembered.  The arithmetic is exactly the emitter's (static.jl:13-46).
+struct IrOp {
+    uint8_t kind;   // 0 MUL(a,b)  1 ADD(a,b)  2 SCALE(a,f)  3 POW(a,n)  4 ROOT(a -> root position n)
+    int32_t a, b;   // operands: value id >= 0, or -(leaf+1) for leaf `leaf`
+    int32_t n;
+    double f;
+};
+enum { IR_MUL = 0, IR_ADD = 1, IR_SCALE = 2, IR_POW = 3, IR_ROOT = 4 };
+
+static void build_ir(const Lowered &low, std::vector<IrOp> &ir) {
+    const auto &st = low.st;
+    const auto &ops = low.ops;
+    std::vector<int32_t> val_of(st.size(), INT32_MIN);  // value id of a materialised statement once computed
+    auto emit = [&](uint8_t kind, int32_t a, int32_t b, int32_t n, double f) -> int32_t {
+        ir.push_back({kind, a, b, n, f});
+        return (int32_t)ir.size() - 1;
+    };
+    struct Frame {
+        int32_t v, i, acc;
+        bool have_ret;
+        int32_t ret;
+    };
+    std::vector<Frame> stack;
+    for (int32_t root_stmt = 0; root_stmt < (int32_t)st.size(); ++root_stmt) {
+        if (st[(size_t)root_stmt].root < 0) continue;
+        if (st[(size_t)root_stmt].op < 0) {  // root[r] = leafVal[k]
+            emit(IR_ROOT, -(st[(size_t)root_stmt].leaf + 1), 0, st[(size_t)root_stmt].root, 1.0);
+            continue;
+        }
+        if (val_of[(size_t)root_stmt] != INT32_MIN) continue;
+        stack.push_back({root_stmt, 0, 0, false, 0});
+        while (!stack.empty()) {
+            Frame &fr = stack.back();
+            const Stmt &s = st[(size_t)fr.v];
+            if (fr.i == s.count) {
+                int32_t res = fr.acc;
+                if (s.op == FDG_OP_POWER) {
+                    res = emit(IR_POW, res, 0, s.pow_n, 1.0);
+                    const double f = ops[(size_t)s.first].f;
+                    if (f != 1.0) res = emit(IR_SCALE, res, 0, 0, f);
+                }
+                if (s.root >= 0) emit(IR_ROOT, res, 0, s.root, 1.0);
+                if (s.root >= 0 || s.uses >= 2) val_of[(size_t)fr.v] = res;
+                stack.pop_back();
+                if (!stack.empty()) {
+                    stack.back().have_ret = true;
+                    stack.back().ret = res;
+                }
+                continue;
+            }
+            const Operand &o = ops[(size_t)(s.first + fr.i)];
+            int32_t t;
+            if (fr.have_ret) {
+                t = fr.ret;
+                fr.have_ret = false;
+            } else if (st[(size_t)o.val].op < 0) {
+                t = -(st[(size_t)o.val].leaf + 1);
+            } else if (val_of[(size_t)o.val] != INT32_MIN) {
+                t = val_of[(size_t)o.val];
+            } else {
+                const int32_t child = o.val;
+                stack.push_back({child, 0, 0, false, 0});  // NB: invalidates fr
+                continue;
+            }
+            if (s.op == FDG_OP_POWER) {
+                fr.acc = t;
+            } else if (s.op == FDG_OP_SUM) {
+                if (o.f != 1.0) t = emit(IR_SCALE, t, 0, 0, o.f);
+                fr.acc = fr.i == 0 ? t : emit(IR_ADD, fr.acc, t, 0, 1.0);
+            } else {
+                if (fr.i == 0) {
+                    fr.acc = o.f != 1.0 ? emit(IR_SCALE, t, 0, 0, o.f) : t;
+                } else {
+                    fr.acc = emit(IR_MUL, fr.acc, t, 0, 1.0);
+                    if (o.f != 1.0) fr.acc = emit(IR_SCALE, fr.acc, 0, 0, o.f);
+                }
+            }
+            stack.back().i++;
+        }
+    }
+}
+
+int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, std::string &err) {
+    if (low.dtype != FDG_F64) {
+        err = "the specialised back end evaluates Float64 programs only";
+        return FDG_ERR_UNSUPPORTED;
+    }
+    plan = JitPlan();
+    plan.spt = spt;
+    plan.acc = acc;
+    std::vector<IrOp> ir;
+    build_ir(low, ir);
+    if (seg_ops <= 0) seg_ops = 6000;
+    const size_t nops = ir.size();
+    const int nseg = std::max<int>(1, (int)((nops + (size_t)seg_ops - 1) / (size_t)seg_ops));
+    auto seg_of = [&](int32_t id) { return (int)((size_t)id / (size_t)seg_ops); };
+    // values read in a later segment than the one defining them travel through the cross buffer
+    std::vector<int32_t> cross(nops, -1);
+    int32_t n_cross = 0;
+    for (size_t i = 0; i < nops; ++i) {
+        const IrOp &o = ir[i];
+        const int32_t operands[2] = {o.a, (o.kind == IR_MUL || o.kind == IR_ADD) ? o.b : -1};
+        for (int q = 0; q < 2; ++q) {
+            const int32_t a = operands[q];
+            if (q == 1 && !(o.kind == IR_MUL || o.kind == IR_ADD)) break;
+            if (a >= 0 && seg_of(a) != seg_of((int32_t)i) && cross[(size_t)a] < 0) cross[(size_t)a] = n_cross++;
+        }
+    }
+    plan.n_cross = n_cross;
+    plan.seg.resize((size_t)nseg);
+    for (int sg = 0; sg < nseg; ++sg) {
+        Emitter e(low, spt, acc);
+        std::ostringstream &os = e.os;
+        const size_t lo = (size_t)sg * (size_t)seg_ops, hi = std::min(nops, lo + (size_t)seg_ops);
+        std::vector<int32_t> reg_of(hi - lo, -1);          // register of a value defined in this segment
+        std::vector<int32_t> leaf_reg((size_t)low.L, -1);  // register of a leaf loaded in this segment
+        std::unordered_map<int32_t, int32_t> cross_reg;    // register of a cross value loaded in this segment
+        auto operand = [&](int32_t a) -> int {
+            if (a < 0) {
+                const int32_t k = -a - 1;
+                if (leaf_reg[(size_t)k] < 0) leaf_reg[(size_t)k] = e.load("ld.global.nc", "%rd1", "%rd2", k);
+                return leaf_reg[(size_t)k];
+            }
+            if ((size_t)a >= lo) return reg_of[(size_t)a - lo];
+            auto it = cross_reg.find(a);
+            if (it != cross_reg.end()) return it->second;
+            const int r = e.load("ld.global", "%rd3", "%rd4", cross[(size_t)a]);
+            cross_reg.emplace(a, r);
+            return r;
+        };
+        for (size_t i = lo; i < hi; ++i) {
+            const IrOp &o = ir[i];
+            int r = -1;
+            switch (o.kind) {
+                case IR_MUL:
+                case IR_ADD: {
+                    const int a = operand(o.a), b = operand(o.b);
+                    r = e.new_val();
+                    e.binop(o.kind == IR_MUL ? "mul" : "add", r, a, b);
+                } break;
+                case IR_SCALE: {
+                    const int a = operand(o.a);
+                    r = e.new_val();
+                    e.scale(r, a, o.f);
+                } break;
+                case IR_POW: {
+                    const int x = operand(o.a);
+                    if (o.n == 2) {
+                        r = e.new_val();
+                        e.binop("mul", r, x, x);
+                    } else if (o.n == 3) {
+                        const int t = e.new_val();
+                        e.binop("mul", t, x, x);
+                        r = e.new_val();
+                        e.binop("mul", r, t, x);
+                    } else {
+                        r = e.pow_body(x, o.n);
+                    }
+                } break;
+                default: e.root_out(operand(o.a), o.n); break;
+            }
+            reg_of[i - lo] = r;
+            if (r >= 0 && cross[i] >= 0) {
+                const int a = e.nrd++;
+                os << "\tmad.lo.u64 %rd" << a << ", %rd4, " << cross[i] << ", %rd3;\n";
+                if (spt == 2)
+                    os << "\tst.global.v2.f64 [%rd" << a << "], {" << e.fd(r, 0) << ", " << e.fd(r, 1) << "};\n";
+                else
+                    os << "\tst.global.f64 [%rd" << a << "], " << e.fd(r, 0) << ";\n";
+            }
+        }
+        const std::string body = os.str();
+        JitSegment &js = plan.seg[(size_t)sg];
+        js.name = "fdg_seg" + std::to_string(sg);
+        js.n_stmts = (int)(hi - lo);
+        std::ostringstream p;
+        p << ".version 8.7\n.target sm_100a\n.address_size 64\n\n";
+        p << ".visible .entry " << js.name << "(\n"
+          << "\t.param .u64 p_leaf, .param .u64 p_ld_leaf, .param .u64 p_cross, .param .u64 p_ld_cross,\n"
+          << "\t.param .u64 p_out, .param .u64 p_ld_root, .param .u64 p_batch, .param .u64 p_nroots)\n"
+          << ".maxntid 128, 1, 1\n{\n";
+        p << "\t.reg .f64 %fd<" << e.nfd + 2 << ">;\n\t.reg .b64 %rd<" << e.nrd + 1 << ">;\n\t.reg .pred %p<" << e.np + 1
+          << ">;\n\t.reg .b32 %r<" << e.nr + 1 << ">;\n";
+        // %rd0 = first sample of the thread, %rd1 = leaf base, %rd2 = ld_leaf bytes, %rd3 = cross base, %rd4 = ld_cross bytes,
+        // %rd5 = ld_root bytes, %rd6 = root base (eval), %rd7 = partial row of the warp (accumulate)
+        p << "\tmov.u32 %r0, %ctaid.x;\n\tmov.u32 %r1, %ntid.x;\n\tmov.u32 %r2, %tid.x;\n"
+          << "\tmul.wide.u32 %rd8, %r0, %r1;\n\tcvt.u64.u32 %rd9, %r2;\n\tadd.u64 %rd8, %rd8, %rd9;\n"  // global thread id
+          << "\tmul.lo.u64 %rd0, %rd8, " << spt << ";\n"
+          << "\tld.param.u64 %rd10, [p_batch];\n"
+          << "\tsetp.lt.s64 %p0, %rd0, %rd10;\n";  // first sample valid
+        if (spt == 2)
+            p << "\tadd.u64 %rd11, %rd0, 1;\n\tsetp.lt.s64 %p1, %rd11, %rd10;\n"  // both samples valid
+              << "\tnot.pred %p4, %p1;\n\tand.pred %p2, %p0, %p4;\n";             // only the first one
+        p << "\tselp.u64 %rd12, %rd0, 0, %p0;\n"  // inactive threads read sample 0: every address stays in bounds
+          << "\tshl.b64 %rd12, %rd12, 3;\n"
+          << "\tld.param.u64 %rd1, [p_leaf];\n\tcvta.to.global.u64 %rd1, %rd1;\n\tadd.u64 %rd1, %rd1, %rd12;\n"
+          << "\tld.param.u64 %rd2, [p_ld_leaf];\n\tshl.b64 %rd2, %rd2, 3;\n"
+          << "\tld.param.u64 %rd3, [p_cross];\n\tcvta.to.global.u64 %rd3, %rd3;\n"
+          << "\tshl.b64 %rd13, %rd0, 3;\n\tadd.u64 %rd3, %rd3, %rd13;\n"
+          << "\tld.param.u64 %rd4, [p_ld_cross];\n\tshl.b64 %rd4, %rd4, 3;\n"
+          << "\tld.param.u64 %rd14, [p_out];\n\tcvta.to.global.u64 %rd14, %rd14;\n";
+        if (!acc) {
+            p << "\tld.param.u64 %rd5, [p_ld_root];\n\tshl.b64 %rd5, %rd5, 3;\n\tadd.u64 %rd6, %rd14, %rd13;\n";
+        } else {
+            p << "\tshr.u64 %rd15, %rd8, 5;\n\tld.param.u64 %rd5, [p_nroots];\n\tmul.lo.u64 %rd15, %rd15, %rd5;\n"
+              << "\tshl.b64 %rd15, %rd15, 3;\n\tadd.u64 %rd7, %rd14, %rd15;\n"
+              << "\tand.b32 %r3, %r2, 31;\n\tsetp.eq.u32 %p3, %r3, 0;\n";
+        }
+        p << body << "\tret;\n}\n";
+        js.ptx = p.str();
+    }
+    (void)err;
+    return FDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX -> cubin (sm_100a), segments in parallel
+// ---------------------------------------------------------------------------------------------------------------------
+static int compile_one(JitSegment &js, std::string &err) {
+    nvPTXCompilerHandle h = nullptr;
+    nvPTXCompileResult rc = nvPTXCompilerCreate(&h, js.ptx.size(), js.ptx.c_str());
+    if (rc != NVPTXCOMPILE_SUCCESS) {
+        err = "nvPTXCompilerCreate failed (" + std::to_string((int)rc) + ")";
+        return FDG_ERR_UNSUPPORTED;
+    }
+    const char *opts[] = {"--gpu-name=sm_100a", "--opt-level=3", "--fmad=false", "--verbose"};
+    rc = nvPTXCompilerCompile(h, 4, opts);
+    size_t n = 0;
+    if (rc != NVPTXCOMPILE_SUCCESS) {
+        nvPTXCompilerGetErrorLogSize(h, &n);
+        std::string log(n + 1, '\0');
+        if (n) nvPTXCompilerGetErrorLog(h, &log[0]);
+        err = "ptxas failed for " + js.name + ": " + log.c_str();
+        nvPTXCompilerDestroy(&h);
+        return FDG_ERR_UNSUPPORTED;
+    }
+    nvPTXCompilerGetCompiledProgramSize(h, &n);
+    js.cubin.resize(n);
+    nvPTXCompilerGetCompiledProgram(h, js.cubin.data());
+    size_t ln = 0;
+    nvPTXCompilerGetInfoLogSize(h, &ln);
+    if (ln) {
+        js.info.assign(ln + 1, '\0');
+        nvPTXCompilerGetInfoLog(h, &js.info[0]);
+        js.info.resize(std::strlen(js.info.c_str()));
+    }
+    nvPTXCompilerDestroy(&h);
+    return FDG_OK;
+}
+
+int jit_compile(JitPlan &plan, std::string &err) {
+    const int n = (int)plan.seg.size();
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nthreads = std::max(1, std::min<int>(n, hw ? (int)hw : 4));
+    std::atomic<int> next{0};
+    std::vector<std::string> errs((size_t)n);
+    std::vector<int> rcs((size_t)n, FDG_OK);
+    auto work = [&]() {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n) break;
+            rcs[(size_t)i] = compile_one(plan.seg[(size_t)i], errs[(size_t)i]);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    for (int i = 0; i < n; ++i)
+        if (rcs[(size_t)i] != FDG_OK) {
+            err = errs[(size_t)i];
+            return rcs[(size_t)i];
+        }
+    return FDG_OK;
+}
+
+}  // namespace fdg

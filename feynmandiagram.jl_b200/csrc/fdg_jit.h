@@ -1,0 +1,32 @@
+// fdg_jit.h -- specialised back end: statements -> PTX -> sm_100a cubin (see fdg_jit.cpp)
+#ifndef FDG_JIT_H
+#define FDG_JIT_H
+#include <string>
+#include <vector>
+
+#include "fdg_lower.h"
+
+namespace fdg {
+
+struct JitSegment {
+    std::string name;         // kernel entry name
+    std::string ptx;          // generated PTX (one .entry)
+    std::vector<char> cubin;  // assembled for sm_100a
+    std::string info;         // ptxas verbose log (registers, spills)
+    int n_stmts = 0;
+};
+
+struct JitPlan {
+    int spt = 2;        // samples per thread
+    bool acc = false;   // accumulate (per-warp partial sums) instead of per-sample roots
+    int32_t n_cross = 0;  // rows of the cross-segment buffer
+    std::vector<JitSegment> seg;
+};
+
+// linearise the emitted function in fold order, cut it into segments of `seg_ops` operations, write their PTX
+int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, std::string &err);
+// assemble every segment with the PTX compiler library (no GPU needed), segments in parallel
+int jit_compile(JitPlan &plan, std::string &err);
+
+}  // namespace fdg
+#endif

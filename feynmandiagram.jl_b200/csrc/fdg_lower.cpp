@@ -25,22 +25,6 @@
 namespace fdg {
 namespace {
 
-struct Operand {
-    int32_t val;
-    double f;
-};
-
-struct Stmt {          // one value of the emitted function, in emitter order
-    int8_t op = -1;    // -1 leaf, else FDG_OP_SUM / PROD / POWER
-    int32_t pow_n = 0;
-    int64_t first = 0;  // operands[first .. first+count)
-    int32_t count = 0;
-    int32_t root = -1;  // root position assigned right after this statement
-    int32_t uses = 0;   // operand references from live statements
-    bool live = false;
-    int32_t leaf = -1;  // leaf index k for leaves
-};
-
 // symbolic (pre-allocation) VM operation
 struct Sym {
     uint8_t op;  // FDG_OP_*
@@ -240,9 +224,66 @@ struct CodeGen {
     int32_t n_values;  // statements + temporaries
     int32_t max_depth = 0;
     bool pending_push = false;
+    // eager: before the fold of a unit starts, every materialised value its (inlined) sub-tree reads is computed as a
+    // unit of its own (statement order of the emitted function, restricted to what the unit needs).  Folds then only
+    // read available slots, so sums of products become TERM blocks and nesting stays shallow; the price is longer
+    // live ranges.  lazy: materialised values are computed in the middle of the fold that uses them first.
+    bool eager = true;
+    std::vector<int32_t> mark;  // scratch for collect()
+    int32_t mark_gen = 0;
 
     CodeGen(const std::vector<Stmt> &s, const std::vector<Operand> &o, const std::vector<uint8_t> &r)
-        : st(s), ops(o), remat(r), computed(s.size(), 0), n_values((int32_t)s.size()) {}
+        : st(s), ops(o), remat(r), computed(s.size(), 0), n_values((int32_t)s.size()), mark(s.size(), 0) {}
+
+    // materialised, not yet computed values read by the fold of `v` (through inlined children), in first-use order
+    void collect(int32_t v, std::vector<int32_t> &deps) {
+        ++mark_gen;
+        std::vector<std::pair<int32_t, int32_t>> stk;  // (statement, next operand)
+        stk.push_back({v, 0});
+        while (!stk.empty()) {
+            auto &top = stk.back();
+            const Stmt &s = st[(size_t)top.first];
+            if (top.second == s.count) {
+                stk.pop_back();
+                continue;
+            }
+            const int32_t c = ops[(size_t)(s.first + top.second++)].val;
+            if (is_leaf(c) || mark[(size_t)c] == mark_gen) continue;
+            mark[(size_t)c] = mark_gen;
+            if (materialised(c)) {
+                if (!computed[(size_t)c]) deps.push_back(c);
+            } else {
+                stk.push_back({c, 0});
+            }
+        }
+    }
+
+    // computes `unit` (and, in eager mode, first everything materialised it depends on) -- iterative
+    void gen_unit(int32_t unit) {
+        if (!eager) {
+            gen_fold(unit);
+            return;
+        }
+        std::vector<std::pair<int32_t, bool>> work;
+        work.push_back({unit, false});
+        std::vector<int32_t> deps;
+        while (!work.empty()) {
+            const int32_t v = work.back().first;
+            if (computed[(size_t)v]) {
+                work.pop_back();
+                continue;
+            }
+            if (!work.back().second) {
+                work.back().second = true;
+                deps.clear();
+                collect(v, deps);
+                for (auto it = deps.rbegin(); it != deps.rend(); ++it) work.push_back({*it, false});
+            } else {
+                work.pop_back();
+                gen_fold(v);
+            }
+        }
+    }
 
     bool is_leaf(int32_t v) const { return st[(size_t)v].op < 0; }
     // kept in the slot file once computed: roots and multi-use nodes (unless rematerialised)
@@ -300,9 +341,9 @@ struct CodeGen {
         int32_t tmp;
     };
 
-    // computes statement `unit` into A with an empty stack; materialised nodes met on the way are computed at
-    // their first use, stored, and read from the slot file afterwards
-    void gen_unit(int32_t unit) {
+    // computes statement `unit` into A with an empty stack; materialised nodes met on the way (lazy mode) are computed
+    // at their first use, stored, and read from the slot file afterwards
+    void gen_fold(int32_t unit) {
         std::vector<Frame> stack;
         int depth = 0;  // stack registers holding partial folds of enclosing nodes
         stack.push_back({unit, 0, 0, 1.0, -1});
@@ -753,8 +794,8 @@ int lower(const fdg_graph_desc &g, const fdg_options &opt, Lowered &out, std::st
     }
     out = Lowered();
     out.dtype = opt.dtype;
-    std::vector<Stmt> st;
-    std::vector<Operand> ops;
+    std::vector<Stmt> &st = out.st;
+    std::vector<Operand> &ops = out.ops;
     int rc = build_statements(g, st, ops, out, err);
     if (rc != FDG_OK) return rc;
 
@@ -795,6 +836,7 @@ int lower(const fdg_graph_desc &g, const fdg_options &opt, Lowered &out, std::st
     std::unique_ptr<Allocator> al_owner;
     for (int iter = 0; iter < 4; ++iter) {
         CodeGen cg(st, ops, remat);
+        cg.eager = opt.schedule != 1;
         cg.run();
         out.max_depth = cg.max_depth;
         code.swap(cg.code);

@@ -59,6 +59,11 @@ enum {
  * whatever its operator tag (static.jl:115). */
 enum { FDG_OP_UNITARY = 0, FDG_OP_SUM = 1, FDG_OP_PROD = 2, FDG_OP_POWER = 3 };
 
+/* back ends.  VM: the packet interpreter kernel (any program, Float64 and ComplexF64).  JIT: the emitted
+ * function written as PTX and assembled for sm_100a at first use (Float64).  AUTO picks JIT where it
+ * applies and falls back to the VM; both compute bit-identical results. */
+enum { FDG_BACKEND_AUTO = 0, FDG_BACKEND_VM = 1, FDG_BACKEND_JIT = 2 };
+
 /* element types of leafVal / root (julia_to_C_typestr, static.jl:135-153) */
 enum { FDG_F64 = 0, FDG_C128 = 1 };
 
@@ -84,7 +89,11 @@ typedef struct fdg_options {
     int32_t dtype;        /* FDG_F64 (default) or FDG_C128                                     */
     int32_t max_slots;    /* cap on on-chip value slots per sample (0 = choose automatically)  */
     int32_t prefetch;     /* leaf prefetch distance in packets (0 = default, <0 = demand only) */
-    int32_t reserved[5];  /* must be zero                                                      */
+    int32_t schedule;     /* 0 = eager: multi-use values are computed as statements of their own
+                             before the fold that reads them (emitter order); 1 = lazy: inside it */
+    int32_t backend;      /* FDG_BACKEND_AUTO (0), FDG_BACKEND_VM (1), FDG_BACKEND_JIT (2)            */
+    int32_t jit_segment;  /* operations per specialised kernel (0 = default)                   */
+    int32_t reserved[2];  /* must be zero                                                      */
 } fdg_options;
 
 typedef struct fdg_program *fdg_handle;
@@ -140,6 +149,14 @@ int fdg_eval_host(fdg_handle h, const void *leaf_host, int64_t ld_leaf, void *ro
 int fdg_set_launch(fdg_handle h, int32_t threads, int32_t samples_per_thread, int32_t blocks_per_sm);
 /* number of kernel launches issued by this handle so far (bench's gpu_launches) */
 int fdg_launch_count(fdg_handle h, int64_t *out);
+/* specialised back end: generate + assemble the kernels now (host only, no GPU needed) instead of at first
+ * use.  accumulate: 0 = fdg_eval variant, 1 = fdg_eval_accumulate variant.  Reports the number of kernels,
+ * the rows of the cross-segment buffer and the total cubin size. */
+int fdg_jit_prepare(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t *n_kernels,
+                    int32_t *n_cross, int64_t *cubin_bytes);
+/* PTX text of kernel `index` of a prepared variant (for inspection / tests) */
+int fdg_jit_ptx(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t index, const char **ptx,
+                const char **ptxas_log);
 
 /* --- multi-GPU: one process per GPU; the only exchange is the sum of the per-root accumulators ---- */
 typedef struct fdg_comm *fdg_comm_t;

@@ -25,9 +25,14 @@ def _dev_eval(ev, leaf_host: np.ndarray, batch: int, spt: int = 0, threads: int 
     return root.cpu().numpy()[: ev.n_roots, :batch]
 
 
-def _parity(roots, dtype=np.float64, batch=1000, ld=0, spt=0, threads=0, max_slots=0, prefetch=0, signed=True, root=None):
+VM, JIT = 1, 2  # FDG_BACKEND_VM (packet interpreter kernel), FDG_BACKEND_JIT (specialised PTX kernels)
+BACKENDS = [VM, JIT]
+
+
+def _parity(roots, dtype=np.float64, batch=1000, ld=0, spt=0, threads=0, max_slots=0, prefetch=0, signed=True, root=None,
+            backend=VM, jit_segment=0):
     raw, _ = fd.flatten(roots, root)
-    ev = fd.compile_raw(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch)
+    ev = fd.compile_raw(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch, backend=backend, jit_segment=jit_segment)
     orc = O.Oracle(raw)
     leaf = graphgen.leaf_values(5, max(ev.n_leaves, 1), batch, dtype=dtype, signed=signed, ld=ld)
     want = orc.eval(np.ascontiguousarray(leaf[:, :batch]), "emitter", root=np.full((orc.n_roots, batch), -3.0, dtype))
@@ -61,18 +66,29 @@ def test_random_dag_f64(seed, spt):
     _parity(graphgen.random_dag(seed, n_leaves=6 + seed, n_inner=40 + 10 * seed, n_roots=3), spt=spt, batch=1536 + 4 * seed)
 
 
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("spt", [1, 2])
+@pytest.mark.parametrize("jit_segment", [0, 37])
+def test_random_dag_f64_jit(seed, spt, jit_segment):
+    # jit_segment=37 cuts the program into many small kernels: exercises the cross-segment buffer
+    _parity(graphgen.random_dag(seed, n_leaves=6 + seed, n_inner=40 + 10 * seed, n_roots=3), spt=spt, batch=1536 + 4 * seed,
+            backend=JIT, jit_segment=jit_segment)
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_random_dag_c128(seed):
     _parity(graphgen.random_dag(200 + seed, n_leaves=7, n_inner=60, n_roots=3, max_pow=5), dtype=np.complex128, batch=777)
 
 
 @pytest.mark.parametrize("seed", range(4))
-def test_random_tree_nesting(seed):
-    _parity(graphgen.random_tree(300 + seed, depth=8), max_slots=6 + seed, batch=515, ld=516)
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_random_tree_nesting(seed, backend):
+    _parity(graphgen.random_tree(300 + seed, depth=8), max_slots=6 + seed, batch=515, ld=516, backend=backend)
 
 
-def test_power_ge_4():
-    _parity(graphgen.random_dag(7, n_leaves=4, n_inner=30, n_roots=2, p_power=0.4, max_pow=7), signed=False)
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_power_ge_4(backend):
+    _parity(graphgen.random_dag(7, n_leaves=4, n_inner=30, n_roots=2, p_power=0.4, max_pow=7), signed=False, backend=backend)
 
 
 @pytest.mark.parametrize("max_slots,prefetch", [(4, -1), (5, 8), (8, 64), (16, 1), (64, 24)])
@@ -84,9 +100,10 @@ def test_spills_and_prefetch(max_slots, prefetch):
 
 
 @pytest.mark.parametrize("batch,ld", [(1, 1), (1, 2), (2, 2), (3, 3), (3, 4), (31, 32), (33, 40), (255, 256), (257, 257), (1025, 1026)])
-def test_ragged_batches(batch, ld):
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_ragged_batches(batch, ld, backend):
     # odd / tiny batches, padded leading dimensions, the one- and two-samples-per-thread kernels
-    _parity(graphgen.random_dag(9, n_leaves=9, n_inner=50, n_roots=3), batch=batch, ld=ld)
+    _parity(graphgen.random_dag(9, n_leaves=9, n_inner=50, n_roots=3), batch=batch, ld=ld, backend=backend)
 
 
 @pytest.mark.parametrize("threads", [32, 64, 128, 256])
@@ -101,13 +118,14 @@ def test_term_blocks_every_operand_count(term_len):
     _parity(graphgen.sum_of_products(6, n_leaves=30, n_terms=70, term_len=term_len, n_roots=2), batch=2050, ld=2052)
 
 
-@pytest.mark.parametrize("name", ["gv_sigma_o3", "gv_ver4_o2", "gv_ver4_o3", "gv_sigma_o5"])
-@pytest.mark.parametrize("spt", [2, 4])
-def test_real_workload_graphs(name, spt):
+@pytest.mark.parametrize("name", ["gv_sigma_o3", "gv_ver4_o2", "gv_ver4_o3", "gv_sigma_o5", "parquet_sigma_o2", "parquet_sigma_o3",
+                                  "parquet_sigma_o4", "parquet_ver4_o3"])
+@pytest.mark.parametrize("spt,backend", [(2, VM), (4, VM), (1, JIT), (2, JIT)])
+def test_real_workload_graphs(name, spt, backend):
     import os
 
     raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", name + ".npz"))
-    ev = fd.compile_raw(raw)
+    ev = fd.compile_raw(raw, backend=backend)
     orc = O.Oracle(raw)
     batch = 4096
     leaf = graphgen.leaf_values(5, ev.n_leaves, batch, signed=True)
@@ -142,11 +160,14 @@ def test_bad_arguments_are_reported_not_executed():
         ev.eval_device(0, 8, x.data_ptr(), 8, 8)  # null leaf
 
 
-def test_accumulate_is_the_sum_of_eval_and_deterministic():
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_accumulate_is_the_sum_of_eval_and_deterministic(backend):
     roots = graphgen.random_dag(21, n_leaves=10, n_inner=60, n_roots=4)
     raw, _ = fd.flatten(roots)
     for dtype, w in ((np.float64, 1), (np.complex128, 2)):
-        ev = fd.compile_raw(raw, dtype=dtype)
+        if backend == JIT and w == 2:
+            continue  # the specialised back end is Float64 only
+        ev = fd.compile_raw(raw, dtype=dtype, backend=backend, jit_segment=50 if backend == JIT else 0)
         batch = 100_003
         leaf_h = graphgen.leaf_values(3, ev.n_leaves, batch, dtype=dtype, signed=True, ld=batch + 1)
         per_sample = _dev_eval(ev, leaf_h, batch)
@@ -194,6 +215,16 @@ def test_torch_tensors_batch_major():
     assert root.T.contiguous().cpu().numpy().tobytes() == orc.eval(leafT).tobytes()
     with pytest.raises(ValueError):
         f(torch.empty(B, f.n_roots, dtype=torch.float64, device="cuda"), leafVal.contiguous())
+
+
+def test_auto_backend_matches_and_complex_uses_the_vm():
+    roots = graphgen.random_dag(55, n_leaves=10, n_inner=60, n_roots=3)
+    _parity(roots, backend=0, batch=3000)  # AUTO: specialised kernels
+    _parity(roots, backend=0, batch=3000, dtype=np.complex128)  # AUTO on ComplexF64: the VM
+    raw, _ = fd.flatten(roots)
+    with pytest.raises(_capi.FdgError) as e:
+        _dev_eval(fd.compile_raw(raw, dtype=np.complex128, backend=JIT), graphgen.leaf_values(1, 11, 8, dtype=np.complex128), 8)
+    assert e.value.code == 3
 
 
 def test_large_batch_properties():

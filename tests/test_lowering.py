@@ -99,6 +99,24 @@ def test_real_workload_graphs(name):
     assert list(ones[:, 0]) == man["all_leaves_one"] and ev.n_leaves == man["n_leaves"]
 
 
+@pytest.mark.parametrize("name", ["gv_sigma_o3", "gv_sigma_o4", "parquet_sigma_o3", "parquet_ver4_o2"])
+@pytest.mark.parametrize("acc", [False, True])
+def test_specialised_kernels_assemble_without_a_gpu(name, acc):
+    """fdg_jit_prepare: the PTX written for the emitted function assembles for sm_100a with the toolkit's PTX compiler
+    library (no driver needed); it contains only rn multiplies / adds (no fma outside Power{N>=4})."""
+    import os
+
+    raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", name + ".npz"))
+    ev = fd.compile_raw(raw, jit_segment=300)
+    info = ev.jit_prepare(2, acc)
+    assert info["kernels"] >= 1 and info["cubin_bytes"] > 0
+    for i in range(info["kernels"]):
+        ptx, log = ev.jit_ptx(2, acc, i)
+        assert ".target sm_100a" in ptx and "fma" not in ptx
+        assert "mul.rn.f64" in ptx
+        assert "registers" in log
+
+
 def test_stats_counts_match_reference_operation_count():
     # count_operation (tree_properties.jl:165-185): sum (fan_in - 1) adds, prod (fan_in - 1) muls; + 1 mul per factor != 1
     a, b, c = fd.Graph([]), fd.Graph([]), fd.Graph([])

@@ -54,9 +54,23 @@ def main():
     for order in (3, 4):
         emit(f"gv_ver4I_o{order}", lambda o=order: gv.diagsGV_ver4(o, channels=[gv.Alli]),
              f"GV.diagsGV_ver4({order}, channels=[Alli]) + optimize!  (groups_vertex4/Vertex4I{order}_0_0.diag)", manifest)
-    extra = os.path.join(OUT, "MANIFEST.extra.json")  # entries written by other generators (Parquet, Taylor)
-    if os.path.exists(extra):
-        manifest.update(json.load(open(extra)))
+    from oracle.frontend import parquet as pq
+
+    def pq_sigma(order):
+        pq._ver4I.clear()
+        return [r["diagram"] for r in pq.sigma(pq.DiagPara(type=pq.SigmaDiag, innerLoopNum=order))]
+
+    def pq_ver4(order):
+        pq._ver4I.clear()
+        return [r["diagram"] for r in pq.vertex4(pq.DiagPara(type=pq.Ver4Diag, innerLoopNum=order))]
+
+    for order in (2, 3, 4):
+        emit(f"parquet_sigma_o{order}", lambda o=order: pq_sigma(o),
+             f"Parquet.sigma(DiagPara(type=SigmaDiag, innerLoopNum={order})) + optimize!  (README.md:59-68)", manifest)
+    for order in (2, 3, 4):
+        emit(f"parquet_ver4_o{order}", lambda o=order: pq_ver4(o),
+             f"Parquet.vertex4(DiagPara(type=Ver4Diag, innerLoopNum={order})) + optimize!  (example/benchmark.jl:13,23-25)",
+             manifest)
     with open(os.path.join(OUT, "MANIFEST.json"), "w") as fh:
         json.dump(manifest, fh, indent=1, sort_keys=True)
 
