@@ -141,8 +141,7 @@ int launch_variant(fdg_program *h, DeviceState &ds, fdg::VmArgs &args, long long
     if (ACC) {
         const int rw = (int)low.R * W;
         if (rw > 0) {
-            fdg::fdg_reduce_partials<<<(rw + 127) / 128, 128, 0, stream>>>(ds.partial, rows, rw,
-                                                                          static_cast<double *>(args.root));
+            fdg::fdg_reduce_partials<<<rw, 256, 0, stream>>>(ds.partial, rows, rw, static_cast<double *>(args.root));
             CUDA_TRY(cudaGetLastError());
             h->launches++;
         }
@@ -254,8 +253,7 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
         }
     }
     if (acc && low.R > 0) {
-        fdg::fdg_reduce_partials<<<((int)low.R + 127) / 128, 128, 0, stream>>>(ds.partial, rows, (int)low.R,
-                                                                              static_cast<double *>(root));
+        fdg::fdg_reduce_partials<<<(int)low.R, 256, 0, stream>>>(ds.partial, rows, (int)low.R, static_cast<double *>(root));
         CUDA_TRY(cudaGetLastError());
         h->launches++;
     }
@@ -304,7 +302,10 @@ int do_eval(fdg_program *h, const void *leaf, int64_t ld_leaf, void *root, int64
     int backend = h->backend;
     if (const char *e = getenv("FDG_BACKEND")) backend = atoi(e);
     if (backend != FDG_BACKEND_VM && low.N + low.R > 0) {
-        const int jspt = (h->spt == 1 || !fits(2)) ? 1 : 2;
+        // two samples per thread pay off only for small programs (everything stays in registers); big ones want
+        // the registers for the program's own live values
+        int jspt = h->spt == 0 ? (low.n_operands <= 400 ? 2 : 1) : (h->spt >= 2 ? 2 : 1);
+        if (jspt == 2 && !fits(2)) jspt = 1;
         int dev = 0;
         cudaGetDevice(&dev);
         rc = jit_launch(h, *ds, dev, jspt, accumulate, leaf, ld_leaf, root, ld_root, batch, st);

@@ -255,7 +255,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
     plan.acc = acc;
     std::vector<IrOp> ir;
     build_ir(low, ir);
-    if (seg_ops <= 0) seg_ops = 6000;
+    if (seg_ops <= 0) seg_ops = 3000;
     const size_t nops = ir.size();
     const int nseg = std::max<int>(1, (int)((nops + (size_t)seg_ops - 1) / (size_t)seg_ops));
     auto seg_of = [&](int32_t id) { return (int)((size_t)id / (size_t)seg_ops); };

@@ -465,13 +465,20 @@ __global__ void __launch_bounds__(256, 2) fdg_vm_kernel(const VmArgs a) {
     }
 }
 
-// acc[r] += sum over rows of partial[row][r], rows added in index order (deterministic)
-__global__ void fdg_reduce_partials(const double *__restrict__ partial, long long rows, int rw, double *acc) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rw) return;
+// acc[r] += sum over rows of partial[row][r].  One block per column r; thread t adds rows t, t+256, ... in order, then a
+// fixed binary tree over the 256 per-thread sums: the order of additions depends only on `rows` (deterministic).
+__global__ void __launch_bounds__(256) fdg_reduce_partials(const double *__restrict__ partial, long long rows, int rw, double *acc) {
+    __shared__ double sh[256];
+    const int r = blockIdx.x;
     double s = 0.0;
-    for (long long i = 0; i < rows; ++i) s = __dadd_rn(s, partial[i * rw + r]);
-    acc[r] = __dadd_rn(acc[r], s);
+    for (long long i = threadIdx.x; i < rows; i += 256) s = __dadd_rn(s, partial[i * rw + r]);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int m = 128; m >= 1; m >>= 1) {
+        if ((int)threadIdx.x < m) sh[threadIdx.x] = __dadd_rn(sh[threadIdx.x], sh[threadIdx.x + m]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) acc[r] = __dadd_rn(acc[r], sh[0]);
 }
 
 }  // namespace fdg

@@ -95,8 +95,8 @@ def test_power_ge_4(backend):
 def test_spills_and_prefetch(max_slots, prefetch):
     roots = graphgen.random_dag(42, n_leaves=20, n_inner=120, n_roots=4)
     ev = _parity(roots, max_slots=max_slots, prefetch=prefetch, batch=4100, ld=4102)
-    if max_slots <= 5:
-        assert ev.stats["n_scratch"] > 0
+    if max_slots <= 16:
+        assert ev.stats["n_scratch"] > 0 or ev.stats["leaf_loads"] > ev.n_leaves  # the small slot file was really exercised
 
 
 @pytest.mark.parametrize("batch,ld", [(1, 1), (1, 2), (2, 2), (3, 3), (3, 4), (31, 32), (33, 40), (255, 256), (257, 257), (1025, 1026)])

@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--prefetch", default="-1,8,24,64")
     ap.add_argument("--mode", default="acc")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--backend", type=int, default=1, help="1 = VM, 2 = JIT")
+    ap.add_argument("--jit-segment", default="0")
     a = ap.parse_args()
     raw = fd.RawGraph.load(os.path.join(ROOT, "workloads", a.workload + ".npz"))
     base = fd.compile_raw(raw)
@@ -35,6 +37,32 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     print(f"# {a.workload}: L={L} R={R} B={B} stats={base.stats}")
     rows = []
+    if a.backend == 2:
+        import time
+
+        for seg, spt in itertools.product([int(x) for x in a.jit_segment.split(",")], [int(x) for x in a.spt.split(",")]):
+            f = fd.compile_raw(raw, backend=2, jit_segment=seg)
+            f.set_launch(0, spt, 0)
+            t0 = time.time()
+            info = f.jit_prepare(spt, a.mode != "eval")
+            tc = time.time() - t0
+            best = 1e30
+            for r in range(a.reps + 1):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if a.mode == "eval":
+                    f.eval_device(leaf.data_ptr(), B, root.data_ptr(), B, B, stream)
+                else:
+                    f.accumulate_device(leaf.data_ptr(), B, B, acc.data_ptr(), stream)
+                e1.record()
+                torch.cuda.synchronize()
+                if r:
+                    best = min(best, e0.elapsed_time(e1))
+            st = f.stats
+            print(json.dumps(dict(backend="jit", seg=seg, spt=spt, compile_s=round(tc, 1), ms=round(best, 3), Msamples_s=round(B / best / 1e3, 2),
+                                  GBs=round(8 * L * B / best / 1e6, 1), gflops=round((st["flops_add"] + st["flops_mul"]) * B / best / 1e6, 1),
+                                  **info)), flush=True)
+        return
     for ms_, pf in itertools.product([int(x) for x in a.slots.split(",")], [int(x) for x in a.prefetch.split(",")]):
         f = fd.compile_raw(raw, max_slots=ms_, prefetch=pf)
         for T, spt in itertools.product([int(x) for x in a.threads.split(",")], [int(x) for x in a.spt.split(",")]):
