@@ -204,15 +204,20 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
         }
     }
     const fdg::Lowered &low = h->low;
-    const int T = 128;
+    int T = 128;
+    if (const char *e = getenv("FDG_JIT_THREADS")) T = std::max(32, std::min(128, atoi(e) / 32 * 32));
     const int64_t per_block = (int64_t)T * spt;
-    // sub-batches keep the cross buffer bounded (about 1 GiB)
+    // sub-batches keep the cross buffer bounded (8 GiB unless FDG_JIT_CROSS_GB says otherwise)
     int64_t sub = batch;
     if (v->plan.n_cross > 0) {
-        const int64_t cap = std::max<int64_t>(per_block * ds.sm_count * 4, ((int64_t)1 << 30) / (8 * (int64_t)v->plan.n_cross));
+        double cross_gb = 8.0;
+        if (const char *e = getenv("FDG_JIT_CROSS_GB")) cross_gb = atof(e);
+        const int64_t cap = std::max<int64_t>(per_block * ds.sm_count * 4,
+                                              (int64_t)(cross_gb * (double)(1 << 30)) / (8 * (int64_t)v->plan.n_cross));
         sub = std::min<int64_t>(batch, cap / per_block * per_block);
     }
-    const int64_t max_grid = (sub + per_block - 1) / per_block;
+    int64_t max_grid = (sub + per_block - 1) / per_block;
+    if (v->plan.persistent) max_grid = std::min<int64_t>(max_grid, (int64_t)ds.sm_count * 16);
     const int64_t ld_cross = max_grid * per_block;
     if (v->plan.n_cross > 0) {
         const size_t need = (size_t)v->plan.n_cross * ld_cross * sizeof(double);
@@ -236,12 +241,12 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
             CUDA_TRY(cudaMalloc((void **)&ds.partial, need));
             ds.partial_bytes = need;
         }
-        CUDA_TRY(cudaMemsetAsync(ds.partial, 0, (size_t)rows * low.R * sizeof(double), stream));
+        if (!v->plan.persistent) CUDA_TRY(cudaMemsetAsync(ds.partial, 0, (size_t)rows * low.R * sizeof(double), stream));
         out = ds.partial;
     }
     for (int64_t b0 = 0; b0 < batch; b0 += sub) {
         const int64_t nb = std::min<int64_t>(sub, batch - b0);
-        const unsigned grid = (unsigned)((nb + per_block - 1) / per_block);
+        const unsigned grid = (unsigned)std::min<int64_t>((nb + per_block - 1) / per_block, max_grid);
         const void *p_leaf = static_cast<const char *>(leaf) + (size_t)b0 * 8;
         void *p_out = acc ? out : static_cast<void *>(static_cast<char *>(root) + (size_t)b0 * 8);
         void *p_cross = ds.cross;

@@ -20,6 +20,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <climits>
 #include <sstream>
@@ -41,6 +42,8 @@ struct Emitter {
     const Lowered &low;
     const int S;      // samples per thread: 1 or 2
     const bool acc;   // accumulate mode
+    bool persistent = false;  // accumulate mode, single kernel: grid-stride loop with per-thread running sums
+    int racc0 = -1;           // first register of the per-root running sums (persistent mode)
     std::ostringstream os;
     int nfd = 0, nrd = 16, np = 8, nr = 16;
     Emitter(const Lowered &l, int s, bool a) : low(l), S(s), acc(a) {}
@@ -134,6 +137,17 @@ struct Emitter {
             } else {
                 os << "\t@%p0 st.global.f64 [%rd" << a << "], " << fd(r, 0) << ";\n";
             }
+            return;
+        }
+        if (persistent) {
+            // running sum of this thread: samples in order, masked
+            const int s = nfd++, t = nfd++;
+            os << "\tselp.f64 %fd" << s << ", " << fd(r, 0) << ", 0d0000000000000000, %p0;\n";
+            if (S == 2) {
+                os << "\tselp.f64 %fd" << t << ", " << fd(r, 1) << ", 0d0000000000000000, %p1;\n";
+                os << "\tadd.rn.f64 %fd" << s << ", %fd" << s << ", %fd" << t << ";\n";
+            }
+            os << "\tadd.rn.f64 %fd" << racc0 + root << ", %fd" << racc0 + root << ", %fd" << s << ";\n";
             return;
         }
         // masked sum of the thread's samples, xor-tree over the warp, lane 0 adds into the warp's partial row
@@ -273,8 +287,16 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
     }
     plan.n_cross = n_cross;
     plan.seg.resize((size_t)nseg);
+    // a single accumulate kernel with few roots runs as a grid-stride loop: per-thread running sums in registers,
+    // one warp reduction per root at the very end (instead of one per tile)
+    plan.persistent = acc && nseg == 1 && low.R <= 32;
     for (int sg = 0; sg < nseg; ++sg) {
         Emitter e(low, spt, acc);
+        e.persistent = plan.persistent;
+        if (e.persistent) {
+            e.racc0 = e.nfd;
+            e.nfd += (int)low.R;
+        }
         std::ostringstream &os = e.os;
         const size_t lo = (size_t)sg * (size_t)seg_ops, hi = std::min(nops, lo + (size_t)seg_ops);
         std::vector<int32_t> reg_of(hi - lo, -1);          // register of a value defined in this segment
@@ -343,7 +365,9 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
         p << ".visible .entry " << js.name << "(\n"
           << "\t.param .u64 p_leaf, .param .u64 p_ld_leaf, .param .u64 p_cross, .param .u64 p_ld_cross,\n"
           << "\t.param .u64 p_out, .param .u64 p_ld_root, .param .u64 p_batch, .param .u64 p_nroots)\n"
-          << ".maxntid 128, 1, 1\n{\n";
+          << ".maxntid 128, 1, 1\n";
+        if (const char *mr = getenv("FDG_JIT_MAXNREG")) p << ".maxnreg " << atoi(mr) << "\n";
+        p << "{\n";
         p << "\t.reg .f64 %fd<" << e.nfd + 2 << ">;\n\t.reg .b64 %rd<" << e.nrd + 1 << ">;\n\t.reg .pred %p<" << e.np + 1
           << ">;\n\t.reg .b32 %r<" << e.nr + 1 << ">;\n";
         // %rd0 = first sample of the thread, %rd1 = leaf base, %rd2 = ld_leaf bytes, %rd3 = cross base, %rd4 = ld_cross bytes,
@@ -352,26 +376,48 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
           << "\tmul.wide.u32 %rd8, %r0, %r1;\n\tcvt.u64.u32 %rd9, %r2;\n\tadd.u64 %rd8, %rd8, %rd9;\n"  // global thread id
           << "\tmul.lo.u64 %rd0, %rd8, " << spt << ";\n"
           << "\tld.param.u64 %rd10, [p_batch];\n"
-          << "\tsetp.lt.s64 %p0, %rd0, %rd10;\n";  // first sample valid
+          << "\tld.param.u64 %rd2, [p_ld_leaf];\n\tshl.b64 %rd2, %rd2, 3;\n"
+          << "\tld.param.u64 %rd4, [p_ld_cross];\n\tshl.b64 %rd4, %rd4, 3;\n"
+          << "\tld.param.u64 %rd14, [p_out];\n\tcvta.to.global.u64 %rd14, %rd14;\n";
+        if (acc) {
+            p << "\tshr.u64 %rd15, %rd8, 5;\n\tld.param.u64 %rd5, [p_nroots];\n\tmul.lo.u64 %rd15, %rd15, %rd5;\n"
+              << "\tshl.b64 %rd15, %rd15, 3;\n\tadd.u64 %rd7, %rd14, %rd15;\n"
+              << "\tand.b32 %r3, %r2, 31;\n\tsetp.eq.u32 %p3, %r3, 0;\n";
+        } else {
+            p << "\tld.param.u64 %rd5, [p_ld_root];\n\tshl.b64 %rd5, %rd5, 3;\n";
+        }
+        if (e.persistent) {
+            for (int r = 0; r < (int)low.R; ++r) p << "\tmov.f64 %fd" << e.racc0 + r << ", 0d0000000000000000;\n";
+            p << "\tmov.u32 %r4, %nctaid.x;\n\tmul.wide.u32 %rd9, %r4, %r1;\n\tmul.lo.u64 %rd9, %rd9, " << spt << ";\n";  // grid stride
+            p << "FDG_LOOP:\n";
+        }
+        // per tile: validity predicates and the bases that depend on the sample index
+        p << "\tsetp.lt.s64 %p0, %rd0, %rd10;\n";  // first sample valid
         if (spt == 2)
             p << "\tadd.u64 %rd11, %rd0, 1;\n\tsetp.lt.s64 %p1, %rd11, %rd10;\n"  // both samples valid
               << "\tnot.pred %p4, %p1;\n\tand.pred %p2, %p0, %p4;\n";             // only the first one
         p << "\tselp.u64 %rd12, %rd0, 0, %p0;\n"  // inactive threads read sample 0: every address stays in bounds
           << "\tshl.b64 %rd12, %rd12, 3;\n"
           << "\tld.param.u64 %rd1, [p_leaf];\n\tcvta.to.global.u64 %rd1, %rd1;\n\tadd.u64 %rd1, %rd1, %rd12;\n"
-          << "\tld.param.u64 %rd2, [p_ld_leaf];\n\tshl.b64 %rd2, %rd2, 3;\n"
-          << "\tld.param.u64 %rd3, [p_cross];\n\tcvta.to.global.u64 %rd3, %rd3;\n"
-          << "\tshl.b64 %rd13, %rd0, 3;\n\tadd.u64 %rd3, %rd3, %rd13;\n"
-          << "\tld.param.u64 %rd4, [p_ld_cross];\n\tshl.b64 %rd4, %rd4, 3;\n"
-          << "\tld.param.u64 %rd14, [p_out];\n\tcvta.to.global.u64 %rd14, %rd14;\n";
-        if (!acc) {
-            p << "\tld.param.u64 %rd5, [p_ld_root];\n\tshl.b64 %rd5, %rd5, 3;\n\tadd.u64 %rd6, %rd14, %rd13;\n";
-        } else {
-            p << "\tshr.u64 %rd15, %rd8, 5;\n\tld.param.u64 %rd5, [p_nroots];\n\tmul.lo.u64 %rd15, %rd15, %rd5;\n"
-              << "\tshl.b64 %rd15, %rd15, 3;\n\tadd.u64 %rd7, %rd14, %rd15;\n"
-              << "\tand.b32 %r3, %r2, 31;\n\tsetp.eq.u32 %p3, %r3, 0;\n";
+          << "\tshl.b64 %rd13, %rd0, 3;\n";
+        if (n_cross > 0) p << "\tld.param.u64 %rd3, [p_cross];\n\tcvta.to.global.u64 %rd3, %rd3;\n\tadd.u64 %rd3, %rd3, %rd13;\n";
+        if (!acc) p << "\tadd.u64 %rd6, %rd14, %rd13;\n";
+        p << body;
+        if (e.persistent) {
+            p << "\tadd.u64 %rd0, %rd0, %rd9;\n\tsetp.lt.s64 %p5, %rd0, %rd10;\n\t@%p5 bra FDG_LOOP;\n";
+            for (int r = 0; r < (int)low.R; ++r) {
+                const int sreg = e.racc0 + r, t = e.nfd;
+                for (int m = 16; m >= 1; m >>= 1) {
+                    p << "\tmov.b64 {%r8, %r9}, %fd" << sreg << ";\n"
+                      << "\tshfl.sync.bfly.b32 %r10, %r8, " << m << ", 31, 0xffffffff;\n"
+                      << "\tshfl.sync.bfly.b32 %r11, %r9, " << m << ", 31, 0xffffffff;\n"
+                      << "\tmov.b64 %fd" << t << ", {%r10, %r11};\n"
+                      << "\tadd.rn.f64 %fd" << sreg << ", %fd" << sreg << ", %fd" << t << ";\n";
+                }
+                p << "\t@%p3 st.global.f64 [%rd7+" << r * 8 << "], %fd" << sreg << ";\n";
+            }
         }
-        p << body << "\tret;\n}\n";
+        p << "\tret;\n}\n";
         js.ptx = p.str();
     }
     (void)err;

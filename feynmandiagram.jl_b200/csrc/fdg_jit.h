@@ -20,6 +20,7 @@ struct JitPlan {
     int spt = 2;        // samples per thread
     bool acc = false;   // accumulate (per-warp partial sums) instead of per-sample roots
     int32_t n_cross = 0;  // rows of the cross-segment buffer
+    bool persistent = false;  // single accumulate kernel run as a grid-stride loop (per-thread running sums)
     std::vector<JitSegment> seg;
 };
 

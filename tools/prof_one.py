@@ -1,6 +1,5 @@
-"""Runs one configuration of the VM kernel a few times (for ncu captures)."""
+"""Runs one configuration a few times (for ncu captures)."""
 import argparse
-import math
 import os
 import sys
 
@@ -11,7 +10,7 @@ import torch  # noqa: E402
 import fdgraph_b200 as fd  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--workload", default="gv_ver4_o4")
+ap.add_argument("--workload", default="parquet_ver4_o4")
 ap.add_argument("--samples", type=int, default=1 << 17)
 ap.add_argument("--slots", type=int, default=0)
 ap.add_argument("--prefetch", type=int, default=0)
@@ -19,9 +18,11 @@ ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--spt", type=int, default=0)
 ap.add_argument("--mode", default="acc")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--backend", type=int, default=0)
+ap.add_argument("--jit-segment", type=int, default=0)
 a = ap.parse_args()
 raw = fd.RawGraph.load(os.path.join(ROOT, "workloads", a.workload + ".npz"))
-f = fd.compile_raw(raw, max_slots=a.slots, prefetch=a.prefetch)
+f = fd.compile_raw(raw, max_slots=a.slots, prefetch=a.prefetch, backend=a.backend, jit_segment=a.jit_segment)
 f.set_launch(a.threads, a.spt, 0)
 L, R, B = f.n_leaves, f.n_roots, a.samples
 leaf = torch.rand(L, B, dtype=torch.float64, device="cuda") + 0.5
@@ -37,4 +38,4 @@ for _ in range(a.reps):
         f.accumulate_device(leaf.data_ptr(), B, B, acc.data_ptr(), s)
     e1.record()
     torch.cuda.synchronize()
-    print(f"{a.workload} B={B} slots={f.stats['n_slots']} {e0.elapsed_time(e1):.3f} ms  {B / e0.elapsed_time(e1) / 1e3:.2f} Msamples/s")
+    print(f"{a.workload} B={B} {e0.elapsed_time(e1):.3f} ms  {B / e0.elapsed_time(e1) / 1e3:.2f} Msamples/s launches={f.launches}")
