@@ -33,13 +33,13 @@ class GraphDesc(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("max_slots", C.c_int32), ("prefetch", C.c_int32), ("schedule", C.c_int32),
-                ("backend", C.c_int32), ("jit_segment", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("backend", C.c_int32), ("jit_segment", C.c_int32), ("no_cse", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class Stats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in (
         "n_leaves", "n_inner", "n_roots", "n_operands", "n_packets", "n_slots", "n_scratch", "leaf_loads",
-        "flops_add", "flops_mul", "bytes_in", "bytes_out", "max_depth")] + [("reserved", C.c_int64 * 3)]
+        "flops_add", "flops_mul", "bytes_in", "bytes_out", "max_depth", "cse_removed")] + [("reserved", C.c_int64 * 2)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved"}
@@ -102,7 +102,7 @@ def _ptr(a: np.ndarray, ctype):
 
 
 def compile_raw(raw, dtype: int = FDG_F64, max_slots: int = 0, prefetch: int = 0, schedule: int = 0, backend: int = 0,
-                jit_segment: int = 0) -> C.c_void_p:
+                jit_segment: int = 0, cse: bool = True) -> C.c_void_p:
     """fdg_compile on a RawGraph; returns the opaque handle."""
     L = lib()
     raw.validate_dtypes()
@@ -118,7 +118,7 @@ def compile_raw(raw, dtype: int = FDG_F64, max_slots: int = 0, prefetch: int = 0
     d.n_roots, d.root_id = int(raw.root_id.shape[0]), _ptr(raw.root_id, C.c_int64)
     o = Options()
     o.dtype, o.max_slots, o.prefetch, o.schedule = int(dtype), int(max_slots), int(prefetch), int(schedule)
-    o.backend, o.jit_segment = int(backend), int(jit_segment)
+    o.backend, o.jit_segment, o.no_cse = int(backend), int(jit_segment), int(not cse)
     h = C.c_void_p()
     check(L.fdg_compile(C.byref(d), C.byref(o), C.byref(h)))
     return h

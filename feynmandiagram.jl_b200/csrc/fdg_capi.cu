@@ -345,7 +345,7 @@ int fdg_compile(const fdg_graph_desc *graph, const fdg_options *opts, fdg_handle
     fdg_options o;
     std::memset(&o, 0, sizeof(o));
     if (opts) o = *opts;
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 1; ++i)
         if (o.reserved[i] != 0) return fail(FDG_ERR_BAD_ARG, "fdg_options.reserved must be zero");
     if (o.backend < FDG_BACKEND_AUTO || o.backend > FDG_BACKEND_JIT) return fail(FDG_ERR_BAD_ARG, "unknown backend");
     fdg_program *p = new (std::nothrow) fdg_program();
@@ -443,6 +443,7 @@ int fdg_stats(fdg_handle h, fdg_stats_t *out) {
     out->bytes_in = (c ? 16 : 8) * l.L;
     out->bytes_out = (c ? 16 : 8) * l.R;
     out->max_depth = l.max_depth;
+    out->cse_removed = l.cse_removed;
     return FDG_OK;
 }
 

@@ -198,7 +198,15 @@ int build_statements(const fdg_graph_desc &g, std::vector<Stmt> &st, std::vector
         err = "too many roots for the packet encoding";
         return FDG_ERR_UNSUPPORTED;
     }
-    // liveness and use counts (operands always precede their users)
+    return FDG_OK;
+}
+
+// liveness and use counts (operands always precede their users)
+void mark_live(std::vector<Stmt> &st, const std::vector<Operand> &ops) {
+    for (Stmt &s : st) {
+        s.live = false;
+        s.uses = 0;
+    }
     for (int64_t v = (int64_t)st.size() - 1; v >= 0; --v) {
         Stmt &s = st[(size_t)v];
         if (s.root >= 0) s.live = true;
@@ -209,7 +217,54 @@ int build_statements(const fdg_graph_desc &g, std::vector<Stmt> &st, std::vector
             c.uses++;
         }
     }
-    return FDG_OK;
+}
+
+// Common-subexpression elimination on the emitted function (the hash-based analogue of the reference's
+// optimize!(level=1) / remove_duplicated_nodes!, src/computational_graph/optimize.jl:345-390): two statements with the
+// same operator and the same (operand, factor) sequence compute the same bits, so later copies read the first one.
+// Operand ORDER is part of the key -- the fold order defines the rounding -- so nothing is re-associated.
+int64_t eliminate_common_subexpressions(std::vector<Stmt> &st, std::vector<Operand> &ops) {
+    std::vector<int32_t> canon(st.size());
+    std::unordered_map<uint64_t, std::vector<int32_t>> buckets;
+    buckets.reserve(st.size() * 2 + 1);
+    int64_t removed = 0;
+    for (int32_t v = 0; v < (int32_t)st.size(); ++v) {
+        Stmt &s = st[(size_t)v];
+        canon[(size_t)v] = v;
+        if (s.op < 0) continue;
+        uint64_t h = 1469598103934665603ull ^ (uint64_t)(s.op * 131 + s.pow_n);
+        for (int32_t i = 0; i < s.count; ++i) {
+            Operand &o = ops[(size_t)(s.first + i)];
+            o.val = canon[(size_t)o.val];
+            uint64_t fb;
+            std::memcpy(&fb, &o.f, 8);
+            h = (h ^ (uint64_t)(uint32_t)o.val) * 1099511628211ull;
+            h = (h ^ fb) * 1099511628211ull;
+        }
+        if (!s.live) continue;
+        auto &b = buckets[h];
+        int32_t found = -1;
+        for (int32_t u : b) {
+            const Stmt &t = st[(size_t)u];
+            if (t.op != s.op || t.pow_n != s.pow_n || t.count != s.count) continue;
+            bool same = true;
+            for (int32_t i = 0; i < s.count && same; ++i) {
+                const Operand &x = ops[(size_t)(s.first + i)], &y = ops[(size_t)(t.first + i)];
+                same = x.val == y.val && std::memcmp(&x.f, &y.f, 8) == 0;
+            }
+            if (same) {
+                found = u;
+                break;
+            }
+        }
+        if (found >= 0 && s.root < 0) {
+            canon[(size_t)v] = found;  // every later reader uses the first copy; this statement becomes dead
+            ++removed;
+        } else if (found < 0) {
+            b.push_back(v);
+        }
+    }
+    return removed;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -798,6 +853,7 @@ int lower(const fdg_graph_desc &g, const fdg_options &opt, Lowered &out, std::st
     std::vector<Operand> &ops = out.ops;
     int rc = build_statements(g, st, ops, out, err);
     if (rc != FDG_OK) return rc;
+    mark_live(st, ops);
 
     // algorithmic operation counts of the reference function (count_operation, tree_properties.jl:165-185,
     // plus one multiply per factor != 1 and N-1 multiplies per Power{N}); independent of how the VM evaluates it
@@ -809,6 +865,11 @@ int lower(const fdg_graph_desc &g, const fdg_options &opt, Lowered &out, std::st
         if (s.op == FDG_OP_SUM) out.adds_vv += s.count - 1;
         if (s.op == FDG_OP_PROD) out.muls_vv += s.count - 1;
         if (s.op == FDG_OP_POWER) out.pow_muls += s.pow_n - 1;
+    }
+
+    if (opt.no_cse == 0) {
+        out.cse_removed = eliminate_common_subexpressions(st, ops);
+        mark_live(st, ops);
     }
 
     int32_t max_slots = opt.max_slots > 0 ? opt.max_slots : 48;

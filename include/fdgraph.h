@@ -93,7 +93,9 @@ typedef struct fdg_options {
                              before the fold that reads them (emitter order); 1 = lazy: inside it */
     int32_t backend;      /* FDG_BACKEND_AUTO (0), FDG_BACKEND_VM (1), FDG_BACKEND_JIT (2)            */
     int32_t jit_segment;  /* operations per specialised kernel (0 = default)                   */
-    int32_t reserved[2];  /* must be zero                                                      */
+    int32_t no_cse;       /* 1 = keep duplicate statements (default 0: common sub-expressions are
+                             evaluated once; bit-identical, optimize.jl:345-390 done by hashing)      */
+    int32_t reserved[1];  /* must be zero                                                      */
 } fdg_options;
 
 typedef struct fdg_program *fdg_handle;
@@ -113,7 +115,8 @@ typedef struct fdg_stats_t {
     int64_t bytes_in;       /* algorithmic input bytes per sample  = sizeof(W) * L             */
     int64_t bytes_out;      /* algorithmic output bytes per sample = sizeof(W) * R (eval mode) */
     int64_t max_depth;      /* accumulator nesting depth of the program                        */
-    int64_t reserved[3];
+    int64_t cse_removed;    /* statements removed as copies of an earlier statement            */
+    int64_t reserved[2];
 } fdg_stats_t;
 
 int fdg_abi_version(void);

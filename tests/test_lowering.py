@@ -12,9 +12,9 @@ from fdgraph_b200 import _capi
 from oracle import oracle as O
 
 
-def _check(roots, dtype=np.float64, max_slots=0, prefetch=0, batch=7, signed=True, root=None):
+def _check(roots, dtype=np.float64, max_slots=0, prefetch=0, batch=7, signed=True, root=None, cse=True, schedule=0):
     raw, nodes = fd.flatten(roots, root)
-    ev = fd.compile_raw(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch)
+    ev = fd.compile_raw(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch, cse=cse, schedule=schedule)
     orc = O.Oracle(raw)
     assert ev.n_leaves == orc.n_leaves and (ev.leaf_nodes == orc.leaf_nodes).all()
     assert ev.last_root == orc.last_root
@@ -76,7 +76,7 @@ def test_sum_of_products_shape():
 
 @pytest.mark.parametrize("term_len", [1, 2, 3, 4, 5, 7, 8, 11, 13])
 def test_term_blocks_every_operand_count(term_len):
-    ev, cnt = _check(graphgen.sum_of_products(6, n_leaves=30, n_terms=70, term_len=term_len, n_roots=2), max_slots=20)
+    ev, cnt = _check(graphgen.sum_of_products(6, n_leaves=30, n_terms=70, term_len=term_len, n_roots=2), max_slots=20, cse=False)
     if term_len <= 11:
         assert cnt["terms"] == 2 * 70
 
@@ -115,6 +115,25 @@ def test_specialised_kernels_assemble_without_a_gpu(name, acc):
         assert ".target sm_100a" in ptx and "fma" not in ptx
         assert "mul.rn.f64" in ptx
         assert "registers" in log
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("cse,schedule", [(False, 0), (False, 1), (True, 1)])
+def test_lowering_options_do_not_change_values(seed, cse, schedule):
+    _check(graphgen.random_dag(500 + seed, n_leaves=8, n_inner=90, n_roots=3), cse=cse, schedule=schedule)
+
+
+def test_common_subexpressions_are_evaluated_once():
+    a, b, c = fd.Graph([]), fd.Graph([]), fd.Graph([])
+    def term():
+        return fd.Graph([a, b], operator=fd.Prod(), subgraph_factors=[1.0, -2.0])  # three distinct node objects, same expression
+    top = fd.Graph([term(), fd.Graph([term(), c], operator=fd.Prod()), term()], operator=fd.Sum(), subgraph_factors=[1.0, 3.0, 0.5])
+    ev, _ = _check([top])
+    assert ev.stats["cse_removed"] == 2 and ev.stats["n_inner"] == 5
+    ev2, _ = _check([top], cse=False)
+    assert ev2.stats["cse_removed"] == 0
+    # flop counts are the reference function's, whatever the back end saves
+    assert ev.stats["flops_mul"] == ev2.stats["flops_mul"] and ev.stats["flops_add"] == ev2.stats["flops_add"]
 
 
 def test_stats_counts_match_reference_operation_count():
