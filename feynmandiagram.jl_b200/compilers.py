@@ -51,7 +51,7 @@ class Evaluator:
     """The callable returned by :func:`compile` -- stands in for the generated ``eval_graph!``."""
 
     def __init__(self, raw: RawGraph, dtype=np.float64, max_slots: int = 0, prefetch: int = 0, schedule: int = 0,
-                 backend: int = 0, jit_segment: int = 0, cse: bool = True):
+                 backend: int = 0, jit_segment: int = 0, cse: bool = False):
         self.dtype = np.dtype(dtype)
         if self.dtype not in _DTYPES:
             # static.jl:151  error("Unsupported type")
@@ -182,7 +182,7 @@ class Evaluator:
 
 def compile(graphs: Sequence[Graph], root: Optional[Sequence[int]] = None, *, dtype=np.float64,
             max_slots: int = 0, prefetch: int = 0, schedule: int = 0, backend: int = 0,
-            jit_segment: int = 0, cse: bool = True) -> Tuple[Evaluator, Dict[int, Graph]]:
+            jit_segment: int = 0, cse: bool = False) -> Tuple[Evaluator, Dict[int, Graph]]:
     """``Compilers.compile(graphs; root)`` (static.jl:221-227) -> ``(eval_graph, leafmap)``.
 
     ``leafmap[k]`` is the leaf Graph whose value is read from column ``k`` of ``leafVal`` (0-based
@@ -196,7 +196,7 @@ def compile(graphs: Sequence[Graph], root: Optional[Sequence[int]] = None, *, dt
 
 
 def compile_raw(raw: RawGraph, *, dtype=np.float64, max_slots: int = 0, prefetch: int = 0, schedule: int = 0,
-                backend: int = 0, jit_segment: int = 0, cse: bool = True) -> Evaluator:
+                backend: int = 0, jit_segment: int = 0, cse: bool = False) -> Evaluator:
     """Compile an already flattened graph (e.g. a workload file written by another host)."""
     return Evaluator(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch, schedule=schedule, backend=backend,
                      jit_segment=jit_segment, cse=cse)

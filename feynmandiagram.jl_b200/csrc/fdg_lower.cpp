@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <unordered_map>
@@ -223,8 +224,9 @@ void mark_live(std::vector<Stmt> &st, const std::vector<Operand> &ops) {
 // optimize!(level=1) / remove_duplicated_nodes!, src/computational_graph/optimize.jl:345-390): two statements with the
 // same operator and the same (operand, factor) sequence compute the same bits, so later copies read the first one.
 // Operand ORDER is part of the key -- the fold order defines the rounding -- so nothing is re-associated.
-int64_t eliminate_common_subexpressions(std::vector<Stmt> &st, std::vector<Operand> &ops) {
+int64_t eliminate_common_subexpressions(std::vector<Stmt> &st, std::vector<Operand> &ops, int64_t min_cost) {
     std::vector<int32_t> canon(st.size());
+    std::vector<int64_t> cost(st.size(), 0);  // operations needed to recompute the statement from leaves
     std::unordered_map<uint64_t, std::vector<int32_t>> buckets;
     buckets.reserve(st.size() * 2 + 1);
     int64_t removed = 0;
@@ -241,7 +243,11 @@ int64_t eliminate_common_subexpressions(std::vector<Stmt> &st, std::vector<Opera
             h = (h ^ (uint64_t)(uint32_t)o.val) * 1099511628211ull;
             h = (h ^ fb) * 1099511628211ull;
         }
-        if (!s.live) continue;
+        int64_t c = s.op == FDG_OP_POWER ? s.pow_n : s.count;
+        for (int32_t i = 0; i < s.count; ++i) c += cost[(size_t)ops[(size_t)(s.first + i)].val] + (ops[(size_t)(s.first + i)].f != 1.0);
+        cost[(size_t)v] = std::min<int64_t>(c, 1 << 30);
+        // a cheap copy is cheaper to recompute where it is needed than to keep alive (registers, slots, cross buffer)
+        if (!s.live || cost[(size_t)v] < min_cost) continue;
         auto &b = buckets[h];
         int32_t found = -1;
         for (int32_t u : b) {
@@ -867,8 +873,10 @@ int lower(const fdg_graph_desc &g, const fdg_options &opt, Lowered &out, std::st
         if (s.op == FDG_OP_POWER) out.pow_muls += s.pow_n - 1;
     }
 
-    if (opt.no_cse == 0) {
-        out.cse_removed = eliminate_common_subexpressions(st, ops);
+    if (opt.cse != 0) {
+        int64_t min_cost = 6;
+        if (const char *e = getenv("FDG_CSE_MIN_COST")) min_cost = atoll(e);
+        out.cse_removed = eliminate_common_subexpressions(st, ops, min_cost);
         mark_live(st, ops);
     }
 

@@ -93,8 +93,10 @@ typedef struct fdg_options {
                              before the fold that reads them (emitter order); 1 = lazy: inside it */
     int32_t backend;      /* FDG_BACKEND_AUTO (0), FDG_BACKEND_VM (1), FDG_BACKEND_JIT (2)            */
     int32_t jit_segment;  /* operations per specialised kernel (0 = default)                   */
-    int32_t no_cse;       /* 1 = keep duplicate statements (default 0: common sub-expressions are
-                             evaluated once; bit-identical, optimize.jl:345-390 done by hashing)      */
+    int32_t cse;          /* 1 = evaluate common sub-expressions once (hash-based analogue of
+                             optimize!(level=1), optimize.jl:345-390; bit-identical).  Default 0: on
+                             the memory-bound order-4 graphs sharing more values costs more traffic
+                             than the saved arithmetic                           */
     int32_t reserved[1];  /* must be zero                                                      */
 } fdg_options;
 

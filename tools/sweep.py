@@ -41,7 +41,7 @@ def main():
         import time
 
         for seg, spt in itertools.product([int(x) for x in a.jit_segment.split(",")], [int(x) for x in a.spt.split(",")]):
-            f = fd.compile_raw(raw, backend=2, jit_segment=seg)
+            f = fd.compile_raw(raw, backend=2, jit_segment=seg, cse=os.environ.get("FDG_CSE") is not None)
             f.set_launch(0, spt, 0)
             t0 = time.time()
             info = f.jit_prepare(spt, a.mode != "eval")
@@ -64,7 +64,7 @@ def main():
                                   **info)), flush=True)
         return
     for ms_, pf in itertools.product([int(x) for x in a.slots.split(",")], [int(x) for x in a.prefetch.split(",")]):
-        f = fd.compile_raw(raw, max_slots=ms_, prefetch=pf)
+        f = fd.compile_raw(raw, max_slots=ms_, prefetch=pf, backend=1)
         for T, spt in itertools.product([int(x) for x in a.threads.split(",")], [int(x) for x in a.spt.split(",")]):
             try:
                 f.set_launch(T, spt, 0)
