@@ -125,7 +125,8 @@ def cpu_reference(raw, dtype, target_seconds, nthreads=0):
     from oracle import oracle as O
 
     orc = O.Oracle(raw)
-    cores = O.lib().oracle_max_threads() if nthreads <= 0 else nthreads
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ask the scheduler, not OpenMP)
+    cores = len(os.sched_getaffinity(0)) if nthreads <= 0 else nthreads
     rng = np.random.default_rng(1234)
     npdt = np.float64 if dtype == "f64" else np.complex128
 

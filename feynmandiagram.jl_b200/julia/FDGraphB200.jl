@@ -1,0 +1,146 @@
+# FDGraphB200.jl -- the Julia side of the drop-in: `ccall` shim over libfdgraph.so (include/fdgraph.h).
+#
+# UNTESTED: there is no julia binary in the build image or on the GPU box (SURVEY.md D2).  The shim is kept
+# deliberately thin -- it only flattens Graph objects through the four getters the reference emitter itself uses
+# (id / operator / subgraphs / subgraph_factors, src/backend/static.jl:106-124) and forwards pointers -- and it is
+# mirrored 1:1 by the Python ctypes binding (feynmandiagram.jl_b200/_capi.py), which IS tested against the library.
+#
+# Usage (drop-in for Compilers.compile / eval_graph!, src/backend/static.jl:221-227):
+#     using FeynmanDiagram, CUDA
+#     include("FDGraphB200.jl")
+#     eval_graph!, leafmap = FDGraphB200.compile(diags)          # same (callable, leafmap::Dict{Int,Graph})
+#     leafVal = CUDA.rand(Float64, B, length(leafmap)) .+ 0.5    # B x L, column-major: batch index unit-stride
+#     root    = CUDA.zeros(Float64, B, length(diags))
+#     eval_graph!(root, leafVal)                                 # all B samples in one call
+module FDGraphB200
+
+using FeynmanDiagram
+import FeynmanDiagram.ComputationalGraphs: AbstractGraph, id, operator, subgraphs, subgraph_factors, Sum, Prod, Power, Unitary
+
+const LIB = get(ENV, "FDGRAPH_LIB", joinpath(@__DIR__, "..", "libfdgraph.so"))
+
+struct GraphDesc
+    n_nodes::Int64
+    n_edges::Int64
+    node_id::Ptr{Int64}
+    node_op::Ptr{Int32}
+    node_pow::Ptr{Int32}
+    child_ptr::Ptr{Int64}
+    child_node::Ptr{Int32}
+    child_factor::Ptr{Float64}
+    n_graphs::Int64
+    graphs::Ptr{Int32}
+    n_roots::Int64
+    root_id::Ptr{Int64}
+end
+
+struct Options
+    dtype::Int32
+    max_slots::Int32
+    prefetch::Int32
+    schedule::Int32
+    backend::Int32
+    jit_segment::Int32
+    cse::Int32
+    reserved::Int32
+end
+
+opcode(::Type{Unitary}) = Int32(0)
+opcode(::Type{Sum}) = Int32(1)
+opcode(::Type{Prod}) = Int32(2)
+opcode(::Type{Power{N}}) where {N} = Int32(3)
+opcode(op) = error("Static representation for computational graph nodes with operator $(op) not yet implemented!")
+pow_n(::Type{Power{N}}) where {N} = Int32(N)
+pow_n(_) = Int32(0)
+
+check(rc) = rc == 0 || error("libfdgraph: " * unsafe_string(ccall((:fdg_last_error, LIB), Cstring, ())))
+
+mutable struct Evaluator
+    handle::Ptr{Cvoid}
+    n_leaves::Int
+    n_roots::Int
+    last_root::Int
+    function Evaluator(h, L, R, last)
+        ev = new(h, L, R, last)
+        finalizer(e -> ccall((:fdg_destroy, LIB), Cint, (Ptr{Cvoid},), e.handle), ev)
+        return ev
+    end
+end
+
+"""
+    compile(graphs; root=[id(g) for g in graphs], dtype=Float64) -> (eval_graph!, leafmap)
+
+Same contract as `Compilers.compile` (static.jl:221-227): `leafmap[k]` is the leaf graph whose value is column `k`
+of `leafVal` (1-based, identical numbering to the reference).
+"""
+function compile(graphs::AbstractVector{G}; root::AbstractVector{Int}=[id(g) for g in graphs], dtype::DataType=Float64) where {G<:AbstractGraph}
+    # one entry per node OBJECT, children before parents (any order is accepted by the library)
+    nodes = G[]
+    index = IdDict{G,Int32}()
+    function visit(g)
+        haskey(index, g) && return
+        for s in subgraphs(g)
+            visit(s)
+        end
+        push!(nodes, g)
+        index[g] = Int32(length(nodes) - 1)
+    end
+    foreach(visit, graphs)
+    node_id = Int64[id(g) for g in nodes]
+    node_op = Int32[isempty(subgraphs(g)) && !(operator(g) <: Union{Sum,Prod,Power,Unitary}) ? 0 : opcode(operator(g)) for g in nodes]
+    node_pow = Int32[pow_n(operator(g)) for g in nodes]
+    child_ptr = Int64[0]
+    child_node = Int32[]
+    child_factor = Float64[]
+    for g in nodes
+        for (s, f) in zip(subgraphs(g), subgraph_factors(g))
+            push!(child_node, index[s])
+            push!(child_factor, Float64(f))
+        end
+        push!(child_ptr, length(child_node))
+    end
+    gidx = Int32[index[g] for g in graphs]
+    rootid = Int64.(root)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve node_id node_op node_pow child_ptr child_node child_factor gidx rootid begin
+        desc = Ref(GraphDesc(length(nodes), length(child_node), pointer(node_id), pointer(node_op), pointer(node_pow),
+            pointer(child_ptr), pointer(child_node), pointer(child_factor), length(gidx), pointer(gidx), length(rootid), pointer(rootid)))
+        opts = Ref(Options(dtype <: Complex ? 1 : 0, 0, 0, 0, 0, 0, 0, 0))
+        check(ccall((:fdg_compile, LIB), Cint, (Ref{GraphDesc}, Ref{Options}, Ref{Ptr{Cvoid}}), desc, opts, h))
+    end
+    stats = zeros(Int64, 16)
+    check(ccall((:fdg_stats, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), h[], stats))
+    L, R = Int(stats[1]), Int(stats[3])
+    leaf_node = zeros(Int32, max(L, 1))
+    check(ccall((:fdg_leafmap, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), h[], leaf_node))
+    last = Ref{Int32}(0)
+    check(ccall((:fdg_last_root, LIB), Cint, (Ptr{Cvoid}, Ref{Int32}), h[], last))
+    leafmap = Dict{Int,G}(k => nodes[leaf_node[k]+1] for k in 1:L)
+    ev = Evaluator(h[], L, R, Int(last[]) + 1)
+    return (rootv, leafVal) -> eval_graph!(ev, rootv, leafVal), leafmap
+end
+
+# device matrices (CuArray{T,2}, B x L and B x R, column-major): one launch sequence for the whole batch
+function eval_graph!(ev::Evaluator, root::AbstractMatrix, leafVal::AbstractMatrix; stream::Ptr{Cvoid}=C_NULL)
+    B = size(leafVal, 1)
+    size(root, 1) == B || throw(DimensionMismatch("root and leafVal must have the same number of rows (samples)"))
+    (size(leafVal, 2) >= ev.n_leaves && size(root, 2) >= ev.n_roots) || throw(BoundsError())
+    if leafVal isa Array   # host matrices: fdg_eval_host does H2D / kernel / D2H
+        check(ccall((:fdg_eval_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64),
+            ev.handle, pointer(leafVal), stride(leafVal, 2), pointer(root), stride(root, 2), B))
+    else                   # CuArray: pointer() gives a CuPtr, reinterpret as the raw device address
+        check(ccall((:fdg_eval, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}),
+            ev.handle, reinterpret(Ptr{Cvoid}, pointer(leafVal)), stride(leafVal, 2), reinterpret(Ptr{Cvoid}, pointer(root)),
+            stride(root, 2), B, stream))
+    end
+    return ev.last_root >= 1 ? view(root, :, ev.last_root) : nothing
+end
+
+# vectors are the B = 1 case of the reference's generated function: returns the last root value (static.jl:127,131)
+function eval_graph!(ev::Evaluator, root::AbstractVector, leafVal::AbstractVector)
+    r = reshape(root, 1, :)
+    eval_graph!(ev, r, reshape(leafVal, 1, :))
+    return ev.last_root >= 1 ? root[ev.last_root] : nothing
+end
+
+end # module
