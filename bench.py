@@ -218,9 +218,9 @@ def main():
     es = 8 if a.dtype == "f64" else 16
     f = fd.compile_raw(raw, dtype=npdt, max_slots=a.max_slots, prefetch=a.prefetch, backend=a.backend, jit_segment=a.jit_segment)
     jit_info = None
-    if a.backend != 1 and a.dtype == "f64":
+    if a.backend != 1:
         try:
-            jit_info = f.jit_prepare(2 if st_small(f) else 1, True)
+            jit_info = f.jit_prepare(2 if (st_small(f) and a.dtype == "f64") else 1, True)
         except Exception:  # noqa: BLE001  (AUTO falls back to the VM inside the library)
             jit_info = None
     f.set_launch(a.threads, a.spt, 0)
@@ -300,7 +300,7 @@ def main():
     flops_launch = (st["flops_add"] + st["flops_mul"]) * res
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and a.dtype == "f64" and jit_info is not None:
         tj = json.load(open(tp)).get(a.workload)
         if tj and tj.get("resident_samples"):
             traffic = tj["dram_bytes_per_launch"] * res / tj["resident_samples"]

@@ -204,6 +204,8 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
         }
     }
     const fdg::Lowered &low = h->low;
+    const int W = low.dtype == FDG_C128 ? 2 : 1;
+    const size_t es = 8 * (size_t)W;
     int T = 128;
     if (const char *e = getenv("FDG_JIT_THREADS")) T = std::max(32, std::min(128, atoi(e) / 32 * 32));
     const int64_t per_block = (int64_t)T * spt;
@@ -213,14 +215,14 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
         double cross_gb = 8.0;
         if (const char *e = getenv("FDG_JIT_CROSS_GB")) cross_gb = atof(e);
         const int64_t cap = std::max<int64_t>(per_block * ds.sm_count * 4,
-                                              (int64_t)(cross_gb * (double)(1 << 30)) / (8 * (int64_t)v->plan.n_cross));
+                                              (int64_t)(cross_gb * (double)(1 << 30)) / ((int64_t)es * (int64_t)v->plan.n_cross));
         sub = std::min<int64_t>(batch, cap / per_block * per_block);
     }
     int64_t max_grid = (sub + per_block - 1) / per_block;
     if (v->plan.persistent) max_grid = std::min<int64_t>(max_grid, (int64_t)ds.sm_count * 16);
     const int64_t ld_cross = max_grid * per_block;
     if (v->plan.n_cross > 0) {
-        const size_t need = (size_t)v->plan.n_cross * ld_cross * sizeof(double);
+        const size_t need = (size_t)v->plan.n_cross * ld_cross * es;
         if (need > ds.cross_bytes) {
             if (ds.cross) CUDA_TRY(cudaFree(ds.cross));
             ds.cross = nullptr;
@@ -233,7 +235,7 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
     void *out = root;
     if (acc) {
         rows = max_grid * (T / 32);
-        const size_t need = std::max<size_t>((size_t)rows * low.R * sizeof(double), 256);
+        const size_t need = std::max<size_t>((size_t)rows * low.R * W * sizeof(double), 256);
         if (need > ds.partial_bytes) {
             if (ds.partial) CUDA_TRY(cudaFree(ds.partial));
             ds.partial = nullptr;
@@ -241,16 +243,16 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
             CUDA_TRY(cudaMalloc((void **)&ds.partial, need));
             ds.partial_bytes = need;
         }
-        if (!v->plan.persistent) CUDA_TRY(cudaMemsetAsync(ds.partial, 0, (size_t)rows * low.R * sizeof(double), stream));
+        if (!v->plan.persistent) CUDA_TRY(cudaMemsetAsync(ds.partial, 0, (size_t)rows * low.R * W * sizeof(double), stream));
         out = ds.partial;
     }
     for (int64_t b0 = 0; b0 < batch; b0 += sub) {
         const int64_t nb = std::min<int64_t>(sub, batch - b0);
         const unsigned grid = (unsigned)std::min<int64_t>((nb + per_block - 1) / per_block, max_grid);
-        const void *p_leaf = static_cast<const char *>(leaf) + (size_t)b0 * 8;
-        void *p_out = acc ? out : static_cast<void *>(static_cast<char *>(root) + (size_t)b0 * 8);
+        const void *p_leaf = static_cast<const char *>(leaf) + (size_t)b0 * es;
+        void *p_out = acc ? out : static_cast<void *>(static_cast<char *>(root) + (size_t)b0 * es);
         void *p_cross = ds.cross;
-        long long a_ld_leaf = ld_leaf, a_ld_cross = ld_cross, a_ld_root = ld_root, a_batch = nb, a_nroots = low.R;
+        long long a_ld_leaf = ld_leaf, a_ld_cross = ld_cross, a_ld_root = ld_root, a_batch = nb, a_nroots = low.R * W;
         void *args[] = {(void *)&p_leaf, &a_ld_leaf, &p_cross, &a_ld_cross, &p_out, &a_ld_root, &a_batch, &a_nroots};
         for (size_t sg = 0; sg < kern.size(); ++sg) {
             CUDA_TRY(cudaLaunchKernel((const void *)kern[sg], dim3(grid), dim3(T), args, 0, stream));
@@ -258,7 +260,7 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
         }
     }
     if (acc && low.R > 0) {
-        fdg::fdg_reduce_partials<<<(int)low.R, 256, 0, stream>>>(ds.partial, rows, (int)low.R, static_cast<double *>(root));
+        fdg::fdg_reduce_partials<<<(int)low.R * W, 256, 0, stream>>>(ds.partial, rows, (int)low.R * W, static_cast<double *>(root));
         CUDA_TRY(cudaGetLastError());
         h->launches++;
     }
@@ -291,8 +293,15 @@ int do_eval(fdg_program *h, const void *leaf, int64_t ld_leaf, void *root, int64
     args.ld_root = ld_root;
     args.batch = batch;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int backend = h->backend;
+    if (const char *e = getenv("FDG_BACKEND")) backend = atoi(e);
     if (cplx) {
-        if (h->backend == FDG_BACKEND_JIT) return fail(FDG_ERR_UNSUPPORTED, "the specialised back end is Float64 only");
+        if (backend != FDG_BACKEND_VM && low.N + low.R > 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            rc = jit_launch(h, *ds, dev, 1, accumulate, leaf, ld_leaf, root, ld_root, batch, st);
+            if (rc == FDG_OK || backend == FDG_BACKEND_JIT) return rc;
+        }
         return accumulate ? launch_variant<fdg::VCplx, true>(h, *ds, args, batch, st)
                           : launch_variant<fdg::VCplx, false>(h, *ds, args, batch, st);
     }
@@ -304,8 +313,6 @@ int do_eval(fdg_program *h, const void *leaf, int64_t ld_leaf, void *root, int64
         const bool root_ok = accumulate || low.R == 0 || (((uintptr_t)root % 16 == 0) && (ld_root % 2 == 0));
         return leaf_ok && root_ok;
     };
-    int backend = h->backend;
-    if (const char *e = getenv("FDG_BACKEND")) backend = atoi(e);
     if (backend != FDG_BACKEND_VM && low.N + low.R > 0) {
         // two samples per thread pay off only for small programs (everything stays in registers); big ones want
         // the registers for the program's own live values

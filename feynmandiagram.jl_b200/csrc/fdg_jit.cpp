@@ -40,8 +40,9 @@ std::string dimm(double f) {  // exact double immediate
 
 struct Emitter {
     const Lowered &low;
-    const int S;      // samples per thread: 1 or 2
+    const int S;      // f64 registers per value: samples per thread (1 or 2), or 2 = (re, im) of ONE ComplexF64 sample
     const bool acc;   // accumulate mode
+    bool cplx = false;
     bool persistent = false;  // accumulate mode, single kernel: grid-stride loop with per-thread running sums
     int racc0 = -1;           // first register of the per-root running sums (persistent mode)
     std::ostringstream os;
@@ -56,7 +57,41 @@ struct Emitter {
     std::string fd(int r, int i) const { return "%fd" + std::to_string(r + i); }
 
     void binop(const char *op, int dst, int a, int b) {
+        if (cplx && op[0] == 'm') {
+            // Julia *(z::Complex, w::Complex) = Complex(re(z)re(w) - im(z)im(w), re(z)im(w) + im(z)re(w)), nothing fused
+            const int t = nfd;
+            nfd += 4;
+            os << "\tmul.rn.f64 %fd" << t << ", " << fd(a, 0) << ", " << fd(b, 0) << ";\n";
+            os << "\tmul.rn.f64 %fd" << t + 1 << ", " << fd(a, 1) << ", " << fd(b, 1) << ";\n";
+            os << "\tmul.rn.f64 %fd" << t + 2 << ", " << fd(a, 0) << ", " << fd(b, 1) << ";\n";
+            os << "\tmul.rn.f64 %fd" << t + 3 << ", " << fd(a, 1) << ", " << fd(b, 0) << ";\n";
+            os << "\tsub.rn.f64 " << fd(dst, 0) << ", %fd" << t << ", %fd" << t + 1 << ";\n";
+            os << "\tadd.rn.f64 " << fd(dst, 1) << ", %fd" << t + 2 << ", %fd" << t + 3 << ";\n";
+            return;
+        }
         for (int i = 0; i < S; ++i) os << "\t" << op << ".rn.f64 " << fd(dst, i) << ", " << fd(a, i) << ", " << fd(b, i) << ";\n";
+    }
+    // Complex z^n, n >= 4: Base.power_by_squaring (base/intfuncs.jl), unrolled for the known exponent
+    int cpow(int x0, unsigned n) {
+        int x = x0;
+        auto sq = [&](int v) {
+            const int r = new_val();
+            binop("mul", r, v, v);
+            return r;
+        };
+        int t = __builtin_ctz(n) + 1;
+        n >>= t;
+        while (--t > 0) x = sq(x);
+        int y = x;
+        while (n > 0) {
+            t = __builtin_ctz(n) + 1;
+            n >>= t;
+            while (--t >= 0) x = sq(x);
+            const int r = new_val();
+            binop("mul", r, y, x);
+            y = r;
+        }
+        return y;
     }
     void scale(int dst, int a, double f) {
         for (int i = 0; i < S; ++i) os << "\tmul.rn.f64 " << fd(dst, i) << ", " << fd(a, i) << ", " << dimm(f) << ";\n";
@@ -131,11 +166,36 @@ struct Emitter {
         if (!acc) {
             const int a = nrd++;
             os << "\tmad.lo.u64 %rd" << a << ", %rd5, " << root << ", %rd6;\n";  // rootbase + root * ld_root_bytes
-            if (S == 2) {
+            if (cplx) {
+                os << "\t@%p0 st.global.v2.f64 [%rd" << a << "], {" << fd(r, 0) << ", " << fd(r, 1) << "};\n";
+            } else if (S == 2) {
                 os << "\t@%p1 st.global.v2.f64 [%rd" << a << "], {" << fd(r, 0) << ", " << fd(r, 1) << "};\n";
                 os << "\t@%p2 st.global.f64 [%rd" << a << "], " << fd(r, 0) << ";\n";  // odd tail: first sample only
             } else {
                 os << "\t@%p0 st.global.f64 [%rd" << a << "], " << fd(r, 0) << ";\n";
+            }
+            return;
+        }
+        if (cplx) {
+            // re and im are summed separately: columns 2r and 2r + 1
+            for (int c = 0; c < 2; ++c) {
+                const int s = nfd++, t = nfd++;
+                os << "\tselp.f64 %fd" << s << ", " << fd(r, c) << ", 0d0000000000000000, %p0;\n";
+                if (persistent) {
+                    os << "\tadd.rn.f64 %fd" << racc0 + 2 * root + c << ", %fd" << racc0 + 2 * root + c << ", %fd" << s << ";\n";
+                    continue;
+                }
+                for (int m = 16; m >= 1; m >>= 1) {
+                    os << "\tmov.b64 {%r8, %r9}, %fd" << s << ";\n";
+                    os << "\tshfl.sync.bfly.b32 %r10, %r8, " << m << ", 31, 0xffffffff;\n";
+                    os << "\tshfl.sync.bfly.b32 %r11, %r9, " << m << ", 31, 0xffffffff;\n";
+                    os << "\tmov.b64 %fd" << t << ", {%r10, %r11};\n";
+                    os << "\tadd.rn.f64 %fd" << s << ", %fd" << s << ", %fd" << t << ";\n";
+                }
+                const int64_t off = ((int64_t)root * 2 + c) * 8;
+                os << "\t@%p3 ld.global.f64 %fd" << t << ", [%rd7+" << off << "];\n";
+                os << "\t@%p3 add.rn.f64 %fd" << t << ", %fd" << t << ", %fd" << s << ";\n";
+                os << "\t@%p3 st.global.f64 [%rd7+" << off << "], %fd" << t << ";\n";
             }
             return;
         }
@@ -260,12 +320,13 @@ static void build_ir(const Lowered &low, std::vector<IrOp> &ir) {
 }
 
 int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, std::string &err) {
-    if (low.dtype != FDG_F64) {
-        err = "the specialised back end evaluates Float64 programs only";
-        return FDG_ERR_UNSUPPORTED;
-    }
+    const bool cplx = low.dtype == FDG_C128;
+    if (cplx) spt = 2;  // two f64 registers per value: (re, im) of one sample
+    const int W = cplx ? 2 : 1;                // doubles per sample
+    const int samples_per_thread = cplx ? 1 : spt;
+    const int esh = cplx ? 4 : 3;              // log2(bytes per sample element)
     plan = JitPlan();
-    plan.spt = spt;
+    plan.spt = samples_per_thread;
     plan.acc = acc;
     std::vector<IrOp> ir;
     build_ir(low, ir);
@@ -289,13 +350,14 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
     plan.seg.resize((size_t)nseg);
     // a single accumulate kernel with few roots runs as a grid-stride loop: per-thread running sums in registers,
     // one warp reduction per root at the very end (instead of one per tile)
-    plan.persistent = acc && nseg == 1 && low.R <= 32;
+    plan.persistent = acc && nseg == 1 && low.R * W <= 32;
     for (int sg = 0; sg < nseg; ++sg) {
         Emitter e(low, spt, acc);
+        e.cplx = cplx;
         e.persistent = plan.persistent;
         if (e.persistent) {
             e.racc0 = e.nfd;
-            e.nfd += (int)low.R;
+            e.nfd += (int)low.R * W;
         }
         std::ostringstream &os = e.os;
         const size_t lo = (size_t)sg * (size_t)seg_ops, hi = std::min(nops, lo + (size_t)seg_ops);
@@ -341,7 +403,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
                         r = e.new_val();
                         e.binop("mul", r, t, x);
                     } else {
-                        r = e.pow_body(x, o.n);
+                        r = cplx ? e.cpow(x, (unsigned)o.n) : e.pow_body(x, o.n);
                     }
                 } break;
                 default: e.root_out(operand(o.a), o.n); break;
@@ -357,6 +419,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
             }
         }
         const std::string body = os.str();
+        const int spt_hdr = samples_per_thread;
         JitSegment &js = plan.seg[(size_t)sg];
         js.name = "fdg_seg" + std::to_string(sg);
         js.n_stmts = (int)(hi - lo);
@@ -374,38 +437,38 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
         // %rd5 = ld_root bytes, %rd6 = root base (eval), %rd7 = partial row of the warp (accumulate)
         p << "\tmov.u32 %r0, %ctaid.x;\n\tmov.u32 %r1, %ntid.x;\n\tmov.u32 %r2, %tid.x;\n"
           << "\tmul.wide.u32 %rd8, %r0, %r1;\n\tcvt.u64.u32 %rd9, %r2;\n\tadd.u64 %rd8, %rd8, %rd9;\n"  // global thread id
-          << "\tmul.lo.u64 %rd0, %rd8, " << spt << ";\n"
+          << "\tmul.lo.u64 %rd0, %rd8, " << spt_hdr << ";\n"
           << "\tld.param.u64 %rd10, [p_batch];\n"
-          << "\tld.param.u64 %rd2, [p_ld_leaf];\n\tshl.b64 %rd2, %rd2, 3;\n"
-          << "\tld.param.u64 %rd4, [p_ld_cross];\n\tshl.b64 %rd4, %rd4, 3;\n"
+          << "\tld.param.u64 %rd2, [p_ld_leaf];\n\tshl.b64 %rd2, %rd2, " << esh << ";\n"
+          << "\tld.param.u64 %rd4, [p_ld_cross];\n\tshl.b64 %rd4, %rd4, " << esh << ";\n"
           << "\tld.param.u64 %rd14, [p_out];\n\tcvta.to.global.u64 %rd14, %rd14;\n";
         if (acc) {
             p << "\tshr.u64 %rd15, %rd8, 5;\n\tld.param.u64 %rd5, [p_nroots];\n\tmul.lo.u64 %rd15, %rd15, %rd5;\n"
               << "\tshl.b64 %rd15, %rd15, 3;\n\tadd.u64 %rd7, %rd14, %rd15;\n"
               << "\tand.b32 %r3, %r2, 31;\n\tsetp.eq.u32 %p3, %r3, 0;\n";
         } else {
-            p << "\tld.param.u64 %rd5, [p_ld_root];\n\tshl.b64 %rd5, %rd5, 3;\n";
+            p << "\tld.param.u64 %rd5, [p_ld_root];\n\tshl.b64 %rd5, %rd5, " << esh << ";\n";
         }
         if (e.persistent) {
-            for (int r = 0; r < (int)low.R; ++r) p << "\tmov.f64 %fd" << e.racc0 + r << ", 0d0000000000000000;\n";
-            p << "\tmov.u32 %r4, %nctaid.x;\n\tmul.wide.u32 %rd9, %r4, %r1;\n\tmul.lo.u64 %rd9, %rd9, " << spt << ";\n";  // grid stride
+            for (int r = 0; r < (int)low.R * W; ++r) p << "\tmov.f64 %fd" << e.racc0 + r << ", 0d0000000000000000;\n";
+            p << "\tmov.u32 %r4, %nctaid.x;\n\tmul.wide.u32 %rd9, %r4, %r1;\n\tmul.lo.u64 %rd9, %rd9, " << spt_hdr << ";\n";  // grid stride
             p << "FDG_LOOP:\n";
         }
         // per tile: validity predicates and the bases that depend on the sample index
         p << "\tsetp.lt.s64 %p0, %rd0, %rd10;\n";  // first sample valid
-        if (spt == 2)
+        if (spt_hdr == 2)
             p << "\tadd.u64 %rd11, %rd0, 1;\n\tsetp.lt.s64 %p1, %rd11, %rd10;\n"  // both samples valid
               << "\tnot.pred %p4, %p1;\n\tand.pred %p2, %p0, %p4;\n";             // only the first one
         p << "\tselp.u64 %rd12, %rd0, 0, %p0;\n"  // inactive threads read sample 0: every address stays in bounds
-          << "\tshl.b64 %rd12, %rd12, 3;\n"
+          << "\tshl.b64 %rd12, %rd12, " << esh << ";\n"
           << "\tld.param.u64 %rd1, [p_leaf];\n\tcvta.to.global.u64 %rd1, %rd1;\n\tadd.u64 %rd1, %rd1, %rd12;\n"
-          << "\tshl.b64 %rd13, %rd0, 3;\n";
+          << "\tshl.b64 %rd13, %rd0, " << esh << ";\n";
         if (n_cross > 0) p << "\tld.param.u64 %rd3, [p_cross];\n\tcvta.to.global.u64 %rd3, %rd3;\n\tadd.u64 %rd3, %rd3, %rd13;\n";
         if (!acc) p << "\tadd.u64 %rd6, %rd14, %rd13;\n";
         p << body;
         if (e.persistent) {
             p << "\tadd.u64 %rd0, %rd0, %rd9;\n\tsetp.lt.s64 %p5, %rd0, %rd10;\n\t@%p5 bra FDG_LOOP;\n";
-            for (int r = 0; r < (int)low.R; ++r) {
+            for (int r = 0; r < (int)low.R * W; ++r) {
                 const int sreg = e.racc0 + r, t = e.nfd;
                 for (int m = 16; m >= 1; m >>= 1) {
                     p << "\tmov.b64 {%r8, %r9}, %fd" << sreg << ";\n"

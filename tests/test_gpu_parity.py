@@ -76,8 +76,10 @@ def test_random_dag_f64_jit(seed, spt, jit_segment):
 
 
 @pytest.mark.parametrize("seed", range(4))
-def test_random_dag_c128(seed):
-    _parity(graphgen.random_dag(200 + seed, n_leaves=7, n_inner=60, n_roots=3, max_pow=5), dtype=np.complex128, batch=777)
+@pytest.mark.parametrize("backend,jit_segment", [(VM, 0), (JIT, 0), (JIT, 41)])
+def test_random_dag_c128(seed, backend, jit_segment):
+    _parity(graphgen.random_dag(200 + seed, n_leaves=7, n_inner=60, n_roots=3, max_pow=5), dtype=np.complex128, batch=777,
+            backend=backend, jit_segment=jit_segment)
 
 
 @pytest.mark.parametrize("seed", range(4))
@@ -165,8 +167,6 @@ def test_accumulate_is_the_sum_of_eval_and_deterministic(backend):
     roots = graphgen.random_dag(21, n_leaves=10, n_inner=60, n_roots=4)
     raw, _ = fd.flatten(roots)
     for dtype, w in ((np.float64, 1), (np.complex128, 2)):
-        if backend == JIT and w == 2:
-            continue  # the specialised back end is Float64 only
         ev = fd.compile_raw(raw, dtype=dtype, backend=backend, jit_segment=50 if backend == JIT else 0)
         batch = 100_003
         leaf_h = graphgen.leaf_values(3, ev.n_leaves, batch, dtype=dtype, signed=True, ld=batch + 1)
@@ -217,14 +217,16 @@ def test_torch_tensors_batch_major():
         f(torch.empty(B, f.n_roots, dtype=torch.float64, device="cuda"), leafVal.contiguous())
 
 
-def test_auto_backend_matches_and_complex_uses_the_vm():
+def test_auto_backend_and_backends_agree():
     roots = graphgen.random_dag(55, n_leaves=10, n_inner=60, n_roots=3)
     _parity(roots, backend=0, batch=3000)  # AUTO: specialised kernels
-    _parity(roots, backend=0, batch=3000, dtype=np.complex128)  # AUTO on ComplexF64: the VM
+    _parity(roots, backend=0, batch=3000, dtype=np.complex128)
+    # the two back ends agree bit for bit on the same program and inputs
     raw, _ = fd.flatten(roots)
-    with pytest.raises(_capi.FdgError) as e:
-        _dev_eval(fd.compile_raw(raw, dtype=np.complex128, backend=JIT), graphgen.leaf_values(1, 11, 8, dtype=np.complex128), 8)
-    assert e.value.code == 3
+    leaf = graphgen.leaf_values(1, 11, 512, dtype=np.complex128, signed=True)
+    a = _dev_eval(fd.compile_raw(raw, dtype=np.complex128, backend=VM), leaf, 512)
+    b = _dev_eval(fd.compile_raw(raw, dtype=np.complex128, backend=JIT), leaf, 512)
+    assert a.tobytes() == b.tobytes()
 
 
 def test_large_batch_properties():

@@ -107,6 +107,8 @@ def test_specialised_kernels_assemble_without_a_gpu(name, acc):
     import os
 
     raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", name + ".npz"))
+    evc = fd.compile_raw(raw, jit_segment=300, dtype=np.complex128)
+    assert evc.jit_prepare(1, acc)["kernels"] >= 1  # ComplexF64: (re, im) pairs, one sample per thread
     ev = fd.compile_raw(raw, jit_segment=300)
     info = ev.jit_prepare(2, acc)
     assert info["kernels"] >= 1 and info["cubin_bytes"] > 0
