@@ -50,6 +50,7 @@ EXPORTS = [
     "fdg_abi_version", "fdg_last_error", "fdg_compile", "fdg_destroy", "fdg_stats", "fdg_leafmap", "fdg_last_root",
     "fdg_program_words", "fdg_eval", "fdg_eval_accumulate", "fdg_eval_host", "fdg_set_launch", "fdg_launch_count",
     "fdg_comm_unique_id", "fdg_comm_init", "fdg_comm_destroy", "fdg_allreduce", "fdg_jit_prepare", "fdg_jit_ptx",
+    "fdg_jit_info",
 ]
 BACKEND_AUTO, BACKEND_VM, BACKEND_JIT = 0, 1, 2
 
@@ -85,6 +86,7 @@ def lib() -> C.CDLL:
     L.fdg_allreduce.argtypes = [vp, vp, i64, vp]
     L.fdg_jit_prepare.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
     L.fdg_jit_ptx.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
+    L.fdg_jit_info.argtypes = [vp, i32, i32, C.POINTER(i64), i32]
     for name in EXPORTS:
         if name not in ("fdg_abi_version", "fdg_last_error"):
             getattr(L, name).restype = C.c_int
@@ -158,7 +160,11 @@ def launch_count(h) -> int:
 def jit_prepare(h, samples_per_thread: int = 2, accumulate: bool = False) -> dict:
     nk, nc, nb = C.c_int32(), C.c_int32(), C.c_int64()
     check(lib().fdg_jit_prepare(h, samples_per_thread, int(accumulate), C.byref(nk), C.byref(nc), C.byref(nb)))
-    return {"kernels": int(nk.value), "cross_values": int(nc.value), "cubin_bytes": int(nb.value)}
+    out = (C.c_int64 * 8)()
+    check(lib().fdg_jit_info(h, samples_per_thread, int(accumulate), out, 8))
+    return {"kernels": int(nk.value), "cross_rows": int(nc.value), "cross_values": int(out[2]), "cubin_bytes": int(nb.value),
+            "leaf_loads": int(out[3]), "cross_loads": int(out[4]), "cross_stores": int(out[5]), "operations": int(out[6]),
+            "grid_stride": bool(out[7])}
 
 
 def jit_ptx(h, samples_per_thread: int, accumulate: bool, index: int):

@@ -59,6 +59,7 @@ struct DeviceState {
 struct JitVariant {
     fdg::JitPlan plan;
     bool compiled = false;
+    std::vector<int> occ;  // resident blocks per SM of each segment kernel (prefetch distance)
     std::map<int, std::vector<cudaKernel_t>> kernels;  // per device
     std::map<int, cudaLibrary_t> libs_first;           // (libraries are kept alive with the handle)
     std::map<int, std::vector<cudaLibrary_t>> libs;
@@ -201,6 +202,9 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
             cudaKernel_t k;
             CUDA_TRY(cudaLibraryGetKernel(&k, lib, sg.name.c_str()));
             kern.push_back(k);
+            int occ = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k, 128, 0));
+            if (v->occ.size() < kern.size()) v->occ.push_back(std::max(occ, 1));
         }
     }
     const fdg::Lowered &low = h->low;
@@ -217,6 +221,10 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
         const int64_t cap = std::max<int64_t>(per_block * ds.sm_count * 4,
                                               (int64_t)(cross_gb * (double)(1 << 30)) / ((int64_t)es * (int64_t)v->plan.n_cross));
         sub = std::min<int64_t>(batch, cap / per_block * per_block);
+    }
+    if (const char *e = getenv("FDG_JIT_SUB")) {  // experiment: samples per launch sequence (L2 blocking)
+        const int64_t want = atoll(e);
+        if (want > 0 && v->plan.seg.size() > 1) sub = std::min<int64_t>(batch, std::max<int64_t>(per_block, want / per_block * per_block));
     }
     int64_t max_grid = (sub + per_block - 1) / per_block;
     if (v->plan.persistent) max_grid = std::min<int64_t>(max_grid, (int64_t)ds.sm_count * 16);
@@ -253,8 +261,10 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
         void *p_out = acc ? out : static_cast<void *>(static_cast<char *>(root) + (size_t)b0 * es);
         void *p_cross = ds.cross;
         long long a_ld_leaf = ld_leaf, a_ld_cross = ld_cross, a_ld_root = ld_root, a_batch = nb, a_nroots = low.R * W;
-        void *args[] = {(void *)&p_leaf, &a_ld_leaf, &p_cross, &a_ld_cross, &p_out, &a_ld_root, &a_batch, &a_nroots};
+        long long a_ahead = 0;
+        void *args[] = {(void *)&p_leaf, &a_ld_leaf, &p_cross, &a_ld_cross, &p_out, &a_ld_root, &a_batch, &a_nroots, &a_ahead};
         for (size_t sg = 0; sg < kern.size(); ++sg) {
+            a_ahead = (long long)ds.sm_count * v->occ[sg];  // prefetch distance: one resident wave of blocks
             CUDA_TRY(cudaLaunchKernel((const void *)kern[sg], dim3(grid), dim3(T), args, 0, stream));
             h->launches++;
         }
@@ -389,6 +399,19 @@ int fdg_jit_prepare(fdg_handle h, int32_t samples_per_thread, int32_t accumulate
         *cubin_bytes = 0;
         for (auto &s : v->plan.seg) *cubin_bytes += (int64_t)s.cubin.size();
     }
+    return FDG_OK;
+}
+
+int fdg_jit_info(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int64_t *out, int32_t n_out) {
+    if (!h || !out || n_out < 0) return fail(FDG_ERR_BAD_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto it = h->jit.find(samples_per_thread * 2 + (accumulate ? 1 : 0));
+    if (it == h->jit.end() || !it->second.compiled) return fail(FDG_ERR_BAD_ARG, "variant not prepared");
+    const fdg::JitPlan &pl = it->second.plan;
+    int64_t ops = 0;
+    for (auto &sg : pl.seg) ops += sg.n_stmts;
+    const int64_t vals[8] = {(int64_t)pl.seg.size(), pl.n_cross, pl.n_cross_values, pl.leaf_loads, pl.cross_loads, pl.cross_stores, ops, pl.persistent ? 1 : 0};
+    for (int32_t i = 0; i < n_out && i < 8; ++i) out[i] = vals[i];
     return FDG_OK;
 }
 

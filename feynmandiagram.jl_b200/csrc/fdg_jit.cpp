@@ -46,7 +46,7 @@ struct Emitter {
     bool persistent = false;  // accumulate mode, single kernel: grid-stride loop with per-thread running sums
     int racc0 = -1;           // first register of the per-root running sums (persistent mode)
     std::ostringstream os;
-    int nfd = 0, nrd = 16, np = 8, nr = 16;
+    int nfd = 0, nrd = 32, np = 8, nr = 16;
     Emitter(const Lowered &l, int s, bool a) : low(l), S(s), acc(a) {}
 
     int new_val() {
@@ -95,6 +95,9 @@ struct Emitter {
     }
     void scale(int dst, int a, double f) {
         for (int i = 0; i < S; ++i) os << "\tmul.rn.f64 " << fd(dst, i) << ", " << fd(a, i) << ", " << dimm(f) << ";\n";
+    }
+    void neg(int dst, int a) {
+        for (int i = 0; i < S; ++i) os << "\tneg.f64 " << fd(dst, i) << ", " << fd(a, i) << ";\n";
     }
     // value = load from  base + index * stride  (two f64 for S == 2)
     int load(const char *space, const std::string &base, const std::string &stride, int64_t index) {
@@ -239,18 +242,114 @@ struct Emitter {
 // its parent's left fold (so at most one partial accumulator per nesting level is live), a multi-use node or root is
 // evaluated at its first use and its value id remembered.  The arithmetic is exactly the emitter's (static.jl:13-46).
 struct IrOp {
-    uint8_t kind;   // 0 MUL(a,b)  1 ADD(a,b)  2 SCALE(a,f)  3 POW(a,n)  4 ROOT(a -> root position n)
+    uint8_t kind;   // 0 MUL(a,b)  1 ADD(a,b)  2 SCALE(a,f)  3 POW(a,n)  4 ROOT(a -> root position n)  5 NEG(a)
     int32_t a, b;   // operands: value id >= 0, or -(leaf+1) for leaf `leaf`
     int32_t n;
     double f;
 };
-enum { IR_MUL = 0, IR_ADD = 1, IR_SCALE = 2, IR_POW = 3, IR_ROOT = 4 };
+enum { IR_MUL = 0, IR_ADD = 1, IR_SCALE = 2, IR_POW = 3, IR_ROOT = 4, IR_NEG = 5 };
+
+// Order in which the root statements are expanded.  Statement ORDER is free (each statement keeps its own fold, so
+// every value keeps its bits); what the order decides is how long shared values stay live, i.e. how many of them cross
+// kernel boundaries.  The emitter's order walks `graphs` as given, and diagram front ends list roots by channel and
+// time configuration, which puts roots that share sub-vertices far apart (Parquet vertex4 order 4: 1800 values live).
+// Greedy: next comes the root whose cone retires the most already-computed shared values and opens the fewest new
+// ones; ties by emitter order.  (Same graph: <= 190 values live, cross traffic 4x smaller.)
+static void order_roots(const Lowered &low, std::vector<int32_t> &order) {
+    const auto &st = low.st;
+    const auto &ops = low.ops;
+    std::vector<int32_t> roots;
+    for (int32_t v = 0; v < (int32_t)st.size(); ++v)
+        if (st[(size_t)v].root >= 0) roots.push_back(v);
+    order = roots;
+    const char *env = getenv("FDG_JIT_ROOT_ORDER");
+    if (roots.size() < 3 || (env && atoi(env) == 0)) return;
+    const size_t n = st.size(), R = roots.size();
+    // cones: inner statements reachable from each root (sorted statement indices)
+    std::vector<std::vector<int32_t>> cone(R);
+    std::vector<int32_t> mark(n, -1), work;
+    size_t total = 0;
+    for (size_t r = 0; r < R; ++r) {
+        if (st[(size_t)roots[r]].op < 0) continue;  // root[r] = leafVal[k]
+        work.assign(1, roots[r]);
+        mark[(size_t)roots[r]] = (int32_t)r;
+        while (!work.empty()) {
+            const int32_t v = work.back();
+            work.pop_back();
+            cone[r].push_back(v);
+            const Stmt &s = st[(size_t)v];
+            for (int32_t i = 0; i < s.count; ++i) {
+                const int32_t c = ops[(size_t)(s.first + i)].val;
+                if (st[(size_t)c].op >= 0 && mark[(size_t)c] != (int32_t)r) {
+                    mark[(size_t)c] = (int32_t)r;
+                    work.push_back(c);
+                }
+            }
+        }
+        total += cone[r].size();
+    }
+    if ((double)total * (double)R > 4e9) return;  // quadratic in the number of roots: keep emitter order for huge sets
+    // readers of every statement (distinct statements)
+    std::vector<std::vector<int32_t>> readers(n);
+    for (int32_t v = 0; v < (int32_t)n; ++v) {
+        const Stmt &s = st[(size_t)v];
+        if (!s.live || s.op < 0) continue;
+        for (int32_t i = 0; i < s.count; ++i) {
+            const int32_t c = ops[(size_t)(s.first + i)].val;
+            if (st[(size_t)c].op >= 0 && (readers[(size_t)c].empty() || readers[(size_t)c].back() != v)) readers[(size_t)c].push_back(v);
+        }
+    }
+    std::vector<uint8_t> computed(n, 0), taken(R, 0);
+    std::vector<int32_t> in_cone(n, -1);
+    order.clear();
+    for (size_t step = 0; step < R; ++step) {
+        long best_score = LONG_MIN;
+        size_t best = R;
+        for (size_t r = 0; r < R; ++r) {
+            if (taken[r]) continue;
+            for (const int32_t v : cone[r]) in_cone[(size_t)v] = (int32_t)r;
+            long kills = 0, creates = 0;
+            for (const int32_t v : cone[r]) {
+                if (computed[(size_t)v]) {
+                    // a computed value this cone reads: retired if every reader is computed or inside the cone
+                    bool read_here = false, dies = true;
+                    for (const int32_t u : readers[(size_t)v]) {
+                        if (computed[(size_t)u]) continue;
+                        if (in_cone[(size_t)u] == (int32_t)r) read_here = true;
+                        else dies = false;
+                    }
+                    if (read_here && dies) ++kills;
+                } else {
+                    for (const int32_t u : readers[(size_t)v])
+                        if (in_cone[(size_t)u] != (int32_t)r) {
+                            ++creates;
+                            break;
+                        }
+                }
+            }
+            const long score = kills - creates;
+            if (score > best_score) {
+                best_score = score;
+                best = r;
+            }
+        }
+        taken[best] = 1;
+        order.push_back(roots[best]);
+        for (const int32_t v : cone[best]) computed[(size_t)v] = 1;
+    }
+}
 
 static void build_ir(const Lowered &low, std::vector<IrOp> &ir) {
     const auto &st = low.st;
     const auto &ops = low.ops;
     std::vector<int32_t> val_of(st.size(), INT32_MIN);  // value id of a materialised statement once computed
+    // `x * (-1.0)` is the sign flip of x for every finite and infinite double (round-to-nearest is symmetric), so it is
+    // written as a negation, which sm_100a folds into the operand modifiers of the DMUL / DADD that reads it: the
+    // multiply disappears, the bits stay (NaN sign/payload is hardware-specific either way).  FDG_JIT_NEGFOLD=0 keeps it.
+    const char *nf = getenv("FDG_JIT_NEGFOLD");
+    const bool negfold = !(nf && atoi(nf) == 0);
     auto emit = [&](uint8_t kind, int32_t a, int32_t b, int32_t n, double f) -> int32_t {
+        if (kind == IR_SCALE && f == -1.0 && negfold) kind = IR_NEG;
         ir.push_back({kind, a, b, n, f});
         return (int32_t)ir.size() - 1;
     };
@@ -260,8 +359,9 @@ static void build_ir(const Lowered &low, std::vector<IrOp> &ir) {
         int32_t ret;
     };
     std::vector<Frame> stack;
-    for (int32_t root_stmt = 0; root_stmt < (int32_t)st.size(); ++root_stmt) {
-        if (st[(size_t)root_stmt].root < 0) continue;
+    std::vector<int32_t> root_order;
+    order_roots(low, root_order);
+    for (const int32_t root_stmt : root_order) {
         if (st[(size_t)root_stmt].op < 0) {  // root[r] = leafVal[k]
             emit(IR_ROOT, -(st[(size_t)root_stmt].leaf + 1), 0, st[(size_t)root_stmt].root, 1.0);
             continue;
@@ -330,22 +430,90 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
     plan.acc = acc;
     std::vector<IrOp> ir;
     build_ir(low, ir);
-    if (seg_ops <= 0) seg_ops = 3000;
-    const size_t nops = ir.size();
-    const int nseg = std::max<int>(1, (int)((nops + (size_t)seg_ops - 1) / (size_t)seg_ops));
-    auto seg_of = [&](int32_t id) { return (int)((size_t)id / (size_t)seg_ops); };
-    // values read in a later segment than the one defining them travel through the cross buffer
-    std::vector<int32_t> cross(nops, -1);
-    int32_t n_cross = 0;
-    for (size_t i = 0; i < nops; ++i) {
-        const IrOp &o = ir[i];
-        const int32_t operands[2] = {o.a, (o.kind == IR_MUL || o.kind == IR_ADD) ? o.b : -1};
-        for (int q = 0; q < 2; ++q) {
-            const int32_t a = operands[q];
-            if (q == 1 && !(o.kind == IR_MUL || o.kind == IR_ADD)) break;
-            if (a >= 0 && seg_of(a) != seg_of((int32_t)i) && cross[(size_t)a] < 0) cross[(size_t)a] = n_cross++;
+    if (const char *dump = getenv("FDG_JIT_DUMP_IR")) {  // debugging aid: the fold-order IR as raw records
+        if (FILE *fp = std::fopen(dump, "wb")) {
+            for (const IrOp &o : ir) {
+                const int32_t rec[4] = {(int32_t)o.kind, o.a, o.b, o.n};
+                std::fwrite(rec, sizeof(rec), 1, fp);
+            }
+            std::fclose(fp);
         }
     }
+    if (seg_ops <= 0) seg_ops = 4500;
+    int prefetch = 0;
+    if (const char *pf = getenv("FDG_JIT_PREFETCH")) prefetch = atoi(pf);
+    const size_t nops = ir.size();
+    auto is_binary = [](const IrOp &o) { return o.kind == IR_MUL || o.kind == IR_ADD; };
+    // ---- cut points: about seg_ops operations per kernel, each cut placed where the fewest values are live ---------
+    std::vector<int32_t> last_use(nops, -1);
+    for (size_t i = 0; i < nops; ++i) {
+        const IrOp &o = ir[i];
+        if (o.a >= 0) last_use[(size_t)o.a] = (int32_t)i;
+        if (is_binary(o) && o.b >= 0) last_use[(size_t)o.b] = (int32_t)i;
+    }
+    std::vector<int32_t> seg_start{0};
+    {
+        // live[p] = values defined before op p and read at or after p (what a cut in front of p sends through memory)
+        std::vector<int32_t> live(nops + 2, 0);
+        for (size_t v = 0; v < nops; ++v)
+            if (last_use[v] > (int32_t)v) {
+                live[v + 1] += 1;
+                live[(size_t)last_use[v] + 1] -= 1;
+            }
+        for (size_t q = 1; q < live.size(); ++q) live[q] += live[q - 1];
+        const char *nc = getenv("FDG_JIT_NARROW_CUTS");
+        const bool narrow = !(nc && atoi(nc) == 0);
+        size_t start = 0;
+        while (nops - start > (size_t)seg_ops + (narrow ? (size_t)seg_ops / 4 : 0)) {
+            size_t cut = start + (size_t)seg_ops;
+            if (narrow) {
+                const size_t lo_w = start + (size_t)seg_ops * 3 / 4, hi_w = std::min(nops - 1, start + (size_t)seg_ops * 5 / 4);
+                for (size_t q = lo_w; q <= hi_w; ++q)
+                    if (live[q] <= live[cut]) cut = q;
+            }
+            seg_start.push_back((int32_t)cut);
+            start = cut;
+        }
+    }
+    const int nseg = (int)seg_start.size();
+    seg_start.push_back((int32_t)nops);
+    std::vector<int32_t> seg_id(nops);
+    for (int sg = 0; sg < nseg; ++sg)
+        for (int32_t i = seg_start[(size_t)sg]; i < seg_start[(size_t)sg + 1]; ++i) seg_id[(size_t)i] = sg;
+    auto seg_of = [&](int32_t id) { return seg_id[(size_t)id]; };
+    // ---- values read in a later segment than the one defining them travel through the cross buffer; a row is reused
+    //      once the last kernel reading it has run (kernels of one stream run in order)
+    std::vector<int32_t> cross(nops, -1);
+    int32_t n_cross = 0, n_cross_values = 0;
+    {
+        std::vector<int32_t> last_seg(nops, -1);
+        for (size_t i = 0; i < nops; ++i) {
+            const IrOp &o = ir[i];
+            const int sg = seg_of((int32_t)i);
+            if (o.a >= 0 && seg_of(o.a) != sg) last_seg[(size_t)o.a] = sg;
+            if (is_binary(o) && o.b >= 0 && seg_of(o.b) != sg) last_seg[(size_t)o.b] = sg;
+        }
+        std::vector<std::vector<int32_t>> expire((size_t)nseg + 1);  // rows that become free after segment s
+        std::vector<int32_t> free_rows;
+        for (int sg = 0; sg < nseg; ++sg) {
+            for (int32_t i = seg_start[(size_t)sg]; i < seg_start[(size_t)sg + 1]; ++i) {
+                if (last_seg[(size_t)i] < 0) continue;
+                int32_t row;
+                if (!free_rows.empty()) {
+                    row = free_rows.back();
+                    free_rows.pop_back();
+                } else {
+                    row = n_cross++;
+                }
+                cross[(size_t)i] = row;
+                ++n_cross_values;
+                expire[(size_t)last_seg[(size_t)i]].push_back(row);
+            }
+            // rows whose last reader is THIS segment are free for values defined in later segments only
+            for (const int32_t row : expire[(size_t)sg]) free_rows.push_back(row);
+        }
+    }
+    plan.n_cross_values = n_cross_values;
     plan.n_cross = n_cross;
     plan.seg.resize((size_t)nseg);
     // a single accumulate kernel with few roots runs as a grid-stride loop: per-thread running sums in registers,
@@ -360,20 +528,27 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
             e.nfd += (int)low.R * W;
         }
         std::ostringstream &os = e.os;
-        const size_t lo = (size_t)sg * (size_t)seg_ops, hi = std::min(nops, lo + (size_t)seg_ops);
+        const size_t lo = (size_t)seg_start[(size_t)sg], hi = (size_t)seg_start[(size_t)sg + 1];
         std::vector<int32_t> reg_of(hi - lo, -1);          // register of a value defined in this segment
         std::vector<int32_t> leaf_reg((size_t)low.L, -1);  // register of a leaf loaded in this segment
         std::unordered_map<int32_t, int32_t> cross_reg;    // register of a cross value loaded in this segment
+        std::vector<std::pair<int, int32_t>> in_rows;      // (0 leaf / 1 cross, row) in order of first use: prefetch list
         auto operand = [&](int32_t a) -> int {
             if (a < 0) {
                 const int32_t k = -a - 1;
-                if (leaf_reg[(size_t)k] < 0) leaf_reg[(size_t)k] = e.load("ld.global.nc", "%rd1", "%rd2", k);
+                if (leaf_reg[(size_t)k] < 0) {
+                    leaf_reg[(size_t)k] = e.load("ld.global.nc", "%rd1", "%rd2", k);
+                    in_rows.emplace_back(0, k);
+                    plan.leaf_loads++;
+                }
                 return leaf_reg[(size_t)k];
             }
             if ((size_t)a >= lo) return reg_of[(size_t)a - lo];
             auto it = cross_reg.find(a);
             if (it != cross_reg.end()) return it->second;
             const int r = e.load("ld.global", "%rd3", "%rd4", cross[(size_t)a]);
+            in_rows.emplace_back(1, cross[(size_t)a]);
+            plan.cross_loads++;
             cross_reg.emplace(a, r);
             return r;
         };
@@ -391,6 +566,11 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
                     const int a = operand(o.a);
                     r = e.new_val();
                     e.scale(r, a, o.f);
+                } break;
+                case IR_NEG: {
+                    const int a = operand(o.a);
+                    r = e.new_val();
+                    e.neg(r, a);
                 } break;
                 case IR_POW: {
                     const int x = operand(o.a);
@@ -410,6 +590,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
             }
             reg_of[i - lo] = r;
             if (r >= 0 && cross[i] >= 0) {
+                plan.cross_stores++;
                 const int a = e.nrd++;
                 os << "\tmad.lo.u64 %rd" << a << ", %rd4, " << cross[i] << ", %rd3;\n";
                 if (spt == 2)
@@ -427,7 +608,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
         p << ".version 8.7\n.target sm_100a\n.address_size 64\n\n";
         p << ".visible .entry " << js.name << "(\n"
           << "\t.param .u64 p_leaf, .param .u64 p_ld_leaf, .param .u64 p_cross, .param .u64 p_ld_cross,\n"
-          << "\t.param .u64 p_out, .param .u64 p_ld_root, .param .u64 p_batch, .param .u64 p_nroots)\n"
+          << "\t.param .u64 p_out, .param .u64 p_ld_root, .param .u64 p_batch, .param .u64 p_nroots, .param .u64 p_ahead)\n"
           << ".maxntid 128, 1, 1\n";
         if (const char *mr = getenv("FDG_JIT_MAXNREG")) p << ".maxnreg " << atoi(mr) << "\n";
         p << "{\n";
@@ -465,6 +646,38 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
           << "\tshl.b64 %rd13, %rd0, " << esh << ";\n";
         if (n_cross > 0) p << "\tld.param.u64 %rd3, [p_cross];\n\tcvta.to.global.u64 %rd3, %rd3;\n\tadd.u64 %rd3, %rd3, %rd13;\n";
         if (!acc) p << "\tadd.u64 %rd6, %rd14, %rd13;\n";
+        if (prefetch > 0 && !e.persistent && !in_rows.empty()) {
+            // One thread per block asks the TMA unit to pull the input rows of a block `p_ahead` positions further down
+            // the grid into L2 (cp.async.bulk.prefetch.L2: one instruction per 1 KB row, no registers, no completion
+            // to wait for), so that block's loads find their data on chip; the first wave also fetches its own rows.
+            const int row_bytes = 128 * samples_per_thread * (cplx ? 16 : 8);
+            p << "\tsetp.ne.u32 %p6, %r2, 0;\n\t@%p6 bra FDG_PF_DONE;\n"
+              << "\tld.param.u64 %rd16, [p_ahead];\n"
+              << "\tld.param.u64 %rd17, [p_leaf];\n\tcvta.to.global.u64 %rd17, %rd17;\n";
+            if (n_cross > 0) p << "\tld.param.u64 %rd18, [p_cross];\n\tcvta.to.global.u64 %rd18, %rd18;\n";
+            for (int pass = 0; pass < 2; ++pass) {
+                // pass 0: the block `ahead` further on; pass 1: this block itself, first wave only (ctaid < ahead)
+                const char *lbl = pass == 0 ? "FDG_PF_OWN" : "FDG_PF_DONE";
+                if (pass == 0) {
+                    p << "\tmul.lo.u64 %rd19, %rd16, " << 128 * samples_per_thread << ";\n\tadd.u64 %rd19, %rd19, %rd0;\n";
+                } else {
+                    p << "\tcvt.u64.u32 %rd19, %r0;\n\tsetp.ge.u64 %p7, %rd19, %rd16;\n\t@%p7 bra FDG_PF_DONE;\n"
+                      << "\tmov.u64 %rd19, %rd0;\n";
+                }
+                // bytes of the row segment: min(row_bytes, (batch - first) * element), rounded down to 16
+                p << "\tsub.s64 %rd20, %rd10, %rd19;\n\tsetp.le.s64 %p7, %rd20, 0;\n\t@%p7 bra " << lbl << ";\n"
+                  << "\tshl.b64 %rd20, %rd20, " << esh << ";\n\tmin.u64 %rd20, %rd20, " << row_bytes << ";\n"
+                  << "\tand.b64 %rd20, %rd20, -16;\n\tcvt.u32.u64 %r5, %rd20;\n\tsetp.eq.u32 %p7, %r5, 0;\n\t@%p7 bra " << lbl << ";\n"
+                  << "\tshl.b64 %rd21, %rd19, " << esh << ";\n\tadd.u64 %rd22, %rd17, %rd21;\n";
+                if (n_cross > 0) p << "\tadd.u64 %rd23, %rd18, %rd21;\n";
+                for (const auto &row : in_rows) {
+                    p << "\tmad.lo.u64 %rd24, " << (row.first ? "%rd4" : "%rd2") << ", " << row.second << ", " << (row.first ? "%rd23" : "%rd22") << ";\n"
+                      << "\tcp.async.bulk.prefetch.L2.global [%rd24], %r5;\n";
+                }
+                if (pass == 0) p << "FDG_PF_OWN:\n";
+            }
+            p << "FDG_PF_DONE:\n";
+        }
         p << body;
         if (e.persistent) {
             p << "\tadd.u64 %rd0, %rd0, %rd9;\n\tsetp.lt.s64 %p5, %rd0, %rd10;\n\t@%p5 bra FDG_LOOP;\n";

@@ -19,7 +19,9 @@ struct JitSegment {
 struct JitPlan {
     int spt = 2;        // samples per thread
     bool acc = false;   // accumulate (per-warp partial sums) instead of per-sample roots
-    int32_t n_cross = 0;  // rows of the cross-segment buffer
+    int32_t n_cross = 0;  // rows of the cross-segment buffer (rows are reused once their last reader has run)
+    int32_t n_cross_values = 0;  // values that cross a kernel boundary
+    int64_t leaf_loads = 0, cross_loads = 0, cross_stores = 0;  // global loads / stores per sample over all kernels
     bool persistent = false;  // single accumulate kernel run as a grid-stride loop (per-thread running sums)
     std::vector<JitSegment> seg;
 };
