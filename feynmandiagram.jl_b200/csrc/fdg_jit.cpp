@@ -442,6 +442,10 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
     if (seg_ops <= 0) seg_ops = 4500;
     int prefetch = 0;
     if (const char *pf = getenv("FDG_JIT_PREFETCH")) prefetch = atoi(pf);
+    bool ring_on = true;
+    int ring_rows = 0;
+    if (const char *rg = getenv("FDG_JIT_RING")) ring_on = atoi(rg) != 0;
+    if (const char *rr = getenv("FDG_JIT_RING_ROWS")) ring_rows = atoi(rr);
     const size_t nops = ir.size();
     auto is_binary = [](const IrOp &o) { return o.kind == IR_MUL || o.kind == IR_ADD; };
     // ---- cut points: about seg_ops operations per kernel, each cut placed where the fewest values are live ---------
@@ -532,13 +536,70 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
         std::vector<int32_t> reg_of(hi - lo, -1);          // register of a value defined in this segment
         std::vector<int32_t> leaf_reg((size_t)low.L, -1);  // register of a leaf loaded in this segment
         std::unordered_map<int32_t, int32_t> cross_reg;    // register of a cross value loaded in this segment
-        std::vector<std::pair<int, int32_t>> in_rows;      // (0 leaf / 1 cross, row) in order of first use: prefetch list
+        // ---- input rows (leaves, cross values) in order of first use ------------------------------------------------
+        std::vector<std::pair<int, int32_t>> in_rows;  // (0 leaf / 1 cross, row)
+        {
+            std::vector<uint8_t> seen_leaf((size_t)low.L, 0);
+            std::unordered_map<int32_t, int> seen_cross;
+            auto note = [&](int32_t a) {
+                if (a < 0) {
+                    if (!seen_leaf[(size_t)(-a - 1)]) {
+                        seen_leaf[(size_t)(-a - 1)] = 1;
+                        in_rows.emplace_back(0, -a - 1);
+                    }
+                } else if ((size_t)a < lo && !seen_cross.count(a)) {
+                    seen_cross.emplace(a, 1);
+                    in_rows.emplace_back(1, cross[(size_t)a]);
+                }
+            };
+            for (size_t i = lo; i < hi; ++i) {
+                note(ir[i].a);
+                if (is_binary(ir[i])) note(ir[i].b);
+            }
+        }
+        // The ring: every thread streams its own element of each input row global -> shared with cp.async (LDGSTS),
+        // `ring_rows` rows ahead of the row the arithmetic is reading, in the order the straight-line code first needs
+        // them.  A copy in flight holds no register and no scoreboard entry, so the depth of the memory pipeline no
+        // longer depends on what ptxas can hoist with 250 registers taken; `cp.async.wait_group` counts are known here.
+        const int n_in = (int)in_rows.size();
+        const int ES = cplx ? 16 : 8 * samples_per_thread;  // bytes per thread per row
+        const int G = 4;
+        int NR = ring_rows > 0 ? ring_rows : (ES == 8 ? 32 : 24);
+        NR = std::max(G, std::min(NR, 49152 / (128 * ES)) / G * G);
+        const bool ring = ring_on && !e.persistent && n_in > 0;
+        const int n_groups = (n_in + G - 1) / G;
+        int next_in = 0;  // rows consumed so far
+        auto ring_issue = [&](std::ostringstream &o2, int j) {  // copy of input row j into its slot
+            const auto &row = in_rows[(size_t)j];
+            const int a = e.nrd++;
+            o2 << "\tmad.lo.u64 %rd" << a << ", " << (row.first ? "%rd4" : "%rd2") << ", " << row.second << ", " << (row.first ? "%rd3" : "%rd1") << ";\n"
+               << "\tcp.async." << (ES == 16 ? "cg" : "ca") << ".shared.global [%r12+" << (j % NR) * 128 * ES << "], [%rd" << a << "], " << ES << ";\n";
+        };
+        auto ring_load = [&](int kind_, int32_t row_) -> int {
+            const int j = next_in++;
+            (void)kind_;
+            (void)row_;
+            const int g = j / G;
+            if (j % G == 0) os << "\tcp.async.wait_group " << std::min(NR / G - 1, n_groups - 1 - g) << ";\n";
+            const int r = e.new_val();
+            if (ES == 16)
+                os << "\tld.shared.v2.f64 {" << e.fd(r, 0) << ", " << e.fd(r, 1) << "}, [%r12+" << (j % NR) * 128 * ES << "];\n";
+            else
+                os << "\tld.shared.f64 " << e.fd(r, 0) << ", [%r12+" << (j % NR) * 128 * ES << "];\n";
+            if (j % G == G - 1 || j == n_in - 1) {
+                const int j0 = (g + NR / G) * G;
+                if (j0 < n_in) {
+                    for (int q = j0; q < std::min(n_in, j0 + G); ++q) ring_issue(os, q);
+                    os << "\tcp.async.commit_group;\n";
+                }
+            }
+            return r;
+        };
         auto operand = [&](int32_t a) -> int {
             if (a < 0) {
                 const int32_t k = -a - 1;
                 if (leaf_reg[(size_t)k] < 0) {
-                    leaf_reg[(size_t)k] = e.load("ld.global.nc", "%rd1", "%rd2", k);
-                    in_rows.emplace_back(0, k);
+                    leaf_reg[(size_t)k] = ring ? ring_load(0, k) : e.load("ld.global.nc", "%rd1", "%rd2", k);
                     plan.leaf_loads++;
                 }
                 return leaf_reg[(size_t)k];
@@ -546,8 +607,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
             if ((size_t)a >= lo) return reg_of[(size_t)a - lo];
             auto it = cross_reg.find(a);
             if (it != cross_reg.end()) return it->second;
-            const int r = e.load("ld.global", "%rd3", "%rd4", cross[(size_t)a]);
-            in_rows.emplace_back(1, cross[(size_t)a]);
+            const int r = ring ? ring_load(1, cross[(size_t)a]) : e.load("ld.global", "%rd3", "%rd4", cross[(size_t)a]);
             plan.cross_loads++;
             cross_reg.emplace(a, r);
             return r;
@@ -612,7 +672,8 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
           << ".maxntid 128, 1, 1\n";
         if (const char *mr = getenv("FDG_JIT_MAXNREG")) p << ".maxnreg " << atoi(mr) << "\n";
         p << "{\n";
-        p << "\t.reg .f64 %fd<" << e.nfd + 2 << ">;\n\t.reg .b64 %rd<" << e.nrd + 1 << ">;\n\t.reg .pred %p<" << e.np + 1
+        if (ring) p << "\t.shared .align 16 .b8 fdg_ring[" << NR * 128 * ES << "];\n";
+        p << "\t.reg .f64 %fd<" << e.nfd + 2 << ">;\n\t.reg .b64 %rd<" << e.nrd + 1 + (ring ? NR : 0) << ">;\n\t.reg .pred %p<" << e.np + 1
           << ">;\n\t.reg .b32 %r<" << e.nr + 1 << ">;\n";
         // %rd0 = first sample of the thread, %rd1 = leaf base, %rd2 = ld_leaf bytes, %rd3 = cross base, %rd4 = ld_cross bytes,
         // %rd5 = ld_root bytes, %rd6 = root base (eval), %rd7 = partial row of the warp (accumulate)
@@ -646,6 +707,15 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
           << "\tshl.b64 %rd13, %rd0, " << esh << ";\n";
         if (n_cross > 0) p << "\tld.param.u64 %rd3, [p_cross];\n\tcvta.to.global.u64 %rd3, %rd3;\n\tadd.u64 %rd3, %rd3, %rd13;\n";
         if (!acc) p << "\tadd.u64 %rd6, %rd14, %rd13;\n";
+        if (ring) {
+            p << "\tmov.u32 %r12, fdg_ring;\n\tmad.lo.u32 %r12, %r2, " << ES << ", %r12;\n";  // this thread's column of the ring
+            std::ostringstream pro;
+            for (int j = 0; j < std::min(NR, n_in); ++j) {
+                ring_issue(pro, j);
+                if (j % G == G - 1 || j == std::min(NR, n_in) - 1) pro << "\tcp.async.commit_group;\n";
+            }
+            p << pro.str();
+        }
         if (prefetch > 0 && !e.persistent && !in_rows.empty()) {
             // One thread per block asks the TMA unit to pull the input rows of a block `p_ahead` positions further down
             // the grid into L2 (cp.async.bulk.prefetch.L2: one instruction per 1 KB row, no registers, no completion

@@ -75,6 +75,18 @@ def test_random_dag_f64_jit(seed, spt, jit_segment):
             backend=JIT, jit_segment=jit_segment)
 
 
+@pytest.mark.parametrize("spt", [1, 2])
+@pytest.mark.parametrize("jit_segment", [0, 300])
+def test_many_inputs_wrap_the_ring(spt, jit_segment):
+    # more input rows than the cp.async ring holds (32 rows of 8 B, 24 of 16 B): slots are refilled while the kernel runs
+    _parity(graphgen.random_dag(77, n_leaves=190, n_inner=900, n_roots=7), spt=spt, batch=4100, ld=4100, backend=JIT,
+            jit_segment=jit_segment)
+
+
+def test_many_inputs_wrap_the_ring_c128():
+    _parity(graphgen.random_dag(78, n_leaves=120, n_inner=500, n_roots=5), dtype=np.complex128, batch=1031, ld=1031, backend=JIT)
+
+
 @pytest.mark.parametrize("seed", range(4))
 @pytest.mark.parametrize("backend,jit_segment", [(VM, 0), (JIT, 0), (JIT, 41)])
 def test_random_dag_c128(seed, backend, jit_segment):

@@ -16,9 +16,6 @@ import torch  # noqa: E402
 
 import fdgraph_b200 as fd  # noqa: E402
 
-ENV_KEYS = ["FDG_JIT_ROOT_ORDER", "FDG_JIT_NEGFOLD", "FDG_JIT_PREFETCH", "FDG_JIT_MAXNREG", "FDG_JIT_SUB", "FDG_JIT_NARROW_CUTS",
-            "FDG_JIT_CROSS_GB", "FDG_JIT_THREADS", "FDG_JIT_LEAF_GAP", "FDG_JIT_MODE", "FDG_JIT_CAP"]
-
 
 def main():
     ap = argparse.ArgumentParser()
@@ -44,7 +41,7 @@ def main():
     ref = None
     for var in a.variants:
         kv = dict(x.split("=") for x in var.split(",") if x)
-        for k in ENV_KEYS:
+        for k in [k for k in os.environ if k.startswith("FDG_")]:
             os.environ.pop(k, None)
         seg, spt, cse = int(kv.pop("seg", 0)), int(kv.pop("spt", 1)), int(kv.pop("cse", 0))
         os.environ.update(kv)
