@@ -172,14 +172,15 @@ int get_device_state(fdg_program *h, DeviceState **out) {
 }
 
 // ---- specialised back end ----------------------------------------------------------------------------------------
-int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out) {
-    JitVariant &v = h->jit[spt * 2 + (acc ? 1 : 0)];
+int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = false) {
+    const int key = spt * 2 + (acc ? 1 : 0) + (wide ? 64 : 0);
+    JitVariant &v = h->jit[key];
     if (!v.compiled) {
         std::string err;
-        int rc = fdg::jit_plan(h->low, spt, acc, h->jit_segment, v.plan, err);
+        int rc = fdg::jit_plan(h->low, spt, acc, h->jit_segment, wide, v.plan, err);
         if (rc == FDG_OK) rc = fdg::jit_compile(v.plan, err);
         if (rc != FDG_OK) {
-            h->jit.erase(spt * 2 + (acc ? 1 : 0));
+            h->jit.erase(key);
             return fail(rc, err);
         }
         v.compiled = true;
@@ -191,7 +192,9 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out) {
 int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, const void *leaf, int64_t ld_leaf, void *root,
                int64_t ld_root, int64_t batch, cudaStream_t stream) {
     JitVariant *v = nullptr;
-    int rc = jit_get(h, spt, acc, &v);
+    // row offsets are formed with one 32-bit multiply-add unless a leading dimension reaches 4 GiB
+    const bool wide = (uint64_t)ld_leaf * (h->low.dtype == FDG_C128 ? 16 : 8) >= (1ull << 32);
+    int rc = jit_get(h, spt, acc, &v, wide);
     if (rc != FDG_OK) return rc;
     auto &kern = v->kernels[dev];
     if (kern.empty()) {
@@ -226,6 +229,7 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
         const int64_t want = atoll(e);
         if (want > 0 && v->plan.seg.size() > 1) sub = std::min<int64_t>(batch, std::max<int64_t>(per_block, want / per_block * per_block));
     }
+    sub = std::min<int64_t>(sub, ((int64_t)((1ull << 32) / es) - per_block) / per_block * per_block);  // ld_cross bytes < 4 GiB
     int64_t max_grid = (sub + per_block - 1) / per_block;
     if (v->plan.persistent) max_grid = std::min<int64_t>(max_grid, (int64_t)ds.sm_count * 16);
     const int64_t ld_cross = max_grid * per_block;

@@ -99,10 +99,18 @@ struct Emitter {
     void neg(int dst, int a) {
         for (int i = 0; i < S; ++i) os << "\tneg.f64 " << fd(dst, i) << ", " << fd(a, i) << ";\n";
     }
+    bool wide = false;  // leading dimensions of 4 GiB or more: 64-bit row offsets (three instructions instead of one)
+    // %rd<a> = base + index * stride; the strides live in %rd2 / %rd4 (bytes, 64 bit) and %r13 / %r14 (low halves)
+    void row_addr(std::ostringstream &o2, int a, const std::string &base, const std::string &stride, int64_t index) {
+        if (wide)
+            o2 << "\tmad.lo.u64 %rd" << a << ", " << stride << ", " << index << ", " << base << ";\n";
+        else
+            o2 << "\tmad.wide.u32 %rd" << a << ", " << (stride == "%rd2" ? "%r13" : "%r14") << ", " << index << ", " << base << ";\n";
+    }
     // value = load from  base + index * stride  (two f64 for S == 2)
     int load(const char *space, const std::string &base, const std::string &stride, int64_t index) {
         const int a = nrd++;
-        os << "\tmad.lo.u64 %rd" << a << ", " << stride << ", " << index << ", " << base << ";\n";
+        row_addr(os, a, base, stride, index);
         const int r = new_val();
         if (S == 2)
             os << "\t" << space << ".v2.f64 {" << fd(r, 0) << ", " << fd(r, 1) << "}, [%rd" << a << "];\n";
@@ -419,7 +427,7 @@ static void build_ir(const Lowered &low, std::vector<IrOp> &ir) {
     }
 }
 
-int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, std::string &err) {
+int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strides, JitPlan &plan, std::string &err) {
     const bool cplx = low.dtype == FDG_C128;
     if (cplx) spt = 2;  // two f64 registers per value: (re, im) of one sample
     const int W = cplx ? 2 : 1;                // doubles per sample
@@ -439,7 +447,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
             std::fclose(fp);
         }
     }
-    if (seg_ops <= 0) seg_ops = 4500;
+    if (seg_ops <= 0) seg_ops = cplx ? 2500 : 4500;  // a complex multiply is six instructions
     int prefetch = 0;
     if (const char *pf = getenv("FDG_JIT_PREFETCH")) prefetch = atoi(pf);
     bool ring_on = true;
@@ -526,6 +534,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
     for (int sg = 0; sg < nseg; ++sg) {
         Emitter e(low, spt, acc);
         e.cplx = cplx;
+        e.wide = wide_strides;
         e.persistent = plan.persistent;
         if (e.persistent) {
             e.racc0 = e.nfd;
@@ -572,8 +581,8 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
         auto ring_issue = [&](std::ostringstream &o2, int j) {  // copy of input row j into its slot
             const auto &row = in_rows[(size_t)j];
             const int a = e.nrd++;
-            o2 << "\tmad.lo.u64 %rd" << a << ", " << (row.first ? "%rd4" : "%rd2") << ", " << row.second << ", " << (row.first ? "%rd3" : "%rd1") << ";\n"
-               << "\tcp.async." << (ES == 16 ? "cg" : "ca") << ".shared.global [%r12+" << (j % NR) * 128 * ES << "], [%rd" << a << "], " << ES << ";\n";
+            e.row_addr(o2, a, row.first ? "%rd3" : "%rd1", row.first ? "%rd4" : "%rd2", row.second);
+            o2 << "\tcp.async." << (ES == 16 ? "cg" : "ca") << ".shared.global [%r12+" << (j % NR) * 128 * ES << "], [%rd" << a << "], " << ES << ";\n";
         };
         auto ring_load = [&](int kind_, int32_t row_) -> int {
             const int j = next_in++;
@@ -652,7 +661,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
             if (r >= 0 && cross[i] >= 0) {
                 plan.cross_stores++;
                 const int a = e.nrd++;
-                os << "\tmad.lo.u64 %rd" << a << ", %rd4, " << cross[i] << ", %rd3;\n";
+                e.row_addr(os, a, "%rd3", "%rd4", cross[i]);
                 if (spt == 2)
                     os << "\tst.global.v2.f64 [%rd" << a << "], {" << e.fd(r, 0) << ", " << e.fd(r, 1) << "};\n";
                 else
@@ -683,6 +692,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, 
           << "\tld.param.u64 %rd10, [p_batch];\n"
           << "\tld.param.u64 %rd2, [p_ld_leaf];\n\tshl.b64 %rd2, %rd2, " << esh << ";\n"
           << "\tld.param.u64 %rd4, [p_ld_cross];\n\tshl.b64 %rd4, %rd4, " << esh << ";\n"
+          << "\tcvt.u32.u64 %r13, %rd2;\n\tcvt.u32.u64 %r14, %rd4;\n"
           << "\tld.param.u64 %rd14, [p_out];\n\tcvta.to.global.u64 %rd14, %rd14;\n";
         if (acc) {
             p << "\tshr.u64 %rd15, %rd8, 5;\n\tld.param.u64 %rd5, [p_nroots];\n\tmul.lo.u64 %rd15, %rd15, %rd5;\n"

@@ -27,7 +27,8 @@ struct JitPlan {
 };
 
 // linearise the emitted function in fold order, cut it into segments of `seg_ops` operations, write their PTX
-int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, JitPlan &plan, std::string &err);
+// wide_strides: row offsets need 64 bits (a leading dimension of 4 GiB or more)
+int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strides, JitPlan &plan, std::string &err);
 // assemble every segment with the PTX compiler library (no GPU needed), segments in parallel
 int jit_compile(JitPlan &plan, std::string &err);
 

@@ -258,3 +258,19 @@ def test_large_batch_properties():
     sub = leaf[:, idx].cpu().numpy()
     want = O.Oracle(f.raw).eval(np.ascontiguousarray(sub))
     assert root[:, idx].cpu().numpy().tobytes() == want.tobytes()
+
+
+def test_leading_dimension_of_4_gib_and_more():
+    """Row offsets are one 32-bit multiply-add in the specialised kernels; a leaf matrix whose leading dimension
+    reaches 4 GiB takes the 64-bit variant.  Only the first `batch` columns of each row are touched."""
+    roots = graphgen.random_dag(91, n_leaves=3, n_inner=12, n_roots=2)
+    raw, _ = fd.flatten(roots)
+    ev = fd.compile_raw(raw, backend=JIT)
+    batch, ld = 2050, (1 << 29) + 16
+    host = graphgen.leaf_values(3, ev.n_leaves, batch, signed=True)
+    leaf = torch.empty(ev.n_leaves, ld, dtype=torch.float64, device="cuda")
+    leaf[:, :batch] = torch.from_numpy(host).cuda()
+    root = torch.zeros(ev.n_roots, batch, dtype=torch.float64, device="cuda")
+    ev.eval_device(leaf.data_ptr(), ld, root.data_ptr(), batch, batch, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert root.cpu().numpy().tobytes() == O.Oracle(raw).eval(host).tobytes()
