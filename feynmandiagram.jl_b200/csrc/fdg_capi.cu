@@ -59,7 +59,6 @@ struct DeviceState {
 struct JitVariant {
     fdg::JitPlan plan;
     bool compiled = false;
-    std::vector<int> occ;  // resident blocks per SM of each segment kernel (prefetch distance)
     std::map<int, std::vector<cudaKernel_t>> kernels;  // per device
     std::map<int, cudaLibrary_t> libs_first;           // (libraries are kept alive with the handle)
     std::map<int, std::vector<cudaLibrary_t>> libs;
@@ -205,9 +204,6 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
             cudaKernel_t k;
             CUDA_TRY(cudaLibraryGetKernel(&k, lib, sg.name.c_str()));
             kern.push_back(k);
-            int occ = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k, 128, 0));
-            if (v->occ.size() < kern.size()) v->occ.push_back(std::max(occ, 1));
         }
     }
     const fdg::Lowered &low = h->low;
@@ -265,10 +261,8 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
         void *p_out = acc ? out : static_cast<void *>(static_cast<char *>(root) + (size_t)b0 * es);
         void *p_cross = ds.cross;
         long long a_ld_leaf = ld_leaf, a_ld_cross = ld_cross, a_ld_root = ld_root, a_batch = nb, a_nroots = low.R * W;
-        long long a_ahead = 0;
-        void *args[] = {(void *)&p_leaf, &a_ld_leaf, &p_cross, &a_ld_cross, &p_out, &a_ld_root, &a_batch, &a_nroots, &a_ahead};
+        void *args[] = {(void *)&p_leaf, &a_ld_leaf, &p_cross, &a_ld_cross, &p_out, &a_ld_root, &a_batch, &a_nroots};
         for (size_t sg = 0; sg < kern.size(); ++sg) {
-            a_ahead = (long long)ds.sm_count * v->occ[sg];  // prefetch distance: one resident wave of blocks
             CUDA_TRY(cudaLaunchKernel((const void *)kern[sg], dim3(grid), dim3(T), args, 0, stream));
             h->launches++;
         }

@@ -448,8 +448,6 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
         }
     }
     if (seg_ops <= 0) seg_ops = cplx ? 2500 : 4500;  // a complex multiply is six instructions
-    int prefetch = 0;
-    if (const char *pf = getenv("FDG_JIT_PREFETCH")) prefetch = atoi(pf);
     bool ring_on = true;
     int ring_rows = 0;
     if (const char *rg = getenv("FDG_JIT_RING")) ring_on = atoi(rg) != 0;
@@ -677,7 +675,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
         p << ".version 8.7\n.target sm_100a\n.address_size 64\n\n";
         p << ".visible .entry " << js.name << "(\n"
           << "\t.param .u64 p_leaf, .param .u64 p_ld_leaf, .param .u64 p_cross, .param .u64 p_ld_cross,\n"
-          << "\t.param .u64 p_out, .param .u64 p_ld_root, .param .u64 p_batch, .param .u64 p_nroots, .param .u64 p_ahead)\n"
+          << "\t.param .u64 p_out, .param .u64 p_ld_root, .param .u64 p_batch, .param .u64 p_nroots)\n"
           << ".maxntid 128, 1, 1\n";
         if (const char *mr = getenv("FDG_JIT_MAXNREG")) p << ".maxnreg " << atoi(mr) << "\n";
         p << "{\n";
@@ -726,38 +724,6 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
             }
             p << pro.str();
         }
-        if (prefetch > 0 && !e.persistent && !in_rows.empty()) {
-            // One thread per block asks the TMA unit to pull the input rows of a block `p_ahead` positions further down
-            // the grid into L2 (cp.async.bulk.prefetch.L2: one instruction per 1 KB row, no registers, no completion
-            // to wait for), so that block's loads find their data on chip; the first wave also fetches its own rows.
-            const int row_bytes = 128 * samples_per_thread * (cplx ? 16 : 8);
-            p << "\tsetp.ne.u32 %p6, %r2, 0;\n\t@%p6 bra FDG_PF_DONE;\n"
-              << "\tld.param.u64 %rd16, [p_ahead];\n"
-              << "\tld.param.u64 %rd17, [p_leaf];\n\tcvta.to.global.u64 %rd17, %rd17;\n";
-            if (n_cross > 0) p << "\tld.param.u64 %rd18, [p_cross];\n\tcvta.to.global.u64 %rd18, %rd18;\n";
-            for (int pass = 0; pass < 2; ++pass) {
-                // pass 0: the block `ahead` further on; pass 1: this block itself, first wave only (ctaid < ahead)
-                const char *lbl = pass == 0 ? "FDG_PF_OWN" : "FDG_PF_DONE";
-                if (pass == 0) {
-                    p << "\tmul.lo.u64 %rd19, %rd16, " << 128 * samples_per_thread << ";\n\tadd.u64 %rd19, %rd19, %rd0;\n";
-                } else {
-                    p << "\tcvt.u64.u32 %rd19, %r0;\n\tsetp.ge.u64 %p7, %rd19, %rd16;\n\t@%p7 bra FDG_PF_DONE;\n"
-                      << "\tmov.u64 %rd19, %rd0;\n";
-                }
-                // bytes of the row segment: min(row_bytes, (batch - first) * element), rounded down to 16
-                p << "\tsub.s64 %rd20, %rd10, %rd19;\n\tsetp.le.s64 %p7, %rd20, 0;\n\t@%p7 bra " << lbl << ";\n"
-                  << "\tshl.b64 %rd20, %rd20, " << esh << ";\n\tmin.u64 %rd20, %rd20, " << row_bytes << ";\n"
-                  << "\tand.b64 %rd20, %rd20, -16;\n\tcvt.u32.u64 %r5, %rd20;\n\tsetp.eq.u32 %p7, %r5, 0;\n\t@%p7 bra " << lbl << ";\n"
-                  << "\tshl.b64 %rd21, %rd19, " << esh << ";\n\tadd.u64 %rd22, %rd17, %rd21;\n";
-                if (n_cross > 0) p << "\tadd.u64 %rd23, %rd18, %rd21;\n";
-                for (const auto &row : in_rows) {
-                    p << "\tmad.lo.u64 %rd24, " << (row.first ? "%rd4" : "%rd2") << ", " << row.second << ", " << (row.first ? "%rd23" : "%rd22") << ";\n"
-                      << "\tcp.async.bulk.prefetch.L2.global [%rd24], %r5;\n";
-                }
-                if (pass == 0) p << "FDG_PF_OWN:\n";
-            }
-            p << "FDG_PF_DONE:\n";
-        }
         p << body;
         if (e.persistent) {
             p << "\tadd.u64 %rd0, %rd0, %rd9;\n\tsetp.lt.s64 %p5, %rd0, %rd10;\n\t@%p5 bra FDG_LOOP;\n";
@@ -804,6 +770,13 @@ static int compile_one(JitSegment &js, std::string &err) {
     nvPTXCompilerGetCompiledProgramSize(h, &n);
     js.cubin.resize(n);
     nvPTXCompilerGetCompiledProgram(h, js.cubin.data());
+    if (const char *dir = getenv("FDG_JIT_DUMP_CUBIN")) {  // debugging aid: cuobjdump -sass / nvdisasm -plr on the kernels
+        const std::string path = std::string(dir) + "/" + js.name + ".cubin";
+        if (FILE *fp = std::fopen(path.c_str(), "wb")) {
+            std::fwrite(js.cubin.data(), 1, js.cubin.size(), fp);
+            std::fclose(fp);
+        }
+    }
     size_t ln = 0;
     nvPTXCompilerGetInfoLogSize(h, &ln);
     if (ln) {
