@@ -133,7 +133,7 @@ def test_term_blocks_every_operand_count(term_len):
 
 
 @pytest.mark.parametrize("name", ["gv_sigma_o3", "gv_ver4_o2", "gv_ver4_o3", "gv_sigma_o5", "parquet_sigma_o2", "parquet_sigma_o3",
-                                  "parquet_sigma_o4", "parquet_ver4_o3"])
+                                  "parquet_sigma_o4", "parquet_ver4_o3", "taylor_sigma_o3"])
 @pytest.mark.parametrize("spt,backend", [(2, VM), (4, VM), (1, JIT), (2, JIT)])
 def test_real_workload_graphs(name, spt, backend):
     import os
@@ -144,6 +144,21 @@ def test_real_workload_graphs(name, spt, backend):
     batch = 4096
     leaf = graphgen.leaf_values(5, ev.n_leaves, batch, signed=True)
     got = _dev_eval(ev, leaf, batch, spt)
+    assert got.tobytes() == orc.eval(leaf).tobytes()
+
+
+@pytest.mark.parametrize("name", ["taylor_sigma_o2", "taylor_sigma_o3", "taylor_sigma_o4", "parquet_ver4_o2"])
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_real_workload_graphs_complex(name, backend):
+    # BASELINE config 5: the Taylor-mode AD self-energy graphs with ComplexF64 leaves
+    import os
+
+    raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", name + ".npz"))
+    ev = fd.compile_raw(raw, dtype=np.complex128, backend=backend)
+    orc = O.Oracle(raw)
+    batch = 2048
+    leaf = graphgen.leaf_values(6, ev.n_leaves, batch, dtype=np.complex128, signed=True)
+    got = _dev_eval(ev, leaf, batch)
     assert got.tobytes() == orc.eval(leaf).tobytes()
 
 

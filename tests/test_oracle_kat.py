@@ -116,3 +116,77 @@ def test_exact_rational_agrees():
         bound = O.eval_abs_bound(orc, leaf[:, b])
         for r in range(orc.n_roots):
             assert abs(out[r, b] - float(exact[r])) <= 64 * 2.3e-16 * bound[r] * orc.n_stmts
+
+
+# ---- Taylor-mode AD (BASELINE config 5): the restated front end against the reference's own known answers ------------
+
+
+def test_taylor_series_known_answers():
+    # reference test/taylor.jl:42-56
+    from oracle.frontend import taylor as T
+
+    a, b, c, d, e = T.set_variables([3, 3, 3, 3, 3])
+    F1 = (a + b) * (a + b) * (a + b)
+    assert F1.coeffs[(2, 1, 0, 0, 0)] == 3.0 and F1.coeffs[(1, 2, 0, 0, 0)] == 3.0
+    assert F1.coeffs[(3, 0, 0, 0, 0)] == 1.0 and F1.coeffs[(0, 3, 0, 0, 0)] == 1.0
+    F2 = (1 + a) * (3 + 2 * c)
+    assert F2.coeffs[(0, 0, 0, 0, 0)] == 3.0 and F2.coeffs[(1, 0, 0, 0, 0)] == 3.0
+    assert F2.coeffs[(0, 0, 1, 0, 0)] == 2.0 and F2.coeffs[(1, 0, 1, 0, 0)] == 2.0
+    F3 = (a + b) ** 3
+    assert F3.coeffs[(2, 1, 0, 0, 0)] == 3.0 and F3.coeffs[(0, 3, 0, 0, 0)] == 1.0
+    assert (4, 0, 0, 0, 0) not in ((a + b) ** 4).coeffs  # truncated at the maximal orders (arithmetic.jl:175)
+
+
+def _graphs_from_raw(d):
+    """Graph objects from flattened arrays (children come before parents in fd.flatten's order)."""
+    nodes = []
+    ops = {0: fd.Unitary(), 1: fd.Sum(), 2: fd.Prod()}
+    for i in range(len(d["node_id"])):
+        lo, hi = d["child_ptr"][i], d["child_ptr"][i + 1]
+        subs = [nodes[c] for c in d["child_node"][lo:hi]]
+        op = fd.Power(d["node_pow"][i]) if d["node_op"][i] == 3 else ops[d["node_op"][i]]
+        g = fd.Graph(subs, subgraph_factors=d["child_factor"][lo:hi], operator=op if subs else fd.Sum())
+        nodes.append(g)
+    return nodes, [nodes[i] for i in d["graphs"]]
+
+
+def test_taylor_expansion_equals_counterterm_diagram_files():
+    """reference test/taylor.jl:96-112: the Taylor coefficients [g, v] of the two order-2 self-energy graphs equal the
+    diagrams of the counter-term files Sigma2_<v>_<g>.diag (all leaves one).  Fixture: tools/gen_golden_taylor.py."""
+    import json
+    import os
+
+    from oracle.frontend import taylor as T
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "taylor_sigma2.json")) as fh:
+        gold = json.load(fh)
+    nodes, roots = _graphs_from_raw(gold["graph"])
+    var = {n.id: [k == "G", k == "W"] for n, k in zip(nodes, gold["node_kind"]) if n.isleaf()}
+    series, _ = T.taylorexpansion(roots, var, [2, 2])
+    assert len(gold["expected"]) == 8
+    for key, want in gold["expected"].items():
+        g, v = (int(x) for x in key.split(","))
+        coeffs = [series[0].coeffs[(g, v)], series[1].coeffs[(g, v)]]
+        raw, _ = fd.flatten(coeffs)
+        orc = O.Oracle(raw)
+        got = orc.eval(np.ones((orc.n_leaves, 1)))[:, 0]
+        assert list(got) == want, (key, list(got), want)
+        assert [O.eval_interp_py(c) for c in coeffs] == want  # eval! with the default leaf weight... every leaf 1.0
+
+
+def test_taylor_workload_checksums():
+    """The committed config-5 graphs: all-leaves-one values of the 6 x 3 coefficient roots of the order-3 self-energy
+    scale with the number of ways to place the counter-term orders (binomial pattern of the order-(0,0) values)."""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    man = json.load(open(os.path.join(root, "workloads", "MANIFEST.json")))
+    raw = fd.RawGraph.load(os.path.join(root, "workloads", "taylor_sigma_o3.npz"))
+    orc = O.Oracle(raw)
+    ones = orc.eval(np.ones((orc.n_leaves, 1)))[:, 0]
+    assert list(ones) == man["taylor_sigma_o3"]["all_leaves_one"]
+    base = ones[:3]
+    # order-3 self-energy: 5 propagators, 3 interactions -> (0,1): C(3,1)=3, (1,0): C(5,1)=5, (2,0): C(6,2)=15, products for mixed
+    for k, mult in enumerate([1, 3, 5, 15, 15, 45]):
+        assert list(ones[3 * k:3 * k + 3]) == list(mult * base)

@@ -23,11 +23,12 @@ from oracle.frontend import gv, optimize as opt  # noqa: E402
 OUT = os.path.join(ROOT, "workloads")
 
 
-def emit(name, builder, source, manifest):
+def emit(name, builder, source, manifest, optimize=True):
     t = time.time()
     fd.uidreset()
     graphs = builder()
-    opt.optimize(graphs)
+    if optimize:
+        opt.optimize(graphs)
     raw, _ = fd.flatten(graphs)
     raw.save(os.path.join(OUT, name + ".npz"))
     orc = O.Oracle(raw)
@@ -41,8 +42,35 @@ def emit(name, builder, source, manifest):
     print(f"{name}: L={orc.n_leaves} stmts={orc.n_stmts} R={orc.n_roots} edges={raw.n_edges}  ({time.time() - t:.1f}s)")
 
 
+def taylor_workloads(manifest):
+    """BASELINE config 5: README.md:59-86 -- Parquet self-energy, optimize!, then taylorAD with Green's-function
+    counter-terms up to order 2 and interaction counter-terms up to order 1; every coefficient graph is a root."""
+    from oracle.frontend import parquet as pq, taylor
+    from oracle.frontend.ids import BareGreenId, BareInteractionId
+
+    def build(order):
+        pq._ver4I.clear()
+        graphs = [r["diagram"] for r in pq.sigma(pq.DiagPara(type=pq.SigmaDiag, innerLoopNum=order))]
+        opt.optimize(graphs)
+        d = taylor.taylorAD(graphs, [2, 1], [lambda p: isinstance(p, BareGreenId), lambda p: isinstance(p, BareInteractionId)])
+        return [g for k in sorted(d) for g in d[k]]
+
+    for order in (2, 3, 4):
+        emit(f"taylor_sigma_o{order}", lambda o=order: build(o),
+             f"taylorAD(optimize!(Parquet.sigma(DiagPara(type=SigmaDiag, innerLoopNum={order}))), [2, 1], [BareGreenId, BareInteractionId]); "
+             "roots = the coefficient graphs of orders (0,0) (0,1) (1,0) (1,1) (2,0) (2,1)  (README.md:59-86, src/utility.jl:48-93)",
+             manifest, optimize=False)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "taylor":  # add / refresh the Taylor workloads only
+        with open(os.path.join(OUT, "MANIFEST.json")) as fh:
+            manifest = json.load(fh)
+        taylor_workloads(manifest)
+        with open(os.path.join(OUT, "MANIFEST.json"), "w") as fh:
+            json.dump(manifest, fh, indent=1, sort_keys=True)
+        return
     manifest = {}
     for order in (2, 3, 4, 5, 6):
         emit(f"gv_sigma_o{order}", lambda o=order: gv.diagsGV("sigma", o),
@@ -71,6 +99,7 @@ def main():
         emit(f"parquet_ver4_o{order}", lambda o=order: pq_ver4(o),
              f"Parquet.vertex4(DiagPara(type=Ver4Diag, innerLoopNum={order})) + optimize!  (example/benchmark.jl:13,23-25)",
              manifest)
+    taylor_workloads(manifest)
     with open(os.path.join(OUT, "MANIFEST.json"), "w") as fh:
         json.dump(manifest, fh, indent=1, sort_keys=True)
 
