@@ -447,7 +447,10 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
             std::fclose(fp);
         }
     }
-    if (seg_ops <= 0) seg_ops = cplx ? 2500 : 4500;  // a complex multiply is six instructions
+    // `seg_ops` is a budget of machine instructions per kernel (estimated below): what bounds a kernel is the
+    // instruction cache -- straight-line code of more than about 100 KB stalls on instruction fetch (measured,
+    // DESIGN.md section 6) -- so a complex multiply counts six and a negation folded into its reader none
+    if (seg_ops <= 0) seg_ops = 4000;
     bool ring_on = true;
     int ring_rows = 0;
     if (const char *rg = getenv("FDG_JIT_RING")) ring_on = atoi(rg) != 0;
@@ -462,6 +465,27 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
         if (is_binary(o) && o.b >= 0) last_use[(size_t)o.b] = (int32_t)i;
     }
     std::vector<int32_t> seg_start{0};
+    std::vector<int64_t> cost(nops + 1, 0);  // prefix sums of the instruction estimate
+    {
+        const int S = samples_per_thread;
+        for (size_t i = 0; i < nops; ++i) {
+            const IrOp &o = ir[i];
+            int64_t w = 0;
+            switch (o.kind) {
+                case IR_MUL: w = cplx ? 6 : S; break;
+                case IR_ADD:
+                case IR_SCALE: w = cplx ? 2 : S; break;
+                case IR_NEG: w = 0; break;
+                case IR_POW: {
+                    int lg = 0;
+                    while ((1 << (lg + 1)) <= o.n) ++lg;
+                    w = o.n <= 3 ? (o.n - 1) * (cplx ? 6 : S) : (cplx ? 12 * lg : 14 * lg * S);
+                } break;
+                default: w = acc ? 28 * W : 2; break;  // a root: warp reduction + partial-row update, or a store
+            }
+            cost[i + 1] = cost[i] + w;
+        }
+    }
     {
         // live[p] = values defined before op p and read at or after p (what a cut in front of p sends through memory)
         std::vector<int32_t> live(nops + 2, 0);
@@ -474,10 +498,15 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
         const char *nc = getenv("FDG_JIT_NARROW_CUTS");
         const bool narrow = !(nc && atoi(nc) == 0);
         size_t start = 0;
-        while (nops - start > (size_t)seg_ops + (narrow ? (size_t)seg_ops / 4 : 0)) {
-            size_t cut = start + (size_t)seg_ops;
+        // first position whose cost since `start` reaches c
+        auto pos_at = [&](size_t from, int64_t c) {
+            return (size_t)(std::lower_bound(cost.begin() + (long)from, cost.end(), cost[from] + c) - cost.begin());
+        };
+        while (cost[nops] - cost[start] > (int64_t)seg_ops + (narrow ? seg_ops / 4 : 0)) {
+            size_t cut = std::min(nops - 1, std::max(start + 1, pos_at(start, seg_ops)));
             if (narrow) {
-                const size_t lo_w = start + (size_t)seg_ops * 3 / 4, hi_w = std::min(nops - 1, start + (size_t)seg_ops * 5 / 4);
+                const size_t lo_w = std::max(start + 1, pos_at(start, (int64_t)seg_ops * 3 / 4));
+                const size_t hi_w = std::min(nops - 1, pos_at(start, (int64_t)seg_ops * 5 / 4));
                 for (size_t q = lo_w; q <= hi_w; ++q)
                     if (live[q] <= live[cut]) cut = q;
             }
