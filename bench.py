@@ -13,8 +13,9 @@ batch from HBM (inputs larger than L2, no cache flush needed).
 `value`   graph-evals/s = samples/s x R roots, whole job over all ranks, inputs resident in HBM.
 `e2e`     same metric through the reference-facing call eval_graph(root, leafVal) with HOST buffers (pinned):
           H2D of the leaves and D2H of the roots inside the timed region.
-`--impl reference` times the CPU restatement of the reference's generated function (oracle/, "port": no julia
-binary exists in this image) on all host cores, on a bounded sample of the same workload.
+`--impl reference` times the reference's own CPU design point for the path -- the emitted C function (to_Cstr text)
+compiled with gcc, one call per sample (oracle/emit_c.py; "port": no julia binary exists in this image) -- on all host
+cores, on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -119,12 +120,34 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference(raw, dtype, target_seconds, nthreads=0):
-    """Times the CPU port of the reference's generated function (oracle/fdg_oracle.c, emitter semantics, one
-    contiguous leafVal per sample, OpenMP over samples).  Returns (samples/s, threads, samples, seconds)."""
+def cpu_evaluator(raw, dtype, compile_timeout):
+    """The CPU arm: the reference's own design point for this path, `Compilers.compile_C` + a C compiler -- the emitted
+    straight-line function (same text as to_Cstr, static.jl:155-197) built with gcc -O2 -ffp-contract=off and called
+    once per sample, OpenMP over samples (oracle/emit_c.py).  Prebuilt by __graft_entry__.build() for the default
+    workloads; compiled here otherwise (bounded by `compile_timeout`).  If that cannot be done in time the array-walking
+    oracle (oracle/fdg_oracle.c, ~20x slower per core) runs instead, and the line says so."""
+    from oracle import emit_c
     from oracle import oracle as O
 
-    orc = O.Oracle(raw)
+    try:
+        em = emit_c.Emitted(raw, dtype, timeout=compile_timeout)
+
+        def run(leaf, root, cores):
+            em.eval(leaf, root=root, nthreads=cores)
+
+        return run, em.orc, "to_Cstr text compiled with gcc -O2 -ffp-contract=off (the reference's compile_C path), one call per sample"
+    except Exception as ex:  # noqa: BLE001
+        orc = O.Oracle(raw)
+
+        def run(leaf, root, cores):
+            orc.eval(leaf, mode="emitter", layout="sample", nthreads=cores, root=root)
+
+        return run, orc, f"array-walking C port of the emitted function (gcc on the emitted text unavailable: {type(ex).__name__})"
+
+
+def cpu_reference(raw, dtype, target_seconds, nthreads=0, compile_timeout=240.0):
+    """Times the CPU arm on a bounded sample.  Returns (samples/s, threads, samples, seconds, description)."""
+    run_fn, orc, what = cpu_evaluator(raw, dtype, compile_timeout)
     # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ask the scheduler, not OpenMP)
     cores = len(os.sched_getaffinity(0)) if nthreads <= 0 else nthreads
     rng = np.random.default_rng(1234)
@@ -132,18 +155,18 @@ def cpu_reference(raw, dtype, target_seconds, nthreads=0):
 
     def run(n):
         leaf = (0.5 + rng.random((n, max(orc.n_leaves, 1)))).astype(npdt)
-        root = np.zeros((n, orc.n_roots), npdt)
+        root = np.zeros((n, max(orc.n_roots, 1)), npdt)
         t = time.perf_counter()
-        orc.eval(leaf, mode="emitter", layout="sample", nthreads=cores, root=root)
+        run_fn(leaf, root, cores)
         return time.perf_counter() - t
 
-    n = max(cores * 4, 64)
+    n = max(cores * 16, 256)
     run(n)  # warm
     t = run(n)
-    n2 = int(min(max(n, n * target_seconds / max(t, 1e-6)), 1 << 24))
+    n2 = int(min(max(n, n * target_seconds / max(t, 1e-6)), 1 << 24, (2 << 30) // max(orc.n_leaves * (8 if dtype == "f64" else 16), 1)))
     n2 = max(cores, (n2 // cores) * cores)
     t2 = run(n2)
-    return n2 / t2, cores, n2, t2
+    return n2 / t2, cores, n2, t2, what
 
 
 def main():
@@ -156,25 +179,30 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        from oracle import oracle as O
-
-        orc = O.Oracle(raw)
+        run_fn, orc, what = cpu_evaluator(raw, a.dtype, 240.0)
         R = orc.n_roots
+        cores = len(os.sched_getaffinity(0))
         per_step = a.cpu_seconds / max(a.steps + a.warmup, 1)
-        rate0, cores, _, _ = cpu_reference(raw, a.dtype, 1.0)
-        n = int(max(cores, rate0 * per_step))
         npdt = np.float64 if a.dtype == "f64" else np.complex128
         rng = np.random.default_rng(1234)
+        probe = max(cores * 16, 256)
+        leaf = (0.5 + rng.random((probe, max(orc.n_leaves, 1)))).astype(npdt)
+        root = np.zeros((probe, max(R, 1)), npdt)
+        run_fn(leaf, root, cores)
+        t = time.perf_counter()
+        run_fn(leaf, root, cores)
+        rate0 = probe / max(time.perf_counter() - t, 1e-6)
+        n = int(max(cores, min(rate0 * per_step, (2 << 30) // max(orc.n_leaves * leaf.itemsize, 1))))
         leaf = (0.5 + rng.random((n, max(orc.n_leaves, 1)))).astype(npdt)
-        root = np.zeros((n, R), npdt)
+        root = np.zeros((n, max(R, 1)), npdt)
         for _ in range(a.warmup):
-            orc.eval(leaf, mode="emitter", layout="sample", nthreads=cores, root=root)
+            run_fn(leaf, root, cores)
         t = time.perf_counter()
         for _ in range(a.steps):
-            orc.eval(leaf, mode="emitter", layout="sample", nthreads=cores, root=root)
+            run_fn(leaf, root, cores)
         dt = time.perf_counter() - t
         val = n * a.steps * R / dt
-        sample = f"{n} samples/step x {a.steps} steps of {a.workload}, sample-major leaves, emitter-order C port, OpenMP"
+        sample = f"{n} samples/step x {a.steps} steps of {a.workload}, sample-major leaves; {what}; OpenMP over samples"
         print(json.dumps({
             "impl": "reference", "metric": "MC-sample graph-evals/sec", "value": val, "unit": "graph-evals/s",
             "samples_per_s": val / R, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
@@ -354,10 +382,9 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------------
     if rank == 0 and world == 1 and not a.no_cpu:
-        rate, cores, n, secs = cpu_reference(raw, a.dtype, a.cpu_seconds)
+        rate, cores, n, secs, what = cpu_reference(raw, a.dtype, a.cpu_seconds)
         out["cpu_baseline"] = {"value": rate * R, "unit": "graph-evals/s", "cores": cores, "kind": "port",
-                               "sample": f"{n} samples of {a.workload} in {secs:.1f} s, emitter-order C port of the generated "
-                                         f"function (oracle/fdg_oracle.c), sample-major leaves, OpenMP over samples"}
+                               "sample": f"{n} samples of {a.workload} in {secs:.1f} s; {what}; sample-major leaves, OpenMP over samples"}
     if rank == 0:
         print(json.dumps(out))
     if comm is not None:

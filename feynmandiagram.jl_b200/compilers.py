@@ -24,6 +24,8 @@ from typing import Dict, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _capi
+from .emitters import (compile_C, compile_Julia, compile_Python, julia_to_C_typestr, to_Cstr, to_julia_str,  # noqa: F401
+                       to_python_str, to_static)
 from .graph import Graph
 from .program import RawGraph, flatten
 

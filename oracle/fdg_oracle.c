@@ -416,6 +416,20 @@ int oracle_run_emitted(emitted_fn fn, double *leaf, int64_t ld_leaf, double *roo
     return used;
 }
 
+/* same for `complex double` (ComplexF64) functions: ld_* count complex elements */
+typedef void (*emitted_fn_c128)(cplx *root, cplx *leafVal);
+int oracle_run_emitted_c128(emitted_fn_c128 fn, cplx *leaf, int64_t ld_leaf, cplx *root, int64_t ld_root, int64_t batch,
+                            int nthreads) {
+    int used = 1;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+    used = nthreads;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+#endif
+    for (int64_t b = 0; b < batch; ++b) fn(root + b * ld_root, leaf + b * ld_leaf);
+    return used;
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
