@@ -380,6 +380,48 @@ def main():
                       "api": "Compilers.compile(graphs) -> eval_graph(root, leafVal) on pinned host arrays (fdg_eval_host)"}
         del hl, hr
 
+    # ---- e2e with the leaves generated on the device: host (K, tau) in, R sums out ----------------
+    side = os.path.join(ROOT, "workloads", a.workload + ".leaves.npz")
+    if not a.no_e2e and a.dtype == "f64" and os.path.exists(side):
+        meta = dict(np.load(side))
+        gen = fd.LeafGenerator(meta)  # kF, beta, lambda of example/benchmark.jl:11-18
+        bg = 1 << 22
+        rows = gen.var_rows
+        hv = torch.empty(rows, bg, dtype=torch.float64).pin_memory()
+        hv_np = hv.numpy()
+        rng = np.random.default_rng(7 + rank)
+        hv_np[...] = rng.random(hv_np.shape) * 2 - 0.7
+        hv_np[gen.dim * gen.n_loops:] = rng.random((gen.n_tau, bg)) * gen.beta
+        hK, hT = hv_np[: gen.dim * gen.n_loops], hv_np[gen.dim * gen.n_loops:]
+        for _ in range(2):
+            gen.accumulate_host(f, hK, hT)
+        barrier()
+        k_gen = max(2, min(a.steps, 5))
+        t = time.perf_counter()
+        for _ in range(k_gen):
+            gen.accumulate_host(f, hK, hT)  # H2D of (K, tau), leaf generation, graph kernels, D2H of the R sums; synchronous
+        dt = time.perf_counter() - t
+        # the generation kernel alone, on device-resident variables
+        dv = hv.cuda()
+        nfill = min(bg, res)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gen.fill_device(dv.data_ptr(), dv[gen.dim * gen.n_loops:].data_ptr(), bg, nfill, leaf.data_ptr(), res, stream)
+        e0.record()
+        gen.fill_device(dv.data_ptr(), dv[gen.dim * gen.n_loops:].data_ptr(), bg, nfill, leaf.data_ptr(), res, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        out["e2e_generated"] = {
+            "value": bg * k_gen * world * R / dt, "unit": "graph-evals/s", "samples_per_s": bg * k_gen * world / dt,
+            "h2d_bytes_per_step": rows * 8 * bg, "d2h_bytes_per_step": R * 8, "samples_per_step_per_gpu": bg, "steps": k_gen,
+            "leafgen_kernel_samples_per_s": nfill / (e0.elapsed_time(e1) * 1e-3),
+            "api": "fdg_eval_generated_host: host (K, tau) of example/benchmark.jl:44-53 -> leaves on device (fdg_leafgen) -> "
+                   "graph kernels -> R per-root sums; leaf values overwrite the synthetic resident batch AFTER the timed region above"}
+        del hv, dv
+
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------------
     if rank == 0 and world == 1 and not a.no_cpu:
         rate, cores, n, secs, what = cpu_reference(raw, a.dtype, a.cpu_seconds)

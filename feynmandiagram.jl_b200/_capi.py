@@ -45,12 +45,22 @@ class Stats(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved"}
 
 
+class LeafGenDesc(C.Structure):
+    _fields_ = [
+        ("n_leaves", C.c_int64), ("leaf_type", C.POINTER(C.c_int32)), ("leaf_order", C.POINTER(C.c_int32)),
+        ("tau_in", C.POINTER(C.c_int32)), ("tau_out", C.POINTER(C.c_int32)), ("loop_index", C.POINTER(C.c_int32)),
+        ("n_basis", C.c_int64), ("n_loops", C.c_int64), ("dim", C.c_int64), ("n_tau", C.c_int64),
+        ("loop_basis", C.POINTER(C.c_double)), ("kF", C.c_double), ("beta", C.c_double), ("lam", C.c_double),
+    ]
+
+
 # every symbol include/fdgraph.h declares; tests check that the library exports each one
 EXPORTS = [
     "fdg_abi_version", "fdg_last_error", "fdg_compile", "fdg_destroy", "fdg_stats", "fdg_leafmap", "fdg_last_root",
     "fdg_program_words", "fdg_eval", "fdg_eval_accumulate", "fdg_eval_host", "fdg_set_launch", "fdg_launch_count",
     "fdg_comm_unique_id", "fdg_comm_init", "fdg_comm_destroy", "fdg_allreduce", "fdg_jit_prepare", "fdg_jit_ptx",
-    "fdg_jit_info",
+    "fdg_jit_info", "fdg_leafgen_create", "fdg_leafgen_destroy", "fdg_leafgen_fill", "fdg_eval_generated_accumulate",
+    "fdg_eval_generated_host",
 ]
 BACKEND_AUTO, BACKEND_VM, BACKEND_JIT = 0, 1, 2
 
@@ -87,6 +97,11 @@ def lib() -> C.CDLL:
     L.fdg_jit_prepare.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
     L.fdg_jit_ptx.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
     L.fdg_jit_info.argtypes = [vp, i32, i32, C.POINTER(i64), i32]
+    L.fdg_leafgen_create.argtypes = [C.POINTER(LeafGenDesc), C.POINTER(vp)]
+    L.fdg_leafgen_destroy.argtypes = [vp]
+    L.fdg_leafgen_fill.argtypes = [vp, vp, vp, i64, i64, vp, i64, vp]
+    L.fdg_eval_generated_accumulate.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp]
+    L.fdg_eval_generated_host.argtypes = [vp, vp, vp, vp, i64, i64, vp]
     for name in EXPORTS:
         if name not in ("fdg_abi_version", "fdg_last_error"):
             getattr(L, name).restype = C.c_int

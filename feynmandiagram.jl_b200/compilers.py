@@ -202,3 +202,64 @@ def compile_raw(raw: RawGraph, *, dtype=np.float64, max_slots: int = 0, prefetch
     """Compile an already flattened graph (e.g. a workload file written by another host)."""
     return Evaluator(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch, schedule=schedule, backend=backend,
                      jit_segment=jit_segment, cse=cse)
+
+
+class LeafGenerator:
+    """Leaf values computed on the device from the Monte-Carlo variables (include/fdgraph.h, fdg_leafgen_*): what the
+    integrand of example/benchmark.jl:44-81 does for every sample with the metadata of `leafstates`
+    (src/frontend/frontends.jl:175-232).  `meta` holds leaf_type, leaf_order (L, 2), tau_in, tau_out, loop_index (0-based)
+    and loop_basis (n_basis, n_loops)."""
+
+    def __init__(self, meta, dim: int = 3, kF: float = 1.919, beta: float = 3.0, lam: float = 1.2, n_tau: int = 0):
+        self._keep = {k: np.ascontiguousarray(meta[k], np.float64 if k == "loop_basis" else np.int32)
+                      for k in ("leaf_type", "leaf_order", "tau_in", "tau_out", "loop_index", "loop_basis")}
+        k = self._keep
+        self.n_leaves = int(k["leaf_type"].shape[0])
+        self.n_basis, self.n_loops = (int(x) for x in k["loop_basis"].shape) if k["loop_basis"].ndim == 2 else (0, 0)
+        self.dim = int(dim)
+        self.n_tau = int(n_tau) if n_tau else (int(max(k["tau_in"].max(initial=-1), k["tau_out"].max(initial=-1))) + 1)
+        d = _capi.LeafGenDesc()
+        d.n_leaves = self.n_leaves
+        i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        d.leaf_type, d.leaf_order = k["leaf_type"].ctypes.data_as(i32p), k["leaf_order"].ctypes.data_as(i32p)
+        d.tau_in, d.tau_out = k["tau_in"].ctypes.data_as(i32p), k["tau_out"].ctypes.data_as(i32p)
+        d.loop_index, d.loop_basis = k["loop_index"].ctypes.data_as(i32p), k["loop_basis"].ctypes.data_as(f64p)
+        d.n_basis, d.n_loops, d.dim, d.n_tau = self.n_basis, self.n_loops, self.dim, self.n_tau
+        d.kF, d.beta, d.lam = float(kF), float(beta), float(lam)
+        self.kF, self.beta, self.lam = float(kF), float(beta), float(lam)
+        self._g = C.c_void_p()
+        _capi.check(_capi.lib().fdg_leafgen_create(C.byref(d), C.byref(self._g)))
+
+    def close(self) -> None:
+        if getattr(self, "_g", None):
+            _capi.lib().fdg_leafgen_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def var_rows(self) -> int:
+        """rows of the (K, T) input per sample: dim * n_loops + n_tau"""
+        return self.dim * self.n_loops + self.n_tau
+
+    def fill_device(self, K_ptr: int, T_ptr: int, ld_var: int, batch: int, leaf_ptr: int, ld_leaf: int, stream: int = 0) -> None:
+        """K[(j * dim + c) * ld_var + b], T[t * ld_var + b] -> leaf[l * ld_leaf + b] (device pointers)."""
+        _capi.check(_capi.lib().fdg_leafgen_fill(self._g, K_ptr, T_ptr, ld_var, batch, leaf_ptr, ld_leaf, stream))
+
+    def accumulate_device(self, ev: Evaluator, K_ptr: int, T_ptr: int, ld_var: int, batch: int, acc_ptr: int, stream: int = 0) -> None:
+        """acc[r] += sum over the batch; the leaf matrix only ever exists one sub-batch at a time."""
+        _capi.check(_capi.lib().fdg_eval_generated_accumulate(ev._h, self._g, K_ptr, T_ptr, ld_var, batch, acc_ptr, stream))
+
+    def accumulate_host(self, ev: Evaluator, K: np.ndarray, T: np.ndarray) -> np.ndarray:
+        """K (dim * n_loops, B) and T (n_tau, B) host arrays, batch unit-stride -> the R per-root sums."""
+        K = np.ascontiguousarray(K, np.float64)
+        T = np.ascontiguousarray(T, np.float64)
+        B = K.shape[1]
+        assert K.shape[0] == self.dim * self.n_loops and T.shape == (self.n_tau, B)
+        acc = np.zeros(max(ev.n_roots, 1))
+        _capi.check(_capi.lib().fdg_eval_generated_host(ev._h, self._g, K.ctypes.data, T.ctypes.data, B, B, acc.ctypes.data))
+        return acc[: ev.n_roots]

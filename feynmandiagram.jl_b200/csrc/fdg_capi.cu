@@ -664,3 +664,301 @@ int fdg_allreduce(fdg_comm_t c, double *acc, int64_t n, void *stream) {
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// N1: leaf values computed on the device from the Monte-Carlo variables (include/fdgraph.h; example/benchmark.jl:44-127)
+// =====================================================================================================================
+namespace {
+
+constexpr int FDG_LG_MAXLOOPS = 8;
+constexpr int FDG_LG_THREADS = 128;
+constexpr int FDG_LG_CHUNK = 64;  // leaves per block in y
+
+struct LeafMeta {  // one per leaf, read with uniform (broadcast) loads
+    int32_t type, order, tau_in, tau_out;
+    double basis[FDG_LG_MAXLOOPS];
+};
+
+// x^n for a run-time integer n >= 0: Julia ^(x::Float64, n::Integer) (base/math.jl): 0 -> 1, 1 -> x, 2 -> x*x,
+// 3 -> x*x*x, else pow_body (compensated power by squaring)
+__device__ __forceinline__ double lg_pow(double x, int n) {
+    if (n == 0) return 1.0;
+    if (n == 1) return x;
+    if (n == 2) return __dmul_rn(x, x);
+    if (n == 3) return __dmul_rn(__dmul_rn(x, x), x);
+    double y = 1.0, xnlo = 0.0, ynlo = 0.0;
+    while (n > 1) {
+        if (n & 1) {
+            const double err = __fma_rn(y, xnlo, __dmul_rn(x, ynlo));
+            const double pr = __dmul_rn(x, y);
+            ynlo = __dadd_rn(__fma_rn(x, y, -pr), err);
+            y = pr;
+        }
+        const double err = __dmul_rn(__dmul_rn(x, 2.0), xnlo);
+        const double pr = __dmul_rn(x, x);
+        xnlo = __dadd_rn(__fma_rn(x, x, -pr), err);
+        x = pr;
+        n >>= 1;
+    }
+    const double err = __fma_rn(y, xnlo, __dmul_rn(x, ynlo));
+    return (isfinite(x) && isfinite(err)) ? __fma_rn(x, y, err) : __dmul_rn(x, y);
+}
+
+// green(tau, omega, beta), example/benchmark.jl:113-127 (TAU_CUTOFF = 1e-10; `tau ≈ 0.0` is `tau == 0` for the default
+// tolerances of isapprox against an exact zero)
+__device__ __forceinline__ double lg_green(double tau, double w, double beta) {
+    if (tau == 0.0) tau = -1e-10;
+    if (tau > 0.0)
+        return w > 0.0 ? exp(-w * tau) / (1.0 + exp(-w * beta)) : exp(w * (beta - tau)) / (1.0 + exp(w * beta));
+    return w > 0.0 ? -exp(-w * (tau + beta)) / (1.0 + exp(-w * beta)) : -exp(-w * tau) / (1.0 + exp(w * beta));
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(FDG_LG_THREADS)
+fdg_leafgen_kernel(const LeafMeta *__restrict__ meta, int n_leaves, int n_loops, const double *__restrict__ K,
+                   const double *__restrict__ T, long long ld_var, long long batch, double *__restrict__ leaf,
+                   long long ld_leaf, double kF2, double beta, double lambda) {
+    const long long b = (long long)blockIdx.x * FDG_LG_THREADS + threadIdx.x;
+    if (b >= batch) return;
+    double k[FDG_LG_MAXLOOPS][DIM];
+#pragma unroll
+    for (int j = 0; j < FDG_LG_MAXLOOPS; ++j)
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) k[j][c] = j < n_loops ? K[(long long)(j * DIM + c) * ld_var + b] : 0.0;
+    const int l0 = blockIdx.y * FDG_LG_CHUNK, l1 = min(n_leaves, l0 + FDG_LG_CHUNK);
+    for (int l = l0; l < l1; ++l) {
+        const LeafMeta m = meta[l];
+        double v = 1.0;
+        if (m.type != 0) {
+            // kq = K * basis, summed over the loop momenta in index order; dot(kq, kq) over the components in order
+            double q2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) {
+                double kq = 0.0;
+#pragma unroll
+                for (int j = 0; j < FDG_LG_MAXLOOPS; ++j) kq = __dadd_rn(kq, __dmul_rn(k[j][c], m.basis[j]));
+                q2 = __dadd_rn(q2, __dmul_rn(kq, kq));
+            }
+            if (m.type == 1) {
+                const double tau = __dadd_rn(T[(long long)m.tau_out * ld_var + b], -T[(long long)m.tau_in * ld_var + b]);
+                v = lg_green(tau, __dadd_rn(q2, -kF2), beta);
+            } else {
+                const double invK = 1.0 / __dadd_rn(q2, lambda);
+                v = __dmul_rn(25.132741228718345 / invK, lg_pow(__dmul_rn(lambda, invK), m.order));  // 8pi / invK * (lambda invK)^order
+            }
+        }
+        leaf[(long long)l * ld_leaf + b] = v;
+    }
+}
+
+}  // namespace
+
+struct fdg_leafgen {
+    std::vector<LeafMeta> meta;
+    int n_loops = 0, dim = 3, n_tau = 0;
+    double kF = 0, beta = 0, lambda = 0;
+    std::map<int, LeafMeta *> d_meta;                  // per device
+    std::map<int, std::pair<double *, size_t>> d_leaf;  // per device: sub-batch leaf matrix of the fused path
+    std::map<int, std::pair<double *, size_t>> d_var;   // per device: staging of (K, T) chunks for the host path
+    std::mutex mu;
+};
+
+namespace {
+int leafgen_meta(fdg_leafgen *g, int dev, LeafMeta **out) {
+    auto it = g->d_meta.find(dev);
+    if (it == g->d_meta.end()) {
+        LeafMeta *p = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&p, std::max<size_t>(g->meta.size(), 1) * sizeof(LeafMeta)));
+        CUDA_TRY(cudaMemcpy(p, g->meta.data(), g->meta.size() * sizeof(LeafMeta), cudaMemcpyHostToDevice));
+        it = g->d_meta.emplace(dev, p).first;
+    }
+    *out = it->second;
+    return FDG_OK;
+}
+
+int leafgen_launch(fdg_leafgen *g, const double *K, const double *T, int64_t ld_var, int64_t batch, double *leaf,
+                   int64_t ld_leaf, cudaStream_t st) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    LeafMeta *meta = nullptr;
+    int rc = leafgen_meta(g, dev, &meta);
+    if (rc != FDG_OK) return rc;
+    const int L = (int)g->meta.size();
+    if (L == 0 || batch == 0) return FDG_OK;
+    dim3 grid((unsigned)((batch + FDG_LG_THREADS - 1) / FDG_LG_THREADS), (unsigned)((L + FDG_LG_CHUNK - 1) / FDG_LG_CHUNK));
+    const double kF2 = g->kF * g->kF;
+    if (g->dim == 3)
+        fdg_leafgen_kernel<3><<<grid, FDG_LG_THREADS, 0, st>>>(meta, L, g->n_loops, K, T, ld_var, batch, leaf, ld_leaf, kF2, g->beta, g->lambda);
+    else
+        fdg_leafgen_kernel<2><<<grid, FDG_LG_THREADS, 0, st>>>(meta, L, g->n_loops, K, T, ld_var, batch, leaf, ld_leaf, kF2, g->beta, g->lambda);
+    CUDA_TRY(cudaGetLastError());
+    return FDG_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int fdg_leafgen_create(const fdg_leafgen_desc *d, fdg_leafgen_t *out) {
+    if (!d || !out) return fail(FDG_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    if (d->n_leaves < 0 || d->n_basis < 0 || d->n_tau < 0) return fail(FDG_ERR_BAD_ARG, "negative size");
+    if (d->n_loops < 0 || d->n_loops > FDG_LG_MAXLOOPS) return fail(FDG_ERR_UNSUPPORTED, "n_loops must be <= 8");
+    if (d->dim != 2 && d->dim != 3) return fail(FDG_ERR_UNSUPPORTED, "dim must be 2 or 3");
+    if (d->n_leaves > 0 && (!d->leaf_type || !d->leaf_order || !d->tau_in || !d->tau_out || !d->loop_index))
+        return fail(FDG_ERR_BAD_ARG, "null leaf metadata");
+    if (d->n_basis > 0 && !d->loop_basis) return fail(FDG_ERR_BAD_ARG, "null loop basis");
+    fdg_leafgen *g = new (std::nothrow) fdg_leafgen();
+    if (!g) return fail(FDG_ERR_BAD_ARG, "out of memory");
+    g->n_loops = (int)d->n_loops, g->dim = (int)d->dim, g->n_tau = (int)d->n_tau;
+    g->kF = d->kF, g->beta = d->beta, g->lambda = d->lambda;
+    g->meta.resize((size_t)d->n_leaves);
+    for (int64_t l = 0; l < d->n_leaves; ++l) {
+        LeafMeta &m = g->meta[(size_t)l];
+        std::memset(&m, 0, sizeof(m));
+        m.type = d->leaf_type[l];
+        if (m.type < 0 || m.type > 2) {
+            delete g;
+            return fail(FDG_ERR_UNSUPPORTED, "leaf type " + std::to_string(m.type) + " not implemented (example/benchmark.jl:76)");
+        }
+        if (m.type == 0) continue;
+        m.order = d->leaf_order[2 * l + (m.type == 1 ? 0 : 1)];
+        if (m.type == 1 && m.order != 0) {
+            delete g;
+            return fail(FDG_ERR_UNSUPPORTED, "Green's function derivative orders need Lehmann.Spectral.kernelFermiT_dw*, which the "
+                                             "reference does not vendor (example/benchmark.jl:93-110): only order 0 is implemented");
+        }
+        if (m.order < 0) {
+            delete g;
+            return fail(FDG_ERR_BAD_ARG, "negative derivative order");
+        }
+        m.tau_in = d->tau_in[l], m.tau_out = d->tau_out[l];
+        const int32_t bi = d->loop_index[l];
+        if (m.tau_in < 0 || m.tau_in >= d->n_tau || m.tau_out < 0 || m.tau_out >= d->n_tau || bi < 0 || bi >= d->n_basis) {
+            delete g;
+            return fail(FDG_ERR_BAD_ARG, "leaf " + std::to_string(l) + ": time or loop-basis index out of range");
+        }
+        for (int64_t j = 0; j < d->n_loops; ++j) m.basis[j] = d->loop_basis[(size_t)bi * (size_t)d->n_loops + (size_t)j];
+    }
+    *out = g;
+    return FDG_OK;
+}
+
+int fdg_leafgen_destroy(fdg_leafgen_t g) {
+    if (!g) return FDG_OK;
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess) {
+        for (auto &kv : g->d_meta) {
+            cudaSetDevice(kv.first);
+            cudaFree(kv.second);
+        }
+        for (auto &kv : g->d_leaf) {
+            cudaSetDevice(kv.first);
+            cudaFree(kv.second.first);
+        }
+        for (auto &kv : g->d_var) {
+            cudaSetDevice(kv.first);
+            cudaFree(kv.second.first);
+        }
+        cudaSetDevice(cur);
+    }
+    delete g;
+    return FDG_OK;
+}
+
+int fdg_leafgen_fill(fdg_leafgen_t g, const double *K, const double *T, int64_t ld_var, int64_t batch, double *leaf,
+                     int64_t ld_leaf, void *stream) {
+    if (!g) return fail(FDG_ERR_BAD_ARG, "null handle");
+    if (batch < 0) return fail(FDG_ERR_BAD_ARG, "negative batch");
+    if (batch == 0 || g->meta.empty()) return FDG_OK;
+    if (!K || !T || !leaf) return fail(FDG_ERR_BAD_ARG, "null pointer");
+    if (ld_var < batch || ld_leaf < batch) return fail(FDG_ERR_BAD_ARG, "leading dimension < batch");
+    std::lock_guard<std::mutex> lock(g->mu);
+    return leafgen_launch(g, K, T, ld_var, batch, leaf, ld_leaf, static_cast<cudaStream_t>(stream));
+}
+
+int fdg_eval_generated_accumulate(fdg_handle h, fdg_leafgen_t g, const double *K, const double *T, int64_t ld_var,
+                                  int64_t batch, double *acc, void *stream) {
+    if (!h || !g) return fail(FDG_ERR_BAD_ARG, "null handle");
+    if (h->low.dtype != FDG_F64) return fail(FDG_ERR_UNSUPPORTED, "generated leaves are Float64");
+    if ((int64_t)g->meta.size() != h->low.L) return fail(FDG_ERR_BAD_ARG, "leaf generator and program have different numbers of leaves");
+    if (batch < 0) return fail(FDG_ERR_BAD_ARG, "negative batch");
+    if (batch == 0) return FDG_OK;
+    if (!K || !T || (!acc && h->low.R > 0)) return fail(FDG_ERR_BAD_ARG, "null pointer");
+    if (ld_var < batch) return fail(FDG_ERR_BAD_ARG, "ld_var < batch");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // sub-batches: the leaf matrix of a sub-batch lives in a scratch buffer of about 2 GiB (>> L2), never more
+    const int64_t L = std::max<int64_t>(h->low.L, 1);
+    double gb = 2.0;
+    if (const char *e = getenv("FDG_LEAFGEN_GB")) gb = atof(e);
+    int64_t sub = std::max<int64_t>(4096, (int64_t)(gb * (double)(1 << 30)) / (8 * L)) / 1024 * 1024;
+    sub = std::min<int64_t>(sub, (batch + 1023) / 1024 * 1024);
+    double *buf = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g->mu);
+        auto &slot = g->d_leaf[dev];
+        const size_t need = (size_t)L * (size_t)sub * sizeof(double);
+        if (need > slot.second) {
+            if (slot.first) CUDA_TRY(cudaFree(slot.first));
+            slot = {nullptr, 0};
+            CUDA_TRY(cudaMalloc((void **)&slot.first, need));
+            slot.second = need;
+        }
+        buf = slot.first;
+    }
+    for (int64_t b0 = 0; b0 < batch; b0 += sub) {
+        const int64_t nb = std::min<int64_t>(sub, batch - b0);
+        int rc;
+        {
+            std::lock_guard<std::mutex> lock(g->mu);
+            rc = leafgen_launch(g, K + b0, T + b0, ld_var, nb, buf, sub, st);
+        }
+        if (rc != FDG_OK) return rc;
+        h->launches++;
+        rc = do_eval(h, buf, sub, acc, 0, nb, st, true);
+        if (rc != FDG_OK) return rc;
+    }
+    return FDG_OK;
+}
+
+int fdg_eval_generated_host(fdg_handle h, fdg_leafgen_t g, const double *K_host, const double *T_host, int64_t ld_var,
+                            int64_t batch, double *acc_host) {
+    if (!h || !g) return fail(FDG_ERR_BAD_ARG, "null handle");
+    if (batch < 0) return fail(FDG_ERR_BAD_ARG, "negative batch");
+    if (!K_host || !T_host || (!acc_host && h->low.R > 0)) return fail(FDG_ERR_BAD_ARG, "null pointer");
+    if (ld_var < batch) return fail(FDG_ERR_BAD_ARG, "ld_var < batch");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    const int64_t rows = (int64_t)g->n_loops * g->dim + g->n_tau;
+    const int64_t R = h->low.R;
+    double *d_var = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g->mu);
+        auto &slot = g->d_var[dev];
+        const size_t need = ((size_t)rows * (size_t)std::max<int64_t>(batch, 1) + (size_t)std::max<int64_t>(R, 1)) * sizeof(double);
+        if (need > slot.second) {
+            if (slot.first) CUDA_TRY(cudaFree(slot.first));
+            slot = {nullptr, 0};
+            CUDA_TRY(cudaMalloc((void **)&slot.first, need));
+            slot.second = need;
+        }
+        d_var = slot.first;
+    }
+    double *d_acc = d_var + (size_t)rows * (size_t)std::max<int64_t>(batch, 1);
+    const int64_t kr = (int64_t)g->n_loops * g->dim;
+    cudaStream_t st = nullptr;  // the legacy default stream: ordered with the copies below
+    if (batch > 0) {
+        CUDA_TRY(cudaMemcpy2DAsync(d_var, (size_t)batch * 8, K_host, (size_t)ld_var * 8, (size_t)batch * 8, (size_t)kr, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpy2DAsync(d_var + (size_t)kr * (size_t)batch, (size_t)batch * 8, T_host, (size_t)ld_var * 8, (size_t)batch * 8,
+                                   (size_t)g->n_tau, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemsetAsync(d_acc, 0, (size_t)std::max<int64_t>(R, 1) * 8, st));
+    int rc = fdg_eval_generated_accumulate(h, g, d_var, d_var + (size_t)kr * (size_t)batch, batch, batch, d_acc, st);
+    if (rc != FDG_OK) return rc;
+    if (R > 0) CUDA_TRY(cudaMemcpyAsync(acc_host, d_acc, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FDG_OK;
+}
+
+}  // extern "C"

@@ -168,6 +168,48 @@ int fdg_jit_info(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, i
 int fdg_jit_ptx(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t index, const char **ptx,
                 const char **ptxas_log);
 
+/* --- leaf values computed on the device from the Monte-Carlo variables ------------------------
+ * What the integrand of the reference's driver does between `compile` and `eval_graph!` for every sample
+ * (example/benchmark.jl:44-81, with the per-leaf metadata of `leafstates`, src/frontend/frontends.jl:175-232):
+ *     kq   = K[:, 1:n_loops] * loop_basis[:, loop_index[l]]                       (FrontEnds.update / loop, pool.jl:69-78)
+ *     type 1 (BareGreenId):        leaf = green(T[tau_out] - T[tau_in], dot(kq, kq) - kF^2, beta)   (benchmark.jl:113-127)
+ *     type 2 (BareInteractionId):  invK = 1 / (dot(kq, kq) + lambda);  leaf = 8pi / invK * (lambda * invK)^order
+ *     type 0:                      leaf = 1.0
+ * Only the order-0 Green's function has a definition inside the reference (derivative orders call
+ * Lehmann.Spectral.kernelFermiT_dw*, a dependency that is not vendored): fdg_leafgen_create returns
+ * FDG_ERR_UNSUPPORTED for a type-1 leaf with order != 0.  exp() is the device's (<= 1 ulp): leaf values agree with a
+ * CPU evaluation of the same formulas to ~1e-15 relative, not bit for bit; the graph evaluation on top of them stays
+ * bit-exact. */
+typedef struct fdg_leafgen_desc {
+    int64_t n_leaves;
+    const int32_t *leaf_type;   /* [n_leaves] 0, 1 or 2 (FrontEnds.index(typeof(properties)), diagram_id.jl:342-354)   */
+    const int32_t *leaf_order;  /* [n_leaves * 2] derivative orders: (Green's function, interaction)                 */
+    const int32_t *tau_in;      /* [n_leaves] 0-based index into T of extT[1]                                        */
+    const int32_t *tau_out;     /* [n_leaves] 0-based index into T of extT[2]                                        */
+    const int32_t *loop_index;  /* [n_leaves] 0-based index into loop_basis                                          */
+    int64_t n_basis;
+    int64_t n_loops;            /* <= 8 */
+    int64_t dim;                /* 2 or 3 */
+    int64_t n_tau;
+    const double *loop_basis;   /* [n_basis * n_loops], basis vector i at loop_basis[i * n_loops ...]                */
+    double kF, beta, lambda;    /* example/benchmark.jl:11-18 */
+} fdg_leafgen_desc;
+typedef struct fdg_leafgen *fdg_leafgen_t;
+int fdg_leafgen_create(const fdg_leafgen_desc *desc, fdg_leafgen_t *out);
+int fdg_leafgen_destroy(fdg_leafgen_t g);
+/* device pointers, batch-major like everything else: component c of loop momentum j of sample b at
+ * K[(j * dim + c) * ld_var + b], time t at T[t * ld_var + b]; writes leaf[l * ld_leaf + b]. */
+int fdg_leafgen_fill(fdg_leafgen_t g, const double *K, const double *T, int64_t ld_var, int64_t batch, double *leaf,
+                     int64_t ld_leaf, void *stream);
+/* generate + evaluate without ever materialising more than a sub-batch of the leaf matrix:
+ * acc[r] += sum over the batch of graph r (device pointers; acc has R doubles). */
+int fdg_eval_generated_accumulate(fdg_handle h, fdg_leafgen_t g, const double *K, const double *T, int64_t ld_var,
+                                  int64_t batch, double *acc, void *stream);
+/* the same from HOST arrays of (K, T) -- (dim * n_loops + n_tau) doubles per sample cross the bus instead of L --
+ * into a host array of R sums; synchronous. */
+int fdg_eval_generated_host(fdg_handle h, fdg_leafgen_t g, const double *K_host, const double *T_host, int64_t ld_var,
+                            int64_t batch, double *acc_host);
+
 /* --- multi-GPU: one process per GPU; the only exchange is the sum of the per-root accumulators ---- */
 typedef struct fdg_comm *fdg_comm_t;
 int fdg_comm_unique_id(void *id128 /* 128 bytes out */);

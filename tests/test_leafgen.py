@@ -1,0 +1,150 @@
+"""N1 -- leaf values computed on the device from the Monte-Carlo variables (fdg_leafgen_*).
+
+CPU part: the restated integrand (oracle/leafgen.py) against a scalar transcription of example/benchmark.jl:44-127 and
+the restated `leafstates` against the committed sidecars.  GPU part: device leaf values against the CPU restatement
+within 2e-14 relative (exp() is the device's, <= 1 ulp; the reference's own `mul!` is a BLAS call whose summation order
+is not specified either), and the graph evaluation on top of the device's leaves bit-exact against the oracle."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import fdgraph_b200 as fd
+from fdgraph_b200 import _capi
+from oracle import leafgen
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KF, BETA, LAM = 1.919, 3.0, 1.2  # example/benchmark.jl:11-18
+
+
+def _load(name):
+    raw = fd.RawGraph.load(os.path.join(ROOT, "workloads", name + ".npz"))
+    meta = dict(np.load(os.path.join(ROOT, "workloads", name + ".leaves.npz")))
+    return raw, meta
+
+
+def _variables(meta, B, seed=1234, dim=3):
+    """varK / varT of example/benchmark.jl:45-53: K1 = K2 = (kF, 0, 0), K3 = 0, inner loops random; T[0] = 0."""
+    rng = np.random.default_rng(seed)
+    n_loops = meta["loop_basis"].shape[1]
+    n_tau = int(max(meta["tau_in"].max(), meta["tau_out"].max())) + 1
+    K = rng.random((dim, n_loops, B)) * 2 - 0.7
+    K[:, 0, :] = K[:, 1, :] = np.array([KF, 0.0, 0.0])[:, None]
+    if n_loops > 2:
+        K[:, 2, :] = 0.0
+    T = rng.random((n_tau, B)) * BETA
+    T[0] = 0.0
+    T[-1, ::7] = T[0, ::7]  # some exactly equal times: the tau == 0 branch (TAU_CUTOFF)
+    return K, T
+
+
+def _green_scalar(tau, w, beta):
+    if tau == 0.0:
+        tau = -1e-10
+    if tau > 0.0:
+        return math.exp(-w * tau) / (1 + math.exp(-w * beta)) if w > 0.0 else math.exp(w * (beta - tau)) / (1 + math.exp(w * beta))
+    return -math.exp(-w * (tau + beta)) / (1 + math.exp(-w * beta)) if w > 0.0 else -math.exp(-w * tau) / (1 + math.exp(w * beta))
+
+
+def test_cpu_restatement_against_a_scalar_transcription():
+    raw, meta = _load("parquet_sigma_o3")
+    K, T = _variables(meta, 5)
+    got = leafgen.leaf_values(meta, K, T, KF, BETA, LAM)
+    for b in range(5):
+        for l in range(len(meta["leaf_type"])):
+            basis = meta["loop_basis"][meta["loop_index"][l]]
+            kq = [sum(K[c, j, b] * basis[j] for j in range(K.shape[1])) for c in range(3)]
+            q2 = sum(x * x for x in kq)
+            if meta["leaf_type"][l] == 1:
+                want = _green_scalar(T[meta["tau_out"][l], b] - T[meta["tau_in"][l], b], q2 - KF * KF, BETA)
+            else:
+                inv = 1.0 / (q2 + LAM)
+                want = 8 * math.pi / inv * (LAM * inv) ** int(meta["leaf_order"][l][1])
+            assert got[l, b] == pytest.approx(want, rel=1e-15)
+    # fermionic sign structure: G(tau -> 0-) = -(1 - n_F), G(tau > 0) > 0
+    assert (leafgen.green(np.array([0.0]), np.array([0.5]), BETA) < 0).all()
+    assert (leafgen.green(np.array([0.3]), np.array([-0.5]), BETA) > 0).all()
+
+
+def test_sidecars_match_the_workloads():
+    for name in ("parquet_sigma_o3", "parquet_ver4_o3", "parquet_ver4_o4", "gv_sigma_o4", "gv_ver4_o3"):
+        raw, meta = _load(name)
+        L = O.Oracle(raw).n_leaves
+        assert len(meta["leaf_type"]) == L == len(meta["tau_in"]) == len(meta["loop_index"])
+        assert set(np.unique(meta["leaf_type"])) <= {1, 2} and (meta["leaf_order"] == 0).all()
+        assert meta["loop_index"].max() == meta["loop_basis"].shape[0] - 1           # every basis vector is used
+        assert len({tuple(b) for b in meta["loop_basis"]}) == meta["loop_basis"].shape[0]  # and distinct
+    assert _load("parquet_ver4_o4")[1]["loop_basis"].shape[1] == 7                  # MaxLoopNum of example/benchmark.jl:21
+
+
+def test_create_rejects_what_the_reference_cannot_compute():
+    _, meta = _load("parquet_sigma_o3")
+    g = fd.LeafGenerator(meta, kF=KF, beta=BETA, lam=LAM)
+    assert (g.n_leaves, g.n_loops, g.n_tau, g.var_rows) == (27, 4, 3, 15)
+    bad = {k: v.copy() for k, v in meta.items()}
+    bad["leaf_order"][np.argmax(meta["leaf_type"] == 1), 0] = 1  # needs Lehmann.Spectral.kernelFermiT_dw
+    with pytest.raises(_capi.FdgError) as e:
+        fd.LeafGenerator(bad)
+    assert e.value.code == 3
+    bad = {k: v.copy() for k, v in meta.items()}
+    bad["leaf_type"][0] = 3  # BareGreenNId: "this leaftype not implemented" (benchmark.jl:76)
+    with pytest.raises(_capi.FdgError):
+        fd.LeafGenerator(bad)
+    bad = {k: v.copy() for k, v in meta.items()}
+    bad["loop_index"][3] = 99
+    with pytest.raises(_capi.FdgError) as e:
+        fd.LeafGenerator(bad)
+    assert e.value.code == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["parquet_sigma_o3", "parquet_ver4_o3", "gv_ver4_o3"])
+def test_device_leaves_and_the_graph_on_top_of_them(name):
+    torch = pytest.importorskip("torch")
+    raw, meta = _load(name)
+    B = 4097
+    K, T = _variables(meta, B)
+    gen = fd.LeafGenerator(meta, kF=KF, beta=BETA, lam=LAM)
+    ev = fd.compile_raw(raw)
+    dK = torch.from_numpy(K.transpose(1, 0, 2).reshape(-1, B).copy()).cuda()  # row (j * dim + c)
+    dT = torch.from_numpy(T).cuda()
+    leaf = torch.zeros(gen.n_leaves, B, dtype=torch.float64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    gen.fill_device(dK.data_ptr(), dT.data_ptr(), B, B, leaf.data_ptr(), B, s)
+    torch.cuda.synchronize()
+    got = leaf.cpu().numpy()
+    want = leafgen.leaf_values(meta, K, T, KF, BETA, LAM)
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() <= 2e-14 * np.abs(want).max()
+    assert (np.abs(got - want) <= 2e-14 * np.abs(want) + 1e-300).all()
+    # evaluation on the device's own leaves is bit-exact against the oracle on the same leaves
+    root = torch.zeros(ev.n_roots, B, dtype=torch.float64, device="cuda")
+    ev.eval_device(leaf.data_ptr(), B, root.data_ptr(), B, B, s)
+    acc = torch.zeros(ev.n_roots, dtype=torch.float64, device="cuda")
+    gen.accumulate_device(ev, dK.data_ptr(), dT.data_ptr(), B, B, acc.data_ptr(), s)
+    torch.cuda.synchronize()
+    ref = O.Oracle(raw).eval(got)
+    assert root.cpu().numpy().tobytes() == ref.tobytes()
+    scale = np.abs(ref).sum(axis=1) + 1e-300
+    assert (np.abs(acc.cpu().numpy() - ref.sum(axis=1)) <= 1e-12 * scale).all()
+    # the host entry point: (K, T) in, R sums out
+    acc_h = gen.accumulate_host(ev, dK.cpu().numpy(), T)
+    assert (np.abs(acc_h - ref.sum(axis=1)) <= 1e-12 * scale).all()
+
+
+@pytest.mark.gpu
+def test_generated_sub_batches_and_ragged_sizes(monkeypatch):
+    torch = pytest.importorskip("torch")
+    raw, meta = _load("parquet_sigma_o3")
+    gen = fd.LeafGenerator(meta, kF=KF, beta=BETA, lam=LAM)
+    ev = fd.compile_raw(raw)
+    monkeypatch.setenv("FDG_LEAFGEN_GB", "0.0001")  # sub-batches of 4096 samples
+    B = 3 * 4096 + 37
+    K, T = _variables(meta, B, seed=5)
+    Kr = K.transpose(1, 0, 2).reshape(-1, B).copy()
+    acc = gen.accumulate_host(ev, Kr, T)
+    leaf = leafgen.leaf_values(meta, K, T, KF, BETA, LAM)
+    ref = O.Oracle(raw).eval(leaf)
+    assert (np.abs(acc - ref.sum(axis=1)) <= 1e-11 * (np.abs(ref).sum(axis=1) + 1e-300)).all()

@@ -62,8 +62,42 @@ def taylor_workloads(manifest):
              manifest, optimize=False)
 
 
+def leaf_sidecars():
+    """workloads/<name>.leaves.npz: the `leafstates` metadata (frontends.jl:175-232) of a workload's leaves, in leafVal
+    order, for the on-device leaf generation (N1).  The graphs are rebuilt and must flatten to the committed arrays."""
+    from oracle.frontend import leafstates as ls, parquet as pq
+
+    def pq_sigma(order):
+        pq._ver4I.clear()
+        return [r["diagram"] for r in pq.sigma(pq.DiagPara(type=pq.SigmaDiag, innerLoopNum=order))]
+
+    def pq_ver4(order):
+        pq._ver4I.clear()
+        return [r["diagram"] for r in pq.vertex4(pq.DiagPara(type=pq.Ver4Diag, innerLoopNum=order))]
+
+    jobs = [("parquet_sigma_o3", lambda: pq_sigma(3), 4), ("parquet_ver4_o3", lambda: pq_ver4(3), 6),
+            ("parquet_ver4_o4", lambda: pq_ver4(4), 7),  # example/benchmark.jl:13,21: MaxLoopNum = 7
+            ("gv_sigma_o4", lambda: gv.diagsGV("sigma", 4), 5), ("gv_ver4_o3", lambda: gv.diagsGV_ver4(3), 6)]
+    for name, builder, max_loops in jobs:
+        fd.uidreset()
+        graphs = builder()
+        opt.optimize(graphs)
+        raw, nodes = fd.flatten(graphs)
+        ref = fd.RawGraph.load(os.path.join(OUT, name + ".npz"))
+        same = all(np.array_equal(getattr(raw, k), getattr(ref, k)) for k in raw.__dataclass_fields__)
+        assert same, f"{name}: the rebuilt graph differs from the committed workload"
+        orc = O.Oracle(raw)
+        meta = ls.leafstates([nodes[i] for i in orc.leaf_nodes], max_loops)
+        np.savez_compressed(os.path.join(OUT, name + ".leaves.npz"), **meta)
+        print(f"{name}.leaves: L={len(meta['leaf_type'])} G={int((meta['leaf_type'] == 1).sum())} W={int((meta['leaf_type'] == 2).sum())} "
+              f"basis={meta['loop_basis'].shape} n_tau={int(max(meta['tau_in'].max(), meta['tau_out'].max())) + 1}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "leaves":
+        leaf_sidecars()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "taylor":  # add / refresh the Taylor workloads only
         with open(os.path.join(OUT, "MANIFEST.json")) as fh:
             manifest = json.load(fh)
@@ -102,6 +136,7 @@ def main():
     taylor_workloads(manifest)
     with open(os.path.join(OUT, "MANIFEST.json"), "w") as fh:
         json.dump(manifest, fh, indent=1, sort_keys=True)
+    leaf_sidecars()
 
 
 if __name__ == "__main__":
