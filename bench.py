@@ -153,20 +153,23 @@ def cpu_reference(raw, dtype, target_seconds, nthreads=0, compile_timeout=240.0)
     rng = np.random.default_rng(1234)
     npdt = np.float64 if dtype == "f64" else np.complex128
 
-    def run(n):
+    def run(n, reps=1):
         leaf = (0.5 + rng.random((n, max(orc.n_leaves, 1)))).astype(npdt)
         root = np.zeros((n, max(orc.n_roots, 1)), npdt)
         t = time.perf_counter()
-        run_fn(leaf, root, cores)
+        for _ in range(reps):
+            run_fn(leaf, root, cores)
         return time.perf_counter() - t
 
     n = max(cores * 16, 256)
     run(n)  # warm
     t = run(n)
+    # about `target_seconds` of CPU work: as many samples as 2 GiB of leaves hold, evaluated `reps` times over
     n2 = int(min(max(n, n * target_seconds / max(t, 1e-6)), 1 << 24, (2 << 30) // max(orc.n_leaves * (8 if dtype == "f64" else 16), 1)))
     n2 = max(cores, (n2 // cores) * cores)
-    t2 = run(n2)
-    return n2 / t2, cores, n2, t2, what
+    reps = max(1, int(round(target_seconds / max(t * n2 / n, 1e-6))))
+    t2 = run(n2, reps)
+    return n2 * reps / t2, cores, n2 * reps, t2, what
 
 
 def main():
@@ -193,22 +196,24 @@ def main():
         run_fn(leaf, root, cores)
         rate0 = probe / max(time.perf_counter() - t, 1e-6)
         n = int(max(cores, min(rate0 * per_step, (2 << 30) // max(orc.n_leaves * leaf.itemsize, 1))))
+        reps = max(1, int(round(rate0 * per_step / n)))  # a step = `reps` passes over the n resident samples
         leaf = (0.5 + rng.random((n, max(orc.n_leaves, 1)))).astype(npdt)
         root = np.zeros((n, max(R, 1)), npdt)
-        for _ in range(a.warmup):
+        for _ in range(a.warmup * reps):
             run_fn(leaf, root, cores)
         t = time.perf_counter()
-        for _ in range(a.steps):
+        for _ in range(a.steps * reps):
             run_fn(leaf, root, cores)
         dt = time.perf_counter() - t
-        val = n * a.steps * R / dt
-        sample = f"{n} samples/step x {a.steps} steps of {a.workload}, sample-major leaves; {what}; OpenMP over samples"
+        val = n * reps * a.steps * R / dt
+        sample = (f"{n * reps} samples/step ({reps} passes over {n} resident samples) x {a.steps} steps of {a.workload}, "
+                  f"sample-major leaves; {what}; OpenMP over samples")
         print(json.dumps({
             "impl": "reference", "metric": "MC-sample graph-evals/sec", "value": val, "unit": "graph-evals/s",
             "samples_per_s": val / R, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": a.workload, "samples_per_step": n, "roots": R, "leaves": orc.n_leaves},
+            "config": {"workload": a.workload, "samples_per_step": n * reps, "roots": R, "leaves": orc.n_leaves},
             "cpu_baseline": {"value": val, "unit": "graph-evals/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "graph-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
