@@ -117,8 +117,11 @@ function compile(graphs::AbstractVector{G}; root::AbstractVector{Int}=[id(g) for
     check(ccall((:fdg_last_root, LIB), Cint, (Ptr{Cvoid}, Ref{Int32}), h[], last))
     leafmap = Dict{Int,G}(k => nodes[leaf_node[k]+1] for k in 1:L)
     ev = Evaluator(h[], L, R, Int(last[]) + 1)
-    return (rootv, leafVal) -> eval_graph!(ev, rootv, leafVal), leafmap
+    return ev, leafmap   # `ev(root, leafVal)` is the generated function (callable struct below)
 end
+
+# the value returned by compile() is called like the reference's generated function
+(ev::Evaluator)(root, leafVal) = eval_graph!(ev, root, leafVal)
 
 # device matrices (CuArray{T,2}, B x L and B x R, column-major): one launch sequence for the whole batch
 function eval_graph!(ev::Evaluator, root::AbstractMatrix, leafVal::AbstractMatrix; stream::Ptr{Cvoid}=C_NULL)
@@ -141,6 +144,68 @@ function eval_graph!(ev::Evaluator, root::AbstractVector, leafVal::AbstractVecto
     r = reshape(root, 1, :)
     eval_graph!(ev, r, reshape(leafVal, 1, :))
     return ev.last_root >= 1 ? root[ev.last_root] : nothing
+end
+
+# ---- leaf values from (K, tau) on the device (include/fdgraph.h, fdg_leafgen_*; SURVEY §8f N1) -----------------------
+struct LeafGenDesc
+    n_leaves::Int64
+    leaf_type::Ptr{Int32}
+    leaf_order::Ptr{Int32}
+    tau_in::Ptr{Int32}
+    tau_out::Ptr{Int32}
+    loop_index::Ptr{Int32}
+    n_basis::Int64
+    n_loops::Int64
+    dim::Int64
+    n_tau::Int64
+    loop_basis::Ptr{Float64}
+    kF::Float64
+    beta::Float64
+    lambda::Float64
+end
+
+mutable struct LeafGen
+    handle::Ptr{Cvoid}
+    n_loops::Int
+    dim::Int
+    n_tau::Int
+end
+
+"""
+    leafgen(leafstat, loopbasis; partition=1, dim=3, kF, β, λ)
+
+`leafstat, loopbasis = FrontEnds.leafstates(leaf_maps, maxloopNum)` (src/frontend/frontends.jl:175-232) as returned by the
+reference; 1-based Julia indices are shifted to the library's 0-based ones here.
+"""
+function leafgen(leafstat, loopbasis::Vector{Vector{Float64}}; partition::Int=1, dim::Int=3, kF::Float64, β::Float64, λ::Float64)
+    _, leafType, leafOrders, leafInTau, leafOutTau, leafLoopIndex = leafstat
+    L = length(leafType[partition])
+    ltype = Int32.(leafType[partition])
+    lorder = Int32[get(leafOrders[partition][l], c, 0) for c in 1:2, l in 1:L]   # 2 x L, column-major == [l*2 + c]
+    tin = Int32.(leafInTau[partition] .- 1)
+    tout = Int32.(leafOutTau[partition] .- 1)
+    lidx = Int32.(leafLoopIndex[partition] .- 1)
+    basis = reduce(hcat, loopbasis)                                               # n_loops x n_basis == [i*n_loops + j]
+    n_tau = max(maximum(tin), maximum(tout)) + 1
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve ltype lorder tin tout lidx basis begin
+        desc = Ref(LeafGenDesc(L, pointer(ltype), pointer(lorder), pointer(tin), pointer(tout), pointer(lidx),
+            size(basis, 2), size(basis, 1), dim, n_tau, pointer(basis), kF, β, λ))
+        check(ccall((:fdg_leafgen_create, LIB), Cint, (Ref{LeafGenDesc}, Ref{Ptr{Cvoid}}), desc, h))
+    end
+    g = LeafGen(h[], size(basis, 1), dim, n_tau)
+    finalizer(x -> ccall((:fdg_leafgen_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), g)
+    return g
+end
+
+# host matrices K (B x dim*n_loops, column (j-1)*dim + c) and T (B x n_tau) -> the R per-root sums over the B samples
+function eval_generated(ev::Evaluator, g::LeafGen, K::Matrix{Float64}, T::Matrix{Float64})
+    B = size(K, 1)
+    (size(K, 2) == g.dim * g.n_loops && size(T) == (B, g.n_tau)) || throw(DimensionMismatch("K must be B x dim*n_loops, T must be B x n_tau"))
+    acc = zeros(Float64, ev.n_roots)
+    check(ccall((:fdg_eval_generated_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ptr{Float64}),
+        ev.handle, g.handle, K, T, B, B, acc))
+    return acc
 end
 
 end # module
