@@ -9,8 +9,8 @@ from .graph import (FeynmanGraph, Graph, Power, Prod, Sum, Unitary, constant_gra
                     linear_combination, multi_product, uidreset)
 from .program import RawGraph, flatten  # noqa: F401
 from . import compilers as Compilers  # noqa: F401  (the reference's module name)
-from .compilers import Evaluator, LeafGenerator, compile, compile_raw  # noqa: F401
+from .compilers import Evaluator, LeafGenerator, compile, compile_file, compile_raw  # noqa: F401
 from .sharding import shard_range  # noqa: F401
 
 __all__ = ["Graph", "FeynmanGraph", "Sum", "Prod", "Power", "Unitary", "constant_graph", "linear_combination",
-           "multi_product", "uidreset", "RawGraph", "flatten", "Compilers", "Evaluator", "LeafGenerator", "compile", "compile_raw", "shard_range"]
+           "multi_product", "uidreset", "RawGraph", "flatten", "Compilers", "Evaluator", "LeafGenerator", "compile", "compile_file", "compile_raw", "shard_range"]

@@ -60,7 +60,7 @@ EXPORTS = [
     "fdg_program_words", "fdg_eval", "fdg_eval_accumulate", "fdg_eval_host", "fdg_set_launch", "fdg_launch_count",
     "fdg_comm_unique_id", "fdg_comm_init", "fdg_comm_destroy", "fdg_allreduce", "fdg_jit_prepare", "fdg_jit_ptx",
     "fdg_jit_info", "fdg_leafgen_create", "fdg_leafgen_destroy", "fdg_leafgen_fill", "fdg_eval_generated_accumulate",
-    "fdg_eval_generated_host",
+    "fdg_eval_generated_host", "fdg_graph_write", "fdg_compile_file",
 ]
 BACKEND_AUTO, BACKEND_VM, BACKEND_JIT = 0, 1, 2
 
@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
     L.fdg_jit_prepare.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
     L.fdg_jit_ptx.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
     L.fdg_jit_info.argtypes = [vp, i32, i32, C.POINTER(i64), i32]
+    L.fdg_graph_write.argtypes = [C.POINTER(GraphDesc), C.c_char_p]
+    L.fdg_compile_file.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(vp)]
     L.fdg_leafgen_create.argtypes = [C.POINTER(LeafGenDesc), C.POINTER(vp)]
     L.fdg_leafgen_destroy.argtypes = [vp]
     L.fdg_leafgen_fill.argtypes = [vp, vp, vp, i64, i64, vp, i64, vp]
@@ -116,6 +118,35 @@ def check(rc: int) -> None:
 
 def _ptr(a: np.ndarray, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _desc(raw) -> GraphDesc:
+    raw.validate_dtypes()
+    d = GraphDesc()
+    d.n_nodes, d.n_edges = raw.n_nodes, raw.n_edges
+    d.node_id = _ptr(raw.node_id, C.c_int64)
+    d.node_op = _ptr(raw.node_op, C.c_int32)
+    d.node_pow = _ptr(raw.node_pow, C.c_int32)
+    d.child_ptr = _ptr(raw.child_ptr, C.c_int64)
+    d.child_node = _ptr(raw.child_node, C.c_int32)
+    d.child_factor = _ptr(raw.child_factor, C.c_double)
+    d.n_graphs, d.graphs = int(raw.graphs.shape[0]), _ptr(raw.graphs, C.c_int32)
+    d.n_roots, d.root_id = int(raw.root_id.shape[0]), _ptr(raw.root_id, C.c_int64)
+    return d
+
+
+def graph_write(raw, path: str) -> None:
+    """fdg_graph_write: the FDGRAPH file of a RawGraph (include/fdgraph.h)."""
+    d = _desc(raw)
+    check(lib().fdg_graph_write(C.byref(d), os.fsencode(path)))
+
+
+def compile_file(path: str, dtype: int = FDG_F64, backend: int = 0, jit_segment: int = 0, cse: bool = False) -> C.c_void_p:
+    o = Options()
+    o.dtype, o.backend, o.jit_segment, o.cse = int(dtype), int(backend), int(jit_segment), int(bool(cse))
+    h = C.c_void_p()
+    check(lib().fdg_compile_file(os.fsencode(path), C.byref(o), C.byref(h)))
+    return h
 
 
 def compile_raw(raw, dtype: int = FDG_F64, max_slots: int = 0, prefetch: int = 0, schedule: int = 0, backend: int = 0,

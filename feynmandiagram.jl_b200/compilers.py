@@ -204,6 +204,22 @@ def compile_raw(raw: RawGraph, *, dtype=np.float64, max_slots: int = 0, prefetch
                      jit_segment=jit_segment, cse=cse)
 
 
+def compile_file(path: str, *, dtype=np.float64, backend: int = 0, jit_segment: int = 0, cse: bool = False) -> Evaluator:
+    """Evaluator of a graph stored as an FDGRAPH file (fdg_compile_file): a graph flattened by a Julia session elsewhere
+    (`FDGraphB200.save_graph`) or by `RawGraph.save_fdg`."""
+    ev = Evaluator.__new__(Evaluator)
+    ev.dtype = np.dtype(dtype)
+    if ev.dtype not in _DTYPES:
+        raise TypeError(f"Unsupported type {ev.dtype}: libfdgraph evaluates float64 or complex128 weights")
+    ev._h = _capi.compile_file(path, _DTYPES[ev.dtype], backend, jit_segment, cse)  # the library reads the file itself
+    ev.raw = RawGraph.load_fdg(path)
+    ev.stats = _capi.stats(ev._h)
+    ev.n_leaves, ev.n_roots = ev.stats["n_leaves"], ev.stats["n_roots"]
+    ev.leaf_nodes = _capi.leafmap(ev._h, ev.n_leaves)
+    ev.last_root = _capi.last_root(ev._h)
+    return ev
+
+
 class LeafGenerator:
     """Leaf values computed on the device from the Monte-Carlo variables (include/fdgraph.h, fdg_leafgen_*): what the
     integrand of example/benchmark.jl:44-81 does for every sample with the metadata of `leafstates`

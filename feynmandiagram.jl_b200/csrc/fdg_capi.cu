@@ -383,6 +383,66 @@ int fdg_compile(const fdg_graph_desc *graph, const fdg_options *opts, fdg_handle
     return FDG_OK;
 }
 
+int fdg_graph_write(const fdg_graph_desc *g, const char *path) {
+    if (!g || !path) return fail(FDG_ERR_BAD_ARG, "null argument");
+    if (g->n_nodes < 0 || g->n_edges < 0 || g->n_graphs < 0 || g->n_roots < 0) return fail(FDG_ERR_BAD_ARG, "negative size");
+    FILE *fp = std::fopen(path, "wb");
+    if (!fp) return fail(FDG_ERR_BAD_ARG, std::string("cannot open ") + path + " for writing");
+    const int64_t hdr[4] = {g->n_nodes, g->n_edges, g->n_graphs, g->n_roots};
+    bool ok = std::fwrite("FDGRAPH\1", 1, 8, fp) == 8 && std::fwrite(hdr, 8, 4, fp) == 4;
+    auto put = [&](const void *p, size_t size, int64_t n) {
+        if (ok && n > 0) ok = p && std::fwrite(p, size, (size_t)n, fp) == (size_t)n;
+    };
+    put(g->node_id, 8, g->n_nodes);
+    put(g->node_op, 4, g->n_nodes);
+    put(g->node_pow, 4, g->n_nodes);
+    put(g->child_ptr, 8, g->n_nodes + 1);
+    put(g->child_node, 4, g->n_edges);
+    put(g->child_factor, 8, g->n_edges);
+    put(g->graphs, 4, g->n_graphs);
+    put(g->root_id, 8, g->n_roots);
+    ok = (std::fclose(fp) == 0) && ok;
+    return ok ? FDG_OK : fail(FDG_ERR_BAD_ARG, std::string("writing ") + path + " failed");
+}
+
+int fdg_compile_file(const char *path, const fdg_options *opts, fdg_handle *out) {
+    if (!path || !out) return fail(FDG_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    FILE *fp = std::fopen(path, "rb");
+    if (!fp) return fail(FDG_ERR_BAD_ARG, std::string("cannot open ") + path);
+    char magic[8];
+    int64_t hdr[4] = {0, 0, 0, 0};
+    bool ok = std::fread(magic, 1, 8, fp) == 8 && std::memcmp(magic, "FDGRAPH\1", 8) == 0 && std::fread(hdr, 8, 4, fp) == 4;
+    const int64_t lim = (int64_t)1 << 31;
+    ok = ok && hdr[0] >= 0 && hdr[1] >= 0 && hdr[2] >= 0 && hdr[3] >= 0 && hdr[0] < lim && hdr[1] < lim && hdr[2] < lim && hdr[3] < lim;
+    if (!ok) {
+        std::fclose(fp);
+        return fail(FDG_ERR_BAD_GRAPH, std::string(path) + " is not an FDGRAPH file");
+    }
+    std::vector<int64_t> node_id((size_t)hdr[0]), child_ptr((size_t)hdr[0] + 1), root_id((size_t)hdr[3]);
+    std::vector<int32_t> node_op((size_t)hdr[0]), node_pow((size_t)hdr[0]), child_node((size_t)hdr[1]), graphs((size_t)hdr[2]);
+    std::vector<double> child_factor((size_t)hdr[1]);
+    auto get = [&](void *p, size_t size, size_t n) {
+        if (ok && n > 0) ok = std::fread(p, size, n, fp) == n;
+    };
+    get(node_id.data(), 8, node_id.size());
+    get(node_op.data(), 4, node_op.size());
+    get(node_pow.data(), 4, node_pow.size());
+    get(child_ptr.data(), 8, child_ptr.size());
+    get(child_node.data(), 4, child_node.size());
+    get(child_factor.data(), 8, child_factor.size());
+    get(graphs.data(), 4, graphs.size());
+    get(root_id.data(), 8, root_id.size());
+    ok = ok && std::fgetc(fp) == EOF;  // nothing may follow
+    std::fclose(fp);
+    if (!ok) return fail(FDG_ERR_BAD_GRAPH, std::string(path) + " is truncated or has trailing bytes");
+    fdg_graph_desc d;
+    d.n_nodes = hdr[0], d.n_edges = hdr[1], d.n_graphs = hdr[2], d.n_roots = hdr[3];
+    d.node_id = node_id.data(), d.node_op = node_op.data(), d.node_pow = node_pow.data(), d.child_ptr = child_ptr.data();
+    d.child_node = child_node.data(), d.child_factor = child_factor.data(), d.graphs = graphs.data(), d.root_id = root_id.data();
+    return fdg_compile(&d, opts, out);
+}
+
 int fdg_jit_prepare(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t *n_kernels, int32_t *n_cross,
                     int64_t *cubin_bytes) {
     if (!h) return fail(FDG_ERR_BAD_ARG, "null handle");

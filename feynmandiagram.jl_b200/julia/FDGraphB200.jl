@@ -73,8 +73,9 @@ end
 Same contract as `Compilers.compile` (static.jl:221-227): `leafmap[k]` is the leaf graph whose value is column `k`
 of `leafVal` (1-based, identical numbering to the reference).
 """
-function compile(graphs::AbstractVector{G}; root::AbstractVector{Int}=[id(g) for g in graphs], dtype::DataType=Float64) where {G<:AbstractGraph}
-    # one entry per node OBJECT, children before parents (any order is accepted by the library)
+# one entry per node OBJECT, children before parents (any order is accepted by the library); returns the arrays of
+# fdg_graph_desc plus the node objects behind them
+function _flatten(graphs::AbstractVector{G}) where {G<:AbstractGraph}
     nodes = G[]
     index = IdDict{G,Int32}()
     function visit(g)
@@ -100,6 +101,11 @@ function compile(graphs::AbstractVector{G}; root::AbstractVector{Int}=[id(g) for
         push!(child_ptr, length(child_node))
     end
     gidx = Int32[index[g] for g in graphs]
+    return node_id, node_op, node_pow, child_ptr, child_node, child_factor, gidx, nodes
+end
+
+function compile(graphs::AbstractVector{G}; root::AbstractVector{Int}=[id(g) for g in graphs], dtype::DataType=Float64) where {G<:AbstractGraph}
+    node_id, node_op, node_pow, child_ptr, child_node, child_factor, gidx, nodes = _flatten(graphs)
     rootid = Int64.(root)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve node_id node_op node_pow child_ptr child_node child_factor gidx rootid begin
@@ -118,6 +124,22 @@ function compile(graphs::AbstractVector{G}; root::AbstractVector{Int}=[id(g) for
     leafmap = Dict{Int,G}(k => nodes[leaf_node[k]+1] for k in 1:L)
     ev = Evaluator(h[], L, R, Int(last[]) + 1)
     return ev, leafmap   # `ev(root, leafVal)` is the generated function (callable struct below)
+end
+
+"""
+    save_graph(graphs, path; root=[id(g) for g in graphs])
+
+Writes the flattened graph as an FDGRAPH file (include/fdgraph.h: fdg_graph_write / fdg_compile_file), so that a graph
+built here can be evaluated on a machine that has the GPU but no Julia (`fdg_compile_file`, `fd.compile_file` in Python).
+"""
+function save_graph(graphs::AbstractVector{G}, path::AbstractString; root::AbstractVector{Int}=[id(g) for g in graphs]) where {G<:AbstractGraph}
+    node_id, node_op, node_pow, child_ptr, child_node, child_factor, graph_idx, _ = _flatten(graphs)
+    open(path, "w") do io
+        write(io, UInt8['F', 'D', 'G', 'R', 'A', 'P', 'H', 0x01])
+        write(io, Int64(length(node_id)), Int64(length(child_node)), Int64(length(graph_idx)), Int64(length(root)))
+        write(io, node_id, node_op, node_pow, child_ptr, child_node, child_factor, graph_idx, Int64.(root))
+    end
+    return path
 end
 
 # the value returned by compile() is called like the reference's generated function

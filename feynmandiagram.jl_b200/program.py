@@ -44,6 +44,31 @@ class RawGraph:
         with np.load(path) as z:
             return RawGraph(**{k: np.ascontiguousarray(z[k]) for k in RawGraph.__dataclass_fields__})
 
+    # the FDGRAPH file of include/fdgraph.h (fdg_graph_write / fdg_compile_file): what a Julia session writes
+    _FDG_FIELDS = (("node_id", np.int64), ("node_op", np.int32), ("node_pow", np.int32), ("child_ptr", np.int64),
+                   ("child_node", np.int32), ("child_factor", np.float64), ("graphs", np.int32), ("root_id", np.int64))
+
+    def save_fdg(self, path: str) -> None:
+        from . import _capi
+
+        _capi.graph_write(self, path)
+
+    @staticmethod
+    def load_fdg(path: str) -> "RawGraph":
+        with open(path, "rb") as fh:
+            data = fh.read()
+        if data[:8] != b"FDGRAPH\x01":
+            raise ValueError(f"{path} is not an FDGRAPH file")
+        n, e, g, r = (int(x) for x in np.frombuffer(data, "<i8", 4, 8))
+        counts = {"node_id": n, "node_op": n, "node_pow": n, "child_ptr": n + 1, "child_node": e, "child_factor": e, "graphs": g, "root_id": r}
+        off, out = 40, {}
+        for name, dt in RawGraph._FDG_FIELDS:
+            out[name] = np.frombuffer(data, np.dtype(dt).newbyteorder("<"), counts[name], off).astype(dt)
+            off += counts[name] * np.dtype(dt).itemsize
+        if off != len(data):
+            raise ValueError(f"{path} is truncated or has trailing bytes")
+        return RawGraph(**out)
+
     def validate_dtypes(self) -> "RawGraph":
         self.node_id = np.ascontiguousarray(self.node_id, dtype=np.int64)
         self.node_op = np.ascontiguousarray(self.node_op, dtype=np.int32)

@@ -127,6 +127,12 @@ const char *fdg_last_error(void);
 /* --- compile: host-only, needs no GPU ---------------------------------------------------------- */
 int fdg_compile(const fdg_graph_desc *graph, const fdg_options *opts /* may be NULL */, fdg_handle *out);
 int fdg_destroy(fdg_handle h);
+/* A flattened graph as a file, so that graphs built by a Julia session elsewhere can be evaluated here.
+ * Little-endian: 8 bytes "FDGRAPH\1", int64 n_nodes, n_edges, n_graphs, n_roots, then the arrays of fdg_graph_desc in
+ * declaration order (node_id, node_op, node_pow, child_ptr[n_nodes+1], child_node, child_factor, graphs, root_id),
+ * each with its own element type and no padding. */
+int fdg_graph_write(const fdg_graph_desc *graph, const char *path);
+int fdg_compile_file(const char *path, const fdg_options *opts /* may be NULL */, fdg_handle *out);
 int fdg_stats(fdg_handle h, fdg_stats_t *out);
 /* leafmap: node index (into the desc arrays) of leaf k, k = 0..L-1 -- same numbering as the
  * reference's `leafmap::Dict{Int,Graph}` (static.jl:118-119), 0-based. */

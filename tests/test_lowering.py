@@ -252,3 +252,29 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(_capi.FdgError) as e:
         ev(np.zeros(1), np.array([1.0, 2.0]))
     assert e.value.code in (6, 4)  # FDG_ERR_NO_DEVICE (or a CUDA error): never a silent CPU result
+
+
+def test_fdgraph_file_round_trip(tmp_path):
+    """a flattened graph as a file (fdg_graph_write / fdg_compile_file), written by the C library and read
+    back by an independent numpy reader and by the library itself: same arrays, same lowered program, same leafmap."""
+    roots = graphgen.random_dag(21, n_leaves=7, n_inner=45, n_roots=3, p_power=0.2)
+    raw, _ = fd.flatten(roots, root=[roots[1].id, 424242, roots[0].id])
+    path = str(tmp_path / "g.fdgraph")
+    raw.save_fdg(path)
+    back = fd.RawGraph.load_fdg(path)
+    for k in raw.__dataclass_fields__:
+        assert np.array_equal(getattr(raw, k), getattr(back, k)) and getattr(raw, k).dtype == getattr(back, k).dtype
+    a, b = fd.compile_raw(raw), fd.compile_file(path)
+    assert a.stats == b.stats and list(a.leaf_nodes) == list(b.leaf_nodes) and a.last_root == b.last_root
+    assert np.array_equal(a.program_words(), b.program_words())
+    with open(path, "ab") as fh:
+        fh.write(b"x")
+    with pytest.raises(_capi.FdgError) as e:
+        fd.compile_file(path)  # trailing bytes
+    assert e.value.code == 2
+    with pytest.raises(ValueError):
+        fd.RawGraph.load_fdg(path)
+    with open(path, "wb") as fh:
+        fh.write(b"not a graph")
+    with pytest.raises(_capi.FdgError):
+        fd.compile_file(path)
