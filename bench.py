@@ -344,6 +344,12 @@ def main():
                 "avg_launch_ms": 1e3 * avg_launch_s, "algorithmic_bytes_per_sample": st["bytes_in"],
                 "fp64_gflops_achieved": flops_launch / avg_launch_s / 1e9, "flops_per_sample": st["flops_add"] + st["flops_mul"],
                 "flop_per_byte": (st["flops_add"] + st["flops_mul"]) / max(st["bytes_in"], 1)}
+    if traffic:
+        # the same launch on the bytes ncu saw move (profiles/traffic.json): how close the kernels run to the HBM peak
+        roofline["traffic_gbs"] = traffic / avg_launch_s / 1e9
+        roofline["traffic_frac_of_peak"] = traffic / avg_launch_s / 1e9 / peak
+    if jit_info is not None:
+        roofline["planned_bytes_per_sample"] = (jit_info["leaf_loads"] + jit_info["cross_loads"] + jit_info["cross_stores"]) * es
 
     out = {
         "metric": "MC-sample graph-evals/sec", "value": value, "unit": "graph-evals/s", "samples_per_s": sps,
