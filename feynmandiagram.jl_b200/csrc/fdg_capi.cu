@@ -1001,7 +1001,10 @@ int fdg_eval_generated_accumulate(fdg_handle h, fdg_leafgen_t g, const double *K
             rc = leafgen_launch(g, K + b0, T + b0, ld_var, nb, buf, sub, st);
         }
         if (rc != FDG_OK) return rc;
-        h->launches++;
+        {
+            std::lock_guard<std::mutex> lock(h->mu);
+            h->launches++;
+        }
         rc = do_eval(h, buf, sub, acc, 0, nb, st, true);
         if (rc != FDG_OK) return rc;
     }
