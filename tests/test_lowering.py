@@ -278,3 +278,25 @@ def test_fdgraph_file_round_trip(tmp_path):
         fh.write(b"not a graph")
     with pytest.raises(_capi.FdgError):
         fd.compile_file(path)
+
+
+def test_planner_of_the_specialised_back_end_on_the_headline_graph(monkeypatch):
+    """Host-side regression guard for the kernel plan of Parquet vertex4 order 4: root ordering
+    keeps the cross traffic small, rows are reused, kernels stay inside the instruction-cache budget."""
+    import os
+
+    raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", "parquet_ver4_o4.npz"))
+    ev = fd.compile_raw(raw, backend=2)
+    info = ev.jit_prepare(1, True)
+    assert info["operations"] == 94500 and not info["grid_stride"]
+    assert 15 <= info["kernels"] <= 24
+    assert info["cross_values"] <= 400 and info["cross_rows"] <= 160
+    assert info["leaf_loads"] <= 3400                      # 984 leaves, each read by ~3.3 kernels
+    assert info["cubin_bytes"] / info["kernels"] < 110e3   # straight-line code above ~100 KB stalls on instruction fetch
+    ptx, log = ev.jit_ptx(1, True, 3)
+    assert "cp.async.ca.shared.global" in ptx and "cp.async.wait_group" in ptx and "neg.f64" in ptx and "mad.wide.u32" in ptx
+    assert "fma.rn.f64" not in ptx                         # nothing is contracted
+    assert "bytes spill stores" not in log or " 0 bytes spill stores" in log
+    monkeypatch.setenv("FDG_JIT_ROOT_ORDER", "0")
+    worse = fd.compile_raw(raw, backend=2).jit_prepare(1, True)
+    assert worse["cross_values"] > 4 * info["cross_values"]
