@@ -289,3 +289,51 @@ def test_leading_dimension_of_4_gib_and_more():
     ev.eval_device(leaf.data_ptr(), ld, root.data_ptr(), batch, batch, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert root.cpu().numpy().tobytes() == O.Oracle(raw).eval(host).tobytes()
+
+
+@pytest.mark.parametrize("name,dtype,log2_batch", [("parquet_sigma_o3", np.float64, 24), ("parquet_ver4_o4", np.float64, 20),
+                                                   ("gv_ver4_o4", np.float64, 19), ("taylor_sigma_o3", np.complex128, 22)])
+def test_full_size_checksums_on_the_baseline_graphs(name, dtype, log2_batch):
+    """BASELINE-size batches (cfg 2 at its full 2^24 samples; the order-4 graphs at one resident batch) through
+    size-independent properties: with every leaf equal to one each root is the signed diagram count of
+    workloads/MANIFEST.json at EVERY sample and the accumulators are count x batch exactly (integers below 2^53);
+    with random leaves a strided subsample is bit-equal to the oracle and accumulate equals the sum of eval."""
+    import json
+    import os
+
+    root_dir = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    raw = fd.RawGraph.load(os.path.join(root_dir, "workloads", name + ".npz"))
+    want = np.array(json.load(open(os.path.join(root_dir, "workloads", "MANIFEST.json")))[name]["all_leaves_one"])
+    ev = fd.compile_raw(raw, dtype=dtype)
+    B = 1 << log2_batch
+    tdt = torch.float64 if dtype == np.float64 else torch.complex128
+    W = 1 if dtype == np.float64 else 2
+    s = torch.cuda.current_stream().cuda_stream
+    leaf = torch.ones(ev.n_leaves, B, dtype=tdt, device="cuda")
+    acc = torch.zeros(ev.n_roots * W, dtype=torch.float64, device="cuda")
+    ev.accumulate_device(leaf.data_ptr(), B, B, acc.data_ptr(), s)
+    torch.cuda.synchronize()
+    got = acc.cpu().numpy().reshape(ev.n_roots, W)
+    assert np.array_equal(got[:, 0], want * B)
+    if W == 2:
+        assert not got[:, 1].any()
+    # eval mode on a slice of the same batch: the count at every sample
+    nb = min(B, 1 << 18)
+    root = torch.zeros(ev.n_roots, nb, dtype=tdt, device="cuda")
+    ev.eval_device(leaf.data_ptr(), B, root.data_ptr(), nb, nb, s)
+    torch.cuda.synchronize()
+    assert torch.equal(root, torch.from_numpy(want.astype(dtype)).cuda()[:, None].expand(ev.n_roots, nb))
+    # random leaves: strided subsample against the oracle, accumulate against the sum of eval
+    g = torch.Generator(device="cuda").manual_seed(99)
+    torch.view_as_real(leaf).copy_(torch.rand(ev.n_leaves, B, 2, dtype=torch.float64, device="cuda", generator=g) + 0.5) if W == 2 else \
+        leaf.copy_(torch.rand(ev.n_leaves, B, dtype=torch.float64, device="cuda", generator=g) + 0.5)
+    ev.eval_device(leaf.data_ptr(), B, root.data_ptr(), nb, nb, s)
+    acc.zero_()
+    ev.accumulate_device(leaf.data_ptr(), B, nb, acc.data_ptr(), s)
+    torch.cuda.synchronize()
+    idx = torch.arange(0, nb, 1021, device="cuda")
+    sub = np.ascontiguousarray(leaf[:, idx].cpu().numpy())
+    assert root[:, idx].cpu().numpy().tobytes() == O.Oracle(raw).eval(sub).tobytes()
+    ref = torch.view_as_real(root).sum(dim=1).reshape(-1) if W == 2 else root.sum(dim=1)
+    scale = (torch.view_as_real(root).abs().sum(dim=1).reshape(-1) if W == 2 else root.abs().sum(dim=1)) + 1e-300
+    assert bool(((acc - ref).abs() <= 1e-12 * scale).all())
