@@ -5,13 +5,17 @@
 // only, in the emitter's left-fold order, never fused -- and assembles it for sm_100a with the PTX compiler
 // library shipped in the CUDA toolkit (libnvptxcompiler_static).  It is the direct analogue of the reference's
 // emit-source design (to_julia_str -> RuntimeGeneratedFunction), with the sample index as the thread index:
-//   * every value of a segment lives in a register (ptxas allocates; 255 registers per thread, spills go to
-//     L1-cached local memory), leaves are read with 16-byte non-coherent loads straight from the batch-major
-//     leaf matrix, nothing is decoded at run time;
-//   * big programs are cut into SEGMENTS of consecutive statements (bounded ptxas time, compiled in parallel);
-//     a value defined in one segment and read in a later one travels through a per-launch "cross" buffer
-//     laid out [value][thread] (coalesced);
-//   * roots are stored per sample (eval) or shuffle-reduced per warp into per-warp partial sums (accumulate).
+//   * every value of a kernel lives in a register (ptxas allocates; 255 registers per thread), nothing is decoded
+//     at run time;
+//   * big programs are cut into kernels of about 4000 machine instructions (what the instruction cache holds), the
+//     roots ordered so that few values are live across a cut, each cut placed where the fewest are; a value defined
+//     in one kernel and read in a later one travels through a per-launch "cross" buffer laid out [row][thread]
+//     (coalesced), rows reused once their last reader has run;
+//   * inputs (leaf rows of the batch-major leaf matrix, cross rows) are streamed global -> shared by cp.async, a ring
+//     of 32 rows ahead of the arithmetic with compile-time wait counts; x * (-1.0) is a folded negation;
+//   * roots are stored per sample (eval) or shuffle-reduced per warp into per-warp partial sums (accumulate);
+//     a single small accumulate kernel runs as a grid-stride loop with per-thread running sums.
+// Every one of these decisions is bit-neutral: each statement keeps its own left fold.
 #include "fdg_jit.h"
 
 #include <nvPTXCompiler.h>

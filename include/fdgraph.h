@@ -60,8 +60,8 @@ enum {
 enum { FDG_OP_UNITARY = 0, FDG_OP_SUM = 1, FDG_OP_PROD = 2, FDG_OP_POWER = 3 };
 
 /* back ends.  VM: the packet interpreter kernel (any program, Float64 and ComplexF64).  JIT: the emitted
- * function written as PTX and assembled for sm_100a at first use (Float64).  AUTO picks JIT where it
- * applies and falls back to the VM; both compute bit-identical results. */
+ * function written as PTX and assembled for sm_100a at first use (Float64 and ComplexF64).  AUTO picks JIT
+ * and falls back to the VM if the kernels cannot be built; both compute bit-identical results. */
 enum { FDG_BACKEND_AUTO = 0, FDG_BACKEND_VM = 1, FDG_BACKEND_JIT = 2 };
 
 /* element types of leafVal / root (julia_to_C_typestr, static.jl:135-153) */
@@ -92,7 +92,7 @@ typedef struct fdg_options {
     int32_t schedule;     /* 0 = eager: multi-use values are computed as statements of their own
                              before the fold that reads them (emitter order); 1 = lazy: inside it */
     int32_t backend;      /* FDG_BACKEND_AUTO (0), FDG_BACKEND_VM (1), FDG_BACKEND_JIT (2)            */
-    int32_t jit_segment;  /* operations per specialised kernel (0 = default)                   */
+    int32_t jit_segment;  /* machine instructions per specialised kernel, estimated (0 = 4000)  */
     int32_t cse;          /* 1 = evaluate common sub-expressions once (hash-based analogue of
                              optimize!(level=1), optimize.jl:345-390; bit-identical).  Default 0: on
                              the memory-bound order-4 graphs sharing more values costs more traffic
