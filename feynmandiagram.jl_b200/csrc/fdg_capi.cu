@@ -838,6 +838,8 @@ struct fdg_leafgen {
     std::map<int, LeafMeta *> d_meta;                  // per device
     std::map<int, std::pair<double *, size_t>> d_leaf;  // per device: sub-batch leaf matrix of the fused path
     std::map<int, std::pair<double *, size_t>> d_var;   // per device: staging of (K, T) chunks for the host path
+    cudaStream_t streams[2] = {nullptr, nullptr};       // host path: copy stream, run stream (created on first use)
+    cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};  // [k] chunk k copied, [2 + k] buffer k consumed
     std::mutex mu;
 };
 
@@ -946,6 +948,10 @@ int fdg_leafgen_destroy(fdg_leafgen_t g) {
             cudaFree(kv.second.first);
         }
         cudaSetDevice(cur);
+        for (int i = 0; i < 2; ++i)
+            if (g->streams[i]) cudaStreamDestroy(g->streams[i]);
+        for (int i = 0; i < 4; ++i)
+            if (g->events[i]) cudaEventDestroy(g->events[i]);
     }
     delete g;
     return FDG_OK;
@@ -1019,13 +1025,16 @@ int fdg_eval_generated_host(fdg_handle h, fdg_leafgen_t g, const double *K_host,
     if (ld_var < batch) return fail(FDG_ERR_BAD_ARG, "ld_var < batch");
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
-    const int64_t rows = (int64_t)g->n_loops * g->dim + g->n_tau;
+    const int64_t kr = (int64_t)g->n_loops * g->dim, rows = kr + g->n_tau;
     const int64_t R = h->low.R;
+    // chunks of (K, T) are copied on one stream while the previous chunk is generated and evaluated on another
+    const int64_t chunk = std::min<int64_t>(std::max<int64_t>(batch, 1), 1 << 19);
     double *d_var = nullptr;
+    cudaStream_t s_copy = nullptr, s_run = nullptr;
     {
         std::lock_guard<std::mutex> lock(g->mu);
         auto &slot = g->d_var[dev];
-        const size_t need = ((size_t)rows * (size_t)std::max<int64_t>(batch, 1) + (size_t)std::max<int64_t>(R, 1)) * sizeof(double);
+        const size_t need = (2 * (size_t)rows * (size_t)chunk + (size_t)std::max<int64_t>(R, 1)) * sizeof(double);
         if (need > slot.second) {
             if (slot.first) CUDA_TRY(cudaFree(slot.first));
             slot = {nullptr, 0};
@@ -1033,20 +1042,32 @@ int fdg_eval_generated_host(fdg_handle h, fdg_leafgen_t g, const double *K_host,
             slot.second = need;
         }
         d_var = slot.first;
+        for (int i = 0; i < 2; ++i)
+            if (!g->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&g->streams[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i)
+            if (!g->events[i]) CUDA_TRY(cudaEventCreateWithFlags(&g->events[i], cudaEventDisableTiming));
+        s_copy = g->streams[0], s_run = g->streams[1];
     }
-    double *d_acc = d_var + (size_t)rows * (size_t)std::max<int64_t>(batch, 1);
-    const int64_t kr = (int64_t)g->n_loops * g->dim;
-    cudaStream_t st = nullptr;  // the legacy default stream: ordered with the copies below
-    if (batch > 0) {
-        CUDA_TRY(cudaMemcpy2DAsync(d_var, (size_t)batch * 8, K_host, (size_t)ld_var * 8, (size_t)batch * 8, (size_t)kr, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpy2DAsync(d_var + (size_t)kr * (size_t)batch, (size_t)batch * 8, T_host, (size_t)ld_var * 8, (size_t)batch * 8,
-                                   (size_t)g->n_tau, cudaMemcpyHostToDevice, st));
+    double *d_acc = d_var + 2 * (size_t)rows * (size_t)chunk;
+    CUDA_TRY(cudaMemsetAsync(d_acc, 0, (size_t)std::max<int64_t>(R, 1) * 8, s_run));
+    int k = 0;
+    for (int64_t c0 = 0; c0 < batch; c0 += chunk, k ^= 1) {
+        const int64_t nb = std::min<int64_t>(chunk, batch - c0);
+        double *buf = d_var + (size_t)k * (size_t)rows * (size_t)chunk;
+        // buffer k is free once the evaluation that read it two chunks ago has finished
+        CUDA_TRY(cudaStreamWaitEvent(s_copy, g->events[2 + k], 0));
+        CUDA_TRY(cudaMemcpy2DAsync(buf, (size_t)chunk * 8, K_host + c0, (size_t)ld_var * 8, (size_t)nb * 8, (size_t)kr, cudaMemcpyHostToDevice, s_copy));
+        CUDA_TRY(cudaMemcpy2DAsync(buf + (size_t)kr * (size_t)chunk, (size_t)chunk * 8, T_host + c0, (size_t)ld_var * 8, (size_t)nb * 8,
+                                   (size_t)g->n_tau, cudaMemcpyHostToDevice, s_copy));
+        CUDA_TRY(cudaEventRecord(g->events[k], s_copy));
+        CUDA_TRY(cudaStreamWaitEvent(s_run, g->events[k], 0));
+        int rc = fdg_eval_generated_accumulate(h, g, buf, buf + (size_t)kr * (size_t)chunk, chunk, nb, d_acc, s_run);
+        if (rc != FDG_OK) return rc;
+        CUDA_TRY(cudaEventRecord(g->events[2 + k], s_run));
     }
-    CUDA_TRY(cudaMemsetAsync(d_acc, 0, (size_t)std::max<int64_t>(R, 1) * 8, st));
-    int rc = fdg_eval_generated_accumulate(h, g, d_var, d_var + (size_t)kr * (size_t)batch, batch, batch, d_acc, st);
-    if (rc != FDG_OK) return rc;
-    if (R > 0) CUDA_TRY(cudaMemcpyAsync(acc_host, d_acc, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    if (R > 0) CUDA_TRY(cudaMemcpyAsync(acc_host, d_acc, (size_t)R * 8, cudaMemcpyDeviceToHost, s_run));
+    CUDA_TRY(cudaStreamSynchronize(s_run));
+    CUDA_TRY(cudaStreamSynchronize(s_copy));
     return FDG_OK;
 }
 
