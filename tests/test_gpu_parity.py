@@ -337,3 +337,28 @@ def test_full_size_checksums_on_the_baseline_graphs(name, dtype, log2_batch):
     ref = torch.view_as_real(root).sum(dim=1).reshape(-1) if W == 2 else root.sum(dim=1)
     scale = (torch.view_as_real(root).abs().sum(dim=1).reshape(-1) if W == 2 else root.abs().sum(dim=1)) + 1e-300
     assert bool(((acc - ref).abs() <= 1e-12 * scale).all())
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_overflow_infinities_signed_zeros_and_nans(backend):
+    """Values that overflow, cancel or vanish: +-inf and +-0 must match the oracle bit for bit (x * (-1.0) is written
+    as a negation in the specialised kernels: same bits for every finite and infinite double); where the result is NaN
+    both sides must say NaN -- its sign and payload are hardware conventions (x86 and NVIDIA differ) and are not compared."""
+    roots = graphgen.random_dag(123, n_leaves=10, n_inner=120, n_roots=6, p_power=0.15, max_pow=5)
+    raw, _ = fd.flatten(roots)
+    ev = fd.compile_raw(raw, backend=backend, jit_segment=60 if backend == JIT else 0)
+    batch = 2048
+    rng = np.random.default_rng(17)
+    leaf = graphgen.leaf_values(9, ev.n_leaves, batch, signed=True)
+    kind = rng.integers(0, 6, size=leaf.shape)
+    leaf = np.where(kind == 0, leaf * 1e200, leaf)       # overflow in products
+    leaf = np.where(kind == 1, leaf * 1e-200, leaf)      # underflow to subnormals / zero
+    leaf = np.where(kind == 2, 0.0 * np.sign(leaf), leaf)  # +-0
+    leaf = np.ascontiguousarray(leaf)
+    with np.errstate(all="ignore"):
+        want = O.Oracle(raw).eval(leaf)
+    got = _dev_eval(ev, leaf, batch)
+    nan_w, nan_g = np.isnan(want), np.isnan(got)
+    assert np.array_equal(nan_w, nan_g)
+    assert nan_w.any() and np.isinf(want).any() and (want == 0).any()  # the case really exercises all three
+    assert np.array_equal(want.view(np.uint64)[~nan_w], got.view(np.uint64)[~nan_w])
