@@ -67,12 +67,6 @@ mutable struct Evaluator
     end
 end
 
-"""
-    compile(graphs; root=[id(g) for g in graphs], dtype=Float64) -> (eval_graph!, leafmap)
-
-Same contract as `Compilers.compile` (static.jl:221-227): `leafmap[k]` is the leaf graph whose value is column `k`
-of `leafVal` (1-based, identical numbering to the reference).
-"""
 # one entry per node OBJECT, children before parents (any order is accepted by the library); returns the arrays of
 # fdg_graph_desc plus the node objects behind them
 function _flatten(graphs::AbstractVector{G}) where {G<:AbstractGraph}
@@ -104,6 +98,12 @@ function _flatten(graphs::AbstractVector{G}) where {G<:AbstractGraph}
     return node_id, node_op, node_pow, child_ptr, child_node, child_factor, gidx, nodes
 end
 
+"""
+    compile(graphs; root=[id(g) for g in graphs], dtype=Float64) -> (eval_graph!, leafmap)
+
+Same contract as `Compilers.compile` (static.jl:221-227): `leafmap[k]` is the leaf graph whose value is column `k`
+of `leafVal` (1-based, identical numbering to the reference).
+"""
 function compile(graphs::AbstractVector{G}; root::AbstractVector{Int}=[id(g) for g in graphs], dtype::DataType=Float64) where {G<:AbstractGraph}
     node_id, node_op, node_pow, child_ptr, child_node, child_factor, gidx, nodes = _flatten(graphs)
     rootid = Int64.(root)
