@@ -249,6 +249,7 @@ def main():
     npdt = np.float64 if a.dtype == "f64" else np.complex128
     tdt = torch.float64 if a.dtype == "f64" else torch.complex128
     es = 8 if a.dtype == "f64" else 16
+    t_compile = time.perf_counter()
     f = fd.compile_raw(raw, dtype=npdt, max_slots=a.max_slots, prefetch=a.prefetch, backend=a.backend, jit_segment=a.jit_segment)
     jit_info = None
     if a.backend != 1:
@@ -256,6 +257,7 @@ def main():
             jit_info = f.jit_prepare(2 if (st_small(f) and a.dtype == "f64") else 1, True)
         except Exception:  # noqa: BLE001  (AUTO falls back to the VM inside the library)
             jit_info = None
+    t_compile = time.perf_counter() - t_compile  # lowering + planning + PTX assembly (what Compilers.compile costs once)
     f.set_launch(a.threads, a.spt, 0)
     st = f.stats
     L, R, W = st["n_leaves"], st["n_roots"], (1 if a.dtype == "f64" else 2)
@@ -358,7 +360,7 @@ def main():
         "config": {"workload": a.workload, "mode": "accumulate (per-root sums on device" + (", NCCL all-reduce)" if world > 1 else ")"),
                    "samples_per_step_per_gpu": samples_step, "resident_samples": res, "passes_per_step": passes,
                    "leaves": L, "statements": st["n_inner"], "roots": R,
-                   "backend": "vm" if jit_info is None else "jit", "jit": jit_info,
+                   "backend": "vm" if jit_info is None else "jit", "jit": jit_info, "compile_seconds": round(t_compile, 2),
                    "vm_packets": st["n_packets"], "vm_slots": st["n_slots"],
                    "l2": f"resident inputs {L * es * res / 2 ** 30:.1f} GiB per GPU >> 126 MB L2, no flush needed",
                    "leaf_values": "0.5 + U[0,1), seed 1234 + rank"},
