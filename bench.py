@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--spt", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-torch-emitter", action="store_true")
     return ap.parse_args()
 
 
@@ -434,6 +435,36 @@ def main():
             "api": "fdg_eval_generated_host: host (K, tau) of example/benchmark.jl:44-53 -> leaves on device (fdg_leafgen) -> "
                    "graph kernels -> R per-root sums; leaf values overwrite the synthetic resident batch AFTER the timed region above"}
         del hv, dv
+
+    # ---- the reference's own batched design point on this GPU: the emitted torch function (compiler_python.jl) ------
+    if rank == 0 and world == 1 and not a.no_torch_emitter and a.dtype == "f64":
+        try:
+            import fdgraph_b200.emitters as em
+
+            graphs = raw.to_graphs()
+            text, _ = em.to_python_str(graphs, root=[int(r) for r in raw.root_id])
+            ns = {}
+            exec(compile(text, "<to_python_str>", "exec"), ns)  # one elementwise torch op per node, every g<ID> kept alive
+            n_stmt = st["n_inner"] + L
+            bt = max(256, min(1 << 20, int(6 * 2 ** 30 // (8 * max(n_stmt, 1)))))  # about 6 GiB of live intermediates
+            bt = 1 << int(math.floor(math.log2(bt)))
+            lt = (torch.rand(bt, max(L, 1), dtype=torch.float64, device="cuda") + 0.5).T.contiguous().T  # leafVal[:, k] unit-stride
+            ns["eval_graph"](lt)
+            torch.cuda.synchronize()
+            reps, t = 0, time.perf_counter()
+            while reps < 3 or (time.perf_counter() - t < 2.0 and reps < 50):
+                ns["eval_graph"](lt)
+                reps += 1
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t
+            out["reference_torch_emitter"] = {
+                "value": bt * reps * R / dt, "unit": "graph-evals/s", "samples_per_s": bt * reps / dt, "batch": bt, "calls": reps,
+                "what": "the text of Compilers.to_python_str (compiler_python.jl:9-52, fdgraph_b200.emitters) executed by torch on this "
+                        "GPU: one kernel launch per node -- what the reference offers on a GPU today"}
+            del lt, ns
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            out["reference_torch_emitter"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------------
     if rank == 0 and world == 1 and not a.no_cpu:

@@ -69,6 +69,40 @@ class RawGraph:
             raise ValueError(f"{path} is truncated or has trailing bytes")
         return RawGraph(**out)
 
+    def to_graphs(self) -> List[Graph]:
+        """Inverse of :func:`flatten`: Graph objects (ids preserved, shared nodes shared) for the entries of `graphs`."""
+        n = self.n_nodes
+        state = np.zeros(n, np.int8)
+        order: List[int] = []
+        for r in range(n):  # children before parents, whatever the order of the arrays
+            if state[r]:
+                continue
+            stack = [(r, 0)]
+            while stack:
+                v, k = stack.pop()
+                if k == 0:
+                    if state[v]:
+                        continue
+                    state[v] = 1
+                lo, hi = int(self.child_ptr[v]), int(self.child_ptr[v + 1])
+                if lo + k < hi:
+                    stack.append((v, k + 1))
+                    c = int(self.child_node[lo + k])
+                    if not state[c]:
+                        stack.append((c, 0))
+                else:
+                    order.append(v)
+        nodes: List[Optional[Graph]] = [None] * n
+        ops = {OP_UNITARY: Unitary(), OP_SUM: Sum(), OP_PROD: Prod()}
+        for i in order:
+            lo, hi = int(self.child_ptr[i]), int(self.child_ptr[i + 1])
+            subs = [nodes[int(c)] for c in self.child_node[lo:hi]]
+            op = Power(int(self.node_pow[i])) if int(self.node_op[i]) == OP_POWER else ops[int(self.node_op[i])]
+            g = Graph(subs, subgraph_factors=[float(f) for f in self.child_factor[lo:hi]], operator=op if subs else Sum())
+            g.id = int(self.node_id[i])
+            nodes[i] = g
+        return [nodes[int(i)] for i in self.graphs]
+
     def validate_dtypes(self) -> "RawGraph":
         self.node_id = np.ascontiguousarray(self.node_id, dtype=np.int64)
         self.node_op = np.ascontiguousarray(self.node_op, dtype=np.int32)

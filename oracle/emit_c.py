@@ -66,45 +66,8 @@ static inline complex double fdg_cpow(complex double x, int p) {
 
 
 def graphs_from_raw(raw):
-    """Graph objects (ids preserved) behind the flattened arrays; children precede parents in fd.flatten's order."""
-    import fdgraph_b200 as fd
-
-    order = _topo(raw)
-    nodes = [None] * raw.n_nodes
-    ops = {0: fd.Unitary(), 1: fd.Sum(), 2: fd.Prod()}
-    for i in order:
-        lo, hi = int(raw.child_ptr[i]), int(raw.child_ptr[i + 1])
-        subs = [nodes[int(c)] for c in raw.child_node[lo:hi]]
-        op = fd.Power(int(raw.node_pow[i])) if int(raw.node_op[i]) == 3 else ops[int(raw.node_op[i])]
-        g = fd.Graph(subs, subgraph_factors=[float(f) for f in raw.child_factor[lo:hi]], operator=op if subs else fd.Sum())
-        g.id = int(raw.node_id[i])
-        nodes[i] = g
-    return [nodes[int(i)] for i in raw.graphs]
-
-
-def _topo(raw):
-    n = raw.n_nodes
-    state = np.zeros(n, np.int8)
-    out = []
-    for r in range(n):
-        if state[r]:
-            continue
-        stack = [(r, 0)]
-        while stack:
-            v, k = stack.pop()
-            if k == 0:
-                if state[v]:
-                    continue
-                state[v] = 1
-            lo, hi = int(raw.child_ptr[v]), int(raw.child_ptr[v + 1])
-            if lo + k < hi:
-                stack.append((v, k + 1))
-                c = int(raw.child_node[lo + k])
-                if not state[c]:
-                    stack.append((c, 0))
-            else:
-                out.append(v)
-    return out
+    """Graph objects (ids preserved) behind the flattened arrays."""
+    return raw.to_graphs()
 
 
 def _key(raw, dtype: str) -> str:
