@@ -37,12 +37,20 @@ int cuda_fail(cudaError_t e, const char *what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #x); \
     } while (0)
 
+// Work buffers of one launch sequence.  They are kept PER STREAM: two sequences of the same handle issued on different
+// streams (fdg_eval_host alternates two) may run at the same time and must not share them.
+struct StreamScratch {
+    void *scratch = nullptr;  // packet VM: spilled values
+    size_t scratch_bytes = 0;
+    double *partial = nullptr;  // accumulate mode: per-warp partial sums
+    size_t partial_bytes = 0;
+    void *cross = nullptr;  // specialised back end: values crossing kernel boundaries, [row][thread * spt]
+    size_t cross_bytes = 0;
+};
+
 struct DeviceState {
     uint4 *d_prog = nullptr;
-    void *scratch = nullptr;
-    size_t scratch_bytes = 0;
-    double *partial = nullptr;
-    size_t partial_bytes = 0;
+    std::map<cudaStream_t, StreamScratch> per_stream;
     int sm_count = 0;
     int max_smem_optin = 0;
     // host pipeline (fdg_eval_host)
@@ -50,8 +58,6 @@ struct DeviceState {
     void *d_leaf[2] = {nullptr, nullptr};
     void *d_root[2] = {nullptr, nullptr};
     size_t d_leaf_bytes = 0, d_root_bytes = 0;
-    void *cross = nullptr;  // specialised back end: values crossing kernel boundaries, [n_cross][threads * spt]
-    size_t cross_bytes = 0;
 };
 
 }  // namespace
@@ -86,6 +92,7 @@ namespace {
 template <class V, bool ACC>
 int launch_variant(fdg_program *h, DeviceState &ds, fdg::VmArgs &args, long long batch, cudaStream_t stream) {
     const fdg::Lowered &low = h->low;
+    StreamScratch &ss = ds.per_stream[stream];
     constexpr int S = V::kSamples;
     constexpr int W = V::kWidth;
     auto kern = fdg::fdg_vm_kernel<V, ACC>;
@@ -113,27 +120,27 @@ int launch_variant(fdg_program *h, DeviceState &ds, fdg::VmArgs &args, long long
     args.n_slots = low.n_slots;
     if (low.n_scratch > 0) {
         const size_t need = (size_t)low.n_scratch * grid * T * sizeof(V);
-        if (need > ds.scratch_bytes) {
-            if (ds.scratch) CUDA_TRY(cudaFree(ds.scratch));
-            ds.scratch = nullptr;
-            ds.scratch_bytes = 0;
-            CUDA_TRY(cudaMalloc(&ds.scratch, need));
-            ds.scratch_bytes = need;
+        if (need > ss.scratch_bytes) {
+            if (ss.scratch) CUDA_TRY(cudaFree(ss.scratch));
+            ss.scratch = nullptr;
+            ss.scratch_bytes = 0;
+            CUDA_TRY(cudaMalloc(&ss.scratch, need));
+            ss.scratch_bytes = need;
         }
-        args.scratch = ds.scratch;
+        args.scratch = ss.scratch;
     }
     long long rows = 0;
     if (ACC) {
         rows = grid * (T / 32);
         const size_t need = (size_t)rows * low.R * W * sizeof(double);
-        if (need > ds.partial_bytes) {
-            if (ds.partial) CUDA_TRY(cudaFree(ds.partial));
-            ds.partial = nullptr;
-            ds.partial_bytes = 0;
-            CUDA_TRY(cudaMalloc((void **)&ds.partial, std::max<size_t>(need, 256)));
-            ds.partial_bytes = std::max<size_t>(need, 256);
+        if (need > ss.partial_bytes) {
+            if (ss.partial) CUDA_TRY(cudaFree(ss.partial));
+            ss.partial = nullptr;
+            ss.partial_bytes = 0;
+            CUDA_TRY(cudaMalloc((void **)&ss.partial, std::max<size_t>(need, 256)));
+            ss.partial_bytes = std::max<size_t>(need, 256);
         }
-        args.partial = ds.partial;
+        args.partial = ss.partial;
     }
     kern<<<(unsigned)grid, T, smem, stream>>>(args);
     CUDA_TRY(cudaGetLastError());
@@ -141,7 +148,7 @@ int launch_variant(fdg_program *h, DeviceState &ds, fdg::VmArgs &args, long long
     if (ACC) {
         const int rw = (int)low.R * W;
         if (rw > 0) {
-            fdg::fdg_reduce_partials<<<rw, 256, 0, stream>>>(ds.partial, rows, rw, static_cast<double *>(args.root));
+            fdg::fdg_reduce_partials<<<rw, 256, 0, stream>>>(ss.partial, rows, rw, static_cast<double *>(args.root));
             CUDA_TRY(cudaGetLastError());
             h->launches++;
         }
@@ -191,6 +198,7 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
 int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, const void *leaf, int64_t ld_leaf, void *root,
                int64_t ld_root, int64_t batch, cudaStream_t stream) {
     JitVariant *v = nullptr;
+    StreamScratch &ss = ds.per_stream[stream];
     // row offsets are formed with one 32-bit multiply-add unless a leading dimension reaches 4 GiB
     const bool wide = (uint64_t)ld_leaf * (h->low.dtype == FDG_C128 ? 16 : 8) >= (1ull << 32);
     int rc = jit_get(h, spt, acc, &v, wide);
@@ -231,12 +239,12 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
     const int64_t ld_cross = max_grid * per_block;
     if (v->plan.n_cross > 0) {
         const size_t need = (size_t)v->plan.n_cross * ld_cross * es;
-        if (need > ds.cross_bytes) {
-            if (ds.cross) CUDA_TRY(cudaFree(ds.cross));
-            ds.cross = nullptr;
-            ds.cross_bytes = 0;
-            CUDA_TRY(cudaMalloc(&ds.cross, need));
-            ds.cross_bytes = need;
+        if (need > ss.cross_bytes) {
+            if (ss.cross) CUDA_TRY(cudaFree(ss.cross));
+            ss.cross = nullptr;
+            ss.cross_bytes = 0;
+            CUDA_TRY(cudaMalloc(&ss.cross, need));
+            ss.cross_bytes = need;
         }
     }
     long long rows = 0;
@@ -244,22 +252,22 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
     if (acc) {
         rows = max_grid * (T / 32);
         const size_t need = std::max<size_t>((size_t)rows * low.R * W * sizeof(double), 256);
-        if (need > ds.partial_bytes) {
-            if (ds.partial) CUDA_TRY(cudaFree(ds.partial));
-            ds.partial = nullptr;
-            ds.partial_bytes = 0;
-            CUDA_TRY(cudaMalloc((void **)&ds.partial, need));
-            ds.partial_bytes = need;
+        if (need > ss.partial_bytes) {
+            if (ss.partial) CUDA_TRY(cudaFree(ss.partial));
+            ss.partial = nullptr;
+            ss.partial_bytes = 0;
+            CUDA_TRY(cudaMalloc((void **)&ss.partial, need));
+            ss.partial_bytes = need;
         }
-        if (!v->plan.persistent) CUDA_TRY(cudaMemsetAsync(ds.partial, 0, (size_t)rows * low.R * W * sizeof(double), stream));
-        out = ds.partial;
+        if (!v->plan.persistent) CUDA_TRY(cudaMemsetAsync(ss.partial, 0, (size_t)rows * low.R * W * sizeof(double), stream));
+        out = ss.partial;
     }
     for (int64_t b0 = 0; b0 < batch; b0 += sub) {
         const int64_t nb = std::min<int64_t>(sub, batch - b0);
         const unsigned grid = (unsigned)std::min<int64_t>((nb + per_block - 1) / per_block, max_grid);
         const void *p_leaf = static_cast<const char *>(leaf) + (size_t)b0 * es;
         void *p_out = acc ? out : static_cast<void *>(static_cast<char *>(root) + (size_t)b0 * es);
-        void *p_cross = ds.cross;
+        void *p_cross = ss.cross;
         long long a_ld_leaf = ld_leaf, a_ld_cross = ld_cross, a_ld_root = ld_root, a_batch = nb, a_nroots = low.R * W;
         void *args[] = {(void *)&p_leaf, &a_ld_leaf, &p_cross, &a_ld_cross, &p_out, &a_ld_root, &a_batch, &a_nroots};
         for (size_t sg = 0; sg < kern.size(); ++sg) {
@@ -268,7 +276,7 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
         }
     }
     if (acc && low.R > 0) {
-        fdg::fdg_reduce_partials<<<(int)low.R * W, 256, 0, stream>>>(ds.partial, rows, (int)low.R * W, static_cast<double *>(root));
+        fdg::fdg_reduce_partials<<<(int)low.R * W, 256, 0, stream>>>(ss.partial, rows, (int)low.R * W, static_cast<double *>(root));
         CUDA_TRY(cudaGetLastError());
         h->launches++;
     }
@@ -493,9 +501,11 @@ int fdg_destroy(fdg_handle h) {
         cudaSetDevice(kv.first);
         DeviceState &ds = kv.second;
         cudaFree(ds.d_prog);
-        cudaFree(ds.scratch);
-        cudaFree(ds.partial);
-        cudaFree(ds.cross);
+        for (auto &ps : ds.per_stream) {
+            cudaFree(ps.second.scratch);
+            cudaFree(ps.second.partial);
+            cudaFree(ps.second.cross);
+        }
         for (auto &kv2 : h->jit) {
             auto it = kv2.second.libs.find(kv.first);
             if (it != kv2.second.libs.end())

@@ -362,3 +362,22 @@ def test_overflow_infinities_signed_zeros_and_nans(backend):
     assert np.array_equal(nan_w, nan_g)
     assert nan_w.any() and np.isinf(want).any() and (want == 0).any()  # the case really exercises all three
     assert np.array_equal(want.view(np.uint64)[~nan_w], got.view(np.uint64)[~nan_w])
+
+
+def test_host_arrays_in_many_chunks_on_a_multi_kernel_program():
+    """fdg_eval_host pipelines 64 MiB chunks over two streams; with a multi-kernel program both streams run launch
+    sequences that need a cross buffer -- each stream has its own.  Bit-exact against the oracle on every sample."""
+    import os
+
+    raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", "parquet_ver4_o3.npz"))
+    ev = fd.compile_raw(raw, backend=JIT, jit_segment=700)
+    assert ev.jit_prepare(1, False)["kernels"] >= 8 and ev.jit_prepare(1, False)["cross_rows"] > 0
+    B = 150000  # 4 chunks of 46080 samples
+    leafT = graphgen.leaf_values(11, ev.n_leaves, B, signed=True)      # (L, B)
+    leafVal = np.asfortranarray(leafT.T)                                # (B, L), batch unit-stride
+    root = np.asfortranarray(np.zeros((B, ev.n_roots)))
+    for _ in range(3):  # repeated: a race would not show every time
+        root[...] = 0.0
+        ev(root, leafVal)
+        want = O.Oracle(raw).eval(leafT, nthreads=8)
+        assert np.ascontiguousarray(root.T).tobytes() == want.tobytes()
