@@ -381,3 +381,33 @@ def test_host_arrays_in_many_chunks_on_a_multi_kernel_program():
         ev(root, leafVal)
         want = O.Oracle(raw).eval(leafT, nthreads=8)
         assert np.ascontiguousarray(root.T).tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_launch_sequences_over_sub_batches(dtype, monkeypatch):
+    """A batch larger than the cross buffer allows is processed as several launch sequences (FDG_JIT_CROSS_GB caps the
+    buffer; the floor is 4 blocks per SM = 75 776 samples): eval and accumulate must not notice."""
+    import os
+
+    monkeypatch.setenv("FDG_JIT_CROSS_GB", "0.0001")
+    raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", "parquet_ver4_o3.npz"))
+    ev = fd.compile_raw(raw, dtype=dtype, backend=JIT, jit_segment=900)
+    B = 3 * 75776 + 1234
+    tdt = torch.float64 if dtype == np.float64 else torch.complex128
+    W = 1 if dtype == np.float64 else 2
+    g = torch.Generator(device="cuda").manual_seed(5)
+    leaf = torch.empty(ev.n_leaves, B, dtype=tdt, device="cuda")
+    torch.view_as_real(leaf).copy_(torch.rand(ev.n_leaves, B, 2, dtype=torch.float64, device="cuda", generator=g) - 0.5) if W == 2 else \
+        leaf.copy_(torch.rand(ev.n_leaves, B, dtype=torch.float64, device="cuda", generator=g) - 0.5)
+    root = torch.zeros(ev.n_roots, B, dtype=tdt, device="cuda")
+    acc = torch.zeros(ev.n_roots * W, dtype=torch.float64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    ev.eval_device(leaf.data_ptr(), B, root.data_ptr(), B, B, s)
+    ev.accumulate_device(leaf.data_ptr(), B, B, acc.data_ptr(), s)
+    torch.cuda.synchronize()
+    idx = torch.cat([torch.arange(0, B, 997, device="cuda"), torch.tensor([75775, 75776, 151551, 151552, B - 1], device="cuda")])
+    sub = np.ascontiguousarray(leaf[:, idx].cpu().numpy())
+    assert root[:, idx].cpu().numpy().tobytes() == O.Oracle(raw).eval(sub).tobytes()
+    ref = torch.view_as_real(root).sum(dim=1).reshape(-1) if W == 2 else root.sum(dim=1)
+    scale = (torch.view_as_real(root).abs().sum(dim=1).reshape(-1) if W == 2 else root.abs().sum(dim=1)) + 1e-300
+    assert bool(((acc - ref).abs() <= 1e-12 * scale).all())
