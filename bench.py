@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-torch-emitter", action="store_true")
+    ap.add_argument("--fma", action="store_true", help="opt-in contraction (fdg_options.fma): NOT the bit-exact default, never the headline")
     return ap.parse_args()
 
 
@@ -251,7 +252,7 @@ def main():
     tdt = torch.float64 if a.dtype == "f64" else torch.complex128
     es = 8 if a.dtype == "f64" else 16
     t_compile = time.perf_counter()
-    f = fd.compile_raw(raw, dtype=npdt, max_slots=a.max_slots, prefetch=a.prefetch, backend=a.backend, jit_segment=a.jit_segment)
+    f = fd.compile_raw(raw, dtype=npdt, max_slots=a.max_slots, prefetch=a.prefetch, backend=a.backend, jit_segment=a.jit_segment, fma=a.fma)
     jit_info = None
     if a.backend != 1:
         try:
@@ -361,7 +362,7 @@ def main():
         "config": {"workload": a.workload, "mode": "accumulate (per-root sums on device" + (", NCCL all-reduce)" if world > 1 else ")"),
                    "samples_per_step_per_gpu": samples_step, "resident_samples": res, "passes_per_step": passes,
                    "leaves": L, "statements": st["n_inner"], "roots": R,
-                   "backend": "vm" if jit_info is None else "jit", "jit": jit_info, "compile_seconds": round(t_compile, 2),
+                   "backend": "vm" if jit_info is None else "jit", "jit": jit_info, "arithmetic": "fma opt-in (not bit-identical)" if a.fma else "bit-exact (no contraction)", "compile_seconds": round(t_compile, 2),
                    "vm_packets": st["n_packets"], "vm_slots": st["n_slots"],
                    "l2": f"resident inputs {L * es * res / 2 ** 30:.1f} GiB per GPU >> 126 MB L2, no flush needed",
                    "leaf_values": "0.5 + U[0,1), seed 1234 + rank"},

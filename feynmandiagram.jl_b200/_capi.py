@@ -33,7 +33,7 @@ class GraphDesc(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("max_slots", C.c_int32), ("prefetch", C.c_int32), ("schedule", C.c_int32),
-                ("backend", C.c_int32), ("jit_segment", C.c_int32), ("cse", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("backend", C.c_int32), ("jit_segment", C.c_int32), ("cse", C.c_int32), ("fma", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -150,7 +150,7 @@ def compile_file(path: str, dtype: int = FDG_F64, backend: int = 0, jit_segment:
 
 
 def compile_raw(raw, dtype: int = FDG_F64, max_slots: int = 0, prefetch: int = 0, schedule: int = 0, backend: int = 0,
-                jit_segment: int = 0, cse: bool = False) -> C.c_void_p:
+                jit_segment: int = 0, cse: bool = False, fma: bool = False) -> C.c_void_p:
     """fdg_compile on a RawGraph; returns the opaque handle."""
     L = lib()
     raw.validate_dtypes()
@@ -166,7 +166,7 @@ def compile_raw(raw, dtype: int = FDG_F64, max_slots: int = 0, prefetch: int = 0
     d.n_roots, d.root_id = int(raw.root_id.shape[0]), _ptr(raw.root_id, C.c_int64)
     o = Options()
     o.dtype, o.max_slots, o.prefetch, o.schedule = int(dtype), int(max_slots), int(prefetch), int(schedule)
-    o.backend, o.jit_segment, o.cse = int(backend), int(jit_segment), int(bool(cse))
+    o.backend, o.jit_segment, o.cse, o.fma = int(backend), int(jit_segment), int(bool(cse)), int(bool(fma))
     h = C.c_void_p()
     check(L.fdg_compile(C.byref(d), C.byref(o), C.byref(h)))
     return h

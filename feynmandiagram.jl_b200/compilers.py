@@ -53,13 +53,13 @@ class Evaluator:
     """The callable returned by :func:`compile` -- stands in for the generated ``eval_graph!``."""
 
     def __init__(self, raw: RawGraph, dtype=np.float64, max_slots: int = 0, prefetch: int = 0, schedule: int = 0,
-                 backend: int = 0, jit_segment: int = 0, cse: bool = False):
+                 backend: int = 0, jit_segment: int = 0, cse: bool = False, fma: bool = False):
         self.dtype = np.dtype(dtype)
         if self.dtype not in _DTYPES:
             # static.jl:151  error("Unsupported type")
             raise TypeError(f"Unsupported type {self.dtype}: libfdgraph evaluates float64 or complex128 weights")
         self.raw = raw
-        self._h = _capi.compile_raw(raw, _DTYPES[self.dtype], max_slots, prefetch, schedule, backend, jit_segment, cse)
+        self._h = _capi.compile_raw(raw, _DTYPES[self.dtype], max_slots, prefetch, schedule, backend, jit_segment, cse, fma)
         self.stats = _capi.stats(self._h)
         self.n_leaves = self.stats["n_leaves"]
         self.n_roots = self.stats["n_roots"]
@@ -184,7 +184,7 @@ class Evaluator:
 
 def compile(graphs: Sequence[Graph], root: Optional[Sequence[int]] = None, *, dtype=np.float64,
             max_slots: int = 0, prefetch: int = 0, schedule: int = 0, backend: int = 0,
-            jit_segment: int = 0, cse: bool = False) -> Tuple[Evaluator, Dict[int, Graph]]:
+            jit_segment: int = 0, cse: bool = False, fma: bool = False) -> Tuple[Evaluator, Dict[int, Graph]]:
     """``Compilers.compile(graphs; root)`` (static.jl:221-227) -> ``(eval_graph, leafmap)``.
 
     ``leafmap[k]`` is the leaf Graph whose value is read from column ``k`` of ``leafVal`` (0-based
@@ -192,16 +192,17 @@ def compile(graphs: Sequence[Graph], root: Optional[Sequence[int]] = None, *, dt
     """
     raw, nodes = flatten(graphs, root)
     ev = Evaluator(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch, schedule=schedule, backend=backend,
-                   jit_segment=jit_segment, cse=cse)
+                   jit_segment=jit_segment, cse=cse, fma=fma)
     leafmap = {k: nodes[int(i)] for k, i in enumerate(ev.leaf_nodes)}
     return ev, leafmap
 
 
 def compile_raw(raw: RawGraph, *, dtype=np.float64, max_slots: int = 0, prefetch: int = 0, schedule: int = 0,
-                backend: int = 0, jit_segment: int = 0, cse: bool = False) -> Evaluator:
-    """Compile an already flattened graph (e.g. a workload file written by another host)."""
+                backend: int = 0, jit_segment: int = 0, cse: bool = False, fma: bool = False) -> Evaluator:
+    """Compile an already flattened graph (e.g. a workload file written by another host).  ``fma=True`` (opt-in) lets
+    the specialised kernels fuse multiplies into adds: faster where FP64 issue is the limit, NOT bit-identical."""
     return Evaluator(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch, schedule=schedule, backend=backend,
-                     jit_segment=jit_segment, cse=cse)
+                     jit_segment=jit_segment, cse=cse, fma=fma)
 
 
 def compile_file(path: str, *, dtype=np.float64, backend: int = 0, jit_segment: int = 0, cse: bool = False) -> Evaluator:

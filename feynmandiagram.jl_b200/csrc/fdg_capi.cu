@@ -74,6 +74,7 @@ struct fdg_program {
     fdg::Lowered low;
     int backend = FDG_BACKEND_AUTO;
     int jit_segment = 0;
+    bool fma = false;  // fdg_options.fma: contraction allowed in the specialised kernels (opt-in, not bit-identical)
     std::map<int, JitVariant> jit;  // key = spt * 2 + accumulate
     int threads = 128;
     int spt = 0;  // samples per thread: 0 auto
@@ -183,7 +184,7 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
     JitVariant &v = h->jit[key];
     if (!v.compiled) {
         std::string err;
-        int rc = fdg::jit_plan(h->low, spt, acc, h->jit_segment, wide, v.plan, err);
+        int rc = fdg::jit_plan(h->low, spt, acc, h->jit_segment, wide, h->fma, v.plan, err);
         if (rc == FDG_OK) rc = fdg::jit_compile(v.plan, err);
         if (rc != FDG_OK) {
             h->jit.erase(key);
@@ -368,8 +369,8 @@ int fdg_compile(const fdg_graph_desc *graph, const fdg_options *opts, fdg_handle
     fdg_options o;
     std::memset(&o, 0, sizeof(o));
     if (opts) o = *opts;
-    for (int i = 0; i < 1; ++i)
-        if (o.reserved[i] != 0) return fail(FDG_ERR_BAD_ARG, "fdg_options.reserved must be zero");
+    if (o.fma != 0 && o.fma != 1) return fail(FDG_ERR_BAD_ARG, "fdg_options.fma must be 0 or 1");
+    if (o.fma == 1 && o.backend == FDG_BACKEND_VM) return fail(FDG_ERR_UNSUPPORTED, "fma applies to the specialised kernels only");
     if (o.backend < FDG_BACKEND_AUTO || o.backend > FDG_BACKEND_JIT) return fail(FDG_ERR_BAD_ARG, "unknown backend");
     fdg_program *p = new (std::nothrow) fdg_program();
     if (!p) return fail(FDG_ERR_BAD_ARG, "out of memory");
@@ -387,6 +388,8 @@ int fdg_compile(const fdg_graph_desc *graph, const fdg_options *opts, fdg_handle
     }
     p->backend = o.backend;
     p->jit_segment = o.jit_segment;
+    p->fma = o.fma == 1;
+    if (p->fma) p->backend = FDG_BACKEND_JIT;  // the packet VM only has the bit-exact arithmetic
     *out = p;
     return FDG_OK;
 }

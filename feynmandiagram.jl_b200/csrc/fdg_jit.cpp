@@ -47,6 +47,7 @@ struct Emitter {
     const int S;      // f64 registers per value: samples per thread (1 or 2), or 2 = (re, im) of ONE ComplexF64 sample
     const bool acc;   // accumulate mode
     bool cplx = false;
+    const char *rnd = ".rn";  // "" in the opt-in contraction mode: ptxas may then fuse a multiply into the add that reads it
     bool persistent = false;  // accumulate mode, single kernel: grid-stride loop with per-thread running sums
     int racc0 = -1;           // first register of the per-root running sums (persistent mode)
     std::ostringstream os;
@@ -65,15 +66,15 @@ struct Emitter {
             // Julia *(z::Complex, w::Complex) = Complex(re(z)re(w) - im(z)im(w), re(z)im(w) + im(z)re(w)), nothing fused
             const int t = nfd;
             nfd += 4;
-            os << "\tmul.rn.f64 %fd" << t << ", " << fd(a, 0) << ", " << fd(b, 0) << ";\n";
-            os << "\tmul.rn.f64 %fd" << t + 1 << ", " << fd(a, 1) << ", " << fd(b, 1) << ";\n";
-            os << "\tmul.rn.f64 %fd" << t + 2 << ", " << fd(a, 0) << ", " << fd(b, 1) << ";\n";
-            os << "\tmul.rn.f64 %fd" << t + 3 << ", " << fd(a, 1) << ", " << fd(b, 0) << ";\n";
-            os << "\tsub.rn.f64 " << fd(dst, 0) << ", %fd" << t << ", %fd" << t + 1 << ";\n";
-            os << "\tadd.rn.f64 " << fd(dst, 1) << ", %fd" << t + 2 << ", %fd" << t + 3 << ";\n";
+            os << "\tmul" << rnd << ".f64 %fd" << t << ", " << fd(a, 0) << ", " << fd(b, 0) << ";\n";
+            os << "\tmul" << rnd << ".f64 %fd" << t + 1 << ", " << fd(a, 1) << ", " << fd(b, 1) << ";\n";
+            os << "\tmul" << rnd << ".f64 %fd" << t + 2 << ", " << fd(a, 0) << ", " << fd(b, 1) << ";\n";
+            os << "\tmul" << rnd << ".f64 %fd" << t + 3 << ", " << fd(a, 1) << ", " << fd(b, 0) << ";\n";
+            os << "\tsub" << rnd << ".f64 " << fd(dst, 0) << ", %fd" << t << ", %fd" << t + 1 << ";\n";
+            os << "\tadd" << rnd << ".f64 " << fd(dst, 1) << ", %fd" << t + 2 << ", %fd" << t + 3 << ";\n";
             return;
         }
-        for (int i = 0; i < S; ++i) os << "\t" << op << ".rn.f64 " << fd(dst, i) << ", " << fd(a, i) << ", " << fd(b, i) << ";\n";
+        for (int i = 0; i < S; ++i) os << "\t" << op << rnd << ".f64 " << fd(dst, i) << ", " << fd(a, i) << ", " << fd(b, i) << ";\n";
     }
     // Complex z^n, n >= 4: Base.power_by_squaring (base/intfuncs.jl), unrolled for the known exponent
     int cpow(int x0, unsigned n) {
@@ -98,7 +99,7 @@ struct Emitter {
         return y;
     }
     void scale(int dst, int a, double f) {
-        for (int i = 0; i < S; ++i) os << "\tmul.rn.f64 " << fd(dst, i) << ", " << fd(a, i) << ", " << dimm(f) << ";\n";
+        for (int i = 0; i < S; ++i) os << "\tmul" << rnd << ".f64 " << fd(dst, i) << ", " << fd(a, i) << ", " << dimm(f) << ";\n";
     }
     void neg(int dst, int a) {
         for (int i = 0; i < S; ++i) os << "\tneg.f64 " << fd(dst, i) << ", " << fd(a, i) << ";\n";
@@ -431,7 +432,7 @@ static void build_ir(const Lowered &low, std::vector<IrOp> &ir) {
     }
 }
 
-int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strides, JitPlan &plan, std::string &err) {
+int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strides, bool fma, JitPlan &plan, std::string &err) {
     const bool cplx = low.dtype == FDG_C128;
     if (cplx) spt = 2;  // two f64 registers per value: (re, im) of one sample
     const int W = cplx ? 2 : 1;                // doubles per sample
@@ -440,6 +441,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
     plan = JitPlan();
     plan.spt = samples_per_thread;
     plan.acc = acc;
+    plan.fma = fma;
     std::vector<IrOp> ir;
     build_ir(low, ir);
     if (const char *dump = getenv("FDG_JIT_DUMP_IR")) {  // debugging aid: the fold-order IR as raw records
@@ -566,6 +568,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
         Emitter e(low, spt, acc);
         e.cplx = cplx;
         e.wide = wide_strides;
+        if (fma) e.rnd = "";
         e.persistent = plan.persistent;
         if (e.persistent) {
             e.racc0 = e.nfd;
@@ -782,14 +785,14 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
 // ---------------------------------------------------------------------------------------------------------------------
 // PTX -> cubin (sm_100a), segments in parallel
 // ---------------------------------------------------------------------------------------------------------------------
-static int compile_one(JitSegment &js, std::string &err) {
+static int compile_one(JitSegment &js, bool fma, std::string &err) {
     nvPTXCompilerHandle h = nullptr;
     nvPTXCompileResult rc = nvPTXCompilerCreate(&h, js.ptx.size(), js.ptx.c_str());
     if (rc != NVPTXCOMPILE_SUCCESS) {
         err = "nvPTXCompilerCreate failed (" + std::to_string((int)rc) + ")";
         return FDG_ERR_UNSUPPORTED;
     }
-    const char *opts[] = {"--gpu-name=sm_100a", "--opt-level=3", "--fmad=false", "--verbose"};
+    const char *opts[] = {"--gpu-name=sm_100a", "--opt-level=3", fma ? "--fmad=true" : "--fmad=false", "--verbose"};
     rc = nvPTXCompilerCompile(h, 4, opts);
     size_t n = 0;
     if (rc != NVPTXCOMPILE_SUCCESS) {
@@ -832,7 +835,7 @@ int jit_compile(JitPlan &plan, std::string &err) {
         for (;;) {
             const int i = next.fetch_add(1);
             if (i >= n) break;
-            rcs[(size_t)i] = compile_one(plan.seg[(size_t)i], errs[(size_t)i]);
+            rcs[(size_t)i] = compile_one(plan.seg[(size_t)i], plan.fma, errs[(size_t)i]);
         }
     };
     std::vector<std::thread> pool;

@@ -42,7 +42,7 @@ struct Options
     backend::Int32
     jit_segment::Int32
     cse::Int32
-    reserved::Int32
+    fma::Int32   # 1 = multiplies may be fused into adds (opt-in, not bit-identical)
 end
 
 opcode(::Type{Unitary}) = Int32(0)

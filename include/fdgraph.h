@@ -97,7 +97,11 @@ typedef struct fdg_options {
                              optimize!(level=1), optimize.jl:345-390; bit-identical).  Default 0: on
                              the memory-bound order-4 graphs sharing more values costs more traffic
                              than the saved arithmetic                           */
-    int32_t reserved[1];  /* must be zero                                                      */
+    int32_t fma;          /* 0 (default): every multiply and add is rounded on its own -- the bits of the
+                             emitted Julia / C function.  1 (opt-in, specialised kernels only): a multiply
+                             may be fused into the add that reads it (DFMA).  One rounding fewer per fused
+                             pair: results differ from the reference in the last bits (|error| stays below
+                             the reference's own bound, see tests) but are NOT bit-identical.                */
 } fdg_options;
 
 typedef struct fdg_program *fdg_handle;

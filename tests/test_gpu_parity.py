@@ -411,3 +411,26 @@ def test_launch_sequences_over_sub_batches(dtype, monkeypatch):
     ref = torch.view_as_real(root).sum(dim=1).reshape(-1) if W == 2 else root.sum(dim=1)
     scale = (torch.view_as_real(root).abs().sum(dim=1).reshape(-1) if W == 2 else root.abs().sum(dim=1)) + 1e-300
     assert bool(((acc - ref).abs() <= 1e-12 * scale).all())
+
+
+@pytest.mark.parametrize("name,dtype", [("parquet_ver4_o3", np.float64), ("taylor_sigma_o3", np.complex128), ("gv_sigma_o5", np.float64)])
+def test_opt_in_fma_is_within_the_tolerance_but_not_the_default(name, dtype):
+    """fdg_options.fma = 1 lets the specialised kernels fuse multiplies into adds.  It is an opt-in: not bit-identical
+    (one rounding fewer per fused pair), error bounded on the scale of the sum of absolute terms well inside the 1e-12
+    of the north star; the default stays bit-exact."""
+    import os
+
+    raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", name + ".npz"))
+    orc = O.Oracle(raw)
+    batch = 512
+    leaf = graphgen.leaf_values(21, orc.n_leaves, batch, dtype=dtype, signed=True)
+    want = orc.eval(leaf)
+    exact = _dev_eval(fd.compile_raw(raw, dtype=dtype, backend=JIT), leaf, batch)
+    assert exact.tobytes() == want.tobytes()
+    fused = _dev_eval(fd.compile_raw(raw, dtype=dtype, backend=JIT, fma=True), leaf, batch)
+    assert fused.tobytes() != want.tobytes()                                   # contraction really happened
+    for b in range(0, batch, 97):
+        bound = np.array(O.eval_abs_bound(orc, np.abs(leaf[:, b]) if dtype == np.float64 else np.abs(leaf[:, b].real) + np.abs(leaf[:, b].imag)))
+        assert (np.abs(fused[:, b] - want[:, b]) <= 1e-12 * bound).all()
+    with pytest.raises(_capi.FdgError):
+        fd.compile_raw(raw, dtype=dtype, backend=VM, fma=True)                  # the packet VM has the exact arithmetic only

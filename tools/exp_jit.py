@@ -43,10 +43,10 @@ def main():
         kv = dict(x.split("=") for x in var.split(",") if x)
         for k in [k for k in os.environ if k.startswith("FDG_")]:
             os.environ.pop(k, None)
-        seg, spt, cse = int(kv.pop("seg", 0)), int(kv.pop("spt", 1)), int(kv.pop("cse", 0))
+        seg, spt, cse, fma = int(kv.pop("seg", 0)), int(kv.pop("spt", 1)), int(kv.pop("cse", 0)), int(kv.pop("fma", 0))
         os.environ.update(kv)
         try:
-            f = fd.compile_raw(raw, dtype=npdt, backend=2, jit_segment=seg, cse=bool(cse))
+            f = fd.compile_raw(raw, dtype=npdt, backend=2, jit_segment=seg, cse=bool(cse), fma=bool(fma))
             f.set_launch(0, spt, 0)
             t0 = time.time()
             info = f.jit_prepare(spt, True)
