@@ -300,8 +300,20 @@ static void order_roots(const Lowered &low, std::vector<int32_t> &order) {
             }
         }
         total += cone[r].size();
+        if (total > 100000000u) return;  // the cones alone would take > 400 MB: keep emitter order
     }
-    if ((double)total * (double)R > 4e9) return;  // quadratic in the number of roots: keep emitter order for huge sets
+    // Scoring every remaining root at every step is quadratic in the number of roots.  For big root sets only a short
+    // list is scored each step: the roots with the most already-computed values in their cone (the ones that can retire
+    // something), plus the next root in emitter order.
+    const char *sl = getenv("FDG_JIT_ROOT_SHORTLIST");
+    const bool shortlist = sl ? atoi(sl) != 0 : (double)total * (double)R > 2e9;
+    std::vector<std::vector<int32_t>> roots_of;  // statement -> roots whose cone holds it (short-list mode only)
+    std::vector<int32_t> warm(R, 0);             // computed values inside the cone of every root not taken yet
+    if (shortlist) {
+        roots_of.resize(n);
+        for (size_t r = 0; r < R; ++r)
+            for (const int32_t v : cone[r]) roots_of[(size_t)v].push_back((int32_t)r);
+    }
     // readers of every statement (distinct statements)
     std::vector<std::vector<int32_t>> readers(n);
     for (int32_t v = 0; v < (int32_t)n; ++v) {
@@ -315,11 +327,30 @@ static void order_roots(const Lowered &low, std::vector<int32_t> &order) {
     std::vector<uint8_t> computed(n, 0), taken(R, 0);
     std::vector<int32_t> in_cone(n, -1);
     order.clear();
+    std::vector<size_t> cand;
+    size_t next_emitter = 0;
     for (size_t step = 0; step < R; ++step) {
         long best_score = LONG_MIN;
         size_t best = R;
-        for (size_t r = 0; r < R; ++r) {
-            if (taken[r]) continue;
+        cand.clear();
+        if (shortlist) {
+            while (next_emitter < R && taken[next_emitter]) ++next_emitter;
+            const size_t K = 32;
+            for (size_t r = 0; r < R; ++r) {
+                if (taken[r] || warm[r] == 0) continue;
+                cand.push_back(r);
+            }
+            if (cand.size() > K) {
+                std::partial_sort(cand.begin(), cand.begin() + (long)K, cand.end(),
+                                  [&](size_t a, size_t b) { return warm[a] != warm[b] ? warm[a] > warm[b] : a < b; });
+                cand.resize(K);
+            }
+            if (next_emitter < R && std::find(cand.begin(), cand.end(), next_emitter) == cand.end()) cand.push_back(next_emitter);
+        } else {
+            for (size_t r = 0; r < R; ++r)
+                if (!taken[r]) cand.push_back(r);
+        }
+        for (const size_t r : cand) {
             for (const int32_t v : cone[r]) in_cone[(size_t)v] = (int32_t)r;
             long kills = 0, creates = 0;
             for (const int32_t v : cone[r]) {
@@ -348,7 +379,11 @@ static void order_roots(const Lowered &low, std::vector<int32_t> &order) {
         }
         taken[best] = 1;
         order.push_back(roots[best]);
-        for (const int32_t v : cone[best]) computed[(size_t)v] = 1;
+        for (const int32_t v : cone[best]) {
+            if (shortlist && !computed[(size_t)v])
+                for (const int32_t r2 : roots_of[(size_t)v]) warm[(size_t)r2]++;
+            computed[(size_t)v] = 1;
+        }
     }
 }
 

@@ -300,3 +300,31 @@ def test_planner_of_the_specialised_back_end_on_the_headline_graph(monkeypatch):
     monkeypatch.setenv("FDG_JIT_ROOT_ORDER", "0")
     worse = fd.compile_raw(raw, backend=2).jit_prepare(1, True)
     assert worse["cross_values"] > 4 * info["cross_values"]
+
+
+def test_root_ordering_brings_sharing_roots_together(monkeypatch):
+    """Roots i and 100 + i share a sub-graph; the emitter's order keeps 100 shared values alive across ~100 roots, the
+    planner's order (exact scoring, or the short list it uses for very large root sets) evaluates the pairs back to back."""
+    fd.uidreset()
+    rng = np.random.default_rng(3)
+    leaves = [fd.Graph([]) for _ in range(40)]
+
+    def tree(k):
+        terms = [fd.Graph([leaves[int(j)] for j in rng.choice(40, 3, replace=False)], operator=fd.Prod()) for _ in range(k)]
+        return fd.Graph(terms, operator=fd.Sum(), subgraph_factors=[1.0 + 0.5 * t for t in range(k)])
+
+    shared = [tree(6) for _ in range(100)]
+    roots = [fd.Graph([shared[i], tree(5)], operator=fd.Prod()) for i in range(100)]
+    roots += [fd.Graph([shared[i], tree(4)], operator=fd.Prod()) for i in range(100)]
+    raw, _ = fd.flatten(roots)
+
+    def cross(env):
+        for k in ("FDG_JIT_ROOT_ORDER", "FDG_JIT_ROOT_SHORTLIST"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        return fd.compile_raw(raw, backend=2, jit_segment=300).jit_prepare(1, False)["cross_values"]
+
+    emitter, exact, short = cross({"FDG_JIT_ROOT_ORDER": "0"}), cross({}), cross({"FDG_JIT_ROOT_SHORTLIST": "1"})
+    assert emitter >= 90
+    assert exact <= 15 and short <= 25
