@@ -782,11 +782,51 @@ __device__ __forceinline__ double lg_pow(double x, int n) {
 // tolerances of isapprox against an exact zero).  The denominator 1 + exp(-|omega| beta) depends on the momentum only:
 // it is computed once per loop-basis vector and divided into every leaf that carries that momentum -- the same
 // operations on the same operands as the formula evaluated leaf by leaf, hence the same bits.
-__device__ __forceinline__ double lg_green_den(double w, double beta) { return w > 0.0 ? 1.0 + exp(-w * beta) : 1.0 + exp(w * beta); }
+__device__ __forceinline__ double lg_green_ebeta(double w, double beta) { return w > 0.0 ? exp(-w * beta) : exp(w * beta); }
 __device__ __forceinline__ double lg_green(double tau, double w, double beta, double den) {
     if (tau == 0.0) tau = -1e-10;
     if (tau > 0.0) return w > 0.0 ? exp(-w * tau) / den : exp(w * (beta - tau)) / den;
     return w > 0.0 ? -exp(-w * (tau + beta)) / den : -exp(-w * tau) / den;
+}
+
+// (-1)^n / n! d^n/dw^n green(tau, w, beta), n = 1..5 (green_derive, example/benchmark.jl:93-111).  The reference takes
+// these from Lehmann.Spectral.kernelFermiT_dw^n (not vendored: its bits are unpinned); here the derivative is written in
+// closed form: green = exp(L(w)), L' = D = -tau' + beta n_F, so d^n green = green * Y_n(D, D', ..., D^(n-1)) with Y_n the
+// complete Bell polynomial and the derivatives of the Fermi function n_F polynomials in n_F (oracle/leafgen.py, checked
+// against 60-digit differentiation).  `ebeta` = exp(-|w| beta), `den` = 1 + ebeta.
+__device__ __forceinline__ double lg_green_derive(double tau, double w, double beta, double ebeta, double den, int order) {
+    if (tau == 0.0) tau = -1e-10;
+    const double g0 = lg_green(tau, w, beta, den);
+    const double tp = tau > 0.0 ? tau : tau + beta;
+    const double n = w > 0.0 ? ebeta / den : 1.0 / den;
+    const double m = n * (1.0 - n);
+    const double b2 = beta * beta;
+    const double D = -tp + beta * n;
+    const double D1 = -b2 * m;
+    double Y = D;
+    if (order >= 2) {
+        const double P2 = D * D;
+        if (order == 2) {
+            Y = P2 + D1;
+        } else {
+            const double D2 = b2 * beta * m * (1.0 - 2.0 * n);
+            const double P3 = P2 * D;
+            if (order == 3) {
+                Y = P3 + 3.0 * D * D1 + D2;
+            } else {
+                const double D3 = -b2 * b2 * m * (1.0 - 6.0 * n + 6.0 * n * n);
+                const double P4 = P3 * D;
+                if (order == 4) {
+                    Y = P4 + 6.0 * P2 * D1 + 4.0 * D * D2 + 3.0 * D1 * D1 + D3;
+                } else {
+                    const double D4 = b2 * b2 * beta * m * (1.0 - 14.0 * n + 36.0 * n * n - 24.0 * n * n * n);
+                    Y = P4 * D + 10.0 * P3 * D1 + 10.0 * P2 * D2 + 15.0 * D * D1 * D1 + 5.0 * D * D3 + 10.0 * D1 * D2 + D4;
+                }
+            }
+        }
+    }
+    const double coef = order == 1 ? -1.0 : order == 2 ? 0.5 : order == 3 ? -1.0 / 6.0 : order == 4 ? 1.0 / 24.0 : -1.0 / 120.0;
+    return coef * (g0 * Y);
 }
 
 template <int DIM>
@@ -803,7 +843,7 @@ fdg_leafgen_kernel(const LeafMeta *__restrict__ meta, int n_leaves, int n_loops,
         for (int c = 0; c < DIM; ++c) k[j][c] = j < n_loops ? K[(long long)(j * DIM + c) * ld_var + b] : 0.0;
     const int l0 = blockIdx.y * FDG_LG_CHUNK, l1 = min(n_leaves, l0 + FDG_LG_CHUNK);
     int cur = -1;
-    double q2 = 0.0, w = 0.0, den = 1.0, invK = 0.0;
+    double q2 = 0.0, w = 0.0, den = 1.0, ebeta = 0.0, invK = 0.0;
     bool have_den = false, have_inv = false;
     for (int l = l0; l < l1; ++l) {
         const LeafMeta m = meta[l];
@@ -825,11 +865,12 @@ fdg_leafgen_kernel(const LeafMeta *__restrict__ meta, int n_leaves, int n_loops,
             }
             if (m.type == 1) {
                 if (!have_den) {
-                    den = lg_green_den(w, beta);
+                    ebeta = lg_green_ebeta(w, beta);
+                    den = 1.0 + ebeta;
                     have_den = true;
                 }
                 const double tau = __dadd_rn(T[(long long)m.tau_out * ld_var + b], -T[(long long)m.tau_in * ld_var + b]);
-                v = lg_green(tau, w, beta, den);
+                v = m.order == 0 ? lg_green(tau, w, beta, den) : lg_green_derive(tau, w, beta, ebeta, den, m.order);
             } else {
                 if (!have_inv) {
                     invK = 1.0 / __dadd_rn(q2, lambda);
@@ -915,10 +956,9 @@ int fdg_leafgen_create(const fdg_leafgen_desc *d, fdg_leafgen_t *out) {
         }
         if (m.type == 0) continue;
         m.order = d->leaf_order[2 * l + (m.type == 1 ? 0 : 1)];
-        if (m.type == 1 && m.order != 0) {
+        if (m.type == 1 && m.order > 5) {
             delete g;
-            return fail(FDG_ERR_UNSUPPORTED, "Green's function derivative orders need Lehmann.Spectral.kernelFermiT_dw*, which the "
-                                             "reference does not vendor (example/benchmark.jl:93-110): only order 0 is implemented");
+            return fail(FDG_ERR_UNSUPPORTED, "Green's function derivative order > 5: \"not implemented!\" (example/benchmark.jl:107)");
         }
         if (m.order < 0) {
             delete g;

@@ -185,11 +185,12 @@ int fdg_jit_ptx(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, in
  *     type 1 (BareGreenId):        leaf = green(T[tau_out] - T[tau_in], dot(kq, kq) - kF^2, beta)   (benchmark.jl:113-127)
  *     type 2 (BareInteractionId):  invK = 1 / (dot(kq, kq) + lambda);  leaf = 8pi / invK * (lambda * invK)^order
  *     type 0:                      leaf = 1.0
- * Only the order-0 Green's function has a definition inside the reference (derivative orders call
- * Lehmann.Spectral.kernelFermiT_dw*, a dependency that is not vendored): fdg_leafgen_create returns
- * FDG_ERR_UNSUPPORTED for a type-1 leaf with order != 0.  exp() is the device's (<= 1 ulp): leaf values agree with a
- * CPU evaluation of the same formulas to ~1e-15 relative, not bit for bit; the graph evaluation on top of them stays
- * bit-exact. */
+ * Green's-function derivative orders 1..5 (green_derive, benchmark.jl:93-111: (-1)^n / n! d^n/dw^n green) are taken by
+ * the reference from Lehmann.Spectral.kernelFermiT_dw^n, a dependency that is not vendored: the function is
+ * unambiguous and is evaluated here in closed form (checked against 60-digit differentiation), its bits in the
+ * reference are unpinned; order > 5 is FDG_ERR_UNSUPPORTED ("not implemented!", benchmark.jl:107).  exp() is the
+ * device's (<= 1 ulp): leaf values agree with a CPU evaluation of the same formulas to ~1e-15 relative, not bit for
+ * bit; the graph evaluation on top of them stays bit-exact. */
 typedef struct fdg_leafgen_desc {
     int64_t n_leaves;
     const int32_t *leaf_type;   /* [n_leaves] 0, 1 or 2 (FrontEnds.index(typeof(properties)), diagram_id.jl:342-354)   */

@@ -58,6 +58,7 @@ def test_cpu_restatement_against_a_scalar_transcription():
             kq = [sum(K[c, j, b] * basis[j] for j in range(K.shape[1])) for c in range(3)]
             q2 = sum(x * x for x in kq)
             if meta["leaf_type"][l] == 1:
+                assert meta["leaf_order"][l][0] == 0
                 want = _green_scalar(T[meta["tau_out"][l], b] - T[meta["tau_in"][l], b], q2 - KF * KF, BETA)
             else:
                 inv = 1.0 / (q2 + LAM)
@@ -68,15 +69,49 @@ def test_cpu_restatement_against_a_scalar_transcription():
     assert (leafgen.green(np.array([0.3]), np.array([-0.5]), BETA) > 0).all()
 
 
+def test_green_derivatives_against_high_precision_differentiation():
+    """green_derive (benchmark.jl:93-111), orders 1..5: the closed form of oracle/leafgen.py (and of the device kernel)
+    against 50-digit numerical differentiation of `green` itself.  The reference's own numbers come from
+    Lehmann.Spectral (not vendored): this pins the FUNCTION, not that dependency's bits."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+
+    def green_mp(tau, w, beta):
+        tau = mp.mpf(tau)
+        if tau == 0:
+            tau = mp.mpf("-1e-10")
+        if tau > 0:
+            return mp.e ** (-w * tau) / (1 + mp.e ** (-w * beta))
+        return -mp.e ** (-w * (tau + beta)) / (1 + mp.e ** (-w * beta))
+
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        tau = 0.0 if trial % 10 == 0 else float(rng.uniform(-BETA, BETA))
+        w = float(rng.uniform(-6, 6))
+        for order in range(1, 6):
+            d = mp.diff(lambda x: green_mp(tau, x, BETA), mp.mpf(w), order)
+            want = (-1) ** order * d / math.factorial(order)
+            got = leafgen.green_derive(np.array([tau]), np.array([w]), BETA, order)[0]
+            scale = abs(green_mp(tau, mp.mpf(w), BETA)) * BETA ** order
+            assert abs(mp.mpf(float(got)) - want) <= 1e-14 * scale
+    with pytest.raises(NotImplementedError):
+        leafgen.green_derive(np.array([0.1]), np.array([0.2]), BETA, 6)
+
+
 def test_sidecars_match_the_workloads():
-    for name in ("parquet_sigma_o3", "parquet_ver4_o3", "parquet_ver4_o4", "gv_sigma_o4", "gv_ver4_o3"):
+    for name in ("parquet_sigma_o3", "parquet_ver4_o3", "parquet_ver4_o4", "gv_sigma_o4", "gv_ver4_o3", "taylor_sigma_o2", "taylor_sigma_o3"):
         raw, meta = _load(name)
         L = O.Oracle(raw).n_leaves
         assert len(meta["leaf_type"]) == L == len(meta["tau_in"]) == len(meta["loop_index"])
-        assert set(np.unique(meta["leaf_type"])) <= {1, 2} and (meta["leaf_order"] == 0).all()
+        assert set(np.unique(meta["leaf_type"])) <= {1, 2} and ((meta["leaf_order"] == 0).all() or name.startswith("taylor"))
         assert meta["loop_index"].max() == meta["loop_basis"].shape[0] - 1           # every basis vector is used
         assert len({tuple(b) for b in meta["loop_basis"]}) == meta["loop_basis"].shape[0]  # and distinct
     assert _load("parquet_ver4_o4")[1]["loop_basis"].shape[1] == 7                  # MaxLoopNum of example/benchmark.jl:21
+    # the Taylor-AD graphs: every propagator / interaction leaf also appears with its counter-term orders (g, v)
+    _, meta = _load("taylor_sigma_o3")
+    orders = {tuple(o) for o in meta["leaf_order"].tolist()}
+    assert orders == {(0, 0), (1, 0), (2, 0), (0, 1)}
+    assert all(o[1] == 0 for o, t in zip(meta["leaf_order"], meta["leaf_type"]) if t == 1)
 
 
 def test_create_rejects_what_the_reference_cannot_compute():
@@ -84,7 +119,7 @@ def test_create_rejects_what_the_reference_cannot_compute():
     g = fd.LeafGenerator(meta, kF=KF, beta=BETA, lam=LAM)
     assert (g.n_leaves, g.n_loops, g.n_tau, g.var_rows) == (27, 4, 3, 15)
     bad = {k: v.copy() for k, v in meta.items()}
-    bad["leaf_order"][np.argmax(meta["leaf_type"] == 1), 0] = 1  # needs Lehmann.Spectral.kernelFermiT_dw
+    bad["leaf_order"][np.argmax(meta["leaf_type"] == 1), 0] = 6  # "not implemented!" (benchmark.jl:107)
     with pytest.raises(_capi.FdgError) as e:
         fd.LeafGenerator(bad)
     assert e.value.code == 3
@@ -100,7 +135,7 @@ def test_create_rejects_what_the_reference_cannot_compute():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["parquet_sigma_o3", "parquet_ver4_o3", "gv_ver4_o3"])
+@pytest.mark.parametrize("name", ["parquet_sigma_o3", "parquet_ver4_o3", "gv_ver4_o3", "taylor_sigma_o2", "taylor_sigma_o3"])
 def test_device_leaves_and_the_graph_on_top_of_them(name):
     torch = pytest.importorskip("torch")
     raw, meta = _load(name)
@@ -118,7 +153,13 @@ def test_device_leaves_and_the_graph_on_top_of_them(name):
     want = leafgen.leaf_values(meta, K, T, KF, BETA, LAM)
     assert np.isfinite(got).all()
     assert np.abs(got - want).max() <= 2e-14 * np.abs(want).max()
-    assert (np.abs(got - want) <= 2e-14 * np.abs(want) + 1e-300).all()
+    # element by element: relative for the plain leaves; the counter-term (derivative) leaves are differences of terms of
+    # size |green| * beta^order, which is the scale their rounding error lives on
+    meta0 = dict(meta, leaf_order=np.zeros_like(meta["leaf_order"]))
+    scale = np.abs(leafgen.leaf_values(meta0, K, T, KF, BETA, LAM)) * (BETA ** meta["leaf_order"].sum(axis=1))[:, None]
+    derived = (meta["leaf_order"].sum(axis=1) > 0)[:, None]
+    tol = np.where(derived, 1e-13 * scale, 2e-14 * np.abs(want))
+    assert (np.abs(got - want) <= tol + 1e-300).all()
     # evaluation on the device's own leaves is bit-exact against the oracle on the same leaves
     root = torch.zeros(ev.n_roots, B, dtype=torch.float64, device="cuda")
     ev.eval_device(leaf.data_ptr(), B, root.data_ptr(), B, B, s)

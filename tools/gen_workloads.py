@@ -75,13 +75,24 @@ def leaf_sidecars():
         pq._ver4I.clear()
         return [r["diagram"] for r in pq.vertex4(pq.DiagPara(type=pq.Ver4Diag, innerLoopNum=order))]
 
-    jobs = [("parquet_sigma_o3", lambda: pq_sigma(3), 4), ("parquet_ver4_o3", lambda: pq_ver4(3), 6),
-            ("parquet_ver4_o4", lambda: pq_ver4(4), 7),  # example/benchmark.jl:13,21: MaxLoopNum = 7
-            ("gv_sigma_o4", lambda: gv.diagsGV("sigma", 4), 5), ("gv_ver4_o3", lambda: gv.diagsGV_ver4(3), 6)]
-    for name, builder, max_loops in jobs:
+    from oracle.frontend import taylor
+    from oracle.frontend.ids import BareGreenId, BareInteractionId
+
+    def taylor_sigma(order):  # as in taylor_workloads(): counter-term leaves carry derivative orders (g, v)
+        graphs = pq_sigma(order)
+        opt.optimize(graphs)
+        d = taylor.taylorAD(graphs, [2, 1], [lambda p: isinstance(p, BareGreenId), lambda p: isinstance(p, BareInteractionId)])
+        return [g for k in sorted(d) for g in d[k]]
+
+    jobs = [("parquet_sigma_o3", lambda: pq_sigma(3), 4, True), ("parquet_ver4_o3", lambda: pq_ver4(3), 6, True),
+            ("parquet_ver4_o4", lambda: pq_ver4(4), 7, True),  # example/benchmark.jl:13,21: MaxLoopNum = 7
+            ("gv_sigma_o4", lambda: gv.diagsGV("sigma", 4), 5, True), ("gv_ver4_o3", lambda: gv.diagsGV_ver4(3), 6, True),
+            ("taylor_sigma_o2", lambda: taylor_sigma(2), 3, False), ("taylor_sigma_o3", lambda: taylor_sigma(3), 4, False)]
+    for name, builder, max_loops, optimize in jobs:
         fd.uidreset()
         graphs = builder()
-        opt.optimize(graphs)
+        if optimize:
+            opt.optimize(graphs)
         raw, nodes = fd.flatten(graphs)
         ref = fd.RawGraph.load(os.path.join(OUT, name + ".npz"))
         same = all(np.array_equal(getattr(raw, k), getattr(ref, k)) for k in raw.__dataclass_fields__)
