@@ -72,7 +72,8 @@ def main():
                     best = min(best, e0.elapsed_time(e1))
             model = (info["leaf_loads"] + info["cross_loads"] + info["cross_stores"]) * es
             print(f"{var:60s} {B / best * 1e3 / 1e6:9.2f} Msamples/s  {best:9.3f} ms  kernels={info['kernels']:3d} rows={info['cross_rows']:5d} "
-                  f"model={model / 1e3:6.1f} KB/sample  compile={tc:5.1f}s  bit-equal-to-first={same}", flush=True)
+                  f"model={model / 1e3:6.1f} KB/sample  code={info['cubin_bytes'] / max(info['kernels'], 1) / 1e3:6.1f} KB/kernel  compile={tc:5.1f}s  "
+                  f"bit-equal-to-first={same}", flush=True)
             del f
         except Exception as ex:  # noqa: BLE001
             print(f"{var:60s} FAILED: {ex}", flush=True)
