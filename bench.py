@@ -348,6 +348,11 @@ def main():
                 "avg_launch_ms": 1e3 * avg_launch_s, "algorithmic_bytes_per_sample": st["bytes_in"],
                 "fp64_gflops_achieved": flops_launch / avg_launch_s / 1e9, "flops_per_sample": st["flops_add"] + st["flops_mul"],
                 "flop_per_byte": (st["flops_add"] + st["flops_mul"]) / max(st["bytes_in"], 1)}
+    # FP64 ceiling of this path: one DMUL or DADD per lane and clock (no contraction), 64 lanes per SM
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    fp64_peak = sms * 64 * 1.965  # GFLOP/s at the maximal SM clock of this pool's B200s (MEASURED_PEAKS.json sm_max_mhz)
+    roofline["fp64_peak_gflops_no_fma"] = fp64_peak
+    roofline["fp64_frac_algorithmic"] = roofline["fp64_gflops_achieved"] / fp64_peak
     if traffic:
         # the same launch on the bytes ncu saw move (profiles/traffic.json): how close the kernels run to the HBM peak
         roofline["traffic_gbs"] = traffic / avg_launch_s / 1e9
