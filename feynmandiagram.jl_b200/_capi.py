@@ -206,11 +206,11 @@ def launch_count(h) -> int:
 def jit_prepare(h, samples_per_thread: int = 2, accumulate: bool = False) -> dict:
     nk, nc, nb = C.c_int32(), C.c_int32(), C.c_int64()
     check(lib().fdg_jit_prepare(h, samples_per_thread, int(accumulate), C.byref(nk), C.byref(nc), C.byref(nb)))
-    out = (C.c_int64 * 8)()
-    check(lib().fdg_jit_info(h, samples_per_thread, int(accumulate), out, 8))
+    out = (C.c_int64 * 9)()
+    check(lib().fdg_jit_info(h, samples_per_thread, int(accumulate), out, 9))
     return {"kernels": int(nk.value), "cross_rows": int(nc.value), "cross_values": int(out[2]), "cubin_bytes": int(nb.value),
             "leaf_loads": int(out[3]), "cross_loads": int(out[4]), "cross_stores": int(out[5]), "operations": int(out[6]),
-            "grid_stride": bool(out[7])}
+            "grid_stride": bool(out[7]), "max_code_bytes": int(out[8])}
 
 
 def jit_ptx(h, samples_per_thread: int, accumulate: bool, index: int):

@@ -184,8 +184,19 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
     JitVariant &v = h->jit[key];
     if (!v.compiled) {
         std::string err;
-        int rc = fdg::jit_plan(h->low, spt, acc, h->jit_segment, wide, h->fma, v.plan, err);
-        if (rc == FDG_OK) rc = fdg::jit_compile(v.plan, err);
+        // The instruction budget of a kernel is an estimate; what counts is the machine code ptxas makes of it: a kernel
+        // beyond the 128 KB instruction cache runs 20-50 % slower.  If the largest kernel of a
+        // multi-kernel plan comes out above 120 KB the plan is redone with a proportionally smaller budget (at most twice).
+        int budget = h->jit_segment > 0 ? h->jit_segment : 4000;
+        int rc = FDG_OK;
+        for (int attempt = 0; attempt < 3; ++attempt) {
+            rc = fdg::jit_plan(h->low, spt, acc, budget, wide, h->fma, v.plan, err);
+            if (rc == FDG_OK) rc = fdg::jit_compile(v.plan, err);
+            if (rc != FDG_OK || v.plan.seg.size() < 2 || v.plan.max_code_bytes <= 120 * 1024 || getenv("FDG_JIT_NO_REFIT")) break;
+            const int smaller = (int)((double)budget * 112.0 * 1024.0 / (double)v.plan.max_code_bytes);
+            if (smaller >= budget || smaller < 64) break;
+            budget = smaller;
+        }
         if (rc != FDG_OK) {
             h->jit.erase(key);
             return fail(rc, err);
@@ -479,8 +490,9 @@ int fdg_jit_info(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, i
     const fdg::JitPlan &pl = it->second.plan;
     int64_t ops = 0;
     for (auto &sg : pl.seg) ops += sg.n_stmts;
-    const int64_t vals[8] = {(int64_t)pl.seg.size(), pl.n_cross, pl.n_cross_values, pl.leaf_loads, pl.cross_loads, pl.cross_stores, ops, pl.persistent ? 1 : 0};
-    for (int32_t i = 0; i < n_out && i < 8; ++i) out[i] = vals[i];
+    const int64_t vals[9] = {(int64_t)pl.seg.size(), pl.n_cross, pl.n_cross_values, pl.leaf_loads, pl.cross_loads, pl.cross_stores, ops,
+                             pl.persistent ? 1 : 0, pl.max_code_bytes};
+    for (int32_t i = 0; i < n_out && i < 9; ++i) out[i] = vals[i];
     return FDG_OK;
 }
 

@@ -859,6 +859,28 @@ static int compile_one(JitSegment &js, bool fma, std::string &err) {
     return FDG_OK;
 }
 
+// bytes of machine code of the kernel in a cubin: the size of its `.text.<name>` section (ELF64, little endian)
+static size_t text_bytes(const std::vector<char> &cubin) {
+    auto rd = [&](size_t off, int bytes) -> uint64_t {
+        uint64_t v = 0;
+        if (off + (size_t)bytes > cubin.size()) return 0;
+        std::memcpy(&v, cubin.data() + off, (size_t)bytes);
+        return v;
+    };
+    if (cubin.size() < 64 || std::memcmp(cubin.data(), "\177ELF", 4) != 0 || cubin[4] != 2) return cubin.size();
+    const uint64_t shoff = rd(0x28, 8);
+    const uint64_t shentsize = rd(0x3A, 2), shnum = rd(0x3C, 2), shstrndx = rd(0x3E, 2);
+    if (shentsize < 64 || shstrndx >= shnum) return cubin.size();
+    const uint64_t stroff = rd(shoff + shstrndx * shentsize + 0x18, 8);
+    size_t best = 0;
+    for (uint64_t i = 0; i < shnum; ++i) {
+        const uint64_t sh = shoff + i * shentsize;
+        const uint64_t name = stroff + rd(sh, 4);
+        if (name + 6 <= cubin.size() && std::memcmp(cubin.data() + name, ".text.", 6) == 0) best = std::max<size_t>(best, (size_t)rd(sh + 0x20, 8));
+    }
+    return best ? best : cubin.size();
+}
+
 int jit_compile(JitPlan &plan, std::string &err) {
     const int n = (int)plan.seg.size();
     unsigned hw = std::thread::hardware_concurrency();
@@ -882,6 +904,8 @@ int jit_compile(JitPlan &plan, std::string &err) {
             err = errs[(size_t)i];
             return rcs[(size_t)i];
         }
+    plan.max_code_bytes = 0;
+    for (auto &sg : plan.seg) plan.max_code_bytes = std::max<int64_t>(plan.max_code_bytes, (int64_t)text_bytes(sg.cubin));
     return FDG_OK;
 }
 

@@ -23,6 +23,7 @@ struct JitPlan {
     int32_t n_cross = 0;  // rows of the cross-segment buffer (rows are reused once their last reader has run)
     int32_t n_cross_values = 0;  // values that cross a kernel boundary
     int64_t leaf_loads = 0, cross_loads = 0, cross_stores = 0;  // global loads / stores per sample over all kernels
+    int64_t max_code_bytes = 0;  // machine code of the largest kernel (the instruction cache holds 128 KB)
     bool persistent = false;  // single accumulate kernel run as a grid-stride loop (per-thread running sums)
     std::vector<JitSegment> seg;
 };

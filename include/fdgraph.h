@@ -171,7 +171,7 @@ int fdg_jit_prepare(fdg_handle h, int32_t samples_per_thread, int32_t accumulate
                     int32_t *n_cross, int64_t *cubin_bytes);
 /* counters of a prepared variant, out[0..n_out): kernels, rows of the cross buffer, values crossing a kernel
  * boundary, then per sample over all kernels: leaf loads, cross loads, cross stores, operations; [7] = 1 if the
- * variant is a single grid-stride kernel.  (leaf loads + cross loads + cross stores) x sizeof(W) is the traffic the
+ * variant is a single grid-stride kernel; [8] = bytes of machine code of the largest kernel.  (leaf loads + cross loads + cross stores) x sizeof(W) is the traffic the
  * plan asks of the memory system per sample -- the figure DESIGN.md compares with ncu's dram bytes. */
 int fdg_jit_info(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int64_t *out, int32_t n_out);
 /* PTX text of kernel `index` of a prepared variant (for inspection / tests) */

@@ -300,6 +300,13 @@ def test_planner_of_the_specialised_back_end_on_the_headline_graph(monkeypatch):
     monkeypatch.setenv("FDG_JIT_ROOT_ORDER", "0")
     worse = fd.compile_raw(raw, backend=2).jit_prepare(1, True)
     assert worse["cross_values"] > 4 * info["cross_values"]
+    monkeypatch.delenv("FDG_JIT_ROOT_ORDER")
+    # a budget that would overflow the 128 KB instruction cache is refitted from the machine code ptxas produced
+    assert info["max_code_bytes"] <= 120 * 1024
+    big = fd.compile_raw(raw, backend=2, jit_segment=9000).jit_prepare(1, True)
+    assert big["max_code_bytes"] <= 120 * 1024 and big["kernels"] >= 12
+    monkeypatch.setenv("FDG_JIT_NO_REFIT", "1")
+    assert fd.compile_raw(raw, backend=2, jit_segment=9000).jit_prepare(1, True)["max_code_bytes"] > 128 * 1024
 
 
 def test_root_ordering_brings_sharing_roots_together(monkeypatch):

@@ -45,6 +45,7 @@ def main():
             os.environ.pop(k, None)
         seg, spt, cse, fma = int(kv.pop("seg", 0)), int(kv.pop("spt", 1)), int(kv.pop("cse", 0)), int(kv.pop("fma", 0))
         os.environ.update(kv)
+        os.environ.setdefault("FDG_JIT_NO_REFIT", "1")  # experiments time the budget they ask for
         try:
             f = fd.compile_raw(raw, dtype=npdt, backend=2, jit_segment=seg, cse=bool(cse), fma=bool(fma))
             f.set_launch(0, spt, 0)
