@@ -40,7 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into feynmandiagram.jl_b200/libfdgraph.so; returns the path."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-lnvptxcompiler_static", "-ldl", "-lpthread"]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-lnvptxcompiler_static", "-lnvJitLink_static", "-ldl", "-lpthread"]
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)

@@ -60,7 +60,7 @@ EXPORTS = [
     "fdg_program_words", "fdg_eval", "fdg_eval_accumulate", "fdg_eval_host", "fdg_set_launch", "fdg_launch_count",
     "fdg_comm_unique_id", "fdg_comm_init", "fdg_comm_destroy", "fdg_allreduce", "fdg_jit_prepare", "fdg_jit_ptx",
     "fdg_jit_info", "fdg_leafgen_create", "fdg_leafgen_destroy", "fdg_leafgen_fill", "fdg_eval_generated_accumulate",
-    "fdg_eval_generated_host", "fdg_graph_write", "fdg_compile_file",
+    "fdg_eval_generated_host", "fdg_graph_write", "fdg_compile_file", "fdg_pipeline_prepare", "fdg_pipeline_stats",
 ]
 BACKEND_AUTO, BACKEND_VM, BACKEND_JIT = 0, 1, 2
 
@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
     L.fdg_jit_prepare.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
     L.fdg_jit_ptx.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
     L.fdg_jit_info.argtypes = [vp, i32, i32, C.POINTER(i64), i32]
+    L.fdg_pipeline_prepare.argtypes = [vp, i32, i32, i32, C.POINTER(i64), i32]
+    L.fdg_pipeline_stats.argtypes = [vp, vp, C.POINTER(i64), i32]
     L.fdg_graph_write.argtypes = [C.POINTER(GraphDesc), C.c_char_p]
     L.fdg_compile_file.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(vp)]
     L.fdg_leafgen_create.argtypes = [C.POINTER(LeafGenDesc), C.POINTER(vp)]
@@ -211,6 +213,29 @@ def jit_prepare(h, samples_per_thread: int = 2, accumulate: bool = False) -> dic
     return {"kernels": int(nk.value), "cross_rows": int(nc.value), "cross_values": int(out[2]), "cubin_bytes": int(nb.value),
             "leaf_loads": int(out[3]), "cross_loads": int(out[4]), "cross_stores": int(out[5]), "operations": int(out[6]),
             "grid_stride": bool(out[7]), "max_code_bytes": int(out[8])}
+
+
+def pipeline_prepare(h, accumulate: bool = True, n_sm: int = 148) -> dict:
+    """Builds the pipeline kernel for a device with n_sm SMs (host only) and returns its plan."""
+    out = (C.c_int64 * 10)()
+    check(lib().fdg_pipeline_prepare(h, int(accumulate), n_sm, 0, out, 10))
+    keys = ("stages", "cross_rows", "cross_values", "leaf_loads", "cross_loads", "cross_stores", "operations", "max_code_bytes",
+            "linked_bytes", "ring_bytes")
+    info = {k: int(out[i]) for i, k in enumerate(keys)}
+    n = info["stages"]
+    buf = (C.c_int64 * n)()
+    check(lib().fdg_pipeline_prepare(h, int(accumulate), n_sm, 1, buf, n))
+    info["stage_blocks"] = [int(x) for x in buf]
+    check(lib().fdg_pipeline_prepare(h, int(accumulate), n_sm, 2, buf, n))
+    info["stage_cost"] = [int(x) for x in buf]
+    return info
+
+
+def pipeline_stats(h, stream: int, n_stages: int) -> dict:
+    out = (C.c_int64 * (1 + 2 * n_stages))()
+    check(lib().fdg_pipeline_stats(h, stream, out, 1 + 2 * n_stages))
+    return {"stalled": bool(out[0]), "busy": [int(out[1 + 2 * k]) for k in range(n_stages)],
+            "waiting": [int(out[2 + 2 * k]) for k in range(n_stages)]}
 
 
 def jit_ptx(h, samples_per_thread: int, accumulate: bool, index: int):

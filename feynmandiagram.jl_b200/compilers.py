@@ -89,6 +89,14 @@ class Evaluator:
         """Generate + assemble the specialised kernels now (host only)."""
         return _capi.jit_prepare(self._h, samples_per_thread, accumulate)
 
+    def pipeline_prepare(self, accumulate: bool = True, n_sm: int = 148) -> dict:
+        """Build the pipeline form of the specialised kernels for a device with ``n_sm`` SMs (host only); its plan."""
+        return _capi.pipeline_prepare(self._h, accumulate, n_sm)
+
+    def pipeline_stats(self, stream: int = 0, n_stages: int = 0) -> dict:
+        """Clocks every stage of the last pipeline launch on ``stream`` spent alive / waiting (synchronises the stream)."""
+        return _capi.pipeline_stats(self._h, stream, n_stages)
+
     def jit_ptx(self, samples_per_thread: int = 2, accumulate: bool = False, index: int = 0):
         return _capi.jit_ptx(self._h, samples_per_thread, accumulate, index)
 

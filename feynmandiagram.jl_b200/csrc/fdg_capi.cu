@@ -46,6 +46,10 @@ struct StreamScratch {
     size_t partial_bytes = 0;
     void *cross = nullptr;  // specialised back end: values crossing kernel boundaries, [row][thread * spt]
     size_t cross_bytes = 0;
+    uint32_t *progress = nullptr;  // pipeline form: stages passed by every tile of 32 samples
+    size_t progress_bytes = 0;
+    unsigned long long *pipe_stats = nullptr;  // pipeline form: [0] stall flag, then (busy, waiting) clocks per stage
+    size_t pipe_stats_bytes = 0;
 };
 
 struct DeviceState {
@@ -65,6 +69,8 @@ struct DeviceState {
 struct JitVariant {
     fdg::JitPlan plan;
     bool compiled = false;
+    std::map<int, cudaKernel_t> pipe_kernel;  // per device: the linked pipeline kernel
+    std::vector<unsigned long long> last_stats;  // pipeline form: statistics of the last launch that was read back
     std::map<int, std::vector<cudaKernel_t>> kernels;  // per device
     std::map<int, cudaLibrary_t> libs_first;           // (libraries are kept alive with the handle)
     std::map<int, std::vector<cudaLibrary_t>> libs;
@@ -179,9 +185,22 @@ int get_device_state(fdg_program *h, DeviceState **out) {
 }
 
 // ---- specialised back end ----------------------------------------------------------------------------------------
-int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = false) {
-    const int key = spt * 2 + (acc ? 1 : 0) + (wide ? 64 : 0);
+int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = false, int pipe_sms = 0) {
+    const int key = spt * 2 + (acc ? 1 : 0) + (wide ? 64 : 0) + (pipe_sms > 0 ? 128 + 1024 * pipe_sms : 0);
     JitVariant &v = h->jit[key];
+    if (!v.compiled && pipe_sms > 0) {
+        std::string err;
+        fdg::PipeOptions po;
+        po.n_sm = pipe_sms;
+        if (const char *e = getenv("FDG_PIPE_THREADS")) po.threads = std::max(32, std::min(256, atoi(e) / 32 * 32));
+        int rc = fdg::jit_plan(h->low, spt, acc, h->jit_segment > 0 ? h->jit_segment : 4000, wide, h->fma, v.plan, err, &po);
+        if (rc == FDG_OK) rc = fdg::jit_compile(v.plan, err);
+        if (rc != FDG_OK) {
+            h->jit.erase(key);
+            return fail(rc, err);
+        }
+        v.compiled = true;
+    }
     if (!v.compiled) {
         std::string err;
         // The instruction budget of a kernel is an estimate; what counts is the machine code ptxas makes of it: a kernel
@@ -207,8 +226,114 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
     return FDG_OK;
 }
 
+template <class P>
+int grow(P *&ptr, size_t &have, size_t need) {
+    if (need <= have) return FDG_OK;
+    if (ptr) CUDA_TRY(cudaFree(ptr));
+    ptr = nullptr;
+    have = 0;
+    CUDA_TRY(cudaMalloc((void **)&ptr, need));
+    have = need;
+    return FDG_OK;
+}
+
+// The pipeline form of the specialised back end (fdg_jit.h): one cooperative launch, one block per SM, stage k's blocks
+// run only segment k.  Cross rows live in a ring of `window` tile slots and never leave L2 if the window is small enough.
+int jit_launch_pipeline(fdg_program *h, DeviceState &ds, int dev, bool acc, const void *leaf, int64_t ld_leaf, void *root, int64_t ld_root,
+                        int64_t batch, cudaStream_t stream) {
+    JitVariant *v = nullptr;
+    StreamScratch &ss = ds.per_stream[stream];
+    const bool wide = (uint64_t)ld_leaf * (h->low.dtype == FDG_C128 ? 16 : 8) >= (1ull << 32);
+    int rc = jit_get(h, 1, acc, &v, wide, ds.sm_count);
+    if (rc != FDG_OK) return rc;
+    const fdg::JitPlan &pl = v->plan;
+    const fdg::Lowered &low = h->low;
+    const int W = low.dtype == FDG_C128 ? 2 : 1;
+    const size_t es = 8 * (size_t)W;
+    int T = 256;
+    if (const char *e = getenv("FDG_PIPE_THREADS")) T = std::max(32, std::min(256, atoi(e) / 32 * 32));
+    // one block per SM: ask for more than half of the shared memory of an SM
+    const size_t smem = std::max<size_t>((size_t)pl.ring_bytes, (size_t)ds.max_smem_optin / 2 + 1024);
+    auto kit = v->pipe_kernel.find(dev);
+    if (kit == v->pipe_kernel.end()) {
+        cudaLibrary_t lib;
+        CUDA_TRY(cudaLibraryLoadData(&lib, pl.linked.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+        v->libs[dev].push_back(lib);
+        cudaKernel_t k;
+        CUDA_TRY(cudaLibraryGetKernel(&k, lib, "fdg_pipe"));
+        CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k, T, smem));
+        if (occ < 1) return fail(FDG_ERR_CAPACITY, "the pipeline kernel cannot be resident");
+        kit = v->pipe_kernel.emplace(dev, k).first;
+    }
+    const int warps = T / 32;
+    const int64_t n_tiles = (batch + 31) / 32;
+    int64_t window = (int64_t)pl.n_sm * warps * 3 / 2;  // tiles in flight: every warp has one, half as many queue between the stages
+    if (const char *e = getenv("FDG_PIPE_WINDOW")) window = std::max<int64_t>(atoll(e), (int64_t)pl.n_sm * warps);
+    window = std::max<int64_t>(window, 1);
+    const int64_t ld_cross = window * 32;
+    if (pl.n_cross > 0) {
+        rc = grow(ss.cross, ss.cross_bytes, (size_t)pl.n_cross * (size_t)ld_cross * es);
+        if (rc != FDG_OK) return rc;
+    }
+    rc = grow(ss.progress, ss.progress_bytes, std::max<size_t>((size_t)n_tiles * 4, 256));
+    if (rc != FDG_OK) return rc;
+    const size_t stats_bytes = 16 + 16 * pl.seg.size();
+    rc = grow(ss.pipe_stats, ss.pipe_stats_bytes, stats_bytes);
+    if (rc != FDG_OK) return rc;
+    CUDA_TRY(cudaMemsetAsync(ss.progress, 0, (size_t)n_tiles * 4, stream));
+    CUDA_TRY(cudaMemsetAsync(ss.pipe_stats, 0, stats_bytes, stream));
+    const long long rows = (long long)pl.n_sm * warps;
+    void *out = root;
+    if (acc) {
+        const size_t need = std::max<size_t>((size_t)rows * low.R * W * sizeof(double), 256);
+        rc = grow(ss.partial, ss.partial_bytes, need);
+        if (rc != FDG_OK) return rc;
+        CUDA_TRY(cudaMemsetAsync(ss.partial, 0, (size_t)rows * low.R * W * sizeof(double), stream));
+        out = ss.partial;
+    }
+    const void *p_leaf = leaf;
+    void *p_cross = ss.cross, *p_progress = ss.progress, *p_stats = ss.pipe_stats;
+    long long a_ld_leaf = ld_leaf, a_ld_cross = ld_cross, a_ld_root = ld_root, a_batch = batch, a_nroots = low.R * W, a_ntiles = n_tiles,
+              a_window = window;
+    void *args[] = {(void *)&p_leaf, &a_ld_leaf, &p_cross, &a_ld_cross, &out, &a_ld_root, &a_batch, &a_nroots, &p_progress, &a_ntiles, &a_window, &p_stats};
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)pl.n_sm);
+    cfg.blockDim = dim3((unsigned)T);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // all blocks resident at once, or the launch fails: the stages wait for each other
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)kit->second, args));
+    h->launches++;
+    if (acc && low.R > 0) {
+        fdg::fdg_reduce_partials<<<(int)low.R * W, 256, 0, stream>>>(ss.partial, rows, (int)low.R * W, static_cast<double *>(root));
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+    }
+    return FDG_OK;
+}
+
+// 1 when the pipeline form should run this call: big program, big batch (FDG_JIT_PIPE = 0 / 1 overrides)
+bool pipeline_wanted(const fdg_program *h, int spt, int64_t batch) {
+    const fdg::Lowered &low = h->low;
+    const int64_t work = (low.muls_vv + low.adds_vv + low.muls_vf + low.pow_muls) * (low.dtype == FDG_C128 ? 4 : 1);
+    const int budget = h->jit_segment > 0 ? h->jit_segment : 4000;
+    bool want = false;  // default until measured: the classic launch sequence
+    if (const char *e = getenv("FDG_JIT_PIPE")) want = atoi(e) != 0;
+    int64_t min_batch = 1 << 18;
+    if (const char *e = getenv("FDG_PIPE_MIN_BATCH")) min_batch = atoll(e);
+    return want && (spt == 1 || low.dtype == FDG_C128) && work >= 3 * (int64_t)budget && batch >= min_batch;
+}
+
 int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, const void *leaf, int64_t ld_leaf, void *root,
                int64_t ld_root, int64_t batch, cudaStream_t stream) {
+    if (pipeline_wanted(h, spt, batch)) return jit_launch_pipeline(h, ds, dev, acc, leaf, ld_leaf, root, ld_root, batch, stream);
     JitVariant *v = nullptr;
     StreamScratch &ss = ds.per_stream[stream];
     // row offsets are formed with one 32-bit multiply-add unless a leading dimension reaches 4 GiB
@@ -496,6 +621,47 @@ int fdg_jit_info(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, i
     return FDG_OK;
 }
 
+int fdg_pipeline_prepare(fdg_handle h, int32_t accumulate, int32_t n_sm, int32_t what, int64_t *out, int32_t n_out) {
+    if (!h || n_sm < 1 || n_out < 0 || (!out && n_out > 0)) return fail(FDG_ERR_BAD_ARG, "bad argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    JitVariant *v = nullptr;
+    int rc = jit_get(h, 1, accumulate != 0, &v, false, n_sm);
+    if (rc != FDG_OK) return rc;
+    const fdg::JitPlan &pl = v->plan;
+    std::vector<int64_t> vals;
+    if (what == 0) {
+        int64_t ops = 0;
+        for (auto &sg : pl.seg) ops += sg.n_stmts;
+        vals = {(int64_t)pl.seg.size(), pl.n_cross, pl.n_cross_values, pl.leaf_loads, pl.cross_loads, pl.cross_stores, ops,
+                pl.max_code_bytes, (int64_t)pl.linked.size(), pl.ring_bytes};
+    } else if (what == 1) {
+        vals.assign(pl.stage_blocks.begin(), pl.stage_blocks.end());
+    } else if (what == 2) {
+        vals.assign(pl.stage_cost.begin(), pl.stage_cost.end());
+    } else {
+        return fail(FDG_ERR_BAD_ARG, "unknown query");
+    }
+    for (int32_t i = 0; i < n_out; ++i) out[i] = i < (int32_t)vals.size() ? vals[(size_t)i] : 0;
+    return FDG_OK;
+}
+
+int fdg_pipeline_stats(fdg_handle h, void *stream, int64_t *out, int32_t n_out) {
+    if (!h || n_out < 0 || (!out && n_out > 0)) return fail(FDG_ERR_BAD_ARG, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceState *ds = nullptr;
+    int rc = get_device_state(h, &ds);
+    if (rc != FDG_OK) return rc;
+    auto it = ds->per_stream.find(st);
+    if (it == ds->per_stream.end() || !it->second.pipe_stats) return fail(FDG_ERR_BAD_ARG, "no pipeline launch on this stream yet");
+    std::vector<unsigned long long> buf(it->second.pipe_stats_bytes / 8);
+    CUDA_TRY(cudaMemcpy(buf.data(), it->second.pipe_stats, buf.size() * 8, cudaMemcpyDeviceToHost));
+    // out[0] = stall flag, then (busy, waiting) clock sums of stage 0, 1, ...
+    for (int32_t i = 0; i < n_out; ++i) out[i] = i == 0 ? (int64_t)(buf[0] & 0xffffffffu) : (i + 1 < (int32_t)buf.size() ? (int64_t)buf[(size_t)i + 1] : 0);
+    return FDG_OK;
+}
+
 int fdg_jit_ptx(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t index, const char **ptx,
                 const char **ptxas_log) {
     if (!h || !ptx) return fail(FDG_ERR_BAD_ARG, "null argument");
@@ -520,6 +686,8 @@ int fdg_destroy(fdg_handle h) {
             cudaFree(ps.second.scratch);
             cudaFree(ps.second.partial);
             cudaFree(ps.second.cross);
+            cudaFree(ps.second.progress);
+            cudaFree(ps.second.pipe_stats);
         }
         for (auto &kv2 : h->jit) {
             auto it = kv2.second.libs.find(kv.first);

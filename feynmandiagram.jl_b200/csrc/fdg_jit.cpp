@@ -18,6 +18,7 @@
 // Every one of these decisions is bit-neutral: each statement keeps its own left fold.
 #include "fdg_jit.h"
 
+#include <nvJitLink.h>
 #include <nvPTXCompiler.h>
 
 #include <algorithm>
@@ -51,7 +52,11 @@ struct Emitter {
     bool persistent = false;  // accumulate mode, single kernel: grid-stride loop with per-thread running sums
     int racc0 = -1;           // first register of the per-root running sums (persistent mode)
     std::ostringstream os;
-    int nfd = 0, nrd = 32, np = 8, nr = 16;
+    // pipeline form: per-thread running sums of the roots in shared memory, [entry][thread] with a padded row, %r16 = the
+    // thread's column; `sacc_pos[j]` = column of the partial-sum row (root, or 2 root + re/im) that entry j belongs to
+    int sacc_cap = 0, sacc_stride = 0;
+    std::vector<int32_t> sacc_pos;
+    int nfd = 0, nrd = 32, np = 8, nr = 24;
     Emitter(const Lowered &l, int s, bool a) : low(l), S(s), acc(a) {}
 
     int new_val() {
@@ -189,6 +194,18 @@ struct Emitter {
                 os << "\t@%p2 st.global.f64 [%rd" << a << "], " << fd(r, 0) << ";\n";  // odd tail: first sample only
             } else {
                 os << "\t@%p0 st.global.f64 [%rd" << a << "], " << fd(r, 0) << ";\n";
+            }
+            return;
+        }
+        if ((int)sacc_pos.size() + (cplx ? 2 : 1) <= sacc_cap) {
+            for (int c = 0; c < (cplx ? 2 : 1); ++c) {
+                const int s = nfd++, t = nfd++;
+                const int off = (int)sacc_pos.size() * sacc_stride;
+                sacc_pos.push_back(cplx ? 2 * root + c : root);
+                os << "\tselp.f64 %fd" << s << ", " << fd(r, c) << ", 0d0000000000000000, %p0;\n";
+                os << "\tld.shared.f64 %fd" << t << ", [%r16+" << off << "];\n";
+                os << "\tadd.rn.f64 %fd" << t << ", %fd" << t << ", %fd" << s << ";\n";
+                os << "\tst.shared.f64 [%r16+" << off << "], %fd" << t << ";\n";
             }
             return;
         }
@@ -467,16 +484,11 @@ static void build_ir(const Lowered &low, std::vector<IrOp> &ir) {
     }
 }
 
-int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strides, bool fma, JitPlan &plan, std::string &err) {
-    const bool cplx = low.dtype == FDG_C128;
-    if (cplx) spt = 2;  // two f64 registers per value: (re, im) of one sample
-    const int W = cplx ? 2 : 1;                // doubles per sample
-    const int samples_per_thread = cplx ? 1 : spt;
-    const int esh = cplx ? 4 : 3;              // log2(bytes per sample element)
-    plan = JitPlan();
-    plan.spt = samples_per_thread;
-    plan.acc = acc;
-    plan.fma = fma;
+static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt, bool acc, int seg_ops, bool wide_strides, bool fma,
+                        JitPlan &plan, std::string &err, const PipeOptions *pipe);
+
+int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strides, bool fma, JitPlan &plan, std::string &err,
+             const PipeOptions *pipe) {
     std::vector<IrOp> ir;
     build_ir(low, ir);
     if (const char *dump = getenv("FDG_JIT_DUMP_IR")) {  // debugging aid: the fold-order IR as raw records
@@ -488,6 +500,85 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
             std::fclose(fp);
         }
     }
+    if (!pipe) return plan_from_ir(low, ir, spt, acc, seg_ops, wide_strides, fma, plan, err, nullptr);
+    // Pipeline form: the cuts follow a cost estimate per operation, but what a stage really costs is only known once its
+    // code is written (input rows are charged where they are first read in the stage, roots cost a warp reduction).  So the
+    // plan is made, the stages are re-weighted with (cost of the written code) / (estimate), and the cuts are placed again.
+    PipeOptions po = *pipe;
+    int rc = FDG_OK;
+    JitPlan best;
+    double best_load = 1e30;
+    // slowest stage relative to a perfect split: max over stages of (cost / SMs) / (total cost / all SMs)
+    auto imbalance = [](const JitPlan &pl) {
+        double tot = 0, worst = 0;
+        for (const int64_t c : pl.stage_cost) tot += (double)c;
+        for (size_t k = 0; k < pl.stage_cost.size(); ++k) worst = std::max(worst, (double)pl.stage_cost[k] / (double)pl.stage_blocks[k]);
+        return worst / (tot / (double)pl.n_sm);
+    };
+    for (int iter = 0; iter < 6; ++iter) {
+        JitPlan cand;
+        rc = plan_from_ir(low, ir, spt, acc, seg_ops, wide_strides, fma, cand, err, &po);
+        if (rc != FDG_OK) return rc;
+        const double load = imbalance(cand);
+        const bool better = load < best_load;
+        if (better) best_load = load;
+        plan = cand;
+        if (better) best = std::move(cand);
+        if (iter == 5 || plan.seg.size() < 2 || best_load < 1.02) break;
+        // estimated cost of each stage as the cuts saw it (already weighted) vs. the cost of the code
+        std::vector<double> w(plan.seg.size());
+        double worst = 0;
+        double sum_c = 0, sum_e = 0;
+        for (size_t k = 0; k < w.size(); ++k) {
+            sum_c += (double)plan.stage_cost[k];
+            sum_e += (double)plan.stage_estimate[k];
+        }
+        for (size_t k = 0; k < w.size(); ++k) {
+            const double r = ((double)plan.stage_cost[k] / sum_c) / std::max((double)plan.stage_estimate[k] / sum_e, 1e-9);
+            worst = std::max(worst, std::fabs(r - 1.0));
+            // the new weight of an operation = its old weight x r of the stage it was in
+            w[k] = r;
+        }
+        if (getenv("FDG_PIPE_TRACE")) {
+            std::fprintf(stderr, "pipeline plan iteration %d: worst %.3f, cost/estimate:", iter, worst);
+            for (size_t k = 0; k < w.size(); ++k) std::fprintf(stderr, " %.2f", w[k]);
+            std::fprintf(stderr, "\n");
+        }
+        if (worst < 0.02 && !pipe->prev_start.size()) break;
+        std::vector<double> neww(w.size());
+        for (size_t k = 0; k < w.size(); ++k) {
+            // weight the stage had in this round (piecewise over the previous boundaries: take the one at the stage's middle)
+            double old = 1.0;
+            if (!po.weight.empty()) {
+                const int32_t mid = (plan.stage_start[k] + plan.stage_start[k + 1]) / 2;
+                const size_t j = (size_t)(std::upper_bound(po.prev_start.begin(), po.prev_start.end(), mid) - po.prev_start.begin());
+                if (j >= 1 && j <= po.weight.size()) old = po.weight[j - 1];
+            }
+            neww[k] = std::max(0.25, std::min(4.0, old * w[k]));
+        }
+        po.prev_start = plan.stage_start;
+        po.weight = neww;
+        po.blocks = plan.stage_blocks;
+    }
+    plan = std::move(best);
+    return rc;
+}
+
+static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt, bool acc, int seg_ops, bool wide_strides, bool fma,
+                        JitPlan &plan, std::string &err, const PipeOptions *pipe) {
+    const bool cplx = low.dtype == FDG_C128;
+    if (pipe && !cplx && spt != 1) {
+        err = "the pipeline form evaluates one sample per thread";
+        return FDG_ERR_BAD_ARG;
+    }
+    if (cplx) spt = 2;  // two f64 registers per value: (re, im) of one sample
+    const int W = cplx ? 2 : 1;                // doubles per sample
+    const int samples_per_thread = cplx ? 1 : spt;
+    const int esh = cplx ? 4 : 3;              // log2(bytes per sample element)
+    plan = JitPlan();
+    plan.spt = samples_per_thread;
+    plan.acc = acc;
+    plan.fma = fma;
     // `seg_ops` is a budget of machine instructions per kernel (estimated below): what bounds a kernel is the
     // instruction cache -- straight-line code of more than about 100 KB stalls on instruction fetch (measured,
     // DESIGN.md section 6) -- so a complex multiply counts six and a negation folded into its reader none
@@ -524,9 +615,19 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
                 } break;
                 default: w = acc ? 28 * W : 2; break;  // a root: warp reduction + partial-row update, or a store
             }
+            if (pipe) {
+                // finer units (1/16 instruction) so that measured stage weights can stretch the cost axis
+                double sc = 16.0;
+                if (!pipe->weight.empty() && pipe->prev_start.size() == pipe->weight.size() + 1) {
+                    const size_t k = (size_t)(std::upper_bound(pipe->prev_start.begin(), pipe->prev_start.end(), (int32_t)i) - pipe->prev_start.begin());
+                    if (k >= 1 && k <= pipe->weight.size()) sc *= std::max(0.25, std::min(4.0, pipe->weight[k - 1]));
+                }
+                w = (int64_t)((double)w * sc + 0.5);
+            }
             cost[i + 1] = cost[i] + w;
         }
     }
+    if (pipe) seg_ops *= 16;
     {
         // live[p] = values defined before op p and read at or after p (what a cut in front of p sends through memory)
         std::vector<int32_t> live(nops + 2, 0);
@@ -543,7 +644,38 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
         auto pos_at = [&](size_t from, int64_t c) {
             return (size_t)(std::lower_bound(cost.begin() + (long)from, cost.end(), cost[from] + c) - cost.begin());
         };
-        while (cost[nops] - cost[start] > (int64_t)seg_ops + (narrow ? seg_ops / 4 : 0)) {
+        if (pipe) {
+            // Pipeline form: stage k gets a whole number of SMs, so the cuts go where the cumulative cost reaches the
+            // cumulative share of SMs (a stage with 7 of 148 SMs gets 7/148 of the work), each one moved inside a
+            // narrow window (+-3 % of a stage) to the position with the fewest live values.
+            const int64_t total = std::max<int64_t>(cost[nops], 1);
+            int S = (int)std::min<int64_t>(std::max<int64_t>((total + seg_ops / 2) / seg_ops, 1), pipe->n_sm);
+            if (const char *e = getenv("FDG_PIPE_STAGES")) S = std::max(1, std::min(atoi(e), pipe->n_sm));
+            std::vector<int> sms((size_t)S, pipe->n_sm / S);
+            for (int k = 0; k < pipe->n_sm % S; ++k) sms[(size_t)((int64_t)k * S / (pipe->n_sm % S))] += 1;  // spread the larger stages
+            if ((int)pipe->blocks.size() == S) sms = pipe->blocks;
+            int64_t cum_sm = 0;
+            size_t prev = 0;
+            for (int k = 0; k + 1 < S; ++k) {
+                cum_sm += sms[(size_t)k];
+                const int64_t target = (int64_t)((double)total * (double)cum_sm / (double)pipe->n_sm);
+                int slack_pct = 3;
+                if (const char *e = getenv("FDG_PIPE_SLACK")) slack_pct = std::max(0, std::min(25, atoi(e)));
+                const int64_t slack = std::max<int64_t>(total / S * slack_pct / 100, 1);
+                size_t cut = std::min(nops - 1, std::max(prev + 1, pos_at(0, target)));
+                if (narrow) {
+                    const size_t lo_w = std::max(prev + 1, pos_at(0, std::max<int64_t>(target - slack, 0)));
+                    const size_t hi_w = std::min(nops - 1, pos_at(0, target + slack));
+                    for (size_t q = lo_w; q <= hi_w; ++q)
+                        if (live[q] < live[cut] || (live[q] == live[cut] && std::llabs(cost[q] - target) < std::llabs(cost[cut] - target))) cut = q;
+                }
+                if (cut <= prev || cut >= nops) continue;
+                seg_start.push_back((int32_t)cut);
+                prev = cut;
+            }
+            start = nops;  // the loop below has nothing left to do
+        }
+        while (start < nops && cost[nops] - cost[start] > (int64_t)seg_ops + (narrow ? seg_ops / 4 : 0)) {
             size_t cut = std::min(nops - 1, std::max(start + 1, pos_at(start, seg_ops)));
             if (narrow) {
                 const size_t lo_w = std::max(start + 1, pos_at(start, (int64_t)seg_ops * 3 / 4));
@@ -598,7 +730,12 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
     plan.seg.resize((size_t)nseg);
     // a single accumulate kernel with few roots runs as a grid-stride loop: per-thread running sums in registers,
     // one warp reduction per root at the very end (instead of one per tile)
-    plan.persistent = acc && nseg == 1 && low.R * W <= 32;
+    plan.persistent = !pipe && acc && nseg == 1 && low.R * W <= 32;
+    plan.pipeline = pipe != nullptr;
+    plan.stage_start.assign(seg_start.begin(), seg_start.end());
+    plan.stage_estimate.clear();
+    for (int sg = 0; sg < nseg; ++sg) plan.stage_estimate.push_back(cost[(size_t)seg_start[(size_t)sg + 1]] - cost[(size_t)seg_start[(size_t)sg]]);
+    int ring_bytes_max = 0;
     for (int sg = 0; sg < nseg; ++sg) {
         Emitter e(low, spt, acc);
         e.cplx = cplx;
@@ -643,15 +780,22 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
         const int ES = cplx ? 16 : 8 * samples_per_thread;  // bytes per thread per row
         const int G = 4;
         int NR = ring_rows > 0 ? ring_rows : (ES == 8 ? 32 : 24);
-        NR = std::max(G, std::min(NR, 49152 / (128 * ES)) / G * G);
+        const int T = pipe ? pipe->threads : 128;  // threads per block
+        // static shared memory stops at 48 KB; the pipeline kernel asks for dynamic shared memory and may go deeper
+        NR = std::max(G, std::min(NR, (pipe ? 98304 : 49152) / (T * ES)) / G * G);
         const bool ring = ring_on && !e.persistent && n_in > 0;
+        const int sacc0 = 256 + (ring ? NR * T * ES : 0);  // pipeline form: where the running sums of the roots start
+        if (pipe && acc) {
+            e.sacc_stride = (T + 1) * 8;
+            e.sacc_cap = std::max(0, (200 * 1024 - sacc0) / e.sacc_stride);
+        }
         const int n_groups = (n_in + G - 1) / G;
         int next_in = 0;  // rows consumed so far
         auto ring_issue = [&](std::ostringstream &o2, int j) {  // copy of input row j into its slot
             const auto &row = in_rows[(size_t)j];
             const int a = e.nrd++;
             e.row_addr(o2, a, row.first ? "%rd3" : "%rd1", row.first ? "%rd4" : "%rd2", row.second);
-            o2 << "\tcp.async." << (ES == 16 ? "cg" : "ca") << ".shared.global [%r12+" << (j % NR) * 128 * ES << "], [%rd" << a << "], " << ES << ";\n";
+            o2 << "\tcp.async." << (ES == 16 ? "cg" : "ca") << ".shared.global [%r12+" << (j % NR) * T * ES << "], [%rd" << a << "], " << ES << ";\n";
         };
         auto ring_load = [&](int kind_, int32_t row_) -> int {
             const int j = next_in++;
@@ -661,9 +805,9 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
             if (j % G == 0) os << "\tcp.async.wait_group " << std::min(NR / G - 1, n_groups - 1 - g) << ";\n";
             const int r = e.new_val();
             if (ES == 16)
-                os << "\tld.shared.v2.f64 {" << e.fd(r, 0) << ", " << e.fd(r, 1) << "}, [%r12+" << (j % NR) * 128 * ES << "];\n";
+                os << "\tld.shared.v2.f64 {" << e.fd(r, 0) << ", " << e.fd(r, 1) << "}, [%r12+" << (j % NR) * T * ES << "];\n";
             else
-                os << "\tld.shared.f64 " << e.fd(r, 0) << ", [%r12+" << (j % NR) * 128 * ES << "];\n";
+                os << "\tld.shared.f64 " << e.fd(r, 0) << ", [%r12+" << (j % NR) * T * ES << "];\n";
             if (j % G == G - 1 || j == n_in - 1) {
                 const int j0 = (g + NR / G) * G;
                 if (j0 < n_in) {
@@ -740,17 +884,150 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
         const std::string body = os.str();
         const int spt_hdr = samples_per_thread;
         JitSegment &js = plan.seg[(size_t)sg];
-        js.name = "fdg_seg" + std::to_string(sg);
+        js.name = (pipe ? "fdg_stage" : "fdg_seg") + std::to_string(sg);
         js.n_stmts = (int)(hi - lo);
         std::ostringstream p;
         p << ".version 8.7\n.target sm_100a\n.address_size 64\n\n";
+        if (pipe) {
+            // ---- stage function of the pipeline kernel -------------------------------------------------------------------
+            // One warp = one tile of 32 samples at a time; the warps of a stage take tiles round-robin (warp w of W: tiles
+            // w, w + W, ...: a fixed assignment, so the accumulators are summed in a fixed order).  progress[tile] = number of
+            // stages the tile has passed: stage k waits for k, publishes k + 1; stage 0 waits until the tile that used its
+            // cross slot `window` tiles ago has passed every stage.
+            // Shared memory: [0, 128) the launch arguments (written by the entry kernel), [128, 256) one word per warp,
+            // then the input ring.  The stage function takes no parameters and re-reads what it needs per tile, so that
+            // nothing but the tile index has to stay in a register across the straight-line code.
+            const int n_sacc = (int)e.sacc_pos.size();
+            ring_bytes_max = std::max(ring_bytes_max, sacc0 + n_sacc * e.sacc_stride);
+            p << ".extern .shared .align 16 .b8 fdg_ring[];\n";
+            if (n_sacc > 0) {
+                p << ".const .align 4 .u32 fdg_rt" << sg << "[" << n_sacc << "] = {";
+                for (int j = 0; j < n_sacc; ++j) p << (j ? ", " : "") << e.sacc_pos[(size_t)j];
+                p << "};\n";
+            }
+            p << ".visible .func " << js.name << "()\n{\n";
+            p << "\t.reg .f64 %fd<" << e.nfd + 2 << ">;\n\t.reg .b64 %rd<" << e.nrd + 1 + (ring ? NR : 0) << ">;\n\t.reg .pred %p<" << e.np + 1
+              << ">;\n\t.reg .b32 %r<" << e.nr + 1 << ">;\n";
+            const int wpb = T / 32;
+            // %rd20 = tile of this warp (the only value that lives across tiles besides what ptxas keeps of the setup)
+            p << "\tmov.u32 %r2, %tid.x;\n\tand.b32 %r3, %r2, 31;\n\tsetp.eq.u32 %p3, %r3, 0;\n"
+              << "\tmov.u32 %r0, %ctaid.x;\n\tshr.u32 %r5, %r2, 5;\n"
+              << "\tld.volatile.shared.u32 %r15, [fdg_ring+96];\n\tsub.u32 %r6, %r0, %r15;\n\tmad.lo.u32 %r6, %r6, " << wpb << ", %r5;\n"
+              << "\tcvt.u64.u32 %rd20, %r6;\n"
+              << "\tmov.u64 %rd21, %clock64;\n\tshl.b32 %r7, %r5, 3;\n\tmov.u32 %r15, fdg_ring;\n\tadd.u32 %r7, %r7, %r15;\n"
+              << "\tst.volatile.shared.u64 [%r7+128], %rd21;\n";
+            if (ring) p << "\tmov.u32 %r12, fdg_ring;\n\tmad.lo.u32 %r12, %r2, " << ES << ", %r12;\n\tadd.u32 %r12, %r12, 256;\n";
+            if (n_sacc > 0) {
+                // running sums of this stage's roots: one column per thread, zeroed here, reduced after the last tile
+                p << "\tmov.u32 %r16, fdg_ring;\n\tmad.lo.u32 %r16, %r2, 8, %r16;\n\tadd.u32 %r16, %r16, " << sacc0 << ";\n"
+                  << "\tmov.u32 %r17, 0;\n\tmov.u32 %r18, %r16;\n\tmov.f64 %fd" << e.nfd << ", 0d0000000000000000;\n"
+                  << "FDG_ZERO:\n\tst.shared.f64 [%r18], %fd" << e.nfd << ";\n\tadd.u32 %r18, %r18, " << e.sacc_stride << ";\n"
+                  << "\tadd.u32 %r17, %r17, 1;\n\tsetp.lt.u32 %p6, %r17, " << n_sacc << ";\n\t@%p6 bra FDG_ZERO;\n";
+            }
+            p << "FDG_TILE:\n\tld.volatile.shared.u64 %rd17, [fdg_ring+64];\n\tsetp.ge.u64 %p6, %rd20, %rd17;\n\t@%p6 bra FDG_DONE;\n"
+              << "\tld.volatile.shared.u64 %rd16, [fdg_ring+56];\n\tld.volatile.shared.u64 %rd19, [fdg_ring+72];\n"
+              << "\tmov.u64 %rd21, %clock64;\n";
+            // ---- wait for the tile ----
+            if (sg == 0) {
+                p << "\tsetp.lt.u64 %p6, %rd20, %rd19;\n\t@%p6 bra FDG_GO;\n"
+                  << "\tsub.u64 %rd22, %rd20, %rd19;\n\tshl.b64 %rd22, %rd22, 2;\n\tadd.u64 %rd22, %rd16, %rd22;\n";
+            } else {
+                p << "\tshl.b64 %rd22, %rd20, 2;\n\tadd.u64 %rd22, %rd16, %rd22;\n";
+            }
+            const int want = sg == 0 ? nseg : sg;
+            p << "\tmov.u64 %rd23, %globaltimer;\n"
+              << "FDG_WAIT:\n\tld.acquire.gpu.global.u32 %r15, [%rd22];\n\tsetp.ge.u32 %p7, %r15, " << want << ";\n\t@%p7 bra FDG_GO;\n"
+              << "\tnanosleep.u32 64;\n\tmov.u64 %rd30, %globaltimer;\n\tsub.u64 %rd30, %rd30, %rd23;\n"
+              << "\tsetp.gt.u64 %p7, %rd30, 4000000000;\n\t@!%p7 bra FDG_WAIT;\n"
+              // a stalled pipeline ends instead of hanging: flag it and leave
+              << "\tld.volatile.shared.u64 %rd30, [fdg_ring+80];\n\tmov.u32 %r15, 1;\n\tst.global.u32 [%rd30], %r15;\n\tbra FDG_DONE;\n"
+              << "FDG_GO:\n\tfence.acq_rel.gpu;\n"
+              << "\tmov.u64 %rd31, %clock64;\n\tsub.u64 %rd21, %rd31, %rd21;\n\tld.volatile.shared.u64 %rd30, [fdg_ring+80];\n"
+              << "\t@%p3 red.global.add.u64 [%rd30+" << 24 + 16 * sg << "], %rd21;\n";
+            // ---- per tile: sample index, validity, bases ----
+            p << "\tcvt.u64.u32 %rd25, %r3;\n\tshl.b64 %rd0, %rd20, 5;\n\tadd.u64 %rd0, %rd0, %rd25;\n"
+              << "\tld.volatile.shared.u64 %rd10, [fdg_ring+48];\n\tsetp.lt.s64 %p0, %rd0, %rd10;\n"
+              << "\tselp.u64 %rd12, %rd0, 0, %p0;\n\tshl.b64 %rd12, %rd12, " << esh << ";\n"
+              << "\tld.volatile.shared.u64 %rd1, [fdg_ring+0];\n\tadd.u64 %rd1, %rd1, %rd12;\n"
+              << "\tld.volatile.shared.u64 %rd2, [fdg_ring+8];\n\tld.volatile.shared.u64 %rd4, [fdg_ring+24];\n"
+              << "\tcvt.u32.u64 %r13, %rd2;\n\tcvt.u32.u64 %r14, %rd4;\n"
+              << "\tld.volatile.shared.u64 %rd14, [fdg_ring+32];\n";
+            if (n_cross > 0)
+                p << "\trem.u64 %rd24, %rd20, %rd19;\n\tshl.b64 %rd13, %rd24, 5;\n\tadd.u64 %rd13, %rd13, %rd25;\n\tshl.b64 %rd13, %rd13, " << esh << ";\n"
+                  << "\tld.volatile.shared.u64 %rd3, [fdg_ring+16];\n\tadd.u64 %rd3, %rd3, %rd13;\n";
+            if (acc)
+                // partial row of this warp: out + (block * warps per block + warp of the block) * nroots * 8
+                p << "\tld.volatile.shared.u64 %rd5, [fdg_ring+40];\n\tmad.lo.u32 %r6, %r0, " << wpb << ", %r5;\n\tcvt.u64.u32 %rd15, %r6;\n"
+                  << "\tmul.lo.u64 %rd15, %rd15, %rd5;\n\tshl.b64 %rd15, %rd15, 3;\n\tadd.u64 %rd7, %rd14, %rd15;\n";
+            else
+                p << "\tld.volatile.shared.u64 %rd5, [fdg_ring+40];\n\tshl.b64 %rd13, %rd0, " << esh << ";\n\tadd.u64 %rd6, %rd14, %rd13;\n";
+            if (ring) {
+                std::ostringstream pro;
+                for (int j = 0; j < std::min(NR, n_in); ++j) {
+                    ring_issue(pro, j);
+                    if (j % G == G - 1 || j == std::min(NR, n_in) - 1) pro << "\tcp.async.commit_group;\n";
+                }
+                p << pro.str();
+            }
+            p << body;
+            // ---- publish the tile, next tile of this warp ----
+            p << "\tfence.acq_rel.gpu;\n\tbar.warp.sync 0xffffffff;\n"
+              << "\tld.volatile.shared.u64 %rd16, [fdg_ring+56];\n\tshl.b64 %rd22, %rd20, 2;\n\tadd.u64 %rd22, %rd16, %rd22;\n\tmov.u32 %r15, " << sg + 1 << ";\n"
+              << "\t@%p3 st.release.gpu.global.u32 [%rd22], %r15;\n"
+              << "\tld.volatile.shared.u64 %rd18, [fdg_ring+88];\n\tadd.u64 %rd20, %rd20, %rd18;\n\tbra FDG_TILE;\n"
+              << "FDG_DONE:\n";
+            if (n_sacc > 0) {
+                // lane l sums entries l, l + 32, ... over the 32 columns of its warp, in lane order, and writes them into the
+                // warp's row of partial sums (each entry of the row has exactly one writer)
+                p << "\tbar.warp.sync 0xffffffff;\n"
+                  << "\tld.volatile.shared.u64 %rd14, [fdg_ring+32];\n\tld.volatile.shared.u64 %rd5, [fdg_ring+40];\n"
+                  << "\tmad.lo.u32 %r6, %r0, " << wpb << ", %r5;\n\tcvt.u64.u32 %rd15, %r6;\n"
+                  << "\tmul.lo.u64 %rd15, %rd15, %rd5;\n\tshl.b64 %rd15, %rd15, 3;\n\tadd.u64 %rd7, %rd14, %rd15;\n"
+                  << "\tmov.u32 %r17, %r3;\n"
+                  << "FDG_RED:\n\tsetp.ge.u32 %p6, %r17, " << n_sacc << ";\n\t@%p6 bra FDG_RED_END;\n"
+                  << "\tmov.u32 %r18, fdg_ring;\n\tmad.lo.u32 %r18, %r17, " << e.sacc_stride << ", %r18;\n\tmad.lo.u32 %r18, %r5, 256, %r18;\n"
+                  << "\tmov.f64 %fd" << e.nfd << ", 0d0000000000000000;\n\tmov.u32 %r19, 0;\n"
+                  << "FDG_RED_IN:\n\tld.shared.f64 %fd" << e.nfd + 1 << ", [%r18+" << sacc0 << "];\n"
+                  << "\tadd.rn.f64 %fd" << e.nfd << ", %fd" << e.nfd << ", %fd" << e.nfd + 1 << ";\n"
+                  << "\tadd.u32 %r18, %r18, 8;\n\tadd.u32 %r19, %r19, 1;\n\tsetp.lt.u32 %p7, %r19, 32;\n\t@%p7 bra FDG_RED_IN;\n"
+                  << "\tmov.u64 %rd22, fdg_rt" << sg << ";\n\tmul.wide.u32 %rd23, %r17, 4;\n\tadd.u64 %rd22, %rd22, %rd23;\n\tld.const.u32 %r19, [%rd22];\n"
+                  << "\tmul.wide.u32 %rd23, %r19, 8;\n\tadd.u64 %rd23, %rd7, %rd23;\n\tst.global.f64 [%rd23], %fd" << e.nfd << ";\n"
+                  << "\tadd.u32 %r17, %r17, 32;\n\tbra FDG_RED;\n"
+                  << "FDG_RED_END:\n";
+            }
+            p
+              // statistics: clocks this stage was alive / spent waiting, summed over its warps (lane 0 of each)
+              << "\tmov.u64 %rd31, %clock64;\n\tld.volatile.shared.u64 %rd21, [%r7+128];\n\tsub.u64 %rd21, %rd31, %rd21;\n"
+              << "\tld.volatile.shared.u64 %rd30, [fdg_ring+80];\n"
+              << "\t@%p3 red.global.add.u64 [%rd30+" << 16 + 16 * sg << "], %rd21;\n"
+              << "\tret;\n}\n";
+            js.ptx = p.str();
+            // issue-cycle estimate of one tile: an FP64 instruction holds the pipe two cycles, everything else one issue slot
+            {
+                int64_t n_fp64 = 0, n_other = 0;
+                size_t pos = 0;
+                while (pos < body.size()) {
+                    const size_t eol = body.find('\n', pos);
+                    const std::string line = body.substr(pos, eol == std::string::npos ? std::string::npos : eol - pos);
+                    pos = eol == std::string::npos ? body.size() : eol + 1;
+                    if (line.size() < 2 || line[0] != '\t') continue;
+                    const bool f64 = line.find(".f64 ") != std::string::npos &&
+                                     (line.compare(1, 3, "mul") == 0 || line.compare(1, 3, "add") == 0 || line.compare(1, 3, "sub") == 0 ||
+                                      line.compare(1, 3, "fma") == 0);
+                    if (f64) ++n_fp64;
+                    else if (line.compare(1, 3, "neg") != 0) ++n_other;
+                }
+                plan.stage_cost.push_back(std::max<int64_t>(2 * n_fp64, n_fp64 + n_other) + 64);
+            }
+            continue;
+        }
         p << ".visible .entry " << js.name << "(\n"
           << "\t.param .u64 p_leaf, .param .u64 p_ld_leaf, .param .u64 p_cross, .param .u64 p_ld_cross,\n"
           << "\t.param .u64 p_out, .param .u64 p_ld_root, .param .u64 p_batch, .param .u64 p_nroots)\n"
           << ".maxntid 128, 1, 1\n";
         if (const char *mr = getenv("FDG_JIT_MAXNREG")) p << ".maxnreg " << atoi(mr) << "\n";
         p << "{\n";
-        if (ring) p << "\t.shared .align 16 .b8 fdg_ring[" << NR * 128 * ES << "];\n";
+        if (ring) p << "\t.shared .align 16 .b8 fdg_ring[" << NR * T * ES << "];\n";
         p << "\t.reg .f64 %fd<" << e.nfd + 2 << ">;\n\t.reg .b64 %rd<" << e.nrd + 1 + (ring ? NR : 0) << ">;\n\t.reg .pred %p<" << e.np + 1
           << ">;\n\t.reg .b32 %r<" << e.nr + 1 << ">;\n";
         // %rd0 = first sample of the thread, %rd1 = leaf base, %rd2 = ld_leaf bytes, %rd3 = cross base, %rd4 = ld_cross bytes,
@@ -813,6 +1090,74 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
         p << "\tret;\n}\n";
         js.ptx = p.str();
     }
+    if (pipe) {
+        // ---- SMs per stage: proportional to the estimated time of one tile, every stage at least one -----------------
+        const int S = nseg;
+        plan.n_sm = pipe->n_sm;
+        plan.ring_bytes = ring_bytes_max;
+        if (S > pipe->n_sm) {
+            err = "more pipeline stages than SMs";
+            return FDG_ERR_CAPACITY;
+        }
+        double total = 0;
+        for (const int64_t c : plan.stage_cost) total += (double)c;
+        plan.stage_blocks.assign((size_t)S, 1);
+        int left = pipe->n_sm - S;
+        std::vector<std::pair<double, int>> frac;
+        for (int k = 0; k < S; ++k) {
+            const double want = (double)plan.stage_cost[(size_t)k] / total * (double)pipe->n_sm;
+            const int extra = std::max(0, std::min(left, (int)want - 1));
+            plan.stage_blocks[(size_t)k] += extra;
+            left -= extra;
+            frac.emplace_back(want - (double)plan.stage_blocks[(size_t)k], k);
+        }
+        std::sort(frac.begin(), frac.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) { return a.first > b.first; });
+        for (int i = 0; left > 0; i = (i + 1) % S, --left) plan.stage_blocks[(size_t)frac[(size_t)i].second] += 1;
+        // ---- the entry kernel: the launch arguments go to shared memory, then block index -> stage --------------------
+        std::ostringstream d;
+        d << ".version 8.7\n.target sm_100a\n.address_size 64\n\n.extern .shared .align 16 .b8 fdg_ring[];\n";
+        for (int k = 0; k < S; ++k) d << ".extern .func fdg_stage" << k << "();\n";
+        d << ".visible .entry fdg_pipe(\n"
+          << "\t.param .u64 p_leaf, .param .u64 p_ld_leaf, .param .u64 p_cross, .param .u64 p_ld_cross,\n"
+          << "\t.param .u64 p_out, .param .u64 p_ld_root, .param .u64 p_batch, .param .u64 p_nroots,\n"
+          << "\t.param .u64 p_progress, .param .u64 p_ntiles, .param .u64 p_window, .param .u64 p_stats)\n"
+          << ".maxntid " << pipe->threads << ", 1, 1\n{\n"
+          << "\t.reg .b64 %rd<20>;\n\t.reg .b32 %r<8>;\n\t.reg .pred %p<2>;\n"
+          << "\tld.param.u64 %rd0, [p_leaf];\n\tcvta.to.global.u64 %rd0, %rd0;\n\tld.param.u64 %rd1, [p_ld_leaf];\n\tshl.b64 %rd1, %rd1, " << esh << ";\n"
+          << "\tld.param.u64 %rd2, [p_cross];\n\tcvta.to.global.u64 %rd2, %rd2;\n\tld.param.u64 %rd3, [p_ld_cross];\n\tshl.b64 %rd3, %rd3, " << esh << ";\n"
+          << "\tld.param.u64 %rd4, [p_out];\n\tcvta.to.global.u64 %rd4, %rd4;\n";
+        if (acc) d << "\tld.param.u64 %rd5, [p_nroots];\n";
+        else d << "\tld.param.u64 %rd5, [p_ld_root];\n\tshl.b64 %rd5, %rd5, " << esh << ";\n";
+        d << "\tld.param.u64 %rd6, [p_batch];\n"
+          << "\tld.param.u64 %rd8, [p_progress];\n\tcvta.to.global.u64 %rd8, %rd8;\n\tld.param.u64 %rd9, [p_ntiles];\n"
+          << "\tld.param.u64 %rd10, [p_window];\n\tld.param.u64 %rd11, [p_stats];\n\tcvta.to.global.u64 %rd11, %rd11;\n"
+          << "\tmov.u32 %r0, %ctaid.x;\n\tmov.u32 %r1, %tid.x;\n\tsetp.eq.u32 %p1, %r1, 0;\n";
+        int first = 0;
+        for (int k = 0; k < S; ++k) {
+            const int nb = plan.stage_blocks[(size_t)k];
+            if (k + 1 < S) d << "\tsetp.lt.u32 %p0, %r0, " << first + nb << ";\n\t@%p0 bra FDG_S" << k << ";\n";
+            else d << "\tbra FDG_S" << k << ";\n";
+            first += nb;
+        }
+        first = 0;
+        for (int k = 0; k < S; ++k) {
+            const int nb = plan.stage_blocks[(size_t)k];
+            d << "FDG_S" << k << ":\n"
+              << "\tmov.u64 %rd12, " << nb * (pipe->threads / 32) << ";\n\tmov.u32 %r2, " << first << ";\n\tbra FDG_ARGS" << k << ";\n";
+            first += nb;
+        }
+        for (int k = 0; k < S; ++k) {
+            d << "FDG_ARGS" << k << ":\n";
+            const int off[11] = {0, 8, 16, 24, 32, 40, 48, 56, 64, 72, 80};
+            const int src[11] = {0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11};
+            for (int q = 0; q < 11; ++q) d << "\t@%p1 st.volatile.shared.u64 [fdg_ring+" << off[q] << "], %rd" << src[q] << ";\n";
+            d << "\t@%p1 st.volatile.shared.u64 [fdg_ring+88], %rd12;\n\t@%p1 st.volatile.shared.u32 [fdg_ring+96], %r2;\n"
+              << "\tbar.sync 0;\n"
+              << "\tcall.uni fdg_stage" << k << ", ();\n\tret;\n";
+        }
+        d << "}\n";
+        plan.dispatch_ptx = d.str();
+    }
     (void)err;
     return FDG_OK;
 }
@@ -820,15 +1165,15 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
 // ---------------------------------------------------------------------------------------------------------------------
 // PTX -> cubin (sm_100a), segments in parallel
 // ---------------------------------------------------------------------------------------------------------------------
-static int compile_one(JitSegment &js, bool fma, std::string &err) {
+static int compile_one(JitSegment &js, bool fma, std::string &err, bool relocatable = false) {
     nvPTXCompilerHandle h = nullptr;
     nvPTXCompileResult rc = nvPTXCompilerCreate(&h, js.ptx.size(), js.ptx.c_str());
     if (rc != NVPTXCOMPILE_SUCCESS) {
         err = "nvPTXCompilerCreate failed (" + std::to_string((int)rc) + ")";
         return FDG_ERR_UNSUPPORTED;
     }
-    const char *opts[] = {"--gpu-name=sm_100a", "--opt-level=3", fma ? "--fmad=true" : "--fmad=false", "--verbose"};
-    rc = nvPTXCompilerCompile(h, 4, opts);
+    const char *opts[] = {"--gpu-name=sm_100a", "--opt-level=3", fma ? "--fmad=true" : "--fmad=false", "--verbose", "--compile-only"};
+    rc = nvPTXCompilerCompile(h, relocatable ? 5 : 4, opts);
     size_t n = 0;
     if (rc != NVPTXCOMPILE_SUCCESS) {
         nvPTXCompilerGetErrorLogSize(h, &n);
@@ -892,7 +1237,7 @@ int jit_compile(JitPlan &plan, std::string &err) {
         for (;;) {
             const int i = next.fetch_add(1);
             if (i >= n) break;
-            rcs[(size_t)i] = compile_one(plan.seg[(size_t)i], plan.fma, errs[(size_t)i]);
+            rcs[(size_t)i] = compile_one(plan.seg[(size_t)i], plan.fma, errs[(size_t)i], plan.pipeline);
         }
     };
     std::vector<std::thread> pool;
@@ -906,6 +1251,45 @@ int jit_compile(JitPlan &plan, std::string &err) {
         }
     plan.max_code_bytes = 0;
     for (auto &sg : plan.seg) plan.max_code_bytes = std::max<int64_t>(plan.max_code_bytes, (int64_t)text_bytes(sg.cubin));
+    if (plan.pipeline) {
+        // the stage functions were assembled as relocatable objects; the entry kernel joins them (device link, no GPU needed)
+        JitSegment entry;
+        entry.name = "fdg_pipe";
+        entry.ptx = plan.dispatch_ptx;
+        int rc = compile_one(entry, plan.fma, err, true);
+        if (rc != FDG_OK) return rc;
+        nvJitLinkHandle lh = nullptr;
+        const char *lopts[] = {"-arch=sm_100a"};
+        if (nvJitLinkCreate(&lh, 1, lopts) != NVJITLINK_SUCCESS) {
+            err = "nvJitLinkCreate failed";
+            return FDG_ERR_UNSUPPORTED;
+        }
+        bool ok = nvJitLinkAddData(lh, NVJITLINK_INPUT_CUBIN, entry.cubin.data(), entry.cubin.size(), "fdg_pipe") == NVJITLINK_SUCCESS;
+        for (auto &sg : plan.seg)
+            ok = ok && nvJitLinkAddData(lh, NVJITLINK_INPUT_CUBIN, sg.cubin.data(), sg.cubin.size(), sg.name.c_str()) == NVJITLINK_SUCCESS;
+        ok = ok && nvJitLinkComplete(lh) == NVJITLINK_SUCCESS;
+        if (!ok) {
+            size_t ln = 0;
+            nvJitLinkGetErrorLogSize(lh, &ln);
+            std::string log(ln + 1, '\0');
+            if (ln) nvJitLinkGetErrorLog(lh, &log[0]);
+            err = std::string("device link of the pipeline kernel failed: ") + log.c_str();
+            nvJitLinkDestroy(&lh);
+            return FDG_ERR_UNSUPPORTED;
+        }
+        size_t nbytes = 0;
+        nvJitLinkGetLinkedCubinSize(lh, &nbytes);
+        plan.linked.resize(nbytes);
+        nvJitLinkGetLinkedCubin(lh, plan.linked.data());
+        nvJitLinkDestroy(&lh);
+        if (const char *dir = getenv("FDG_JIT_DUMP_CUBIN")) {
+            const std::string path = std::string(dir) + "/fdg_pipe.cubin";
+            if (FILE *fp = std::fopen(path.c_str(), "wb")) {
+                std::fwrite(plan.linked.data(), 1, plan.linked.size(), fp);
+                std::fclose(fp);
+            }
+        }
+    }
     return FDG_OK;
 }
 

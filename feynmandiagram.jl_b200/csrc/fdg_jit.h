@@ -26,11 +26,35 @@ struct JitPlan {
     int64_t max_code_bytes = 0;  // machine code of the largest kernel (the instruction cache holds 128 KB)
     bool persistent = false;  // single accumulate kernel run as a grid-stride loop (per-thread running sums)
     std::vector<JitSegment> seg;
+    // ---- pipeline form: ONE kernel, one resident block per SM; the blocks of stage k run only
+    // the code of segment k (it stays in that SM's instruction cache) and tiles of 32 samples flow from stage to stage
+    // through L2: cross rows live in a ring of `window` tile slots, progress[tile] counts the stages a tile has passed.
+    bool pipeline = false;
+    int n_sm = 0;                    // blocks of the kernel (= SMs of the device the plan was made for)
+    std::vector<int> stage_blocks;   // blocks (SMs) given to each stage, sum == n_sm
+    std::vector<int64_t> stage_cost; // issue-cycle estimate of one tile in each stage (what the split is based on)
+    std::vector<int64_t> stage_estimate; // the same as the cuts saw it (per-operation estimate, weighted)
+    std::vector<int32_t> stage_start; // first operation of each stage, and the total as the last entry
+    std::string dispatch_ptx;        // the entry kernel: block index -> stage function
+    std::vector<char> linked;        // stages + entry linked into one cubin (nvJitLink)
+    int ring_bytes = 0;              // dynamic shared memory of the kernel
+};
+
+struct PipeOptions {
+    int n_sm = 148;        // SMs of the target device
+    int threads = 256;     // threads per block (one block per SM)
+    // profile-guided re-cut: the stage boundaries of a previous plan (operation indices, n + 1 entries) and the measured
+    // time per estimated cost of each of its stages; the cost of an operation is scaled by the weight of the stage it was in
+    std::vector<int32_t> prev_start;
+    std::vector<double> weight;
+    std::vector<int> blocks;  // SMs per stage the cuts should aim at (the allocation of the previous plan); empty: even split
 };
 
 // linearise the emitted function in fold order, cut it into segments of `seg_ops` operations, write their PTX
 // wide_strides: row offsets need 64 bits (a leading dimension of 4 GiB or more)
-int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strides, bool fma, JitPlan &plan, std::string &err);
+// pipe != nullptr: pipeline form (stage functions + entry kernel, linked by jit_compile)
+int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strides, bool fma, JitPlan &plan, std::string &err,
+             const PipeOptions *pipe = nullptr);
 // assemble every segment with the PTX compiler library (no GPU needed), segments in parallel
 int jit_compile(JitPlan &plan, std::string &err);
 

@@ -174,6 +174,16 @@ int fdg_jit_prepare(fdg_handle h, int32_t samples_per_thread, int32_t accumulate
  * variant is a single grid-stride kernel; [8] = bytes of machine code of the largest kernel.  (leaf loads + cross loads + cross stores) x sizeof(W) is the traffic the
  * plan asks of the memory system per sample -- the figure DESIGN.md compares with ncu's dram bytes. */
 int fdg_jit_info(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int64_t *out, int32_t n_out);
+/* Pipeline form of the specialised back end: ONE cooperative kernel, one block per SM; the blocks
+ * of stage k run only the code of segment k (resident in that SM's instruction cache) and tiles of 32 samples flow from
+ * stage to stage through L2.  fdg_pipeline_prepare builds it for a device with n_sm SMs (host only, no GPU needed) and
+ * answers a query: what = 0: stages, cross rows, cross values, then per sample leaf loads, cross loads, cross stores,
+ * operations, bytes of machine code of the largest stage, bytes of the linked kernel, bytes of the input ring;
+ * what = 1: SMs given to each stage; what = 2: estimated issue cycles of one tile in each stage. */
+int fdg_pipeline_prepare(fdg_handle h, int32_t accumulate, int32_t n_sm, int32_t what, int64_t *out, int32_t n_out);
+/* after a pipeline launch on `stream` (synchronises it): out[0] = 1 if a stage gave up waiting (the results are then
+ * invalid), out[1 + 2k], out[2 + 2k] = clocks stage k spent computing / waiting, summed over its warps. */
+int fdg_pipeline_stats(fdg_handle h, void *stream, int64_t *out, int32_t n_out);
 /* PTX text of kernel `index` of a prepared variant (for inspection / tests) */
 int fdg_jit_ptx(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t index, const char **ptx,
                 const char **ptxas_log);
