@@ -217,10 +217,10 @@ def jit_prepare(h, samples_per_thread: int = 2, accumulate: bool = False) -> dic
 
 def pipeline_prepare(h, accumulate: bool = True, n_sm: int = 148) -> dict:
     """Builds the pipeline kernel for a device with n_sm SMs (host only) and returns its plan."""
-    out = (C.c_int64 * 10)()
-    check(lib().fdg_pipeline_prepare(h, int(accumulate), n_sm, 0, out, 10))
+    out = (C.c_int64 * 12)()
+    check(lib().fdg_pipeline_prepare(h, int(accumulate), n_sm, 0, out, 12))
     keys = ("stages", "cross_rows", "cross_values", "leaf_loads", "cross_loads", "cross_stores", "operations", "max_code_bytes",
-            "linked_bytes", "ring_bytes")
+            "linked_bytes", "ring_bytes", "passes", "boundary_rows")
     info = {k: int(out[i]) for i, k in enumerate(keys)}
     n = info["stages"]
     buf = (C.c_int64 * n)()

@@ -115,7 +115,7 @@ struct Emitter {
         if (wide)
             o2 << "\tmad.lo.u64 %rd" << a << ", " << stride << ", " << index << ", " << base << ";\n";
         else
-            o2 << "\tmad.wide.u32 %rd" << a << ", " << (stride == "%rd2" ? "%r13" : "%r14") << ", " << index << ", " << base << ";\n";
+            o2 << "\tmad.wide.u32 %rd" << a << ", " << (stride == "%rd2" ? "%r13" : (stride == "%rd4" ? "%r14" : "%r20")) << ", " << index << ", " << base << ";\n";
     }
     // value = load from  base + index * stride  (two f64 for S == 2)
     int load(const char *space, const std::string &base, const std::string &stride, int64_t index) {
@@ -508,12 +508,17 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
     int rc = FDG_OK;
     JitPlan best;
     double best_load = 1e30;
-    // slowest stage relative to a perfect split: max over stages of (cost / SMs) / (total cost / all SMs)
+    // time of all passes (each as slow as its slowest stage) relative to a perfect split of the work over all SMs
     auto imbalance = [](const JitPlan &pl) {
-        double tot = 0, worst = 0;
+        double tot = 0, t = 0;
         for (const int64_t c : pl.stage_cost) tot += (double)c;
-        for (size_t k = 0; k < pl.stage_cost.size(); ++k) worst = std::max(worst, (double)pl.stage_cost[k] / (double)pl.stage_blocks[k]);
-        return worst / (tot / (double)pl.n_sm);
+        for (int p0 = 0; p0 < (int)pl.stage_cost.size(); p0 += pl.stages_per_pass) {
+            double worst = 0;
+            for (int k = p0; k < std::min<int>(p0 + pl.stages_per_pass, (int)pl.stage_cost.size()); ++k)
+                worst = std::max(worst, (double)pl.stage_cost[(size_t)k] / (double)pl.stage_blocks[(size_t)k]);
+            t += worst;
+        }
+        return t / (tot / (double)pl.n_sm);
     };
     for (int iter = 0; iter < 6; ++iter) {
         JitPlan cand;
@@ -544,7 +549,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
             for (size_t k = 0; k < w.size(); ++k) std::fprintf(stderr, " %.2f", w[k]);
             std::fprintf(stderr, "\n");
         }
-        if (worst < 0.02 && !pipe->prev_start.size()) break;
+        if (worst < 0.02) break;
         std::vector<double> neww(w.size());
         for (size_t k = 0; k < w.size(); ++k) {
             // weight the stage had in this round (piecewise over the previous boundaries: take the one at the stage's middle)
@@ -558,7 +563,6 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
         }
         po.prev_start = plan.stage_start;
         po.weight = neww;
-        po.blocks = plan.stage_blocks;
     }
     plan = std::move(best);
     return rc;
@@ -628,6 +632,8 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         }
     }
     if (pipe) seg_ops *= 16;
+    int pipe_stages_per_pass = 1, pipe_n_pass = 1;
+    std::vector<int> pipe_stage_sms;
     {
         // live[p] = values defined before op p and read at or after p (what a cut in front of p sends through memory)
         std::vector<int32_t> live(nops + 2, 0);
@@ -645,33 +651,49 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
             return (size_t)(std::lower_bound(cost.begin() + (long)from, cost.end(), cost[from] + c) - cost.begin());
         };
         if (pipe) {
-            // Pipeline form: stage k gets a whole number of SMs, so the cuts go where the cumulative cost reaches the
-            // cumulative share of SMs (a stage with 7 of 148 SMs gets 7/148 of the work), each one moved inside a
-            // narrow window (+-3 % of a stage) to the position with the fewest live values.
+            // Pipeline form: a pass has one stage per instruction-cache group and the stage's share of the pass is the
+            // group's share of the SMs, so the cuts go where the cumulative cost reaches those shares, each one moved inside
+            // a narrow window (+-3 % of a stage) to the position with the fewest live values.  The number of passes follows
+            // from the code the groups can hold: `seg_ops` estimated instructions per stage.
             const int64_t total = std::max<int64_t>(cost[nops], 1);
-            int S = (int)std::min<int64_t>(std::max<int64_t>((total + seg_ops / 2) / seg_ops, 1), pipe->n_sm);
-            if (const char *e = getenv("FDG_PIPE_STAGES")) S = std::max(1, std::min(atoi(e), pipe->n_sm));
-            std::vector<int> sms((size_t)S, pipe->n_sm / S);
-            for (int k = 0; k < pipe->n_sm % S; ++k) sms[(size_t)((int64_t)k * S / (pipe->n_sm % S))] += 1;  // spread the larger stages
-            if ((int)pipe->blocks.size() == S) sms = pipe->blocks;
-            int64_t cum_sm = 0;
+            const int G = (int)pipe->groups.size();
+            const int n_sm = pipe->n_sm();
+            int n_pass = (int)std::max<int64_t>((total + (int64_t)seg_ops * G - 1) / ((int64_t)seg_ops * G), 1);
+            if (const char *e = getenv("FDG_PIPE_PASSES")) n_pass = std::max(1, atoi(e));
+            // a small program does not need every group to run its own stage: neighbouring groups then share one
+            int gs = G;  // stages per pass
+            if (n_pass == 1) gs = (int)std::max<int64_t>(1, std::min<int64_t>(G, (total + seg_ops / 4 - 1) / (seg_ops / 4)));
+            if (const char *e = getenv("FDG_PIPE_STAGES")) gs = std::max(1, std::min(atoi(e), G));
+            pipe_stages_per_pass = gs;
+            pipe_n_pass = n_pass;
+            // groups of one stage: stage j of a pass gets groups [j * G / gs, (j + 1) * G / gs)
+            pipe_stage_sms.assign((size_t)gs, 0);
+            for (int g = 0; g < G; ++g) pipe_stage_sms[(size_t)((int64_t)g * gs / G)] += pipe->groups[(size_t)g];
+            int slack_pct = 3;
+            if (const char *e = getenv("FDG_PIPE_SLACK")) slack_pct = std::max(0, std::min(25, atoi(e)));
+            const int64_t slack = std::max<int64_t>(total / ((int64_t)gs * n_pass) * slack_pct / 100, 1);
             size_t prev = 0;
-            for (int k = 0; k + 1 < S; ++k) {
-                cum_sm += sms[(size_t)k];
-                const int64_t target = (int64_t)((double)total * (double)cum_sm / (double)pipe->n_sm);
-                int slack_pct = 3;
-                if (const char *e = getenv("FDG_PIPE_SLACK")) slack_pct = std::max(0, std::min(25, atoi(e)));
-                const int64_t slack = std::max<int64_t>(total / S * slack_pct / 100, 1);
-                size_t cut = std::min(nops - 1, std::max(prev + 1, pos_at(0, target)));
-                if (narrow) {
-                    const size_t lo_w = std::max(prev + 1, pos_at(0, std::max<int64_t>(target - slack, 0)));
-                    const size_t hi_w = std::min(nops - 1, pos_at(0, target + slack));
-                    for (size_t q = lo_w; q <= hi_w; ++q)
-                        if (live[q] < live[cut] || (live[q] == live[cut] && std::llabs(cost[q] - target) < std::llabs(cost[cut] - target))) cut = q;
+            for (int ps = 0; ps < n_pass; ++ps) {
+                int64_t cum_sm = 0;
+                for (int j = 0; j < gs; ++j) {
+                    cum_sm += pipe_stage_sms[(size_t)j];
+                    if (ps == n_pass - 1 && j == gs - 1) break;
+                    const int64_t target = (int64_t)((double)total * ((double)ps + (double)cum_sm / (double)n_sm) / (double)n_pass);
+                    size_t cut = std::min(nops - 1, std::max(prev + 1, pos_at(0, target)));
+                    if (narrow) {
+                        const size_t lo_w = std::max(prev + 1, pos_at(0, std::max<int64_t>(target - slack, 0)));
+                        const size_t hi_w = std::min(nops - 1, pos_at(0, target + slack));
+                        for (size_t q = lo_w; q <= hi_w; ++q)
+                            if (live[q] < live[cut] || (live[q] == live[cut] && std::llabs(cost[q] - target) < std::llabs(cost[cut] - target))) cut = q;
+                    }
+                    if (cut <= prev || cut >= nops) {
+                        // an empty stage cannot be expressed: give up on the pipeline form for this program
+                        err = "program too small for the pipeline form";
+                        return FDG_ERR_CAPACITY;
+                    }
+                    seg_start.push_back((int32_t)cut);
+                    prev = cut;
                 }
-                if (cut <= prev || cut >= nops) continue;
-                seg_start.push_back((int32_t)cut);
-                prev = cut;
             }
             start = nops;  // the loop below has nothing left to do
         }
@@ -696,7 +718,8 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
     // ---- values read in a later segment than the one defining them travel through the cross buffer; a row is reused
     //      once the last kernel reading it has run (kernels of one stream run in order)
     std::vector<int32_t> cross(nops, -1);
-    int32_t n_cross = 0, n_cross_values = 0;
+    std::vector<int32_t> bcross(nops, -1);  // pipeline form: row of the pass-boundary buffer instead (value read in a later pass)
+    int32_t n_cross = 0, n_cross_values = 0, n_boundary = 0;
     {
         std::vector<int32_t> last_seg(nops, -1);
         for (size_t i = 0; i < nops; ++i) {
@@ -705,11 +728,31 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
             if (o.a >= 0 && seg_of(o.a) != sg) last_seg[(size_t)o.a] = sg;
             if (is_binary(o) && o.b >= 0 && seg_of(o.b) != sg) last_seg[(size_t)o.b] = sg;
         }
+        const int spp = pipe ? pipe_stages_per_pass : nseg + 1;  // stages per pass (classic: everything is one "pass")
         std::vector<std::vector<int32_t>> expire((size_t)nseg + 1);  // rows that become free after segment s
-        std::vector<int32_t> free_rows;
+        std::vector<std::vector<int32_t>> bexpire((size_t)nseg / (size_t)spp + 2);  // boundary rows free after pass p
+        std::vector<int32_t> free_rows, bfree_rows;
         for (int sg = 0; sg < nseg; ++sg) {
+            if (pipe && sg % spp == 0) {
+                // a new pass: the ring rows start afresh, boundary rows whose last reader was an earlier pass are free
+                if (sg > 0)
+                    for (const int32_t row : bexpire[(size_t)(sg / spp - 1)]) bfree_rows.push_back(row);
+            }
             for (int32_t i = seg_start[(size_t)sg]; i < seg_start[(size_t)sg + 1]; ++i) {
                 if (last_seg[(size_t)i] < 0) continue;
+                ++n_cross_values;
+                if (pipe && last_seg[(size_t)i] / spp != sg / spp) {
+                    int32_t row;
+                    if (!bfree_rows.empty()) {
+                        row = bfree_rows.back();
+                        bfree_rows.pop_back();
+                    } else {
+                        row = n_boundary++;
+                    }
+                    bcross[(size_t)i] = row;
+                    bexpire[(size_t)(last_seg[(size_t)i] / spp)].push_back(row);
+                    continue;
+                }
                 int32_t row;
                 if (!free_rows.empty()) {
                     row = free_rows.back();
@@ -718,13 +761,13 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
                     row = n_cross++;
                 }
                 cross[(size_t)i] = row;
-                ++n_cross_values;
                 expire[(size_t)last_seg[(size_t)i]].push_back(row);
             }
             // rows whose last reader is THIS segment are free for values defined in later segments only
             for (const int32_t row : expire[(size_t)sg]) free_rows.push_back(row);
         }
     }
+    plan.n_boundary = n_boundary;
     plan.n_cross_values = n_cross_values;
     plan.n_cross = n_cross;
     plan.seg.resize((size_t)nseg);
@@ -764,7 +807,8 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
                     }
                 } else if ((size_t)a < lo && !seen_cross.count(a)) {
                     seen_cross.emplace(a, 1);
-                    in_rows.emplace_back(1, cross[(size_t)a]);
+                    if (bcross[(size_t)a] >= 0) in_rows.emplace_back(2, bcross[(size_t)a]);
+                    else in_rows.emplace_back(1, cross[(size_t)a]);
                 }
             };
             for (size_t i = lo; i < hi; ++i) {
@@ -794,7 +838,7 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         auto ring_issue = [&](std::ostringstream &o2, int j) {  // copy of input row j into its slot
             const auto &row = in_rows[(size_t)j];
             const int a = e.nrd++;
-            e.row_addr(o2, a, row.first ? "%rd3" : "%rd1", row.first ? "%rd4" : "%rd2", row.second);
+            e.row_addr(o2, a, row.first == 2 ? "%rd9" : (row.first ? "%rd3" : "%rd1"), row.first == 2 ? "%rd11" : (row.first ? "%rd4" : "%rd2"), row.second);
             o2 << "\tcp.async." << (ES == 16 ? "cg" : "ca") << ".shared.global [%r12+" << (j % NR) * T * ES << "], [%rd" << a << "], " << ES << ";\n";
         };
         auto ring_load = [&](int kind_, int32_t row_) -> int {
@@ -829,7 +873,8 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
             if ((size_t)a >= lo) return reg_of[(size_t)a - lo];
             auto it = cross_reg.find(a);
             if (it != cross_reg.end()) return it->second;
-            const int r = ring ? ring_load(1, cross[(size_t)a]) : e.load("ld.global", "%rd3", "%rd4", cross[(size_t)a]);
+            const int r = ring ? ring_load(1, cross[(size_t)a])
+                               : (bcross[(size_t)a] >= 0 ? e.load("ld.global", "%rd9", "%rd11", bcross[(size_t)a]) : e.load("ld.global", "%rd3", "%rd4", cross[(size_t)a]));
             plan.cross_loads++;
             cross_reg.emplace(a, r);
             return r;
@@ -871,10 +916,11 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
                 default: e.root_out(operand(o.a), o.n); break;
             }
             reg_of[i - lo] = r;
-            if (r >= 0 && cross[i] >= 0) {
+            if (r >= 0 && (cross[i] >= 0 || bcross[i] >= 0)) {
                 plan.cross_stores++;
                 const int a = e.nrd++;
-                e.row_addr(os, a, "%rd3", "%rd4", cross[i]);
+                if (bcross[i] >= 0) e.row_addr(os, a, "%rd9", "%rd11", bcross[i]);
+                else e.row_addr(os, a, "%rd3", "%rd4", cross[i]);
                 if (spt == 2)
                     os << "\tst.global.v2.f64 [%rd" << a << "], {" << e.fd(r, 0) << ", " << e.fd(r, 1) << "};\n";
                 else
@@ -912,7 +958,7 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
             // %rd20 = tile of this warp (the only value that lives across tiles besides what ptxas keeps of the setup)
             p << "\tmov.u32 %r2, %tid.x;\n\tand.b32 %r3, %r2, 31;\n\tsetp.eq.u32 %p3, %r3, 0;\n"
               << "\tmov.u32 %r0, %ctaid.x;\n\tshr.u32 %r5, %r2, 5;\n"
-              << "\tld.volatile.shared.u32 %r15, [fdg_ring+96];\n\tsub.u32 %r6, %r0, %r15;\n\tmad.lo.u32 %r6, %r6, " << wpb << ", %r5;\n"
+              << "\tld.volatile.shared.u32 %r15, [fdg_ring+96];\n\tmad.lo.u32 %r6, %r15, " << wpb << ", %r5;\n"
               << "\tcvt.u64.u32 %rd20, %r6;\n"
               << "\tmov.u64 %rd21, %clock64;\n\tshl.b32 %r7, %r5, 3;\n\tmov.u32 %r15, fdg_ring;\n\tadd.u32 %r7, %r7, %r15;\n"
               << "\tst.volatile.shared.u64 [%r7+128], %rd21;\n";
@@ -928,15 +974,20 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
               << "\tld.volatile.shared.u64 %rd16, [fdg_ring+56];\n\tld.volatile.shared.u64 %rd19, [fdg_ring+72];\n"
               << "\tmov.u64 %rd21, %clock64;\n";
             // ---- wait for the tile ----
-            if (sg == 0) {
+            // The first stage of a pass waits until the tile that used its ring slot `window` tiles ago has passed every stage
+            // of the pass (the tile itself is ready: the previous pass is a previous kernel); the others wait for the stage
+            // before them.  Polling is a relaxed load; the fence after it orders everything that follows.
+            const int spp = pipe_stages_per_pass;
+            const bool first_of_pass = sg % spp == 0;
+            if (first_of_pass) {
                 p << "\tsetp.lt.u64 %p6, %rd20, %rd19;\n\t@%p6 bra FDG_GO;\n"
                   << "\tsub.u64 %rd22, %rd20, %rd19;\n\tshl.b64 %rd22, %rd22, 2;\n\tadd.u64 %rd22, %rd16, %rd22;\n";
             } else {
                 p << "\tshl.b64 %rd22, %rd20, 2;\n\tadd.u64 %rd22, %rd16, %rd22;\n";
             }
-            const int want = sg == 0 ? nseg : sg;
+            const int want = first_of_pass ? std::min(nseg, (sg / spp + 1) * spp) : sg;
             p << "\tmov.u64 %rd23, %globaltimer;\n"
-              << "FDG_WAIT:\n\tld.acquire.gpu.global.u32 %r15, [%rd22];\n\tsetp.ge.u32 %p7, %r15, " << want << ";\n\t@%p7 bra FDG_GO;\n"
+              << "FDG_WAIT:\n\tld.relaxed.gpu.global.u32 %r15, [%rd22];\n\tsetp.ge.u32 %p7, %r15, " << want << ";\n\t@%p7 bra FDG_GO;\n"
               << "\tnanosleep.u32 64;\n\tmov.u64 %rd30, %globaltimer;\n\tsub.u64 %rd30, %rd30, %rd23;\n"
               << "\tsetp.gt.u64 %p7, %rd30, 4000000000;\n\t@!%p7 bra FDG_WAIT;\n"
               // a stalled pipeline ends instead of hanging: flag it and leave
@@ -952,6 +1003,9 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
               << "\tld.volatile.shared.u64 %rd2, [fdg_ring+8];\n\tld.volatile.shared.u64 %rd4, [fdg_ring+24];\n"
               << "\tcvt.u32.u64 %r13, %rd2;\n\tcvt.u32.u64 %r14, %rd4;\n"
               << "\tld.volatile.shared.u64 %rd14, [fdg_ring+32];\n";
+            if (n_boundary > 0)
+                p << "\tshl.b64 %rd13, %rd0, " << esh << ";\n\tld.volatile.shared.u64 %rd9, [fdg_ring+104];\n\tadd.u64 %rd9, %rd9, %rd13;\n"
+                  << "\tld.volatile.shared.u64 %rd11, [fdg_ring+112];\n\tcvt.u32.u64 %r20, %rd11;\n";
             if (n_cross > 0)
                 p << "\trem.u64 %rd24, %rd20, %rd19;\n\tshl.b64 %rd13, %rd24, 5;\n\tadd.u64 %rd13, %rd13, %rd25;\n\tshl.b64 %rd13, %rd13, " << esh << ";\n"
                   << "\tld.volatile.shared.u64 %rd3, [fdg_ring+16];\n\tadd.u64 %rd3, %rd3, %rd13;\n";
@@ -1091,72 +1145,56 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         js.ptx = p.str();
     }
     if (pipe) {
-        // ---- SMs per stage: proportional to the estimated time of one tile, every stage at least one -----------------
-        const int S = nseg;
-        plan.n_sm = pipe->n_sm;
+        const int S = nseg, spp = pipe_stages_per_pass;
+        plan.n_sm = pipe->n_sm();
+        plan.n_pass = (S + spp - 1) / spp;
+        plan.stages_per_pass = spp;
         plan.ring_bytes = ring_bytes_max;
-        if (S > pipe->n_sm) {
-            err = "more pipeline stages than SMs";
-            return FDG_ERR_CAPACITY;
-        }
-        double total = 0;
-        for (const int64_t c : plan.stage_cost) total += (double)c;
-        plan.stage_blocks.assign((size_t)S, 1);
-        int left = pipe->n_sm - S;
-        std::vector<std::pair<double, int>> frac;
-        for (int k = 0; k < S; ++k) {
-            const double want = (double)plan.stage_cost[(size_t)k] / total * (double)pipe->n_sm;
-            const int extra = std::max(0, std::min(left, (int)want - 1));
-            plan.stage_blocks[(size_t)k] += extra;
-            left -= extra;
-            frac.emplace_back(want - (double)plan.stage_blocks[(size_t)k], k);
-        }
-        std::sort(frac.begin(), frac.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) { return a.first > b.first; });
-        for (int i = 0; left > 0; i = (i + 1) % S, --left) plan.stage_blocks[(size_t)frac[(size_t)i].second] += 1;
-        // ---- the entry kernel: the launch arguments go to shared memory, then block index -> stage --------------------
-        std::ostringstream d;
-        d << ".version 8.7\n.target sm_100a\n.address_size 64\n\n.extern .shared .align 16 .b8 fdg_ring[];\n";
-        for (int k = 0; k < S; ++k) d << ".extern .func fdg_stage" << k << "();\n";
-        d << ".visible .entry fdg_pipe(\n"
-          << "\t.param .u64 p_leaf, .param .u64 p_ld_leaf, .param .u64 p_cross, .param .u64 p_ld_cross,\n"
-          << "\t.param .u64 p_out, .param .u64 p_ld_root, .param .u64 p_batch, .param .u64 p_nroots,\n"
-          << "\t.param .u64 p_progress, .param .u64 p_ntiles, .param .u64 p_window, .param .u64 p_stats)\n"
-          << ".maxntid " << pipe->threads << ", 1, 1\n{\n"
-          << "\t.reg .b64 %rd<20>;\n\t.reg .b32 %r<8>;\n\t.reg .pred %p<2>;\n"
-          << "\tld.param.u64 %rd0, [p_leaf];\n\tcvta.to.global.u64 %rd0, %rd0;\n\tld.param.u64 %rd1, [p_ld_leaf];\n\tshl.b64 %rd1, %rd1, " << esh << ";\n"
-          << "\tld.param.u64 %rd2, [p_cross];\n\tcvta.to.global.u64 %rd2, %rd2;\n\tld.param.u64 %rd3, [p_ld_cross];\n\tshl.b64 %rd3, %rd3, " << esh << ";\n"
-          << "\tld.param.u64 %rd4, [p_out];\n\tcvta.to.global.u64 %rd4, %rd4;\n";
-        if (acc) d << "\tld.param.u64 %rd5, [p_nroots];\n";
-        else d << "\tld.param.u64 %rd5, [p_ld_root];\n\tshl.b64 %rd5, %rd5, " << esh << ";\n";
-        d << "\tld.param.u64 %rd6, [p_batch];\n"
-          << "\tld.param.u64 %rd8, [p_progress];\n\tcvta.to.global.u64 %rd8, %rd8;\n\tld.param.u64 %rd9, [p_ntiles];\n"
-          << "\tld.param.u64 %rd10, [p_window];\n\tld.param.u64 %rd11, [p_stats];\n\tcvta.to.global.u64 %rd11, %rd11;\n"
-          << "\tmov.u32 %r0, %ctaid.x;\n\tmov.u32 %r1, %tid.x;\n\tsetp.eq.u32 %p1, %r1, 0;\n";
-        int first = 0;
-        for (int k = 0; k < S; ++k) {
-            const int nb = plan.stage_blocks[(size_t)k];
-            if (k + 1 < S) d << "\tsetp.lt.u32 %p0, %r0, " << first + nb << ";\n\t@%p0 bra FDG_S" << k << ";\n";
-            else d << "\tbra FDG_S" << k << ";\n";
-            first += nb;
-        }
-        first = 0;
-        for (int k = 0; k < S; ++k) {
-            const int nb = plan.stage_blocks[(size_t)k];
-            d << "FDG_S" << k << ":\n"
-              << "\tmov.u64 %rd12, " << nb * (pipe->threads / 32) << ";\n\tmov.u32 %r2, " << first << ";\n\tbra FDG_ARGS" << k << ";\n";
-            first += nb;
-        }
-        for (int k = 0; k < S; ++k) {
-            d << "FDG_ARGS" << k << ":\n";
-            const int off[11] = {0, 8, 16, 24, 32, 40, 48, 56, 64, 72, 80};
-            const int src[11] = {0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11};
-            for (int q = 0; q < 11; ++q) d << "\t@%p1 st.volatile.shared.u64 [fdg_ring+" << off[q] << "], %rd" << src[q] << ";\n";
+        plan.stage_blocks.assign((size_t)S, 0);
+        for (int k = 0; k < S; ++k) plan.stage_blocks[(size_t)k] = pipe_stage_sms[(size_t)(k % spp)];
+        // ---- the entry kernel of each pass: the launch arguments go to shared memory, then SM -> stage ------------------
+        // Which stage a block runs is looked up by the SM it landed on (p_smtab[smid] = stage of the pass, index of the block
+        // within the stage, blocks of the stage): SMs that share an instruction cache run the same stage, and only the host
+        // knows which SMs those are (fdg_capi.cu).
+        plan.dispatch_ptx.clear();
+        for (int ps = 0; ps < plan.n_pass; ++ps) {
+            const int k0 = ps * spp, k1 = std::min(S, k0 + spp);
+            std::ostringstream d;
+            d << ".version 8.7\n.target sm_100a\n.address_size 64\n\n.extern .shared .align 16 .b8 fdg_ring[];\n";
+            for (int k = k0; k < k1; ++k) d << ".extern .func fdg_stage" << k << "();\n";
+            d << ".visible .entry fdg_pipe" << ps << "(\n"
+              << "\t.param .u64 p_leaf, .param .u64 p_ld_leaf, .param .u64 p_cross, .param .u64 p_ld_cross,\n"
+              << "\t.param .u64 p_out, .param .u64 p_ld_root, .param .u64 p_batch, .param .u64 p_nroots,\n"
+              << "\t.param .u64 p_progress, .param .u64 p_ntiles, .param .u64 p_window, .param .u64 p_stats, .param .u64 p_smtab,\n"
+              << "\t.param .u64 p_boundary, .param .u64 p_ld_boundary)\n"
+              << ".maxntid " << pipe->threads << ", 1, 1\n{\n"
+              << "\t.reg .b64 %rd<20>;\n\t.reg .b32 %r<8>;\n\t.reg .pred %p<2>;\n"
+              << "\tld.param.u64 %rd0, [p_leaf];\n\tcvta.to.global.u64 %rd0, %rd0;\n\tld.param.u64 %rd1, [p_ld_leaf];\n\tshl.b64 %rd1, %rd1, " << esh << ";\n"
+              << "\tld.param.u64 %rd2, [p_cross];\n\tcvta.to.global.u64 %rd2, %rd2;\n\tld.param.u64 %rd3, [p_ld_cross];\n\tshl.b64 %rd3, %rd3, " << esh << ";\n"
+              << "\tld.param.u64 %rd4, [p_out];\n\tcvta.to.global.u64 %rd4, %rd4;\n";
+            if (acc) d << "\tld.param.u64 %rd5, [p_nroots];\n";
+            else d << "\tld.param.u64 %rd5, [p_ld_root];\n\tshl.b64 %rd5, %rd5, " << esh << ";\n";
+            d << "\tld.param.u64 %rd6, [p_batch];\n"
+              << "\tld.param.u64 %rd8, [p_progress];\n\tcvta.to.global.u64 %rd8, %rd8;\n\tld.param.u64 %rd9, [p_ntiles];\n"
+              << "\tld.param.u64 %rd10, [p_window];\n\tld.param.u64 %rd11, [p_stats];\n\tcvta.to.global.u64 %rd11, %rd11;\n"
+              << "\tld.param.u64 %rd15, [p_boundary];\n\tcvta.to.global.u64 %rd15, %rd15;\n\tld.param.u64 %rd16, [p_ld_boundary];\n\tshl.b64 %rd16, %rd16, " << esh << ";\n"
+              << "\tmov.u32 %r1, %tid.x;\n\tsetp.eq.u32 %p1, %r1, 0;\n"
+              << "\tld.param.u64 %rd13, [p_smtab];\n\tcvta.to.global.u64 %rd13, %rd13;\n\tmov.u32 %r0, %smid;\n"
+              << "\tmul.wide.u32 %rd14, %r0, 16;\n\tadd.u64 %rd13, %rd13, %rd14;\n"
+              << "\tld.global.v4.u32 {%r3, %r2, %r4, %r5}, [%rd13];\n"  // stage of the pass, index within the stage, blocks of the stage
+              << "\tmul.lo.u32 %r4, %r4, " << pipe->threads / 32 << ";\n\tcvt.u64.u32 %rd12, %r4;\n";  // warps of the stage
+            const int off[13] = {0, 8, 16, 24, 32, 40, 48, 56, 64, 72, 80, 104, 112};
+            const int src[13] = {0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11, 15, 16};
+            for (int q = 0; q < 13; ++q) d << "\t@%p1 st.volatile.shared.u64 [fdg_ring+" << off[q] << "], %rd" << src[q] << ";\n";
             d << "\t@%p1 st.volatile.shared.u64 [fdg_ring+88], %rd12;\n\t@%p1 st.volatile.shared.u32 [fdg_ring+96], %r2;\n"
-              << "\tbar.sync 0;\n"
-              << "\tcall.uni fdg_stage" << k << ", ();\n\tret;\n";
+              << "\tbar.sync 0;\n";
+            for (int k = k0; k < k1; ++k) d << "\tsetp.eq.u32 %p0, %r3, " << k - k0 << ";\n\t@%p0 bra FDG_S" << k << ";\n";
+            // an SM the table does not know: flag the launch as stalled and leave (the other blocks give up after their time limit)
+            d << "\tmov.u32 %r6, 1;\n\t@%p1 st.global.u32 [%rd11], %r6;\n\tret;\n";
+            for (int k = k0; k < k1; ++k) d << "FDG_S" << k << ":\n\tcall.uni fdg_stage" << k << ", ();\n\tret;\n";
+            d << "}\n";
+            plan.dispatch_ptx.push_back(d.str());
         }
-        d << "}\n";
-        plan.dispatch_ptx = d.str();
     }
     (void)err;
     return FDG_OK;
@@ -1200,6 +1238,30 @@ static int compile_one(JitSegment &js, bool fma, std::string &err, bool relocata
         nvPTXCompilerGetInfoLog(h, &js.info[0]);
         js.info.resize(std::strlen(js.info.c_str()));
     }
+    nvPTXCompilerDestroy(&h);
+    return FDG_OK;
+}
+
+int jit_assemble(const std::string &ptx, int opt_level, std::vector<char> &cubin, std::string &err) {
+    nvPTXCompilerHandle h = nullptr;
+    if (nvPTXCompilerCreate(&h, ptx.size(), ptx.c_str()) != NVPTXCOMPILE_SUCCESS) {
+        err = "nvPTXCompilerCreate failed";
+        return FDG_ERR_UNSUPPORTED;
+    }
+    const std::string ol = "--opt-level=" + std::to_string(opt_level);
+    const char *opts[] = {"--gpu-name=sm_100a", ol.c_str()};
+    size_t n = 0;
+    if (nvPTXCompilerCompile(h, 2, opts) != NVPTXCOMPILE_SUCCESS) {
+        nvPTXCompilerGetErrorLogSize(h, &n);
+        std::string log(n + 1, '\0');
+        if (n) nvPTXCompilerGetErrorLog(h, &log[0]);
+        err = std::string("ptxas failed: ") + log.c_str();
+        nvPTXCompilerDestroy(&h);
+        return FDG_ERR_UNSUPPORTED;
+    }
+    nvPTXCompilerGetCompiledProgramSize(h, &n);
+    cubin.resize(n);
+    nvPTXCompilerGetCompiledProgram(h, cubin.data());
     nvPTXCompilerDestroy(&h);
     return FDG_OK;
 }
@@ -1252,41 +1314,48 @@ int jit_compile(JitPlan &plan, std::string &err) {
     plan.max_code_bytes = 0;
     for (auto &sg : plan.seg) plan.max_code_bytes = std::max<int64_t>(plan.max_code_bytes, (int64_t)text_bytes(sg.cubin));
     if (plan.pipeline) {
-        // the stage functions were assembled as relocatable objects; the entry kernel joins them (device link, no GPU needed)
-        JitSegment entry;
-        entry.name = "fdg_pipe";
-        entry.ptx = plan.dispatch_ptx;
-        int rc = compile_one(entry, plan.fma, err, true);
-        if (rc != FDG_OK) return rc;
-        nvJitLinkHandle lh = nullptr;
-        const char *lopts[] = {"-arch=sm_100a"};
-        if (nvJitLinkCreate(&lh, 1, lopts) != NVJITLINK_SUCCESS) {
-            err = "nvJitLinkCreate failed";
-            return FDG_ERR_UNSUPPORTED;
-        }
-        bool ok = nvJitLinkAddData(lh, NVJITLINK_INPUT_CUBIN, entry.cubin.data(), entry.cubin.size(), "fdg_pipe") == NVJITLINK_SUCCESS;
-        for (auto &sg : plan.seg)
-            ok = ok && nvJitLinkAddData(lh, NVJITLINK_INPUT_CUBIN, sg.cubin.data(), sg.cubin.size(), sg.name.c_str()) == NVJITLINK_SUCCESS;
-        ok = ok && nvJitLinkComplete(lh) == NVJITLINK_SUCCESS;
-        if (!ok) {
-            size_t ln = 0;
-            nvJitLinkGetErrorLogSize(lh, &ln);
-            std::string log(ln + 1, '\0');
-            if (ln) nvJitLinkGetErrorLog(lh, &log[0]);
-            err = std::string("device link of the pipeline kernel failed: ") + log.c_str();
+        // the stage functions were assembled as relocatable objects; the entry kernel of a pass joins the stages of that pass
+        // (device link, no GPU needed)
+        plan.linked.clear();
+        for (int ps = 0; ps < plan.n_pass; ++ps) {
+            JitSegment entry;
+            entry.name = "fdg_pipe" + std::to_string(ps);
+            entry.ptx = plan.dispatch_ptx[(size_t)ps];
+            int rc = compile_one(entry, plan.fma, err, true);
+            if (rc != FDG_OK) return rc;
+            nvJitLinkHandle lh = nullptr;
+            const char *lopts[] = {"-arch=sm_100a"};
+            if (nvJitLinkCreate(&lh, 1, lopts) != NVJITLINK_SUCCESS) {
+                err = "nvJitLinkCreate failed";
+                return FDG_ERR_UNSUPPORTED;
+            }
+            bool ok = nvJitLinkAddData(lh, NVJITLINK_INPUT_CUBIN, entry.cubin.data(), entry.cubin.size(), entry.name.c_str()) == NVJITLINK_SUCCESS;
+            const int k0 = ps * plan.stages_per_pass, k1 = std::min<int>((int)plan.seg.size(), k0 + plan.stages_per_pass);
+            for (int k = k0; k < k1; ++k) {
+                auto &sg = plan.seg[(size_t)k];
+                ok = ok && nvJitLinkAddData(lh, NVJITLINK_INPUT_CUBIN, sg.cubin.data(), sg.cubin.size(), sg.name.c_str()) == NVJITLINK_SUCCESS;
+            }
+            ok = ok && nvJitLinkComplete(lh) == NVJITLINK_SUCCESS;
+            if (!ok) {
+                size_t ln = 0;
+                nvJitLinkGetErrorLogSize(lh, &ln);
+                std::string log(ln + 1, '\0');
+                if (ln) nvJitLinkGetErrorLog(lh, &log[0]);
+                err = std::string("device link of the pipeline kernel failed: ") + log.c_str();
+                nvJitLinkDestroy(&lh);
+                return FDG_ERR_UNSUPPORTED;
+            }
+            size_t nbytes = 0;
+            nvJitLinkGetLinkedCubinSize(lh, &nbytes);
+            plan.linked.emplace_back(nbytes);
+            nvJitLinkGetLinkedCubin(lh, plan.linked.back().data());
             nvJitLinkDestroy(&lh);
-            return FDG_ERR_UNSUPPORTED;
-        }
-        size_t nbytes = 0;
-        nvJitLinkGetLinkedCubinSize(lh, &nbytes);
-        plan.linked.resize(nbytes);
-        nvJitLinkGetLinkedCubin(lh, plan.linked.data());
-        nvJitLinkDestroy(&lh);
-        if (const char *dir = getenv("FDG_JIT_DUMP_CUBIN")) {
-            const std::string path = std::string(dir) + "/fdg_pipe.cubin";
-            if (FILE *fp = std::fopen(path.c_str(), "wb")) {
-                std::fwrite(plan.linked.data(), 1, plan.linked.size(), fp);
-                std::fclose(fp);
+            if (const char *dir = getenv("FDG_JIT_DUMP_CUBIN")) {
+                const std::string path = std::string(dir) + "/" + entry.name + ".cubin";
+                if (FILE *fp = std::fopen(path.c_str(), "wb")) {
+                    std::fwrite(plan.linked.back().data(), 1, plan.linked.back().size(), fp);
+                    std::fclose(fp);
+                }
             }
         }
     }
