@@ -228,6 +228,9 @@ def pipeline_prepare(h, accumulate: bool = True, n_sm: int = 148) -> dict:
     info["stage_blocks"] = [int(x) for x in buf]
     check(lib().fdg_pipeline_prepare(h, int(accumulate), n_sm, 2, buf, n))
     info["stage_cost"] = [int(x) for x in buf]
+    buf2 = (C.c_int64 * (n + 1))()
+    check(lib().fdg_pipeline_prepare(h, int(accumulate), n_sm, 3, buf2, n + 1))
+    info["stage_start"] = [int(x) for x in buf2]
     return info
 
 

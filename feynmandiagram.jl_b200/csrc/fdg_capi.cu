@@ -9,6 +9,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/fdgraph.h"
@@ -204,6 +205,20 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
         if (const char *e = getenv("FDG_PIPE_THREADS")) po.threads = std::max(32, std::min(256, atoi(e) / 32 * 32));
         int budget = h->jit_segment > 0 ? h->jit_segment : 4800;
         if (const char *e = getenv("FDG_PIPE_BUDGET")) budget = std::max(64, atoi(e));
+        // profile-guided re-cut (experiments): "start0,start1,...,startS" and "w0,...,w(S-1)" of a previous plan
+        auto parse = [](const char *txt, auto &out) {
+            std::string t(txt);
+            size_t pos = 0;
+            while (pos < t.size()) {
+                size_t q = t.find(',', pos);
+                if (q == std::string::npos) q = t.size();
+                out.push_back((typename std::remove_reference<decltype(out)>::type::value_type)atof(t.substr(pos, q - pos).c_str()));
+                pos = q + 1;
+            }
+        };
+        if (const char *e = getenv("FDG_PIPE_PREV")) parse(e, po.prev_start);
+        if (const char *e = getenv("FDG_PIPE_MEASURED")) parse(e, po.measured);
+        if (po.prev_start.size() != po.measured.size() + 1) po.prev_start.clear(), po.measured.clear();
         int rc = fdg::jit_plan(h->low, spt, acc, budget, wide, h->fma, v.plan, err, &po);
         if (rc == FDG_OK) rc = fdg::jit_compile(v.plan, err);
         if (rc != FDG_OK) {
@@ -875,6 +890,8 @@ int fdg_pipeline_prepare(fdg_handle h, int32_t accumulate, int32_t n_sm, int32_t
         vals.assign(pl.stage_blocks.begin(), pl.stage_blocks.end());
     } else if (what == 2) {
         vals.assign(pl.stage_cost.begin(), pl.stage_cost.end());
+    } else if (what == 3) {
+        vals.assign(pl.stage_start.begin(), pl.stage_start.end());
     } else {
         return fail(FDG_ERR_BAD_ARG, "unknown query");
     }

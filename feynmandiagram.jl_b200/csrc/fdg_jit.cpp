@@ -487,6 +487,40 @@ static void build_ir(const Lowered &low, std::vector<IrOp> &ir) {
 static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt, bool acc, int seg_ops, bool wide_strides, bool fma,
                         JitPlan &plan, std::string &err, const PipeOptions *pipe);
 
+// prefix sums of the per-operation instruction estimate (pipeline form: in 1/16 instructions, stretched by the stage weights)
+static void plan_costs(const Lowered &low, const std::vector<IrOp> &ir, int spt, bool acc, const PipeOptions *pipe, std::vector<int64_t> &cost) {
+    const bool cplx = low.dtype == FDG_C128;
+    const int W = cplx ? 2 : 1;
+    const int S = cplx ? 1 : spt;
+    const size_t nops = ir.size();
+    cost.assign(nops + 1, 0);
+    for (size_t i = 0; i < nops; ++i) {
+        const IrOp &o = ir[i];
+        int64_t w = 0;
+        switch (o.kind) {
+            case IR_MUL: w = cplx ? 6 : S; break;
+            case IR_ADD:
+            case IR_SCALE: w = cplx ? 2 : S; break;
+            case IR_NEG: w = 0; break;
+            case IR_POW: {
+                int lg = 0;
+                while ((1 << (lg + 1)) <= o.n) ++lg;
+                w = o.n <= 3 ? (o.n - 1) * (cplx ? 6 : S) : (cplx ? 12 * lg : 14 * lg * S);
+            } break;
+            default: w = acc ? (pipe ? 4 * W : 28 * W) : 2; break;  // a root: warp reduction + partial-row update, or a store
+        }
+        if (pipe) {
+            double sc = 16.0;
+            if (!pipe->weight.empty() && pipe->prev_start.size() == pipe->weight.size() + 1) {
+                const size_t k = (size_t)(std::upper_bound(pipe->prev_start.begin(), pipe->prev_start.end(), (int32_t)i) - pipe->prev_start.begin());
+                if (k >= 1 && k <= pipe->weight.size()) sc *= std::max(0.25, std::min(4.0, pipe->weight[k - 1]));
+            }
+            w = (int64_t)((double)w * sc + 0.5);
+        }
+        cost[i + 1] = cost[i] + w;
+    }
+}
+
 int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strides, bool fma, JitPlan &plan, std::string &err,
              const PipeOptions *pipe) {
     std::vector<IrOp> ir;
@@ -506,6 +540,22 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
     // plan is made, the stages are re-weighted with (cost of the written code) / (estimate), and the cuts are placed again.
     PipeOptions po = *pipe;
     int rc = FDG_OK;
+    if (!po.measured.empty() && po.prev_start.size() == po.measured.size() + 1) {
+        // weights from a profile: (share of the measured time) / (share of the estimate) of every stage of the previous plan
+        PipeOptions plain = *pipe;
+        plain.weight.clear();
+        plain.prev_start.clear();
+        plain.measured.clear();
+        std::vector<int64_t> c;
+        plan_costs(low, ir, spt, acc, &plain, c);
+        double sum_m = 0, sum_c = (double)std::max<int64_t>(c.back(), 1);
+        for (const double m : po.measured) sum_m += m;
+        po.weight.assign(po.measured.size(), 1.0);
+        for (size_t k = 0; k < po.measured.size(); ++k) {
+            const double ck = (double)(c[(size_t)po.prev_start[k + 1]] - c[(size_t)po.prev_start[k]]);
+            if (ck > 0 && sum_m > 0) po.weight[k] = (po.measured[k] / sum_m) / (ck / sum_c);
+        }
+    }
     JitPlan best;
     double best_load = 1e30;
     // time of all passes (each as slow as its slowest stage) relative to a perfect split of the work over all SMs
@@ -529,7 +579,8 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
         if (better) best_load = load;
         plan = cand;
         if (better) best = std::move(cand);
-        if (iter == 5 || plan.seg.size() < 2 || best_load < 1.02) break;
+        // measured weights (a profile of a previous plan) are used as given: the model must not pull them back
+        if (iter == 5 || plan.seg.size() < 2 || best_load < 1.02 || !pipe->weight.empty() || !pipe->measured.empty()) break;
         // estimated cost of each stage as the cuts saw it (already weighted) vs. the cost of the code
         std::vector<double> w(plan.seg.size());
         double worst = 0;
@@ -601,36 +652,8 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         if (is_binary(o) && o.b >= 0) last_use[(size_t)o.b] = (int32_t)i;
     }
     std::vector<int32_t> seg_start{0};
-    std::vector<int64_t> cost(nops + 1, 0);  // prefix sums of the instruction estimate
-    {
-        const int S = samples_per_thread;
-        for (size_t i = 0; i < nops; ++i) {
-            const IrOp &o = ir[i];
-            int64_t w = 0;
-            switch (o.kind) {
-                case IR_MUL: w = cplx ? 6 : S; break;
-                case IR_ADD:
-                case IR_SCALE: w = cplx ? 2 : S; break;
-                case IR_NEG: w = 0; break;
-                case IR_POW: {
-                    int lg = 0;
-                    while ((1 << (lg + 1)) <= o.n) ++lg;
-                    w = o.n <= 3 ? (o.n - 1) * (cplx ? 6 : S) : (cplx ? 12 * lg : 14 * lg * S);
-                } break;
-                default: w = acc ? 28 * W : 2; break;  // a root: warp reduction + partial-row update, or a store
-            }
-            if (pipe) {
-                // finer units (1/16 instruction) so that measured stage weights can stretch the cost axis
-                double sc = 16.0;
-                if (!pipe->weight.empty() && pipe->prev_start.size() == pipe->weight.size() + 1) {
-                    const size_t k = (size_t)(std::upper_bound(pipe->prev_start.begin(), pipe->prev_start.end(), (int32_t)i) - pipe->prev_start.begin());
-                    if (k >= 1 && k <= pipe->weight.size()) sc *= std::max(0.25, std::min(4.0, pipe->weight[k - 1]));
-                }
-                w = (int64_t)((double)w * sc + 0.5);
-            }
-            cost[i + 1] = cost[i] + w;
-        }
-    }
+    std::vector<int64_t> cost;  // prefix sums of the instruction estimate
+    plan_costs(low, ir, spt, acc, pipe, cost);
     if (pipe) seg_ops *= 16;
     int pipe_stages_per_pass = 1, pipe_n_pass = 1;
     std::vector<int> pipe_stage_sms;
@@ -826,7 +849,7 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         int NR = ring_rows > 0 ? ring_rows : (ES == 8 ? 32 : 24);
         const int T = pipe ? pipe->threads : 128;  // threads per block
         // static shared memory stops at 48 KB; the pipeline kernel asks for dynamic shared memory and may go deeper
-        NR = std::max(G, std::min(NR, (pipe ? 98304 : 49152) / (T * ES)) / G * G);
+        NR = std::max(G, std::min(NR, (pipe ? 131072 : 49152) / (T * ES)) / G * G);
         const bool ring = ring_on && !e.persistent && n_in > 0;
         const int sacc0 = 256 + (ring ? NR * T * ES : 0);  // pipeline form: where the running sums of the roots start
         if (pipe && acc) {

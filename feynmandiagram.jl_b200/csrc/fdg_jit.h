@@ -53,6 +53,8 @@ struct PipeOptions {
     // time per estimated cost of each of its stages; the cost of an operation is scaled by the weight of the stage it was in
     std::vector<int32_t> prev_start;
     std::vector<double> weight;
+    // ... or the measured time of each stage of that plan (any unit): the weights are then derived from it
+    std::vector<double> measured;
     int n_sm() const {
         int n = 0;
         for (const int g : groups) n += g;

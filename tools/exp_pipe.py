@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--check", type=int, default=1 << 16)
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--no-classic", action="store_true", help="skip the classic timing (profiling runs)")
+    ap.add_argument("--tune", type=int, default=0, help="rounds of profile-guided re-cutting")
     ap.add_argument("variants", nargs="*")
     a = ap.parse_args()
     raw = fd.RawGraph.load(os.path.join(ROOT, "workloads", a.workload + ".npz"))
@@ -115,6 +116,26 @@ def main():
             n_tiles = (B + 31) // 32
             print("   busy clocks per tile:", " ".join(f"{x / n_tiles:.0f}" for x in work), flush=True)
             print("   estimated issue cycles per tile:", " ".join(f"{x:.0f}" for x in est), flush=True)
+            # profile-guided re-cut: the measured busy time per estimated cost of every stage stretches the cost axis
+            for rnd in range(a.tune):
+                os.environ["FDG_PIPE_PREV"] = ",".join(str(x) for x in info["stage_start"])
+                os.environ["FDG_PIPE_MEASURED"] = ",".join(f"{x:.0f}" for x in work)
+                del f
+                f = fd.compile_raw(raw, dtype=npdt, backend=2, cse=bool(cse))
+                info2 = f.pipeline_prepare(True, sms)
+                if info2["stages"] != S:
+                    print("   (stage count changed; stop tuning)")
+                    break
+                acc, ms = run(f, f"   pipeline {var} tuned x{rnd + 1}")
+                st = f.pipeline_stats(stream, S)
+                alive = np.array(st["busy"], float)
+                wait = np.array(st["waiting"], float)
+                work = alive - wait
+                # the estimate the next weights refer to is the unweighted one of the new cuts
+                est = np.array(info2["stage_cost"], float)
+                info = info2
+                print("   waiting fraction per stage:", " ".join(f"{x:.2f}" for x in wait / np.maximum(alive, 1)), flush=True)
+                print("   busy clocks per tile:", " ".join(f"{x / n_tiles:.0f}" for x in work), flush=True)
             del f
         except Exception as ex:  # noqa: BLE001
             print(f"{var:60s} FAILED: {ex}", flush=True)
