@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -31,6 +32,19 @@ int cuda_fail(cudaError_t e, const char *what) {
         return fail(FDG_ERR_NO_DEVICE, std::string(what) + ": " + cudaGetErrorString(e) +
                                            " (libfdgraph has no CPU fallback; a CUDA device is required)");
     return fail(FDG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+// nothing may be thrown across the C ABI: every entry point that can allocate runs inside this
+template <class F>
+int guarded(F &&f) noexcept {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return fail(FDG_ERR_BAD_ARG, "out of memory");
+    } catch (const std::exception &e) {
+        return fail(FDG_ERR_BAD_ARG, std::string("internal error: ") + e.what());
+    } catch (...) {
+        return fail(FDG_ERR_BAD_ARG, "internal error");
+    }
 }
 #define CUDA_TRY(x)                                    \
     do {                                               \
@@ -91,8 +105,9 @@ struct fdg_program {
     int spt = 0;  // samples per thread: 0 auto
     int blocks_per_sm = 0;
     std::map<int, DeviceState> dev;
-    long long launches = 0;
+    std::atomic<long long> launches{0};
     std::mutex mu;
+    std::mutex host_mu;  // fdg_eval_host: its staging buffers and streams belong to one caller at a time
 };
 
 struct fdg_comm {
@@ -613,7 +628,12 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
         const int64_t want = atoll(e);
         if (want > 0 && v->plan.seg.size() > 1) sub = std::min<int64_t>(batch, std::max<int64_t>(per_block, want / per_block * per_block));
     }
-    sub = std::min<int64_t>(sub, ((int64_t)((1ull << 32) / es) - per_block) / per_block * per_block);  // ld_cross bytes < 4 GiB
+    // ld_cross bytes < 4 GiB (row offsets are 32-bit multiplies); a plan without a cross buffer has no such limit
+    if (v->plan.n_cross > 0) sub = std::min<int64_t>(sub, ((int64_t)((1ull << 32) / es) - per_block) / per_block * per_block);
+    if (const char *e = getenv("FDG_JIT_MAX_SUB")) {  // tests: force several launch sequences whatever the plan
+        const int64_t want = atoll(e);
+        if (want > 0) sub = std::min<int64_t>(sub, std::max<int64_t>(per_block, want / per_block * per_block));
+    }
     int64_t max_grid = (sub + per_block - 1) / per_block;
     if (v->plan.persistent) max_grid = std::min<int64_t>(max_grid, (int64_t)ds.sm_count * 16);
     const int64_t ld_cross = max_grid * per_block;
@@ -654,6 +674,14 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
             CUDA_TRY(cudaLaunchKernel((const void *)kern[sg], dim3(grid), dim3(T), args, 0, stream));
             h->launches++;
         }
+        if (acc && v->plan.persistent && low.R > 0 && b0 + sub < batch) {
+            // The grid-stride kernel STORES its warps' sums (the rows are not zeroed): with more launch sequences to come
+            // this one's rows -- exactly the rows its grid wrote -- are folded into the result before they are overwritten.
+            fdg::fdg_reduce_partials<<<(int)low.R * W, 256, 0, stream>>>(ss.partial, (long long)grid * (T / 32), (int)low.R * W, static_cast<double *>(root));
+            CUDA_TRY(cudaGetLastError());
+            h->launches++;
+        }
+        if (acc && v->plan.persistent) rows = (long long)grid * (T / 32);  // rows the last launch wrote
     }
     if (acc && low.R > 0) {
         fdg::fdg_reduce_partials<<<(int)low.R * W, 256, 0, stream>>>(ss.partial, rows, (int)low.R * W, static_cast<double *>(root));
@@ -742,7 +770,7 @@ extern "C" {
 int fdg_abi_version(void) { return FDG_ABI_VERSION; }
 const char *fdg_last_error(void) { return g_err.c_str(); }
 
-int fdg_compile(const fdg_graph_desc *graph, const fdg_options *opts, fdg_handle *out) {
+static int fdg_compile_impl(const fdg_graph_desc *graph, const fdg_options *opts, fdg_handle *out) {
     if (!graph || !out) return fail(FDG_ERR_BAD_ARG, "null argument");
     *out = nullptr;
     fdg_options o;
@@ -773,7 +801,7 @@ int fdg_compile(const fdg_graph_desc *graph, const fdg_options *opts, fdg_handle
     return FDG_OK;
 }
 
-int fdg_graph_write(const fdg_graph_desc *g, const char *path) {
+static int fdg_graph_write_impl(const fdg_graph_desc *g, const char *path) {
     if (!g || !path) return fail(FDG_ERR_BAD_ARG, "null argument");
     if (g->n_nodes < 0 || g->n_edges < 0 || g->n_graphs < 0 || g->n_roots < 0) return fail(FDG_ERR_BAD_ARG, "negative size");
     FILE *fp = std::fopen(path, "wb");
@@ -795,7 +823,7 @@ int fdg_graph_write(const fdg_graph_desc *g, const char *path) {
     return ok ? FDG_OK : fail(FDG_ERR_BAD_ARG, std::string("writing ") + path + " failed");
 }
 
-int fdg_compile_file(const char *path, const fdg_options *opts, fdg_handle *out) {
+static int fdg_compile_file_impl(const char *path, const fdg_options *opts, fdg_handle *out) {
     if (!path || !out) return fail(FDG_ERR_BAD_ARG, "null argument");
     *out = nullptr;
     FILE *fp = std::fopen(path, "rb");
@@ -809,9 +837,28 @@ int fdg_compile_file(const char *path, const fdg_options *opts, fdg_handle *out)
         std::fclose(fp);
         return fail(FDG_ERR_BAD_GRAPH, std::string(path) + " is not an FDGRAPH file");
     }
-    std::vector<int64_t> node_id((size_t)hdr[0]), child_ptr((size_t)hdr[0] + 1), root_id((size_t)hdr[3]);
-    std::vector<int32_t> node_op((size_t)hdr[0]), node_pow((size_t)hdr[0]), child_node((size_t)hdr[1]), graphs((size_t)hdr[2]);
-    std::vector<double> child_factor((size_t)hdr[1]);
+    {
+        // the header must agree with the length of the file BEFORE anything is sized from it (a corrupt count would
+        // otherwise ask for gigabytes)
+        const long long want = 40 + hdr[0] * (8 + 4 + 4) + (hdr[0] + 1) * 8 + hdr[1] * (4 + 8) + hdr[2] * 4 + hdr[3] * 8;
+        long long have = -1;
+        if (std::fseek(fp, 0, SEEK_END) == 0) have = std::ftell(fp);
+        if (have != want || std::fseek(fp, 40, SEEK_SET) != 0) {
+            std::fclose(fp);
+            return fail(FDG_ERR_BAD_GRAPH, std::string(path) + " is truncated or has trailing bytes");
+        }
+    }
+    std::vector<int64_t> node_id, child_ptr, root_id;
+    std::vector<int32_t> node_op, node_pow, child_node, graphs;
+    std::vector<double> child_factor;
+    try {
+        node_id.resize((size_t)hdr[0]), child_ptr.resize((size_t)hdr[0] + 1), root_id.resize((size_t)hdr[3]);
+        node_op.resize((size_t)hdr[0]), node_pow.resize((size_t)hdr[0]), child_node.resize((size_t)hdr[1]), graphs.resize((size_t)hdr[2]);
+        child_factor.resize((size_t)hdr[1]);
+    } catch (const std::exception &) {
+        std::fclose(fp);
+        return fail(FDG_ERR_BAD_ARG, "out of memory reading " + std::string(path));
+    }
     auto get = [&](void *p, size_t size, size_t n) {
         if (ok && n > 0) ok = std::fread(p, size, n, fp) == n;
     };
@@ -833,7 +880,7 @@ int fdg_compile_file(const char *path, const fdg_options *opts, fdg_handle *out)
     return fdg_compile(&d, opts, out);
 }
 
-int fdg_jit_prepare(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t *n_kernels, int32_t *n_cross,
+static int fdg_jit_prepare_impl(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t *n_kernels, int32_t *n_cross,
                     int64_t *cubin_bytes) {
     if (!h) return fail(FDG_ERR_BAD_ARG, "null handle");
     if (samples_per_thread != 1 && samples_per_thread != 2) return fail(FDG_ERR_BAD_ARG, "samples_per_thread must be 1 or 2");
@@ -850,7 +897,7 @@ int fdg_jit_prepare(fdg_handle h, int32_t samples_per_thread, int32_t accumulate
     return FDG_OK;
 }
 
-int fdg_jit_info(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int64_t *out, int32_t n_out) {
+static int fdg_jit_info_impl(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int64_t *out, int32_t n_out) {
     if (!h || !out || n_out < 0) return fail(FDG_ERR_BAD_ARG, "null argument");
     std::lock_guard<std::mutex> lock(h->mu);
     auto it = h->jit.find(samples_per_thread * 2 + (accumulate ? 1 : 0));
@@ -864,7 +911,7 @@ int fdg_jit_info(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, i
     return FDG_OK;
 }
 
-int fdg_pipeline_prepare(fdg_handle h, int32_t accumulate, int32_t n_sm, int32_t what, int64_t *out, int32_t n_out) {
+static int fdg_pipeline_prepare_impl(fdg_handle h, int32_t accumulate, int32_t n_sm, int32_t what, int64_t *out, int32_t n_out) {
     if (!h || n_sm < 1 || n_out < 0 || (!out && n_out > 0)) return fail(FDG_ERR_BAD_ARG, "bad argument");
     std::lock_guard<std::mutex> lock(h->mu);
     JitVariant *v = nullptr;
@@ -899,7 +946,7 @@ int fdg_pipeline_prepare(fdg_handle h, int32_t accumulate, int32_t n_sm, int32_t
     return FDG_OK;
 }
 
-int fdg_pipeline_stats(fdg_handle h, void *stream, int64_t *out, int32_t n_out) {
+static int fdg_pipeline_stats_impl(fdg_handle h, void *stream, int64_t *out, int32_t n_out) {
     if (!h || n_out < 0 || (!out && n_out > 0)) return fail(FDG_ERR_BAD_ARG, "bad argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -916,7 +963,7 @@ int fdg_pipeline_stats(fdg_handle h, void *stream, int64_t *out, int32_t n_out) 
     return FDG_OK;
 }
 
-int fdg_jit_ptx(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t index, const char **ptx,
+static int fdg_jit_ptx_impl(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t index, const char **ptx,
                 const char **ptxas_log) {
     if (!h || !ptx) return fail(FDG_ERR_BAD_ARG, "null argument");
     std::lock_guard<std::mutex> lock(h->mu);
@@ -928,7 +975,7 @@ int fdg_jit_ptx(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, in
     return FDG_OK;
 }
 
-int fdg_destroy(fdg_handle h) {
+static int fdg_destroy_impl(fdg_handle h) {
     if (!h) return FDG_OK;
     for (auto &kv : h->dev) {
         int cur = -1;
@@ -960,7 +1007,7 @@ int fdg_destroy(fdg_handle h) {
     return FDG_OK;
 }
 
-int fdg_stats(fdg_handle h, fdg_stats_t *out) {
+static int fdg_stats_impl(fdg_handle h, fdg_stats_t *out) {
     if (!h || !out) return fail(FDG_ERR_BAD_ARG, "null argument");
     std::memset(out, 0, sizeof(*out));
     const fdg::Lowered &l = h->low;
@@ -983,7 +1030,7 @@ int fdg_stats(fdg_handle h, fdg_stats_t *out) {
     return FDG_OK;
 }
 
-int fdg_leafmap(fdg_handle h, int32_t *leaf_node) {
+static int fdg_leafmap_impl(fdg_handle h, int32_t *leaf_node) {
     if (!h || (!leaf_node && h->low.L > 0)) return fail(FDG_ERR_BAD_ARG, "null argument");
     std::copy(h->low.leaf_node.begin(), h->low.leaf_node.end(), leaf_node);
     return FDG_OK;
@@ -1002,16 +1049,16 @@ int fdg_program_words(fdg_handle h, const uint32_t **words, int64_t *n_words) {
     return FDG_OK;
 }
 
-int fdg_eval(fdg_handle h, const void *leaf, int64_t ld_leaf, void *root, int64_t ld_root, int64_t batch,
+static int fdg_eval_impl(fdg_handle h, const void *leaf, int64_t ld_leaf, void *root, int64_t ld_root, int64_t batch,
              void *stream) {
     return do_eval(h, leaf, ld_leaf, root, ld_root, batch, stream, false);
 }
 
-int fdg_eval_accumulate(fdg_handle h, const void *leaf, int64_t ld_leaf, int64_t batch, double *acc, void *stream) {
+static int fdg_eval_accumulate_impl(fdg_handle h, const void *leaf, int64_t ld_leaf, int64_t batch, double *acc, void *stream) {
     return do_eval(h, leaf, ld_leaf, acc, 0, batch, stream, true);
 }
 
-int fdg_eval_host(fdg_handle h, const void *leaf_host, int64_t ld_leaf, void *root_host, int64_t ld_root,
+static int fdg_eval_host_impl(fdg_handle h, const void *leaf_host, int64_t ld_leaf, void *root_host, int64_t ld_root,
                   int64_t batch) {
     if (!h) return fail(FDG_ERR_BAD_ARG, "null handle");
     if (batch < 0) return fail(FDG_ERR_BAD_ARG, "negative batch");
@@ -1021,6 +1068,9 @@ int fdg_eval_host(fdg_handle h, const void *leaf_host, int64_t ld_leaf, void *ro
     if ((low.L > 0 && ld_leaf < batch) || (low.R > 0 && ld_root < batch))
         return fail(FDG_ERR_BAD_ARG, "leading dimension < batch");
     const size_t es = low.dtype == FDG_C128 ? 16 : 8;
+    // one host call at a time per handle: the staging buffers and the two streams are the handle's (callers on other
+    // threads wait here; device-pointer calls on their own streams are not affected)
+    std::lock_guard<std::mutex> host_lock(h->host_mu);
     DeviceState *ds = nullptr;
     {
         std::lock_guard<std::mutex> lock(h->mu);
@@ -1062,7 +1112,12 @@ int fdg_eval_host(fdg_handle h, const void *leaf_host, int64_t ld_leaf, void *ro
                                        static_cast<const char *>(leaf_host) + (size_t)c0 * es, (size_t)ld_leaf * es,
                                        (size_t)nb * es, (size_t)low.L, cudaMemcpyHostToDevice, st));
         int rc = do_eval(h, ds->d_leaf[k], chunk, ds->d_root[k], chunk, nb, st, false);
-        if (rc != FDG_OK) return rc;
+        if (rc != FDG_OK) {
+            const std::string msg = g_err;  // copies still in flight read and write the caller's arrays: let them finish
+            cudaStreamSynchronize(ds->streams[0]);
+            cudaStreamSynchronize(ds->streams[1]);
+            return fail(rc, msg);
+        }
         if (low.R > 0)
             CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(root_host) + (size_t)c0 * es, (size_t)ld_root * es,
                                        ds->d_root[k], (size_t)chunk * es, (size_t)nb * es, (size_t)low.R,
@@ -1073,7 +1128,7 @@ int fdg_eval_host(fdg_handle h, const void *leaf_host, int64_t ld_leaf, void *ro
     return FDG_OK;
 }
 
-int fdg_set_launch(fdg_handle h, int32_t threads, int32_t samples_per_thread, int32_t blocks_per_sm) {
+static int fdg_set_launch_impl(fdg_handle h, int32_t threads, int32_t samples_per_thread, int32_t blocks_per_sm) {
     if (!h) return fail(FDG_ERR_BAD_ARG, "null handle");
     if (threads != 0 && (threads < 32 || threads > 256 || (threads & (threads - 1))))
         return fail(FDG_ERR_BAD_ARG, "threads must be 32, 64, 128 or 256");
@@ -1089,7 +1144,7 @@ int fdg_set_launch(fdg_handle h, int32_t threads, int32_t samples_per_thread, in
 
 int fdg_launch_count(fdg_handle h, int64_t *out) {
     if (!h || !out) return fail(FDG_ERR_BAD_ARG, "null argument");
-    *out = h->launches;
+    *out = h->launches.load();
     return FDG_OK;
 }
 
@@ -1131,7 +1186,7 @@ int nccl_fail(int rc, const char *what) {
 }
 }  // namespace
 
-int fdg_comm_unique_id(void *id128) {
+static int fdg_comm_unique_id_impl(void *id128) {
     if (!id128) return fail(FDG_ERR_BAD_ARG, "null argument");
     int rc = load_nccl();
     if (rc != FDG_OK) return rc;
@@ -1139,7 +1194,7 @@ int fdg_comm_unique_id(void *id128) {
     return n == 0 ? FDG_OK : nccl_fail(n, "ncclGetUniqueId");
 }
 
-int fdg_comm_init(fdg_comm_t *out, int32_t nranks, int32_t rank, const void *id128) {
+static int fdg_comm_init_impl(fdg_comm_t *out, int32_t nranks, int32_t rank, const void *id128) {
     if (!out || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(FDG_ERR_BAD_ARG, "bad argument");
     int rc = load_nccl();
     if (rc != FDG_OK) return rc;
@@ -1156,14 +1211,14 @@ int fdg_comm_init(fdg_comm_t *out, int32_t nranks, int32_t rank, const void *id1
     return FDG_OK;
 }
 
-int fdg_comm_destroy(fdg_comm_t c) {
+static int fdg_comm_destroy_impl(fdg_comm_t c) {
     if (!c) return FDG_OK;
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     delete c;
     return FDG_OK;
 }
 
-int fdg_allreduce(fdg_comm_t c, double *acc, int64_t n, void *stream) {
+static int fdg_allreduce_impl(fdg_comm_t c, double *acc, int64_t n, void *stream) {
     if (!c || !c->nccl_comm || (!acc && n > 0) || n < 0) return fail(FDG_ERR_BAD_ARG, "bad argument");
     if (n == 0) return FDG_OK;
     // ncclFloat64 = 8, ncclSum = 0 (nccl.h)
@@ -1325,11 +1380,12 @@ struct fdg_leafgen {
     int n_loops = 0, dim = 3, n_tau = 0;
     double kF = 0, beta = 0, lambda = 0;
     std::map<int, LeafMeta *> d_meta;                  // per device
-    std::map<int, std::pair<double *, size_t>> d_leaf;  // per device: sub-batch leaf matrix of the fused path
+    std::map<std::pair<int, cudaStream_t>, std::pair<double *, size_t>> d_leaf;  // per device and stream: sub-batch leaf matrix of the fused path
     std::map<int, std::pair<double *, size_t>> d_var;   // per device: staging of (K, T) chunks for the host path
     cudaStream_t streams[2] = {nullptr, nullptr};       // host path: copy stream, run stream (created on first use)
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};  // [k] chunk k copied, [2 + k] buffer k consumed
     std::mutex mu;
+    std::mutex host_mu;  // fdg_eval_generated_host: staging buffer, streams and events belong to one caller at a time
 };
 
 namespace {
@@ -1367,7 +1423,7 @@ int leafgen_launch(fdg_leafgen *g, const double *K, const double *T, int64_t ld_
 
 extern "C" {
 
-int fdg_leafgen_create(const fdg_leafgen_desc *d, fdg_leafgen_t *out) {
+static int fdg_leafgen_create_impl(const fdg_leafgen_desc *d, fdg_leafgen_t *out) {
     if (!d || !out) return fail(FDG_ERR_BAD_ARG, "null argument");
     *out = nullptr;
     if (d->n_leaves < 0 || d->n_basis < 0 || d->n_tau < 0) return fail(FDG_ERR_BAD_ARG, "negative size");
@@ -1419,7 +1475,7 @@ int fdg_leafgen_create(const fdg_leafgen_desc *d, fdg_leafgen_t *out) {
     return FDG_OK;
 }
 
-int fdg_leafgen_destroy(fdg_leafgen_t g) {
+static int fdg_leafgen_destroy_impl(fdg_leafgen_t g) {
     if (!g) return FDG_OK;
     int cur = -1;
     if (cudaGetDevice(&cur) == cudaSuccess) {
@@ -1428,7 +1484,7 @@ int fdg_leafgen_destroy(fdg_leafgen_t g) {
             cudaFree(kv.second);
         }
         for (auto &kv : g->d_leaf) {
-            cudaSetDevice(kv.first);
+            cudaSetDevice(kv.first.first);
             cudaFree(kv.second.first);
         }
         for (auto &kv : g->d_var) {
@@ -1445,7 +1501,7 @@ int fdg_leafgen_destroy(fdg_leafgen_t g) {
     return FDG_OK;
 }
 
-int fdg_leafgen_fill(fdg_leafgen_t g, const double *K, const double *T, int64_t ld_var, int64_t batch, double *leaf,
+static int fdg_leafgen_fill_impl(fdg_leafgen_t g, const double *K, const double *T, int64_t ld_var, int64_t batch, double *leaf,
                      int64_t ld_leaf, void *stream) {
     if (!g) return fail(FDG_ERR_BAD_ARG, "null handle");
     if (batch < 0) return fail(FDG_ERR_BAD_ARG, "negative batch");
@@ -1456,7 +1512,7 @@ int fdg_leafgen_fill(fdg_leafgen_t g, const double *K, const double *T, int64_t 
     return leafgen_launch(g, K, T, ld_var, batch, leaf, ld_leaf, static_cast<cudaStream_t>(stream));
 }
 
-int fdg_eval_generated_accumulate(fdg_handle h, fdg_leafgen_t g, const double *K, const double *T, int64_t ld_var,
+static int fdg_eval_generated_accumulate_impl(fdg_handle h, fdg_leafgen_t g, const double *K, const double *T, int64_t ld_var,
                                   int64_t batch, double *acc, void *stream) {
     if (!h || !g) return fail(FDG_ERR_BAD_ARG, "null handle");
     if (h->low.dtype != FDG_F64) return fail(FDG_ERR_UNSUPPORTED, "generated leaves are Float64");
@@ -1477,7 +1533,7 @@ int fdg_eval_generated_accumulate(fdg_handle h, fdg_leafgen_t g, const double *K
     double *buf = nullptr;
     {
         std::lock_guard<std::mutex> lock(g->mu);
-        auto &slot = g->d_leaf[dev];
+        auto &slot = g->d_leaf[std::make_pair(dev, st)];  // calls on different streams may run at the same time
         const size_t need = (size_t)L * (size_t)sub * sizeof(double);
         if (need > slot.second) {
             if (slot.first) CUDA_TRY(cudaFree(slot.first));
@@ -1495,17 +1551,14 @@ int fdg_eval_generated_accumulate(fdg_handle h, fdg_leafgen_t g, const double *K
             rc = leafgen_launch(g, K + b0, T + b0, ld_var, nb, buf, sub, st);
         }
         if (rc != FDG_OK) return rc;
-        {
-            std::lock_guard<std::mutex> lock(h->mu);
-            h->launches++;
-        }
+        h->launches++;
         rc = do_eval(h, buf, sub, acc, 0, nb, st, true);
         if (rc != FDG_OK) return rc;
     }
     return FDG_OK;
 }
 
-int fdg_eval_generated_host(fdg_handle h, fdg_leafgen_t g, const double *K_host, const double *T_host, int64_t ld_var,
+static int fdg_eval_generated_host_impl(fdg_handle h, fdg_leafgen_t g, const double *K_host, const double *T_host, int64_t ld_var,
                             int64_t batch, double *acc_host) {
     if (!h || !g) return fail(FDG_ERR_BAD_ARG, "null handle");
     if (batch < 0) return fail(FDG_ERR_BAD_ARG, "negative batch");
@@ -1517,6 +1570,7 @@ int fdg_eval_generated_host(fdg_handle h, fdg_leafgen_t g, const double *K_host,
     const int64_t R = h->low.R;
     // chunks of (K, T) are copied on one stream while the previous chunk is generated and evaluated on another
     const int64_t chunk = std::min<int64_t>(std::max<int64_t>(batch, 1), 1 << 19);
+    std::lock_guard<std::mutex> host_lock(g->host_mu);
     double *d_var = nullptr;
     cudaStream_t s_copy = nullptr, s_run = nullptr;
     {
@@ -1550,7 +1604,12 @@ int fdg_eval_generated_host(fdg_handle h, fdg_leafgen_t g, const double *K_host,
         CUDA_TRY(cudaEventRecord(g->events[k], s_copy));
         CUDA_TRY(cudaStreamWaitEvent(s_run, g->events[k], 0));
         int rc = fdg_eval_generated_accumulate(h, g, buf, buf + (size_t)kr * (size_t)chunk, chunk, nb, d_acc, s_run);
-        if (rc != FDG_OK) return rc;
+        if (rc != FDG_OK) {
+            const std::string msg = g_err;
+            cudaStreamSynchronize(s_run);
+            cudaStreamSynchronize(s_copy);
+            return fail(rc, msg);
+        }
         CUDA_TRY(cudaEventRecord(g->events[2 + k], s_run));
     }
     if (R > 0) CUDA_TRY(cudaMemcpyAsync(acc_host, d_acc, (size_t)R * 8, cudaMemcpyDeviceToHost, s_run));
@@ -1559,4 +1618,80 @@ int fdg_eval_generated_host(fdg_handle h, fdg_leafgen_t g, const double *K_host,
     return FDG_OK;
 }
 
+}  // extern "C"
+
+// ---- the exported entry points: the implementations above behind an exception barrier ----------------------------------
+extern "C" {
+int fdg_compile(const fdg_graph_desc *graph, const fdg_options *opts, fdg_handle *out) {
+    return guarded([&] { return fdg_compile_impl(graph, opts, out); });
+}
+int fdg_graph_write(const fdg_graph_desc *g, const char *path) {
+    return guarded([&] { return fdg_graph_write_impl(g, path); });
+}
+int fdg_compile_file(const char *path, const fdg_options *opts, fdg_handle *out) {
+    return guarded([&] { return fdg_compile_file_impl(path, opts, out); });
+}
+int fdg_jit_prepare(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t *n_kernels, int32_t *n_cross, int64_t *cubin_bytes) {
+    return guarded([&] { return fdg_jit_prepare_impl(h, samples_per_thread, accumulate, n_kernels, n_cross, cubin_bytes); });
+}
+int fdg_jit_info(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int64_t *out, int32_t n_out) {
+    return guarded([&] { return fdg_jit_info_impl(h, samples_per_thread, accumulate, out, n_out); });
+}
+int fdg_pipeline_prepare(fdg_handle h, int32_t accumulate, int32_t n_sm, int32_t what, int64_t *out, int32_t n_out) {
+    return guarded([&] { return fdg_pipeline_prepare_impl(h, accumulate, n_sm, what, out, n_out); });
+}
+int fdg_pipeline_stats(fdg_handle h, void *stream, int64_t *out, int32_t n_out) {
+    return guarded([&] { return fdg_pipeline_stats_impl(h, stream, out, n_out); });
+}
+int fdg_jit_ptx(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t index, const char **ptx, const char **ptxas_log) {
+    return guarded([&] { return fdg_jit_ptx_impl(h, samples_per_thread, accumulate, index, ptx, ptxas_log); });
+}
+int fdg_destroy(fdg_handle h) {
+    return guarded([&] { return fdg_destroy_impl(h); });
+}
+int fdg_stats(fdg_handle h, fdg_stats_t *out) {
+    return guarded([&] { return fdg_stats_impl(h, out); });
+}
+int fdg_leafmap(fdg_handle h, int32_t *leaf_node) {
+    return guarded([&] { return fdg_leafmap_impl(h, leaf_node); });
+}
+int fdg_eval(fdg_handle h, const void *leaf, int64_t ld_leaf, void *root, int64_t ld_root, int64_t batch, void *stream) {
+    return guarded([&] { return fdg_eval_impl(h, leaf, ld_leaf, root, ld_root, batch, stream); });
+}
+int fdg_eval_accumulate(fdg_handle h, const void *leaf, int64_t ld_leaf, int64_t batch, double *acc, void *stream) {
+    return guarded([&] { return fdg_eval_accumulate_impl(h, leaf, ld_leaf, batch, acc, stream); });
+}
+int fdg_eval_host(fdg_handle h, const void *leaf_host, int64_t ld_leaf, void *root_host, int64_t ld_root, int64_t batch) {
+    return guarded([&] { return fdg_eval_host_impl(h, leaf_host, ld_leaf, root_host, ld_root, batch); });
+}
+int fdg_set_launch(fdg_handle h, int32_t threads, int32_t samples_per_thread, int32_t blocks_per_sm) {
+    return guarded([&] { return fdg_set_launch_impl(h, threads, samples_per_thread, blocks_per_sm); });
+}
+int fdg_comm_unique_id(void *id128) {
+    return guarded([&] { return fdg_comm_unique_id_impl(id128); });
+}
+int fdg_comm_init(fdg_comm_t *out, int32_t nranks, int32_t rank, const void *id128) {
+    return guarded([&] { return fdg_comm_init_impl(out, nranks, rank, id128); });
+}
+int fdg_comm_destroy(fdg_comm_t c) {
+    return guarded([&] { return fdg_comm_destroy_impl(c); });
+}
+int fdg_allreduce(fdg_comm_t c, double *acc, int64_t n, void *stream) {
+    return guarded([&] { return fdg_allreduce_impl(c, acc, n, stream); });
+}
+int fdg_leafgen_create(const fdg_leafgen_desc *d, fdg_leafgen_t *out) {
+    return guarded([&] { return fdg_leafgen_create_impl(d, out); });
+}
+int fdg_leafgen_destroy(fdg_leafgen_t g) {
+    return guarded([&] { return fdg_leafgen_destroy_impl(g); });
+}
+int fdg_leafgen_fill(fdg_leafgen_t g, const double *K, const double *T, int64_t ld_var, int64_t batch, double *leaf, int64_t ld_leaf, void *stream) {
+    return guarded([&] { return fdg_leafgen_fill_impl(g, K, T, ld_var, batch, leaf, ld_leaf, stream); });
+}
+int fdg_eval_generated_accumulate(fdg_handle h, fdg_leafgen_t g, const double *K, const double *T, int64_t ld_var, int64_t batch, double *acc, void *stream) {
+    return guarded([&] { return fdg_eval_generated_accumulate_impl(h, g, K, T, ld_var, batch, acc, stream); });
+}
+int fdg_eval_generated_host(fdg_handle h, fdg_leafgen_t g, const double *K_host, const double *T_host, int64_t ld_var, int64_t batch, double *acc_host) {
+    return guarded([&] { return fdg_eval_generated_host_impl(h, g, K_host, T_host, ld_var, batch, acc_host); });
+}
 }  // extern "C"

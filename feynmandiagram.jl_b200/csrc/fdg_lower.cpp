@@ -159,7 +159,19 @@ int build_statements(const fdg_graph_desc &g, std::vector<Stmt> &st, std::vector
             stack.pop_back();
             color[u] = 2;
             const int64_t uid = g.node_id[u];
-            if (val_of_id.count(uid)) continue;  // `g_id in inds_visited... && continue`
+            {
+                auto seen = val_of_id.find(uid);
+                if (seen != val_of_id.end()) {  // `g_id in inds_visited... && continue`
+                    // static.jl:116,122 keep one visited list for leaves and one for inner nodes: an id carried by both kinds
+                    // of object would be emitted twice there.  That graph is ambiguous: reject it.
+                    const bool was_leaf = st[(size_t)seen->second].op < 0, is_leaf = g.child_ptr[u] == g.child_ptr[u + 1];
+                    if (was_leaf != is_leaf) {
+                        err = "node id " + std::to_string(uid) + " is carried by a leaf and by an inner node";
+                        return FDG_ERR_BAD_GRAPH;
+                    }
+                    continue;
+                }
+            }
             Stmt s;
             const int64_t a = g.child_ptr[u], b = g.child_ptr[u + 1];
             if (a == b) {  // leaf: isempty(subgraphs(g)), whatever the operator tag (static.jl:115)

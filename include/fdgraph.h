@@ -20,6 +20,11 @@
  *     fdg_last_error() returns a thread-local message for the last non-zero status.
  *   - the caller owns every data buffer and the CUDA stream; a handle owns the lowered program
  *     and its device copy (one per device, uploaded lazily on first evaluation).
+ *   - a handle may be used from several threads: device-pointer calls are serialised while they are ISSUED (work buffers
+ *     are kept per stream, so calls on different streams overlap on the device); the host-buffer calls run one at a time.
+ *   - node ids: the reference emitter keeps separate visited lists for leaves and inner nodes (static.jl:116,122), so an id
+ *     carried by a leaf object AND by an inner object would be emitted twice there.  Such a graph is ambiguous and is
+ *     rejected here with FDG_ERR_BAD_GRAPH.
  *   - data layout is batch-major ("one column per leaf / root", the layout of a Julia B x L
  *     matrix and of the reference's torch emitter): leaf value l of sample b lives at
  *     leaf[l * ld_leaf + b], root r of sample b at root[r * ld_root + b].  Element type is
@@ -157,7 +162,9 @@ int fdg_eval(fdg_handle h, const void *leaf, int64_t ld_leaf, void *root, int64_
 int fdg_eval_accumulate(fdg_handle h, const void *leaf, int64_t ld_leaf, int64_t batch, double *acc,
                         void *stream);
 /* host-buffer convenience (the reference-facing call: leafVal / root are ordinary host arrays):
- * chunked H2D -> fdg_eval -> D2H through pinned staging on two streams; synchronous. */
+ * chunked H2D -> fdg_eval -> D2H on two streams straight from / into the caller's arrays; synchronous.  The copies run at
+ * full PCIe speed when the arrays are page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory); pageable memory
+ * works and is slower.  One host call at a time per handle: callers on other threads wait their turn. */
 int fdg_eval_host(fdg_handle h, const void *leaf_host, int64_t ld_leaf, void *root_host, int64_t ld_root,
                   int64_t batch);
 /* choose launch shape: threads per block, samples per thread (1, 2 or 4), blocks per SM (0 = auto). */

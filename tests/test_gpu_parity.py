@@ -434,3 +434,100 @@ def test_opt_in_fma_is_within_the_tolerance_but_not_the_default(name, dtype):
         assert (np.abs(fused[:, b] - want[:, b]) <= 1e-12 * bound).all()
     with pytest.raises(_capi.FdgError):
         fd.compile_raw(raw, dtype=dtype, backend=VM, fma=True)                  # the packet VM has the exact arithmetic only
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_grid_stride_kernel_over_several_launch_sequences(dtype, monkeypatch):
+    """A single small accumulate kernel runs as a grid-stride loop whose warps STORE their sums.  When the batch is
+    processed as several launch sequences (FDG_JIT_MAX_SUB forces that here; huge batches do it on their own) every
+    sequence must be folded into the result before the next one overwrites the rows -- also when the last sequence runs
+    a smaller grid than the others."""
+    monkeypatch.setenv("FDG_JIT_MAX_SUB", "40000")
+    roots = graphgen.random_dag(11, n_leaves=9, n_inner=40, n_roots=3)
+    raw, _ = fd.flatten(roots)
+    ev = fd.compile_raw(raw, dtype=dtype, backend=JIT)
+    W = 1 if dtype == np.float64 else 2
+    info = ev.jit_prepare(1 if W == 2 else 2, True)
+    assert info["grid_stride"] and info["kernels"] == 1
+    B = 3 * 40000 + 777  # three full launch sequences and a short one
+    leaf_h = graphgen.leaf_values(3, ev.n_leaves, B, dtype=dtype, signed=True)
+    leaf = torch.from_numpy(leaf_h).cuda()
+    acc = torch.zeros(ev.n_roots * W, dtype=torch.float64, device="cuda")
+    ev.accumulate_device(leaf.data_ptr(), B, B, acc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = O.Oracle(raw).eval(leaf_h)
+    ref = want.sum(axis=1)
+    ref = np.stack([ref.real, ref.imag], axis=1).reshape(-1) if W == 2 else ref
+    scale = np.abs(want).sum(axis=1)
+    scale = np.repeat(scale, 2) if W == 2 else scale
+    assert np.all(np.abs(acc.cpu().numpy() - ref) <= 1e-12 * (scale + 1e-300))
+
+
+@pytest.mark.parametrize("name,dtype", [("parquet_ver4_o3", np.float64), ("taylor_sigma_o4", np.complex128)])
+def test_pipeline_form_is_bit_exact(name, dtype, monkeypatch):
+    """The pipeline form of the specialised kernels (one cooperative kernel per pass, one code stage per instruction-cache
+    group, tiles of 32 samples flowing between the stages; opt-in with FDG_JIT_PIPE=1): same bits as the oracle in eval
+    mode, same sums in accumulate mode, no stage ever gave up waiting."""
+    import os
+
+    monkeypatch.setenv("FDG_JIT_PIPE", "1")
+    monkeypatch.setenv("FDG_PIPE_MIN_BATCH", "1")
+    raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", name + ".npz"))
+    ev = fd.compile_raw(raw, dtype=dtype, backend=JIT, jit_segment=1200)
+    W = 1 if dtype == np.float64 else 2
+    tdt = torch.float64 if W == 1 else torch.complex128
+    B = 70001  # more tiles than the window of tiles in flight, and a ragged last tile
+    leaf_h = graphgen.leaf_values(9, ev.n_leaves, B, dtype=dtype, signed=True)
+    leaf = torch.from_numpy(leaf_h).cuda()
+    root = torch.full((ev.n_roots, B), -3.0, dtype=tdt, device="cuda")
+    acc = torch.zeros(ev.n_roots * W, dtype=torch.float64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    launches = ev.launches
+    ev.eval_device(leaf.data_ptr(), B, root.data_ptr(), B, B, s)
+    n_eval = ev.pipeline_prepare(False, torch.cuda.get_device_properties(0).multi_processor_count)["stages"]
+    assert not ev.pipeline_stats(s, n_eval)["stalled"]
+    ev.accumulate_device(leaf.data_ptr(), B, B, acc.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert ev.launches > launches
+    idx = np.unique(np.concatenate([np.arange(0, B, 53), [31, 32, B - 2, B - 1]]))
+    want = O.Oracle(raw).eval(np.ascontiguousarray(leaf_h[:, idx]))
+    assert root.cpu().numpy()[:, idx].tobytes() == want.tobytes()
+    got = root.cpu().numpy()
+    ref = got.sum(axis=1)
+    ref = np.stack([ref.real, ref.imag], axis=1).reshape(-1) if W == 2 else ref
+    scale = np.abs(got).sum(axis=1)
+    scale = np.repeat(scale, 2) if W == 2 else scale
+    assert np.all(np.abs(acc.cpu().numpy() - ref) <= 1e-12 * (scale + 1e-300))
+
+
+def test_two_host_callers_on_one_handle():
+    """include/fdgraph.h: a handle may be used from several threads.  Two threads push different host batches through the
+    SAME handle's host entry point (fdg_eval_host: chunked H2D -> kernels -> D2H on the handle's two streams) at the same
+    time, several times over; each must get exactly the oracle's bytes for its own batch."""
+    import threading
+
+    roots = graphgen.random_dag(17, n_leaves=14, n_inner=120, n_roots=4)
+    ev, _ = fd.compile(roots)
+    orc = O.Oracle(ev.raw)
+    B = 300_000  # several 64 MiB chunks per call would need more leaves; this is two chunks of ~150 k samples... per caller
+    leaves = [np.asfortranarray(graphgen.leaf_values(100 + t, ev.n_leaves, B, signed=True).T) for t in range(2)]
+    wants = [orc.eval(np.ascontiguousarray(lv.T)) for lv in leaves]
+    errors = []
+
+    def work(t):
+        try:
+            for _ in range(4):
+                root = np.asfortranarray(np.zeros((B, ev.n_roots)))
+                ev(root, leaves[t])
+                if np.ascontiguousarray(root.T).tobytes() != wants[t].tobytes():
+                    errors.append(f"thread {t}: result differs from the oracle")
+        except Exception as ex:  # noqa: BLE001
+            errors.append(f"thread {t}: {ex!r}")
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    assert ev.launches >= 8

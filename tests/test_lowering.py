@@ -335,3 +335,48 @@ def test_root_ordering_brings_sharing_roots_together(monkeypatch):
     emitter, exact, short = cross({"FDG_JIT_ROOT_ORDER": "0"}), cross({}), cross({"FDG_JIT_ROOT_SHORTLIST": "1"})
     assert emitter >= 90
     assert exact <= 15 and short <= 25
+
+
+def test_corrupt_fdgraph_header_is_an_error_not_an_abort(tmp_path):
+    """A file whose header announces 2^31 - 1 nodes must come back as FDG_ERR_BAD_GRAPH before anything is sized from it
+    (the C ABI never throws and never aborts the host process)."""
+    path = str(tmp_path / "bad.fdgraph")
+    with open(path, "wb") as fh:
+        fh.write(b"FDGRAPH\x01" + np.array([2 ** 31 - 1, 0, 0, 0], "<i8").tobytes())
+    with pytest.raises(_capi.FdgError) as e:
+        fd.compile_file(path)
+    assert e.value.code == 2 and "truncated" in str(e.value)
+    with open(path, "wb") as fh:  # counts that agree with nothing
+        fh.write(b"FDGRAPH\x01" + np.array([3, 2 ** 31 - 1, 5, 1], "<i8").tobytes() + b"\0" * 64)
+    with pytest.raises(_capi.FdgError) as e:
+        fd.compile_file(path)
+    assert e.value.code == 2
+
+
+def test_id_shared_by_a_leaf_and_an_inner_node_is_rejected():
+    """static.jl:116,122 keep separate visited lists for leaves and inner nodes, so an id carried by both kinds of object
+    is emitted twice by the reference (later readers see the last assignment).  The evaluator refuses the ambiguity."""
+    a, b, c = fd.Graph([]), fd.Graph([]), fd.Graph([])
+    inner = a * b
+    c.id = inner.id  # a leaf object with the id of an inner node, e.g. graphs merged from two sessions
+    raw, _ = fd.flatten([fd.Graph([inner, c], operator=fd.Sum())])  # (`inner + c` would merge the two by id)
+    with pytest.raises(_capi.FdgError) as e:
+        fd.compile_raw(raw)
+    assert e.value.code == 2 and "leaf and by an inner node" in str(e.value)
+
+
+def test_pipeline_plan_of_the_headline_graph():
+    """Host-side guard for the pipeline form on Parquet vertex4 order 4 for the B200 layout of
+    instruction-cache groups: one stage per group and pass, stage sizes follow the group sizes, code fits the cache."""
+    import os
+
+    raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", "parquet_ver4_o4.npz"))
+    ev = fd.compile_raw(raw, backend=2)
+    info = ev.pipeline_prepare(True, 148)
+    assert info["passes"] == 2 and info["stages"] == 16 and info["operations"] == 94500
+    assert info["stage_blocks"] == [12, 18, 18, 20, 20, 20, 20, 20] * 2
+    assert info["max_code_bytes"] <= 120 * 1024 and info["ring_bytes"] <= 200 * 1024
+    cost, blocks = np.array(info["stage_cost"], float), np.array(info["stage_blocks"], float)
+    per_pass = [(cost[p:p + 8] / blocks[p:p + 8]).max() for p in (0, 8)]
+    assert sum(per_pass) / (cost.sum() / 148) < 1.08  # the slowest stage of each pass is within 8 % of a perfect split
+    assert 0 < info["boundary_rows"] <= 80            # values that go from the first pass to the second
