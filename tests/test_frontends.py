@@ -1,0 +1,254 @@
+"""The restated front ends (oracle/frontend/: the producers of every workload graph) pinned on the reference's own golden
+numbers.  They are test / workload infrastructure -- nothing on the evaluation path imports them -- but the headline
+workload is their output, so their known answers belong in the suite:
+
+  * closed-form diagram counts, all leaves = 1 (test/front_end.jl:600-656 with
+    src/frontend/parquet/benchmark/diagram_count.jl:53-66): Sigma in the G^2 v expansion, loops 1-4 = 1, 1+s, 4+5s+s^2,
+    27+40s+14s^2+s^3;
+  * which Green's functions / self-energies a filter allows (test/front_end.jl:186-219, :660-700);
+  * the RPA chain of the 4-point vertex, +-2^3 2^4 (test/front_end.jl:398-443);
+  * value invariance under optimize! for the 4-point vertex, loops 1-3, every channel (test/front_end.jl:446-598) and
+    for a hand-built graph (test/computational_graph.jl:471-491);
+  * the hand-built diagram of test/front_end.jl:221-310 and its Taylor coefficients, closed forms (-2+spin) f {1, 2, 2}.
+
+Not restated (no BASELINE configuration needs them): Parquet.vertex3 and Parquet.polarization, hence no Gamma3 /
+polarisation counts (test/front_end.jl:701-825)."""
+import math
+
+import numpy as np
+import pytest
+
+import fdgraph_b200 as fd
+from fdgraph_b200.graph import Graph, Power, Prod, Sum
+from oracle import oracle as O
+from oracle.frontend import optimize as opt
+from oracle.frontend import parquet as pq
+from oracle.frontend import taylor
+from oracle.frontend.ids import (Alli, BareGreenId, BareInteractionId, ChargeCharge, Dynamic, GenericId, Girreducible, Instant,
+                                 NoFock, NoHartree, PHEr, PHr, PPr, UpDown, UpUp)
+
+
+def _eval(graphs, leaf_value=lambda leaf: 1.0):
+    """Graphs.eval! restated on Graph objects (eval.jl:15-39): post-order, Prod as prod(g_i * f_i), each object once."""
+    val = {}
+    for node in fd.graph.post_order_unique(list(graphs)):
+        if not node.subgraphs:
+            val[id(node)] = leaf_value(node)
+            continue
+        terms = [val[id(s)] * f for s, f in zip(node.subgraphs, node.subgraph_factors)]
+        if isinstance(node.operator, Sum):
+            val[id(node)] = sum(terms)
+        elif isinstance(node.operator, Prod):
+            val[id(node)] = math.prod(terms)
+        else:
+            assert isinstance(node.operator, Power)
+            val[id(node)] = terms[0] ** node.operator.N
+    return [val[id(g)] for g in graphs]
+
+
+def _leaf_by_content(leaf):
+    """A reproducible value that depends on WHAT the leaf is (its properties), so that optimize!'s merging of equal leaves
+    keeps the assignment: the physical-propagator evaluation of the reference tests, without the physics."""
+    h = hash(repr(opt._prop_key(leaf.properties))) & 0xFFFFFFFF
+    return 0.5 + (h % 100003) / 100003.0
+
+
+def count_sigma_G2v(loops, spin):  # benchmark/diagram_count.jl:53-66
+    return {1: 1, 2: 1 + spin, 3: 4 + 5 * spin + spin ** 2, 4: 27 + 40 * spin + 14 * spin ** 2 + spin ** 3}[loops]
+
+
+@pytest.mark.parametrize("loops", [1, 2, 3, 4])
+def test_sigma_diagram_counts(loops):
+    # test/front_end.jl:600-656
+    fd.uidreset()
+    pq._ver4I.clear()
+    spin = 2
+    para = pq.DiagPara(type=pq.SigmaDiag, hasTau=True, innerLoopNum=loops, totalLoopNum=loops + 1, totalTauNum=loops, isFermi=False,
+                       spin=spin, firstLoopIdx=2, firstTauIdx=1, filter=(NoHartree, Girreducible),
+                       interaction=(pq.Interaction(ChargeCharge, Instant),), extra=pq.ParquetBlocks(phi=[PHEr, PPr], ppi=[PHr, PHEr]))
+    ext_k = [0.0] * para.totalLoopNum
+    ext_k[0] = 1.0
+    rows = pq.sigma(para, ext_k, False)
+    merged = pq.mergeby_vec([r["diagram"] for r in rows])
+    assert len(merged) == 1
+    (w,) = _eval(merged)
+    assert w * (-1) ** loops == pytest.approx(count_sigma_G2v(loops, spin), rel=0, abs=1e-9)
+    assert [1, 3, 18, 171][loops - 1] == count_sigma_G2v(loops, 2)
+    # the evaluator's own interpreter agrees (flattened graph, all leaves one)
+    raw, _ = fd.flatten(merged)
+    orc = O.Oracle(raw)
+    assert orc.eval(np.ones((orc.n_leaves, 1)), "eval")[0, 0] == w
+
+
+def test_which_green_functions_and_self_energies_a_filter_allows():
+    # test/front_end.jl:186-219
+    assert pq.is_valid_g((Girreducible,), 0) is True and pq.is_valid_g((Girreducible,), 1) is False and pq.is_valid_g((Girreducible,), 2) is False
+    assert pq.is_valid_g((NoFock,), 0) is True and pq.is_valid_g((NoFock,), 1) is True and pq.is_valid_g((NoFock, NoHartree), 1) is False
+    assert pq.is_valid_g((NoFock, NoHartree), 2) is True
+    for loops, sub, want in ((0, True, False), (1, True, False), (2, True, False), (0, False, False), (1, False, True), (2, False, True)):
+        assert pq.is_valid_sigma((Girreducible,), loops, sub) is want
+    assert pq.is_valid_sigma((NoFock,), 0, True) is False
+    assert pq.is_valid_sigma((NoFock,), 1, True) is True        # a one-loop self-energy is Hartree or Fock ...
+    assert pq.is_valid_sigma((NoFock, NoHartree), 1, True) is False  # ... and gone only if both are filtered
+    assert pq.is_valid_sigma((NoFock, NoHartree), 2, True) is True
+    assert pq.is_valid_sigma((NoFock,), 0, False) is False
+    assert pq.is_valid_sigma((NoFock,), 1, False) is True
+    assert pq.is_valid_sigma((NoFock, NoHartree), 1, False) is True
+    assert pq.is_valid_sigma((NoFock,), 2, False) is True
+
+    # test/front_end.jl:660-700
+    def build_g(loops, flt):
+        para = pq.DiagPara(type=pq.GreenDiag, hasTau=True, innerLoopNum=loops, isFermi=True, spin=2, filter=flt,
+                           interaction=(pq.Interaction(ChargeCharge, Instant),))
+        ext_k = [0.0] * para.totalLoopNum
+        ext_k[0] = 1.0
+        return pq.green(para, ext_k, (1, 2)) if pq.is_valid_g(para.filter, para.innerLoopNum) else None
+
+    fd.uidreset()
+    pq._ver4I.clear()
+    assert isinstance(build_g(0, (NoHartree, Girreducible)), Graph)
+    assert build_g(1, (NoHartree, Girreducible)) is None and build_g(2, (NoHartree, Girreducible)) is None
+    assert isinstance(build_g(0, (NoHartree, NoFock)), Graph)
+    assert build_g(1, (NoHartree, NoFock)) is None
+    assert isinstance(build_g(2, (NoHartree, NoFock)), Graph)  # a higher-order sub-diagram is allowed
+
+
+def test_rpa_chain_of_the_four_point_vertex():
+    # test/front_end.jl:398-443: each bubble contributes 2, each dynamic interaction 2, two spin configurations
+    loops = 3
+    fd.uidreset()
+    pq._ver4I.clear()
+    para = pq.DiagPara(type=pq.Ver4Diag, hasTau=True, innerLoopNum=loops, interaction=(pq.Interaction(ChargeCharge, [Instant, Dynamic]),))
+    k1, k2, k3 = (pq.get_k(para.totalLoopNum, i) for i in (1, 2, 3))
+    ext_k = [k1, k2, k3, [a + c - b for a, b, c in zip(k1, k2, k3)]]
+    weight = (2 ** loops) * (2 ** (loops + 1))
+
+    def chain(chan):
+        rows = []
+        pq.rpa_chain(rows, para, ext_k, chan, 0, "RPA", -1.0)
+        merged = pq.mergeby_df(rows, ["response"])
+        by_resp = {r["response"]: _eval([r["diagram"]])[0] for r in merged}
+        return by_resp.get(UpUp, 0.0), by_resp.get(UpDown, 0.0)
+
+    upup, updown = chain(PHEr)
+    assert upup == pytest.approx(-weight) and updown == pytest.approx(0.0)  # exchange: extra sign, no up-down
+    upup, updown = chain(PHr)
+    assert upup == pytest.approx(weight) and updown == pytest.approx(weight)
+
+
+@pytest.mark.parametrize("loops", [1, 2, 3])
+@pytest.mark.parametrize("chan", [(PHr,), (PHEr,), (PPr,), (PHr, PHEr, PPr)])
+def test_vertex4_value_is_invariant_under_optimize(loops, chan):
+    # test/front_end.jl:446-598 (`@assert w1 ≈ w1opt`), with content-keyed leaf values in place of the physical propagators
+    fd.uidreset()
+    pq._ver4I.clear()
+    k0 = [0.0] * (loops + 2)
+    kin_l, kin_r = list(k0), list(k0)
+    kin_l[0] = 1.0
+    kin_r[1] = 1.0
+    leg_k = [kin_l, list(kin_l), kin_r, list(kin_r)]
+    blocks = pq.ParquetBlocks(phi=[PHEr, PPr], ppi=[PHr, PHEr])
+    para = pq.DiagPara(type=pq.Ver4Diag, isFermi=True, hasTau=True, innerLoopNum=loops, totalLoopNum=len(kin_l), totalTauNum=loops + 1,
+                       spin=2, firstLoopIdx=3, firstTauIdx=1, filter=(NoHartree, Girreducible), transferLoop=tuple(0.0 for _ in kin_l),
+                       interaction=(pq.Interaction(ChargeCharge, Instant),), extra=blocks)
+    rows = pq.vertex4(para, leg_k, channels=chan, blocks=blocks)
+    merged = [r["diagram"] for r in pq.mergeby_df(rows, ["response"])]
+    assert len(merged) == 2
+    w1 = _eval(merged, _leaf_by_content)
+    ones1 = _eval(merged)
+    optimised = list(opt.optimize(merged))
+    w2 = _eval(optimised, _leaf_by_content)
+    assert w2 == pytest.approx(w1, rel=1e-12)
+    assert _eval(optimised) == pytest.approx(ones1, rel=0, abs=1e-9)
+    n_before = len(fd.graph.post_order_unique(merged))
+    assert len(fd.graph.post_order_unique(optimised)) <= n_before
+
+
+def test_optimize_on_a_hand_built_graph():
+    # test/computational_graph.jl:471-491
+    fd.uidreset()
+    g1 = Graph([])
+    g2 = 2 * g1
+    g3 = Graph([g2], subgraph_factors=[3], operator=Prod())
+    g4 = Graph([g3], subgraph_factors=[5], operator=Prod())
+    g5 = Graph([], factor=3.0)
+    g6 = Graph([g5, g1], subgraph_factors=[1.0, 2.0], operator=Sum())
+    g = Graph([g4, g6], operator=Sum())
+    before = _eval([g])[0]
+    (h,) = opt.optimize([g])
+    assert _eval([h])[0] == before
+    assert len([n for n in fd.graph.post_order_unique([h]) if not n.subgraphs]) <= 2
+
+
+def _getdiagram(spin=2.0, D=3, Nk=4, Nt=2):
+    """test/front_end.jl:221-263 (the direct part of a two-bubble diagram)."""
+    fd.uidreset()
+    para = pq.DiagPara(type=pq.GreenDiag, innerLoopNum=0, totalLoopNum=Nk, hasTau=True, totalTauNum=Nt)
+    gK = [[0.0, 0.0, 1.0, 1.0], [0.0, 0.0, 0.0, 1.0]]
+    gT = [(1, 2), (2, 1)]
+    g = [Graph([], properties=BareGreenId(k=gK[i], t=gT[i]), name="G") for i in range(2)]
+    vdK = [[0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 1.0, 0.0]]
+    vd = [Graph([], properties=BareInteractionId(ChargeCharge, k=vdK[i]), name="Vd") for i in range(2)]
+    veK = [[1, 0, -1, -1], [0, 1, 0, -1]]
+    ve = [Graph([], properties=BareInteractionId(ChargeCharge, k=veK[i]), name="Ve") for i in range(2)]
+    gid = GenericId(para)
+    ggn = Graph([g[0], g[1]], properties=gid, operator=Prod())
+    vdd = Graph([vd[0], vd[1]], properties=gid, operator=Prod(), factor=spin)
+    vde = Graph([vd[0], ve[1]], properties=gid, operator=Prod(), factor=-1.0)
+    ved = Graph([ve[0], vd[1]], properties=gid, operator=Prod(), factor=-1.0)
+    vsum = Graph([vdd, vde, ved], properties=gid, operator=Sum())
+    return Graph([vsum, ggn], properties=gid, operator=Prod(), factor=1 / (2 * math.pi) ** D, name="root")
+
+
+def test_hand_built_parquet_like_graph_and_its_taylor_coefficients():
+    # test/front_end.jl:284-310
+    spin, D = 1.0, 3
+    root = _getdiagram(spin, D)
+    factor = 1 / (2 * math.pi) ** D
+    rootval = _eval([root])[0]
+    assert rootval == pytest.approx((-2 + spin) * factor)
+    (root_o,) = opt.optimize([root])
+    assert _eval([root_o])[0] == rootval
+    # one derivative with respect to the fermionic ("x") and one to the bosonic ("y") propagators; every derivative = 1,
+    # i.e. the coefficient leaf of order o carries 1 / o!
+    root = _getdiagram(spin, D)
+    dep = {}
+    for node in fd.graph.post_order_unique([root]):
+        if not node.subgraphs:
+            dep[node.id] = [isinstance(node.properties, BareGreenId), isinstance(node.properties, BareInteractionId)]
+    (series,), _ = taylor.taylorexpansion([root], dep, [1, 1])
+
+    def coeff_leaf(leaf):
+        orders = getattr(leaf, "orders", None) or [0, 0]
+        return 1.0 / math.prod(math.factorial(int(o)) for o in orders)
+
+    c = {o: _eval([g], coeff_leaf)[0] for o, g in series.coeffs.items()}
+    assert c[(0, 0)] == pytest.approx((-2 + spin) * factor)
+    assert c[(0, 1)] == pytest.approx((-2 + spin) * 2 * factor)
+    assert c[(1, 0)] == pytest.approx((-2 + spin) * 2 * factor)
+
+
+def test_committed_workloads_are_what_the_front_ends_build():
+    """The headline workload file is the restated Parquet front end's output: rebuild the small orders here (the big ones
+    take minutes) and compare with the committed arrays; the all-leaves-one checksums of every workload are in the
+    manifest and are re-derived from the files by the oracle."""
+    import json
+    import os
+
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(here, "workloads", "MANIFEST.json")) as fh:
+        manifest = json.load(fh)
+    for order in (2, 3):
+        fd.uidreset()
+        pq._ver4I.clear()
+        graphs = [r["diagram"] for r in pq.vertex4(pq.DiagPara(type=pq.Ver4Diag, innerLoopNum=order))]
+        opt.optimize(graphs)
+        raw, _ = fd.flatten(graphs)
+        ref = fd.RawGraph.load(os.path.join(here, "workloads", f"parquet_ver4_o{order}.npz"))
+        assert all(np.array_equal(getattr(raw, k), getattr(ref, k)) for k in raw.__dataclass_fields__)
+    for name in ("parquet_ver4_o4", "gv_ver4_o4", "parquet_sigma_o3", "taylor_sigma_o3"):
+        raw = fd.RawGraph.load(os.path.join(here, "workloads", name + ".npz"))
+        orc = O.Oracle(raw)
+        ones = orc.eval(np.ones((orc.n_leaves, 1)))[:, 0]
+        assert [float(x) for x in ones] == manifest[name]["all_leaves_one"]
+        assert orc.n_leaves == manifest[name]["n_leaves"] and orc.n_roots == manifest[name]["n_roots"]

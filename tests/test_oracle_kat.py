@@ -190,3 +190,68 @@ def test_taylor_workload_checksums():
     # order-3 self-energy: 5 propagators, 3 interactions -> (0,1): C(3,1)=3, (1,0): C(5,1)=5, (2,0): C(6,2)=15, products for mixed
     for k, mult in enumerate([1, 3, 5, 15, 15, 45]):
         assert list(ones[3 * k:3 * k + 3]) == list(mult * base)
+
+
+def test_derivative_known_answers_through_the_taylor_series():
+    """reference test/computational_graph.jl:930-1071 (`forwardAD_root!`, `build_derivative_graph`): explicit leaf vectors
+    -> 120 / 5 / 1, 570 / 3 / 1, 120 / 2 / 0, 300, 3840, 480, 1002, 426, 90, 0, 5568, 1003, 3708, 1638, 234.  The
+    reference's graph-level AD is not restated; the same numbers are pinned on the restated Taylor-series expansion, which
+    is what the Taylor-AD workloads (BASELINE config 5) are made with: the derivative of order n is n! times the Taylor
+    coefficient, a leaf's own first derivative is the seed of the test's leaf vector and its higher derivatives are 0."""
+    import math
+
+    import fdgraph_b200 as fd
+    from oracle.frontend import taylor as T
+
+    fd.uidreset()
+    g1, g2 = fd.Graph([]), fd.Graph([])
+    g3 = fd.Graph([], factor=2.0)
+    l3 = g3.eldest()
+    F3 = g1 + g2
+    F2 = fd.graph.linear_combination([g1, g3, F3], [2, 1, 3])
+    F1 = fd.Graph([g1, F2, F3], operator=fd.Prod(), subgraph_factors=[3.0, 1.0, 1.0])
+    F0 = F1 * F3
+    F0_r1 = F1 + F3
+    dep = {g1.id: [True, False, False], g2.id: [False, True, False], l3.id: [False, False, True]}
+    (s1, s2, s3, s0, s0r), _ = T.taylorexpansion([F1, F2, F3, F0, F0_r1], dep, [3, 2, 2])
+    var_of = {g1.id: 0, g2.id: 1, l3.id: 2}
+
+    def derivative(series, order, leaf):
+        """leaf = [g1, g2, l3, seed1, seed2, seed3] as in the reference's leaf vectors"""
+        val = {}
+
+        def leaf_value(node):
+            orders = tuple(getattr(node, "orders", None) or (0, 0, 0))
+            if sum(orders) == 0:
+                return leaf[var_of[node.id]]
+            v = next(i for i, o in enumerate(orders) if o)
+            return leaf[3 + v] if sum(orders) == 1 else 0.0
+
+        g = series.coeffs.get(order)
+        if g is None:
+            return 0.0
+        for node in fd.graph.post_order_unique([g]):
+            if not node.subgraphs:
+                val[id(node)] = leaf_value(node)
+                continue
+            terms = [val[id(s)] * f for s, f in zip(node.subgraphs, node.subgraph_factors)]
+            val[id(node)] = sum(terms) if isinstance(node.operator, fd.Sum) else math.prod(terms)
+        return val[id(g)] * math.prod(math.factorial(o) for o in order)
+
+    x, y, z = (1, 0, 0), (0, 1, 0), (0, 0, 1)
+    # forwardAD_root!: first derivatives along g1, g2, eldest(g3)
+    leaf = [1.0, 1.0, 1.0, 1.0, 0.0, 0.0]
+    assert (derivative(s1, x, leaf), derivative(s2, x, leaf), derivative(s3, x, leaf)) == (120.0, 5.0, 1.0)
+    leaf = [5.0, -1.0, 2.0, 0.0, 1.0, 0.0]
+    assert (derivative(s1, y, leaf), derivative(s2, y, leaf), derivative(s3, y, leaf)) == (570.0, 3.0, 1.0)
+    leaf = [5.0, -1.0, 2.0, 0.0, 0.0, 1.0]
+    assert (derivative(s1, z, leaf), derivative(s2, z, leaf), derivative(s3, z, leaf)) == (120.0, 2.0, 0.0)
+    assert derivative(s0, x, [1.0, 1.0, 1.0, 1.0, 0.0, 0.0]) == 300.0
+    assert derivative(s0, y, [5.0, -1.0, 2.0, 0.0, 1.0, 0.0]) == 3840.0
+    assert derivative(s0, z, [5.0, -1.0, 2.0, 0.0, 0.0, 1.0]) == 480.0
+    assert derivative(s0r, z, [5.0, -1.0, 2.0, 0.0, 0.0, 1.0]) == 120.0
+    # build_derivative_graph: orders up to (3, 2, 2), every first derivative seeded with 1
+    leaf = [5.0, -1.0, 2.0, 1.0, 1.0, 1.0]
+    assert [derivative(s1, o, leaf) for o in ((1, 0, 0), (2, 0, 0), (3, 0, 0), (3, 1, 0))] == [1002.0, 426.0, 90.0, 0.0]
+    assert [derivative(s0, o, leaf) for o in ((1, 0, 0), (2, 0, 0), (3, 0, 0), (3, 1, 0), (3, 2, 0))] == [5568.0, 3708.0, 1638.0, 234.0, 0.0]
+    assert [derivative(s0r, o, leaf) for o in ((1, 0, 0), (2, 0, 0), (3, 0, 0), (3, 1, 0), (3, 2, 0))] == [1003.0, 426.0, 90.0, 0.0, 0.0]
