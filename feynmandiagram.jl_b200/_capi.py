@@ -143,16 +143,21 @@ def graph_write(raw, path: str) -> None:
     check(lib().fdg_graph_write(C.byref(d), os.fsencode(path)))
 
 
-def compile_file(path: str, dtype: int = FDG_F64, backend: int = 0, jit_segment: int = 0, cse: bool = False) -> C.c_void_p:
+def _cse_mode(cse) -> int:
+    """None -> 0 (automatic), True -> 1 (always), False -> -1 (never)"""
+    return 0 if cse is None else (1 if cse else -1)
+
+
+def compile_file(path: str, dtype: int = FDG_F64, backend: int = 0, jit_segment: int = 0, cse=None) -> C.c_void_p:
     o = Options()
-    o.dtype, o.backend, o.jit_segment, o.cse = int(dtype), int(backend), int(jit_segment), int(bool(cse))
+    o.dtype, o.backend, o.jit_segment, o.cse = int(dtype), int(backend), int(jit_segment), _cse_mode(cse)
     h = C.c_void_p()
     check(lib().fdg_compile_file(os.fsencode(path), C.byref(o), C.byref(h)))
     return h
 
 
 def compile_raw(raw, dtype: int = FDG_F64, max_slots: int = 0, prefetch: int = 0, schedule: int = 0, backend: int = 0,
-                jit_segment: int = 0, cse: bool = False, fma: bool = False) -> C.c_void_p:
+                jit_segment: int = 0, cse=None, fma: bool = False) -> C.c_void_p:
     """fdg_compile on a RawGraph; returns the opaque handle."""
     L = lib()
     raw.validate_dtypes()
@@ -168,7 +173,7 @@ def compile_raw(raw, dtype: int = FDG_F64, max_slots: int = 0, prefetch: int = 0
     d.n_roots, d.root_id = int(raw.root_id.shape[0]), _ptr(raw.root_id, C.c_int64)
     o = Options()
     o.dtype, o.max_slots, o.prefetch, o.schedule = int(dtype), int(max_slots), int(prefetch), int(schedule)
-    o.backend, o.jit_segment, o.cse, o.fma = int(backend), int(jit_segment), int(bool(cse)), int(bool(fma))
+    o.backend, o.jit_segment, o.cse, o.fma = int(backend), int(jit_segment), _cse_mode(cse), int(bool(fma))
     h = C.c_void_p()
     check(L.fdg_compile(C.byref(d), C.byref(o), C.byref(h)))
     return h
@@ -208,11 +213,12 @@ def launch_count(h) -> int:
 def jit_prepare(h, samples_per_thread: int = 2, accumulate: bool = False) -> dict:
     nk, nc, nb = C.c_int32(), C.c_int32(), C.c_int64()
     check(lib().fdg_jit_prepare(h, samples_per_thread, int(accumulate), C.byref(nk), C.byref(nc), C.byref(nb)))
-    out = (C.c_int64 * 9)()
-    check(lib().fdg_jit_info(h, samples_per_thread, int(accumulate), out, 9))
+    out = (C.c_int64 * 12)()
+    check(lib().fdg_jit_info(h, samples_per_thread, int(accumulate), out, 12))
     return {"kernels": int(nk.value), "cross_rows": int(nc.value), "cross_values": int(out[2]), "cubin_bytes": int(nb.value),
             "leaf_loads": int(out[3]), "cross_loads": int(out[4]), "cross_stores": int(out[5]), "operations": int(out[6]),
-            "grid_stride": bool(out[7]), "max_code_bytes": int(out[8])}
+            "grid_stride": bool(out[7]), "max_code_bytes": int(out[8]), "cse": bool(out[9]), "fp64_instr": int(out[10]),
+            "model_ns": out[11] / 1000.0}
 
 
 def pipeline_prepare(h, accumulate: bool = True, n_sm: int = 148) -> dict:

@@ -53,7 +53,7 @@ class Evaluator:
     """The callable returned by :func:`compile` -- stands in for the generated ``eval_graph!``."""
 
     def __init__(self, raw: RawGraph, dtype=np.float64, max_slots: int = 0, prefetch: int = 0, schedule: int = 0,
-                 backend: int = 0, jit_segment: int = 0, cse: bool = False, fma: bool = False):
+                 backend: int = 0, jit_segment: int = 0, cse=None, fma: bool = False):
         self.dtype = np.dtype(dtype)
         if self.dtype not in _DTYPES:
             # static.jl:151  error("Unsupported type")
@@ -192,7 +192,7 @@ class Evaluator:
 
 def compile(graphs: Sequence[Graph], root: Optional[Sequence[int]] = None, *, dtype=np.float64,
             max_slots: int = 0, prefetch: int = 0, schedule: int = 0, backend: int = 0,
-            jit_segment: int = 0, cse: bool = False, fma: bool = False) -> Tuple[Evaluator, Dict[int, Graph]]:
+            jit_segment: int = 0, cse=None, fma: bool = False) -> Tuple[Evaluator, Dict[int, Graph]]:
     """``Compilers.compile(graphs; root)`` (static.jl:221-227) -> ``(eval_graph, leafmap)``.
 
     ``leafmap[k]`` is the leaf Graph whose value is read from column ``k`` of ``leafVal`` (0-based
@@ -206,14 +206,14 @@ def compile(graphs: Sequence[Graph], root: Optional[Sequence[int]] = None, *, dt
 
 
 def compile_raw(raw: RawGraph, *, dtype=np.float64, max_slots: int = 0, prefetch: int = 0, schedule: int = 0,
-                backend: int = 0, jit_segment: int = 0, cse: bool = False, fma: bool = False) -> Evaluator:
+                backend: int = 0, jit_segment: int = 0, cse=None, fma: bool = False) -> Evaluator:
     """Compile an already flattened graph (e.g. a workload file written by another host).  ``fma=True`` (opt-in) lets
     the specialised kernels fuse multiplies into adds: faster where FP64 issue is the limit, NOT bit-identical."""
     return Evaluator(raw, dtype=dtype, max_slots=max_slots, prefetch=prefetch, schedule=schedule, backend=backend,
                      jit_segment=jit_segment, cse=cse, fma=fma)
 
 
-def compile_file(path: str, *, dtype=np.float64, backend: int = 0, jit_segment: int = 0, cse: bool = False) -> Evaluator:
+def compile_file(path: str, *, dtype=np.float64, backend: int = 0, jit_segment: int = 0, cse=None) -> Evaluator:
     """Evaluator of a graph stored as an FDGRAPH file (fdg_compile_file): a graph flattened by a Julia session elsewhere
     (`FDGraphB200.save_graph`) or by `RawGraph.save_fdg`."""
     ev = Evaluator.__new__(Evaluator)

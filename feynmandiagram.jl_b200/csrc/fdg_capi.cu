@@ -97,6 +97,8 @@ struct JitVariant {
 
 struct fdg_program {
     fdg::Lowered low;
+    fdg::Lowered low_cse;  // fdg_options.cse == 0 (automatic): the same program with common sub-expressions merged ...
+    bool has_cse = false;  // ... if that removes anything; the specialised back end plans both and keeps the faster plan
     int backend = FDG_BACKEND_AUTO;
     int jit_segment = 0;
     bool fma = false;  // fdg_options.fma: contraction allowed in the specialised kernels (opt-in, not bit-identical)
@@ -249,8 +251,20 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
         // multi-kernel plan comes out above 120 KB the plan is redone with a proportionally smaller budget (at most twice).
         int budget = h->jit_segment > 0 ? h->jit_segment : 4000;
         int rc = FDG_OK;
+        // automatic CSE: plan the program with and without merged sub-expressions (planning is cheap, assembling is not) and
+        // keep the plan whose modelled time is lower: fewer operations against more values crossing kernel boundaries
+        const fdg::Lowered *lowp = &h->low;
+        if (h->has_cse) {
+            fdg::JitPlan a, b;
+            std::string e1, e2;
+            const int es = h->low.dtype == FDG_C128 ? 16 : 8;
+            if (fdg::jit_plan(h->low, spt, acc, budget, wide, h->fma, a, e1) == FDG_OK &&
+                fdg::jit_plan(h->low_cse, spt, acc, budget, wide, h->fma, b, e2) == FDG_OK && fdg::jit_model_ns(b, es) < 0.97 * fdg::jit_model_ns(a, es))
+                lowp = &h->low_cse;
+        }
         for (int attempt = 0; attempt < 3; ++attempt) {
-            rc = fdg::jit_plan(h->low, spt, acc, budget, wide, h->fma, v.plan, err);
+            rc = fdg::jit_plan(*lowp, spt, acc, budget, wide, h->fma, v.plan, err);
+            v.plan.uses_cse = lowp == &h->low_cse || h->low.cse_removed > 0;
             if (rc == FDG_OK) rc = fdg::jit_compile(v.plan, err);
             if (rc != FDG_OK || v.plan.seg.size() < 2 || v.plan.max_code_bytes <= 120 * 1024 || getenv("FDG_JIT_NO_REFIT")) break;
             const int smaller = (int)((double)budget * 112.0 * 1024.0 / (double)v.plan.max_code_bytes);
@@ -779,6 +793,9 @@ static int fdg_compile_impl(const fdg_graph_desc *graph, const fdg_options *opts
     if (o.fma != 0 && o.fma != 1) return fail(FDG_ERR_BAD_ARG, "fdg_options.fma must be 0 or 1");
     if (o.fma == 1 && o.backend == FDG_BACKEND_VM) return fail(FDG_ERR_UNSUPPORTED, "fma applies to the specialised kernels only");
     if (o.backend < FDG_BACKEND_AUTO || o.backend > FDG_BACKEND_JIT) return fail(FDG_ERR_BAD_ARG, "unknown backend");
+    if (o.cse < -1 || o.cse > 1) return fail(FDG_ERR_BAD_ARG, "fdg_options.cse must be -1 (never), 0 (automatic) or 1 (always)");
+    const int cse_mode = o.cse;
+    o.cse = cse_mode == 1 ? 1 : 0;  // what lower() sees: merge or not
     fdg_program *p = new (std::nothrow) fdg_program();
     if (!p) return fail(FDG_ERR_BAD_ARG, "out of memory");
     std::string err;
@@ -792,6 +809,16 @@ static int fdg_compile_impl(const fdg_graph_desc *graph, const fdg_options *opts
     if (rc != FDG_OK) {
         delete p;
         return fail(rc, err);
+    }
+    if (cse_mode == 0 && o.backend != FDG_BACKEND_VM && p->low.N >= 16) {
+        fdg_options oc = o;
+        oc.cse = 1;
+        std::string e2;
+        try {
+            if (fdg::lower(*graph, oc, p->low_cse, e2) == FDG_OK && p->low_cse.cse_removed > 0) p->has_cse = true;
+        } catch (const std::exception &) {
+        }
+        if (!p->has_cse) p->low_cse = fdg::Lowered();
     }
     p->backend = o.backend;
     p->jit_segment = o.jit_segment;
@@ -905,9 +932,10 @@ static int fdg_jit_info_impl(fdg_handle h, int32_t samples_per_thread, int32_t a
     const fdg::JitPlan &pl = it->second.plan;
     int64_t ops = 0;
     for (auto &sg : pl.seg) ops += sg.n_stmts;
-    const int64_t vals[9] = {(int64_t)pl.seg.size(), pl.n_cross, pl.n_cross_values, pl.leaf_loads, pl.cross_loads, pl.cross_stores, ops,
-                             pl.persistent ? 1 : 0, pl.max_code_bytes};
-    for (int32_t i = 0; i < n_out && i < 9; ++i) out[i] = vals[i];
+    const int64_t vals[12] = {(int64_t)pl.seg.size(), pl.n_cross, pl.n_cross_values, pl.leaf_loads, pl.cross_loads, pl.cross_stores, ops,
+                              pl.persistent ? 1 : 0, pl.max_code_bytes, pl.uses_cse ? 1 : 0, pl.fp64_instr,
+                              (int64_t)(1000.0 * fdg::jit_model_ns(pl, h->low.dtype == FDG_C128 ? 16 : 8))};
+    for (int32_t i = 0; i < n_out && i < 12; ++i) out[i] = vals[i];
     return FDG_OK;
 }
 

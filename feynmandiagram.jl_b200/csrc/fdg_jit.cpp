@@ -791,6 +791,16 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         }
     }
     plan.n_boundary = n_boundary;
+    for (const IrOp &o : ir) {
+        switch (o.kind) {
+            case IR_MUL: plan.fp64_instr += cplx ? 6 : samples_per_thread; break;
+            case IR_ADD:
+            case IR_SCALE: plan.fp64_instr += cplx ? 2 : samples_per_thread; break;
+            case IR_POW: plan.fp64_instr += (o.n <= 3 ? (o.n - 1) : 14) * (cplx ? 6 : samples_per_thread); break;
+            default: break;
+        }
+    }
+    plan.fp64_instr /= samples_per_thread;  // per sample
     plan.n_cross_values = n_cross_values;
     plan.n_cross = n_cross;
     plan.seg.resize((size_t)nseg);
@@ -1263,6 +1273,13 @@ static int compile_one(JitSegment &js, bool fma, std::string &err, bool relocata
     }
     nvPTXCompilerDestroy(&h);
     return FDG_OK;
+}
+
+double jit_model_ns(const JitPlan &plan, int bytes_per_element) {
+    const double bytes = (double)(plan.leaf_loads + plan.cross_loads + plan.cross_stores) * bytes_per_element;
+    const double t_mem = bytes / (0.78 * 6555.0);                          // bytes / (GB/s) = ns
+    const double t_fp = (double)plan.fp64_instr / (0.70 * 148 * 64 * 1.7);  // instructions / (G lane-instructions/s) = ns
+    return std::max(t_mem, t_fp) + 0.01 * (double)plan.seg.size();
 }
 
 int jit_assemble(const std::string &ptx, int opt_level, std::vector<char> &cubin, std::string &err) {

@@ -24,6 +24,8 @@ struct JitPlan {
     int32_t n_cross_values = 0;  // values that cross a kernel boundary
     int64_t leaf_loads = 0, cross_loads = 0, cross_stores = 0;  // global loads / stores per sample over all kernels
     int64_t max_code_bytes = 0;  // machine code of the largest kernel (the instruction cache holds 128 KB)
+    int64_t fp64_instr = 0;      // FP64 arithmetic instructions per sample the kernels execute (folded negations are none)
+    bool uses_cse = false;       // planned from the program with common sub-expressions merged
     bool persistent = false;  // single accumulate kernel run as a grid-stride loop (per-thread running sums)
     std::vector<JitSegment> seg;
     // ---- pipeline form: ONE kernel, one resident block per SM; the blocks of stage k run only
@@ -61,6 +63,11 @@ struct PipeOptions {
         return n;
     }
 };
+
+// Modelled time of one sample on a B200, ns: the slower of the plan's memory traffic at the HBM rate such kernels reach
+// (78 % of the measured copy bandwidth) and its FP64 instructions at the rate they reach (70 % of 148 SMs x 64 lanes at
+// 1.7 GHz under the power cap), DESIGN.md section 5.  Used to choose between plans, not reported as a result.
+double jit_model_ns(const JitPlan &plan, int bytes_per_element);
 
 // linearise the emitted function in fold order, cut it into segments of `seg_ops` operations, write their PTX
 // wide_strides: row offsets need 64 bits (a leading dimension of 4 GiB or more)

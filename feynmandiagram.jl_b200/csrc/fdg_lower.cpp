@@ -886,7 +886,7 @@ int lower(const fdg_graph_desc &g, const fdg_options &opt, Lowered &out, std::st
     }
 
     if (opt.cse != 0) {
-        int64_t min_cost = 6;
+        int64_t min_cost = 2;  // everything that saves at least one operation
         if (const char *e = getenv("FDG_CSE_MIN_COST")) min_cost = atoll(e);
         out.cse_removed = eliminate_common_subexpressions(st, ops, min_cost);
         mark_live(st, ops);

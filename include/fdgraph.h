@@ -98,10 +98,12 @@ typedef struct fdg_options {
                              before the fold that reads them (emitter order); 1 = lazy: inside it */
     int32_t backend;      /* FDG_BACKEND_AUTO (0), FDG_BACKEND_VM (1), FDG_BACKEND_JIT (2)            */
     int32_t jit_segment;  /* machine instructions per specialised kernel, estimated (0 = 4000)  */
-    int32_t cse;          /* 1 = evaluate common sub-expressions once (hash-based analogue of
-                             optimize!(level=1), optimize.jl:345-390; bit-identical).  Default 0: on
-                             the memory-bound order-4 graphs sharing more values costs more traffic
-                             than the saved arithmetic                           */
+    int32_t cse;          /* common sub-expressions evaluated once (hash-based analogue of optimize!(level=1),
+                             optimize.jl:345-390; operand order is part of the key, so every value keeps its bits):
+                             0 (default) = automatic: the specialised back end plans the program with and without
+                             merging and keeps the plan whose modelled time is lower -- merging saves operations but
+                             makes more values cross kernel boundaries, which the memory-bound order-4 graphs cannot
+                             afford; 1 = always; -1 = never                      */
     int32_t fma;          /* 0 (default): every multiply and add is rounded on its own -- the bits of the
                              emitted Julia / C function.  1 (opt-in, specialised kernels only): a multiply
                              may be fused into the add that reads it (DFMA).  One rounding fewer per fused
@@ -178,7 +180,9 @@ int fdg_jit_prepare(fdg_handle h, int32_t samples_per_thread, int32_t accumulate
                     int32_t *n_cross, int64_t *cubin_bytes);
 /* counters of a prepared variant, out[0..n_out): kernels, rows of the cross buffer, values crossing a kernel
  * boundary, then per sample over all kernels: leaf loads, cross loads, cross stores, operations; [7] = 1 if the
- * variant is a single grid-stride kernel; [8] = bytes of machine code of the largest kernel.  (leaf loads + cross loads + cross stores) x sizeof(W) is the traffic the
+ * variant is a single grid-stride kernel; [8] = bytes of machine code of the largest kernel; [9] = 1 if the plan was made
+ * from the program with common sub-expressions merged; [10] = FP64 instructions per sample the kernels execute;
+ * [11] = modelled time of one sample, ps.  (leaf loads + cross loads + cross stores) x sizeof(W) is the traffic the
  * plan asks of the memory system per sample -- the figure DESIGN.md compares with ncu's dram bytes. */
 int fdg_jit_info(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int64_t *out, int32_t n_out);
 /* Pipeline form of the specialised back end: ONE cooperative kernel, one block per SM; the blocks

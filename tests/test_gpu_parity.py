@@ -531,3 +531,75 @@ def test_two_host_callers_on_one_handle():
         th.join()
     assert not errors, errors
     assert ev.launches >= 8
+
+
+def _workload(name):
+    import os
+
+    return fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", name + ".npz"))
+
+
+@pytest.mark.parametrize("name,dtype", [("parquet_ver4_o3", np.float64), ("parquet_ver4_o4", np.float64), ("gv_ver4_o4", np.float64),
+                                        ("taylor_sigma_o3", np.complex128), ("taylor_sigma_o4", np.complex128), ("parquet_sigma_o4", np.float64)])
+@pytest.mark.parametrize("cse", [True, None])
+def test_common_subexpressions_merged_same_bits(name, dtype, cse):
+    """SURVEY section 8f N4 (optimize.jl:345-390): merging equal sub-expressions keeps every bit (operand order is part of
+    the key).  cse=True forces it, cse=None lets the planner's model decide; both against the oracle of the UNMERGED graph,
+    eval mode bit for bit and accumulate against the sum."""
+    raw = _workload(name)
+    ev = fd.compile_raw(raw, dtype=dtype, backend=JIT, cse=cse)
+    W = 1 if dtype == np.float64 else 2
+    info = ev.jit_prepare(1 if (W == 2 or ev.stats["n_operands"] > 400) else 2, False)
+    if cse:
+        assert info["cse"]
+    B = 4096
+    leaf_h = graphgen.leaf_values(21, ev.n_leaves, B, dtype=dtype, signed=True)
+    got = _dev_eval(ev, leaf_h, B)
+    want = O.Oracle(raw).eval(leaf_h)
+    assert got.tobytes() == want.tobytes()
+    leaf = torch.from_numpy(leaf_h).cuda()
+    acc = torch.zeros(ev.n_roots * W, dtype=torch.float64, device="cuda")
+    ev.accumulate_device(leaf.data_ptr(), B, B, acc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = want.sum(axis=1)
+    ref = np.stack([ref.real, ref.imag], axis=1).reshape(-1) if W == 2 else ref
+    scale = np.abs(want).sum(axis=1)
+    scale = np.repeat(scale, 2) if W == 2 else scale
+    assert np.all(np.abs(acc.cpu().numpy() - ref) <= 1e-12 * (scale + 1e-300))
+
+
+def test_automatic_cse_follows_the_model():
+    """The planner keeps the merged program where its modelled time is lower (FP64-bound graphs: Taylor-AD, Parquet sigma
+    order 4) and the unmerged one where the extra values crossing kernels cost more than the saved arithmetic (the
+    memory-bound order-4 vertices)."""
+    picks = {}
+    for name, dtype in (("taylor_sigma_o3", np.complex128), ("parquet_sigma_o4", np.float64), ("parquet_ver4_o4", np.float64), ("gv_ver4_o4", np.float64)):
+        ev = fd.compile_raw(_workload(name), dtype=dtype, backend=JIT)
+        picks[name] = ev.jit_prepare(1, True)["cse"]
+    assert picks == {"taylor_sigma_o3": True, "parquet_sigma_o4": True, "parquet_ver4_o4": False, "gv_ver4_o4": False}
+
+
+@pytest.mark.parametrize("name", ["parquet_ver4_o4", "gv_ver4_o4"])
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_order_four_vertices_against_the_full_oracle(name, backend):
+    """The headline graph (Parquet vertex4 order 4) and GV vertex4 order 4 at 4096 samples, EVERY sample against the
+    oracle, on both back ends."""
+    raw = _workload(name)
+    ev = fd.compile_raw(raw, backend=backend)
+    B = 4096
+    leaf = graphgen.leaf_values(31, ev.n_leaves, B, signed=True)
+    got = _dev_eval(ev, leaf, B)
+    assert got.tobytes() == O.Oracle(raw).eval(leaf).tobytes()
+
+
+def test_opt_in_fma_on_the_headline_graph():
+    """fdg_options.fma = 1 on Parquet vertex4 order 4: not the reference's bits, but within 1e-12 of them on the scale of
+    the sum of the absolute terms (leaves in [0.5, 1.5): no cancellation to amplify the single roundings saved)."""
+    raw = _workload("parquet_ver4_o4")
+    ev = fd.compile_raw(raw, backend=JIT, fma=True)
+    B = 2048
+    leaf = graphgen.leaf_values(41, ev.n_leaves, B, signed=False)
+    got = _dev_eval(ev, leaf, B)
+    want = O.Oracle(raw).eval(leaf)
+    assert got.tobytes() != want.tobytes()
+    assert np.all(np.abs(got - want) <= 1e-12 * np.abs(want).max(axis=1, keepdims=True))
