@@ -1263,7 +1263,6 @@ namespace {
 
 constexpr int FDG_LG_MAXLOOPS = 8;
 constexpr int FDG_LG_THREADS = 128;
-constexpr int FDG_LG_CHUNK = 64;  // leaves per block in y
 
 struct LeafMeta {  // one per leaf, read with uniform (broadcast) loads; sorted by loop-basis vector
     int32_t type, order, tau_in, tau_out;
@@ -1347,57 +1346,135 @@ __device__ __forceinline__ double lg_green_derive(double tau, double w, double b
     return coef * (g0 * Y);
 }
 
+// ---- the generation kernel proper -------------------------------------------------------------------------------------
+// Leaves are grouped by loop-basis vector.  A block of 128 threads (one sample each) stages the sample's variables -- the
+// loop momenta K and the times T -- in shared memory ([row][thread]: conflict-free and indexable by the table), then walks
+// the basis vectors of its chunk: |K . basis|^2 from the NON-ZERO coefficients of the vector only (3 to 5 of the 7 or 8
+// loops of the order-4 graphs), the momentum-only factors exp(-|w| beta) and 1 / (1 + exp(-|w| beta)) once per vector, then
+// one exp and one multiply per Green's-function leaf, no exp at all per interaction leaf.  All table reads are uniform over
+// the block (broadcast).  Against the reference's formulas evaluated leaf by leaf this changes the last bits (fused
+// multiply-adds in the dot products, a multiply by the reciprocal instead of a division): leaf values agree to ~1e-15
+// relative (tests: <= 2e-14), which is the bar for this off-path producer (its bits are unpinned in the reference: BLAS
+// `mul!` and Lehmann's kernels); the graph evaluation on top of the leaves stays bit-exact.
+// exp(x) for x <= 0, the only arguments the propagators produce (-|w| x with x in (0, beta]).  n = round(x log2 e),
+// r = x - n ln 2 in two pieces, exp(r) as the degree-13 Taylor polynomial on |r| <= ln 2 / 2 (remainder below 1e-17
+// relative), 2^n applied as two factors so that results in the denormal range come out right.  About 25 instructions
+// against ~40 of the library's exp; error <= 2 ulp (the leaf values' bar is 2e-14 relative, tests/test_leafgen.py).
+__device__ __forceinline__ double lg_exp_neg(double x) {
+    x = fmax(x, -746.0);  // exp(-746) = 0 in double: keeps the exponent arithmetic below in range
+    const double t = rint(x * 1.4426950408889634074);
+    double r = fma(t, -6.93147180369123816490e-01, x);
+    r = fma(t, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;               // 1 / 13!
+    p = fma(p, r, 2.08767569878680989792e-09);       // 1 / 12!
+    p = fma(p, r, 2.50521083854417187751e-08);       // 1 / 11!
+    p = fma(p, r, 2.75573192239858906526e-07);       // 1 / 10!
+    p = fma(p, r, 2.75573192239858906526e-06);       // 1 / 9!
+    p = fma(p, r, 2.48015873015873015873e-05);       // 1 / 8!
+    p = fma(p, r, 1.98412698412698412698e-04);       // 1 / 7!
+    p = fma(p, r, 1.38888888888888888889e-03);       // 1 / 6!
+    p = fma(p, r, 8.33333333333333333333e-03);       // 1 / 5!
+    p = fma(p, r, 4.16666666666666666667e-02);       // 1 / 4!
+    p = fma(p, r, 1.66666666666666666667e-01);       // 1 / 3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int n = (int)t, h = n >> 1;  // 2^n = 2^h 2^(n - h), both factors normal for n >= -1077
+    return p * __hiloint2double((h + 1023) << 20, 0) * __hiloint2double((n - h + 1023) << 20, 0);
+}
+
+struct LgBasis {
+    int32_t nnz, leaf0, n_leaves, pad;
+    int32_t idx[FDG_LG_MAXLOOPS];
+    double coef[FDG_LG_MAXLOOPS];
+};
+struct LgLeaf {
+    int32_t type, order, tau_in, tau_out, out, pad[3];
+};
+constexpr int FDG_LG_BASES_PER_BLOCK = 24;
+
+constexpr int FDG_LG_SPT = 1;  // samples per thread (2 was measured slower: 124 vs 142 M samples/s on Parquet vertex4 order 4)
+
 template <int DIM>
 __global__ void __launch_bounds__(FDG_LG_THREADS)
-fdg_leafgen_kernel(const LeafMeta *__restrict__ meta, int n_leaves, int n_loops, const double *__restrict__ K,
-                   const double *__restrict__ T, long long ld_var, long long batch, double *__restrict__ leaf,
-                   long long ld_leaf, double kF2, double beta, double lambda) {
-    const long long b = (long long)blockIdx.x * FDG_LG_THREADS + threadIdx.x;
-    if (b >= batch) return;
-    double k[FDG_LG_MAXLOOPS][DIM];
+fdg_leafgen2_kernel(const LgBasis *__restrict__ bases, int n_bases, const LgLeaf *__restrict__ leaves, int n_loops, int n_tau,
+                    const double *__restrict__ K, const double *__restrict__ T, long long ld_var, long long batch, double *__restrict__ leaf,
+                    long long ld_leaf, double kF2, double beta, double lambda) {
+    constexpr int S = FDG_LG_SPT, COLS = FDG_LG_THREADS * S;
+    extern __shared__ double lg_var[];  // [(n_loops * DIM + n_tau)][COLS]
+    const int tid = threadIdx.x;
+    const long long base = (long long)blockIdx.x * COLS;
+    const int kr = n_loops * DIM;
+    bool valid[S];
 #pragma unroll
-    for (int j = 0; j < FDG_LG_MAXLOOPS; ++j)
+    for (int s = 0; s < S; ++s) {
+        const long long b = base + s * FDG_LG_THREADS + tid;  // the block's samples as S coalesced rows of 128
+        valid[s] = b < batch;
+        const long long bs = valid[s] ? b : 0;
+        for (int r = 0; r < kr; ++r) lg_var[r * COLS + s * FDG_LG_THREADS + tid] = K[(long long)r * ld_var + bs];
+        for (int r = 0; r < n_tau; ++r) lg_var[(kr + r) * COLS + s * FDG_LG_THREADS + tid] = T[(long long)r * ld_var + bs];
+    }
+    // (every thread reads back only its own columns: no barrier needed)
+    const double *kv = lg_var + tid;
+    const double *tv = lg_var + kr * COLS + tid;
+    const int b0 = blockIdx.y * FDG_LG_BASES_PER_BLOCK, b1 = min(n_bases, b0 + FDG_LG_BASES_PER_BLOCK);
+    for (int ib = b0; ib < b1; ++ib) {
+        const LgBasis *B = bases + ib;  // read field by field (uniform loads): a local copy would be indexed through local memory
+        const int nnz = B->nnz, leaf0 = B->leaf0, n_leaves = B->n_leaves;
+        double kq[S][3];
 #pragma unroll
-        for (int c = 0; c < DIM; ++c) k[j][c] = j < n_loops ? K[(long long)(j * DIM + c) * ld_var + b] : 0.0;
-    const int l0 = blockIdx.y * FDG_LG_CHUNK, l1 = min(n_leaves, l0 + FDG_LG_CHUNK);
-    int cur = -1;
-    double q2 = 0.0, w = 0.0, den = 1.0, ebeta = 0.0, invK = 0.0;
-    bool have_den = false, have_inv = false;
-    for (int l = l0; l < l1; ++l) {
-        const LeafMeta m = meta[l];
-        double v = 1.0;
-        if (m.type != 0) {
-            if (m.basis_id != cur) {  // uniform over the block: every thread handles the same leaf
-                // kq = K * basis, summed over the loop momenta in index order; dot(kq, kq) over the components in order
-                cur = m.basis_id;
-                q2 = 0.0;
+        for (int s = 0; s < S; ++s) kq[s][0] = kq[s][1] = kq[s][2] = 0.0;
+        for (int n = 0; n < nnz; ++n) {
+            const double cf = B->coef[n];
+            const double *kp = kv + B->idx[n] * DIM * COLS;
 #pragma unroll
-                for (int c = 0; c < DIM; ++c) {
-                    double kq = 0.0;
+            for (int s = 0; s < S; ++s)
 #pragma unroll
-                    for (int j = 0; j < FDG_LG_MAXLOOPS; ++j) kq = __dadd_rn(kq, __dmul_rn(k[j][c], m.basis[j]));
-                    q2 = __dadd_rn(q2, __dmul_rn(kq, kq));
+                for (int c = 0; c < DIM; ++c) kq[s][c] = fma(kp[c * COLS + s * FDG_LG_THREADS], cf, kq[s][c]);
+        }
+        double q2[S], w[S], aw[S], ebeta[S], den[S], inv_den[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            q2[s] = 0.0;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) q2[s] = fma(kq[s][c], kq[s][c], q2[s]);
+            w[s] = q2[s] - kF2, aw[s] = fabs(w[s]);
+            ebeta[s] = 0.0, den[s] = inv_den[s] = 1.0;
+        }
+        bool have_den = false;
+        for (int il = leaf0; il < leaf0 + n_leaves; ++il) {
+            const LgLeaf m = leaves[il];
+            if (m.type == 1 && !have_den) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    ebeta[s] = lg_exp_neg(-aw[s] * beta);
+                    den[s] = 1.0 + ebeta[s];
+                    inv_den[s] = 1.0 / den[s];
                 }
-                w = __dadd_rn(q2, -kF2);
-                have_den = have_inv = false;
+                have_den = true;
             }
-            if (m.type == 1) {
-                if (!have_den) {
-                    ebeta = lg_green_ebeta(w, beta);
-                    den = 1.0 + ebeta;
-                    have_den = true;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                double v = 1.0;
+                if (m.type == 1) {
+                    double tau = tv[m.tau_out * COLS + s * FDG_LG_THREADS] - tv[m.tau_in * COLS + s * FDG_LG_THREADS];
+                    if (m.order == 0) {
+                        if (tau == 0.0) tau = -1e-10;
+                        // green(tau, w, beta) = s exp(-|w| x) / (1 + exp(-|w| beta)),  x in (0, beta], s = sign(tau)
+                        const double x = tau > 0.0 ? (w[s] > 0.0 ? tau : beta - tau) : (w[s] > 0.0 ? tau + beta : -tau);
+                        const double e = lg_exp_neg(-aw[s] * x) * inv_den[s];
+                        v = tau > 0.0 ? e : -e;
+                    } else {
+                        v = lg_green_derive(tau, w[s], beta, ebeta[s], den[s], m.order);
+                    }
+                } else if (m.type == 2) {
+                    // 8 pi / invK * (lambda invK)^order with invK = 1 / (q2 + lambda)
+                    const double sm = q2[s] + lambda;
+                    v = m.order == 0 ? 25.132741228718345 * sm : (25.132741228718345 * sm) * lg_pow(lambda / sm, m.order);
                 }
-                const double tau = __dadd_rn(T[(long long)m.tau_out * ld_var + b], -T[(long long)m.tau_in * ld_var + b]);
-                v = m.order == 0 ? lg_green(tau, w, beta, den) : lg_green_derive(tau, w, beta, ebeta, den, m.order);
-            } else {
-                if (!have_inv) {
-                    invK = 1.0 / __dadd_rn(q2, lambda);
-                    have_inv = true;
-                }
-                v = __dmul_rn(25.132741228718345 / invK, lg_pow(__dmul_rn(lambda, invK), m.order));  // 8pi / invK * (lambda invK)^order
+                if (valid[s]) leaf[(long long)m.out * ld_leaf + base + s * FDG_LG_THREADS + tid] = v;
             }
         }
-        leaf[(long long)m.out * ld_leaf + b] = v;
     }
 }
 
@@ -1405,9 +1482,11 @@ fdg_leafgen_kernel(const LeafMeta *__restrict__ meta, int n_leaves, int n_loops,
 
 struct fdg_leafgen {
     std::vector<LeafMeta> meta;
+    std::vector<LgBasis> bases;  // leaves grouped by loop-basis vector (non-zero coefficients only)
+    std::vector<LgLeaf> leaves;
+    std::map<int, std::pair<LgBasis *, LgLeaf *>> d_tab;  // per device
     int n_loops = 0, dim = 3, n_tau = 0;
     double kF = 0, beta = 0, lambda = 0;
-    std::map<int, LeafMeta *> d_meta;                  // per device
     std::map<std::pair<int, cudaStream_t>, std::pair<double *, size_t>> d_leaf;  // per device and stream: sub-batch leaf matrix of the fused path
     std::map<int, std::pair<double *, size_t>> d_var;   // per device: staging of (K, T) chunks for the host path
     cudaStream_t streams[2] = {nullptr, nullptr};       // host path: copy stream, run stream (created on first use)
@@ -1417,33 +1496,36 @@ struct fdg_leafgen {
 };
 
 namespace {
-int leafgen_meta(fdg_leafgen *g, int dev, LeafMeta **out) {
-    auto it = g->d_meta.find(dev);
-    if (it == g->d_meta.end()) {
-        LeafMeta *p = nullptr;
-        CUDA_TRY(cudaMalloc((void **)&p, std::max<size_t>(g->meta.size(), 1) * sizeof(LeafMeta)));
-        CUDA_TRY(cudaMemcpy(p, g->meta.data(), g->meta.size() * sizeof(LeafMeta), cudaMemcpyHostToDevice));
-        it = g->d_meta.emplace(dev, p).first;
-    }
-    *out = it->second;
-    return FDG_OK;
-}
-
 int leafgen_launch(fdg_leafgen *g, const double *K, const double *T, int64_t ld_var, int64_t batch, double *leaf,
                    int64_t ld_leaf, cudaStream_t st) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
-    LeafMeta *meta = nullptr;
-    int rc = leafgen_meta(g, dev, &meta);
-    if (rc != FDG_OK) return rc;
     const int L = (int)g->meta.size();
     if (L == 0 || batch == 0) return FDG_OK;
-    dim3 grid((unsigned)((batch + FDG_LG_THREADS - 1) / FDG_LG_THREADS), (unsigned)((L + FDG_LG_CHUNK - 1) / FDG_LG_CHUNK));
+    auto it = g->d_tab.find(dev);
+    if (it == g->d_tab.end()) {
+        LgBasis *db = nullptr;
+        LgLeaf *dl = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&db, g->bases.size() * sizeof(LgBasis)));
+        CUDA_TRY(cudaMalloc((void **)&dl, g->leaves.size() * sizeof(LgLeaf)));
+        CUDA_TRY(cudaMemcpy(db, g->bases.data(), g->bases.size() * sizeof(LgBasis), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dl, g->leaves.data(), g->leaves.size() * sizeof(LgLeaf), cudaMemcpyHostToDevice));
+        it = g->d_tab.emplace(dev, std::make_pair(db, dl)).first;
+    }
+    const int nb = (int)g->bases.size();
+    const int64_t cols = (int64_t)FDG_LG_THREADS * FDG_LG_SPT;
+    dim3 grid((unsigned)((batch + cols - 1) / cols), (unsigned)((nb + FDG_LG_BASES_PER_BLOCK - 1) / FDG_LG_BASES_PER_BLOCK));
     const double kF2 = g->kF * g->kF;
-    if (g->dim == 3)
-        fdg_leafgen_kernel<3><<<grid, FDG_LG_THREADS, 0, st>>>(meta, L, g->n_loops, K, T, ld_var, batch, leaf, ld_leaf, kF2, g->beta, g->lambda);
-    else
-        fdg_leafgen_kernel<2><<<grid, FDG_LG_THREADS, 0, st>>>(meta, L, g->n_loops, K, T, ld_var, batch, leaf, ld_leaf, kF2, g->beta, g->lambda);
+    const size_t smem = (size_t)(g->n_loops * g->dim + g->n_tau) * FDG_LG_THREADS * FDG_LG_SPT * sizeof(double);
+    if (g->dim == 3) {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(fdg_leafgen2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fdg_leafgen2_kernel<3><<<grid, FDG_LG_THREADS, smem, st>>>(it->second.first, nb, it->second.second, g->n_loops, g->n_tau, K, T, ld_var, batch,
+                                                                  leaf, ld_leaf, kF2, g->beta, g->lambda);
+    } else {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(fdg_leafgen2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fdg_leafgen2_kernel<2><<<grid, FDG_LG_THREADS, smem, st>>>(it->second.first, nb, it->second.second, g->n_loops, g->n_tau, K, T, ld_var, batch,
+                                                                  leaf, ld_leaf, kF2, g->beta, g->lambda);
+    }
     CUDA_TRY(cudaGetLastError());
     return FDG_OK;
 }
@@ -1499,6 +1581,30 @@ static int fdg_leafgen_create_impl(const fdg_leafgen_desc *d, fdg_leafgen_t *out
     // leaves that carry the same momentum are handled back to back: |K . basis|^2 and the momentum-only factors are
     // computed once per basis vector (404 of them for the 984 leaves of Parquet vertex4 order 4)
     std::stable_sort(g->meta.begin(), g->meta.end(), [](const LeafMeta &a, const LeafMeta &b) { return a.basis_id < b.basis_id; });
+    for (size_t i = 0; i < g->meta.size();) {
+        size_t j = i;
+        while (j < g->meta.size() && g->meta[j].basis_id == g->meta[i].basis_id) ++j;
+        LgBasis B;
+        std::memset(&B, 0, sizeof(B));
+        B.leaf0 = (int32_t)g->leaves.size();
+        B.n_leaves = (int32_t)(j - i);
+        if (g->meta[i].basis_id >= 0)
+            for (int q = 0; q < g->n_loops; ++q)
+                if (g->meta[i].basis[q] != 0.0) {
+                    B.idx[B.nnz] = q;
+                    B.coef[B.nnz] = g->meta[i].basis[q];
+                    B.nnz++;
+                }
+        for (size_t q = i; q < j; ++q) {
+            LgLeaf lf;
+            std::memset(&lf, 0, sizeof(lf));
+            lf.type = g->meta[q].type, lf.order = g->meta[q].order, lf.tau_in = g->meta[q].tau_in, lf.tau_out = g->meta[q].tau_out;
+            lf.out = g->meta[q].out;
+            g->leaves.push_back(lf);
+        }
+        g->bases.push_back(B);
+        i = j;
+    }
     *out = g;
     return FDG_OK;
 }
@@ -1507,13 +1613,14 @@ static int fdg_leafgen_destroy_impl(fdg_leafgen_t g) {
     if (!g) return FDG_OK;
     int cur = -1;
     if (cudaGetDevice(&cur) == cudaSuccess) {
-        for (auto &kv : g->d_meta) {
-            cudaSetDevice(kv.first);
-            cudaFree(kv.second);
-        }
         for (auto &kv : g->d_leaf) {
             cudaSetDevice(kv.first.first);
             cudaFree(kv.second.first);
+        }
+        for (auto &kv : g->d_tab) {
+            cudaSetDevice(kv.first);
+            cudaFree(kv.second.first);
+            cudaFree(kv.second.second);
         }
         for (auto &kv : g->d_var) {
             cudaSetDevice(kv.first);
