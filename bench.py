@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-torch-emitter", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the compact lines of the other BASELINE configurations")
     ap.add_argument("--fma", action="store_true", help="opt-in contraction (fdg_options.fma): NOT the bit-exact default, never the headline")
     return ap.parse_args()
 
@@ -76,6 +77,140 @@ def peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def bind_to_gpu_numa(local):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs: the PCI device's local_cpulist): the pinned
+    staging buffers of the host-buffer path are then first-touched on that node and the copies do not cross sockets.
+    Returns a short description for the bench line; silently does nothing where sysfs says nothing."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        cpus = open(path + "/local_cpulist").read().strip()
+        node = open(path + "/numa_node").read().strip()
+        want = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            want.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = sorted(want & allowed)
+        if use and len(use) < len(allowed):
+            os.sched_setaffinity(0, use)
+            return f"process bound to the {len(use)} CPUs of NUMA node {node} (GPU {local}, {path})"
+        return f"NUMA node {node}: all {len(allowed)} allowed CPUs are local"
+    except Exception as ex:  # noqa: BLE001
+        return f"not bound ({type(ex).__name__})"
+
+
+_M64 = (1 << 64) - 1
+
+
+def _i64(c):
+    c &= _M64
+    return c - (1 << 64) if c >= (1 << 63) else c
+
+
+def fill_leaves(torch, leaf, dtype, first_sample, seed):
+    """leaf[l, b] = 0.5 + u, u in [0, 1) from a counter-based generator (splitmix64 of seed, leaf, GLOBAL sample index,
+    component): the value of a sample does not depend on which rank holds it or on the batch it is generated in."""
+    L, B = leaf.shape
+    comp = 1 if dtype == "f64" else 2
+    view = leaf if comp == 1 else torch.view_as_real(leaf)
+    b = torch.arange(first_sample, first_sample + B, dtype=torch.int64, device=leaf.device)
+    rows = max(1, (1 << 25) // max(B, 1))
+
+    def lsr(z, k):  # logical shift right of an int64 tensor
+        return (z >> k) & _i64((1 << (64 - k)) - 1)
+
+    for l0 in range(0, L, rows):
+        l1 = min(L, l0 + rows)
+        li = torch.arange(l0, l1, dtype=torch.int64, device=leaf.device)[:, None]
+        for c in range(comp):
+            z = (li * _i64(0x9E3779B97F4A7C15) + b[None, :] * _i64(0xD1B54A32D192ED03) + _i64(seed * 0x632BE59BD9B4E019 + c * 0x94D049BB133111EB))
+            z = (z ^ lsr(z, 30)) * _i64(0xBF58476D1CE4E5B9)
+            z = (z ^ lsr(z, 27)) * _i64(0x94D049BB133111EB)
+            z = z ^ lsr(z, 31)
+            u = lsr(z, 11).to(torch.float64) * (1.0 / (1 << 53))
+            if comp == 1:
+                view[l0:l1] = u + 0.5
+            else:
+                view[l0:l1, :, c] = u + 0.5
+            del z, u
+
+
+def probe_fp64(torch, _capi, stream):
+    """The FP64 rate of this GPU, measured in this run (fdg_probe_fp64): chains of DMUL + DADD (what the bit-exact kernels
+    may issue) and of DFMA, 8 independent chains per thread, timed with CUDA events after a warm-up launch."""
+    import ctypes
+
+    sink = torch.zeros(8, dtype=torch.float64, device="cuda")
+    res = {}
+    for fma, key in ((0, "dmul_dadd_gops"), (1, "dfma_gops")):
+        ops = ctypes.c_int64()
+        best = 0.0
+        for rep in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _capi.check(_capi.lib().fdg_probe_fp64(fma, 20000, stream, sink.data_ptr(), ctypes.byref(ops)))
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        res[key] = best
+    res["how"] = ("measured in this run: fdg_probe_fp64, 8 independent chains per thread, 8 x 256 threads per SM, ~50 ms per launch; "
+                  "G instruction-lanes/s (a DFMA counts once; x2 for its flops)")
+    return res
+
+
+def probe_pcie(torch):
+    """Pinned-memory copy bandwidth of this GPU's PCIe link, both directions, 1 GiB, best of 3 (beside the e2e number)."""
+    n = 1 << 27
+    h = torch.empty(n, dtype=torch.float64).pin_memory()
+    d = torch.empty(n, dtype=torch.float64, device="cuda")
+    out = {}
+    for key, (dst, src) in (("h2d_gbs", (d, h)), ("d2h_gbs", (h, d))):
+        best = 0.0
+        for rep in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                best = max(best, n * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        out[key] = best
+    out["how"] = "torch copy_ of 1 GiB between pinned host memory and the device, CUDA events, best of 3"
+    del h, d
+    return out
+
+
+def parity_check(torch, w, stream, n=2048):
+    """The checker beside the CPU baseline: `n` strided samples of the batch the GPU was timed on, evaluated in eval mode on
+    the device and by the CPU arm's oracle; the bytes must be equal (the fma opt-in: within 1e-12)."""
+    from oracle import oracle as O
+
+    f, leaf, res = w["f"], w["leaf"], w["res"]
+    if leaf is None:
+        return "skipped"
+    stride = max(1, res // n)
+    idx = torch.arange(0, res, stride, device="cuda")[:n]
+    sub = leaf[:, idx].contiguous()
+    nb = sub.shape[1]
+    root = torch.zeros(max(w["R"], 1), nb, dtype=w["tdt"], device="cuda")
+    f.eval_device(sub.data_ptr(), nb, root.data_ptr(), nb, nb, stream)
+    torch.cuda.synchronize()
+    want = O.Oracle(w["raw"]).eval(np.ascontiguousarray(sub.cpu().numpy()))
+    got = root.cpu().numpy()[: w["R"]]
+    if got.tobytes() == want.tobytes():
+        return f"{nb} strided samples of the timed batch: device bytes == oracle bytes"
+    err = float(np.max(np.abs(got - want) / (np.abs(want).max(axis=1, keepdims=True) + 1e-300)))
+    if err <= 1e-12:
+        return f"{nb} strided samples of the timed batch: max relative difference {err:.2e} (not bit-equal)"
+    raise SystemExit(f"parity check failed: device result differs from the oracle by {err}")
 
 
 class ClockSampler:
@@ -229,6 +364,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local)  # before any pinned allocation: first touch then lands on the GPU's own NUMA node
     dist = None
     comm = None
     if world > 1:
@@ -248,135 +384,149 @@ def main():
         idbuf = (ctypes.c_ubyte * 128).from_buffer_copy(ident[0])
         _capi.check(_capi.lib().fdg_comm_init(ctypes.byref(comm), world, rank, idbuf))
 
-    npdt = np.float64 if a.dtype == "f64" else np.complex128
-    tdt = torch.float64 if a.dtype == "f64" else torch.complex128
-    es = 8 if a.dtype == "f64" else 16
-    t_compile = time.perf_counter()
-    f = fd.compile_raw(raw, dtype=npdt, max_slots=a.max_slots, prefetch=a.prefetch, backend=a.backend, jit_segment=a.jit_segment, fma=a.fma)
-    jit_info = None
-    if a.backend != 1:
-        try:
-            jit_info = f.jit_prepare(2 if (st_small(f) and a.dtype == "f64") else 1, True)
-        except Exception:  # noqa: BLE001  (AUTO falls back to the VM inside the library)
-            jit_info = None
-    t_compile = time.perf_counter() - t_compile  # lowering + planning + PTX assembly (what Compilers.compile costs once)
-    f.set_launch(a.threads, a.spt, 0)
-    st = f.stats
-    L, R, W = st["n_leaves"], st["n_roots"], (1 if a.dtype == "f64" else 2)
-
-    # ---- resident batch, generated on device (untimed) ---------------------------------------------------------
-    budget = int(a.resident_gb * 2 ** 30)
-    res = min(a.samples, max(1024, budget // max(L * es, 1)))
-    res = 1 << int(math.floor(math.log2(res)))
-    passes = max(1, -(-a.samples // res))
-    samples_step = passes * res
-    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    leaf = torch.empty(max(L, 1), res, dtype=tdt, device="cuda")
-    chunk = max(1, (1 << 28) // max(res, 1))
-    for l0 in range(0, max(L, 1), chunk):
-        rows = leaf[l0:l0 + chunk]
-        if a.dtype == "f64":
-            rows.copy_(torch.rand(rows.shape, dtype=torch.float64, device="cuda", generator=gen) + 0.5)
-        else:
-            rr = torch.view_as_real(rows)
-            rr.copy_(torch.rand(rr.shape, dtype=torch.float64, device="cuda", generator=gen) + 0.5)
-    acc = torch.zeros(max(R * W, 1), dtype=torch.float64, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def step(events=None):
-        for _ in range(passes):
-            if events is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            f.accumulate_device(leaf.data_ptr(), res, res, acc.data_ptr(), stream)
-            if events is not None:
-                e1.record()
-                events.append((e0, e1))
-        if comm is not None:
-            _capi.check(_capi.lib().fdg_allreduce(comm, acc.data_ptr(), R * W, stream))
-
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(a.warmup, 0)):
-        acc.zero_()
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = f.launches
-    events = []
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0.record()
-    for _ in range(a.steps):
-        step(events)
-    t1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = t0.elapsed_time(t1)
-    launches = f.launches - launches0
-    kern_ms = [e0.elapsed_time(e1) for e0, e1 in events]
-    if dist is not None:
-        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
-    samples_total = samples_step * a.steps * world
-    sps = samples_total / (ms * 1e-3)
-    value = sps * R
+        return float(tt.item())
 
-    # ---- roofline of the dominant kernel (the VM kernel; the partial-sum reduce kernel is ~microseconds) ---------
     peak, peak_src = peaks()
-    avg_launch_s = 1e-3 * float(np.mean(kern_ms)) if kern_ms else float("nan")
-    bytes_launch = st["bytes_in"] * res  # accumulate mode: sizeof(W) * L per sample
-    achieved = bytes_launch / avg_launch_s / 1e9
-    flops_launch = (st["flops_add"] + st["flops_mul"]) * res
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp) and a.dtype == "f64" and jit_info is not None:
-        tj = json.load(open(tp)).get(a.workload)
-        if tj and tj.get("resident_samples"):
-            traffic = tj["dram_bytes_per_launch"] * res / tj["resident_samples"]
-    kernel = "fdg_vm_kernel (packet VM)" if jit_info is None else \
-        f"fdg_seg0..{jit_info['kernels'] - 1} (specialised PTX kernels, {jit_info['kernels']} per pass, timed as a group)"
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": kernel,
-                "avg_launch_ms": 1e3 * avg_launch_s, "algorithmic_bytes_per_sample": st["bytes_in"],
-                "fp64_gflops_achieved": flops_launch / avg_launch_s / 1e9, "flops_per_sample": st["flops_add"] + st["flops_mul"],
-                "flop_per_byte": (st["flops_add"] + st["flops_mul"]) / max(st["bytes_in"], 1)}
-    # FP64 ceiling of this path: one DMUL or DADD per lane and clock (no contraction), 64 lanes per SM
     sms = torch.cuda.get_device_properties(local).multi_processor_count
-    fp64_peak = sms * 64 * 1.965  # GFLOP/s at the maximal SM clock of this pool's B200s (MEASURED_PEAKS.json sm_max_mhz)
-    roofline["fp64_peak_gflops_no_fma"] = fp64_peak
-    roofline["fp64_frac_algorithmic"] = roofline["fp64_gflops_achieved"] / fp64_peak
-    if traffic:
-        # the same launch on the bytes ncu saw move (profiles/traffic.json): how close the kernels run to the HBM peak
-        roofline["traffic_gbs"] = traffic / avg_launch_s / 1e9
-        roofline["traffic_frac_of_peak"] = traffic / avg_launch_s / 1e9 / peak
-    if jit_info is not None:
-        roofline["planned_bytes_per_sample"] = (jit_info["leaf_loads"] + jit_info["cross_loads"] + jit_info["cross_stores"]) * es
+    stream = torch.cuda.current_stream().cuda_stream
+    fp64 = probe_fp64(torch, _capi, stream) if rank == 0 else None
+    pcie = probe_pcie(torch) if rank == 0 and not a.no_e2e else None
 
-    out = {
-        "metric": "MC-sample graph-evals/sec", "value": value, "unit": "graph-evals/s", "samples_per_s": sps,
-        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-        "config": {"workload": a.workload, "mode": "accumulate (per-root sums on device" + (", NCCL all-reduce)" if world > 1 else ")"),
-                   "samples_per_step_per_gpu": samples_step, "resident_samples": res, "passes_per_step": passes,
-                   "leaves": L, "statements": st["n_inner"], "roots": R,
-                   "backend": "vm" if jit_info is None else "jit", "jit": jit_info, "arithmetic": "fma opt-in (not bit-identical)" if a.fma else "bit-exact (no contraction)", "compile_seconds": round(t_compile, 2),
-                   "vm_packets": st["n_packets"], "vm_slots": st["n_slots"],
-                   "l2": f"resident inputs {L * es * res / 2 ** 30:.1f} GiB per GPU >> 126 MB L2, no flush needed",
-                   "leaf_values": "0.5 + U[0,1), seed 1234 + rank"},
-        "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
-    }
+    def run_workload(name, dtype, samples, steps, warmup, headline):
+        """One workload: compile, resident batch (counter-based values keyed by the GLOBAL sample index, so that the ranks of
+        an N-GPU run hold the shards [rank * S, (rank + 1) * S) of one sample stream), timed accumulate steps, roofline."""
+        raw_w = load_workload(name)
+        npdt = np.float64 if dtype == "f64" else np.complex128
+        tdt = torch.float64 if dtype == "f64" else torch.complex128
+        es = 8 if dtype == "f64" else 16
+        t_compile = time.perf_counter()
+        f = fd.compile_raw(raw_w, dtype=npdt, max_slots=a.max_slots, prefetch=a.prefetch, backend=a.backend, jit_segment=a.jit_segment, fma=a.fma)
+        jit_info = None
+        if a.backend != 1:
+            try:
+                jit_info = f.jit_prepare(2 if (st_small(f) and dtype == "f64") else 1, True)
+            except Exception:  # noqa: BLE001  (AUTO falls back to the VM inside the library)
+                jit_info = None
+        t_compile = time.perf_counter() - t_compile  # lowering + planning + PTX assembly (what Compilers.compile costs once)
+        f.set_launch(a.threads, a.spt, 0)
+        st = f.stats
+        L, R, W = st["n_leaves"], st["n_roots"], (1 if dtype == "f64" else 2)
+        budget = int((a.resident_gb if headline else min(a.resident_gb, 16.0)) * 2 ** 30)
+        res = min(samples, max(1024, budget // max(L * es, 1)))
+        res = 1 << int(math.floor(math.log2(res)))
+        passes = max(1, -(-samples // res))
+        samples_step = passes * res
+        lo, hi = fd.shard_range(res * world, world, rank)  # this rank's shard of the global resident sample set
+        assert hi - lo == res
+        leaf = torch.empty(max(L, 1), res, dtype=tdt, device="cuda")
+        fill_leaves(torch, leaf, dtype, first_sample=lo, seed=1234)
+        acc = torch.zeros(max(R * W, 1), dtype=torch.float64, device="cuda")
 
-    # ---- e2e: the reference-facing call with host buffers ------------------------------------------------------
-    if not a.no_e2e:
-        be = a.e2e_samples or max(1024, min(a.samples, (2 << 30) // max(L * es, 1)))
+        def step(events=None):
+            for _ in range(passes):
+                if events is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                f.accumulate_device(leaf.data_ptr(), res, res, acc.data_ptr(), stream)
+                if events is not None:
+                    e1.record()
+                    events.append((e0, e1))
+            if comm is not None:
+                _capi.check(_capi.lib().fdg_allreduce(comm, acc.data_ptr(), R * W, stream))
+
+        for _ in range(max(warmup, 0)):
+            acc.zero_()
+            step()
+        barrier()
+        sampler = ClockSampler(local) if headline else None
+        if sampler and rank == 0:
+            sampler.start()
+        launches0 = f.launches
+        events = []
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0.record()
+        for _ in range(steps):
+            step(events)
+        t1.record()
+        barrier()
+        clocks = sampler.stop() if (sampler and rank == 0) else None
+        ms = max_over_ranks(t0.elapsed_time(t1))
+        launches = f.launches - launches0
+        kern_ms = [e0.elapsed_time(e1) for e0, e1 in events]
+        sps = samples_step * steps * world / (ms * 1e-3)
+
+        # the one collective of the path, checked once outside the timed region: every rank's own sums, added up by
+        # fdg_allreduce (our communicator) and by torch.distributed, must agree to rounding
+        allreduce_check = None
+        if comm is not None:
+            acc.zero_()
+            f.accumulate_device(leaf.data_ptr(), res, res, acc.data_ptr(), stream)
+            torch.cuda.synchronize()
+            mine = acc.clone()
+            _capi.check(_capi.lib().fdg_allreduce(comm, acc.data_ptr(), R * W, stream))
+            torch.cuda.synchronize()
+            ref = mine.clone()
+            dist.all_reduce(ref)
+            mag = mine.abs().clone()
+            dist.all_reduce(mag)
+            rel = float(((acc - ref).abs() / (mag + 1e-300)).max().item())
+            allreduce_check = {"max_rel_diff_vs_torch_distributed": rel, "ok": rel <= 64 * 2.3e-16, "n": R * W}
+            if not allreduce_check["ok"]:
+                raise SystemExit(f"fdg_allreduce disagrees with torch.distributed: {rel}")
+
+        avg_launch_s = 1e-3 * float(np.mean(kern_ms)) if kern_ms else float("nan")
+        bytes_launch = st["bytes_in"] * res  # accumulate mode: sizeof(W) * L per sample (SURVEY.md §8d)
+        achieved = bytes_launch / avg_launch_s / 1e9
+        flops_launch = (st["flops_add"] + st["flops_mul"]) * res
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp) and jit_info is not None:
+            tj = json.load(open(tp)).get(name + ("" if dtype == "f64" else "_c128"))
+            if tj and tj.get("resident_samples"):
+                traffic = tj["dram_bytes_per_launch"] * res / tj["resident_samples"]
+                traffic_src = "profiles/traffic.json: " + tj.get("source", "ncu dram bytes per sample of an earlier run") + ", scaled to this launch"
+        kernel = "fdg_vm_kernel (packet VM)" if jit_info is None else \
+            f"fdg_seg0..{jit_info['kernels'] - 1} (specialised PTX kernels, {jit_info['kernels']} per pass, timed as a group)"
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel,
+                    "avg_launch_ms": 1e3 * avg_launch_s, "algorithmic_bytes_per_sample": st["bytes_in"],
+                    "fp64_gflops_achieved": flops_launch / avg_launch_s / 1e9, "flops_per_sample": st["flops_add"] + st["flops_mul"],
+                    "flop_per_byte": (st["flops_add"] + st["flops_mul"]) / max(st["bytes_in"], 1)}
+        if fp64:
+            # FP64 ceiling of this path, MEASURED in this run: one DMUL or DADD per lane and issue (nothing is contracted)
+            roofline["fp64_peak_gflops_no_fma"] = fp64["dmul_dadd_gops"]
+            roofline["fp64_peak_gflops_fma"] = fp64["dfma_gops"] * 2
+            roofline["fp64_peak_source"] = fp64["how"]
+            roofline["fp64_frac_algorithmic"] = roofline["fp64_gflops_achieved"] / fp64["dmul_dadd_gops"]
+            if jit_info is not None:
+                roofline["fp64_instr_executed_per_sample"] = jit_info["fp64_instr"]
+                roofline["fp64_frac_executed"] = jit_info["fp64_instr"] * res / avg_launch_s / 1e9 / fp64["dmul_dadd_gops"]
+        if traffic:
+            roofline["traffic_gbs"] = traffic / avg_launch_s / 1e9
+            roofline["traffic_frac_of_peak"] = traffic / avg_launch_s / 1e9 / peak
+        if jit_info is not None:
+            roofline["planned_bytes_per_sample"] = (jit_info["leaf_loads"] + jit_info["cross_loads"] + jit_info["cross_stores"]) * es
+            roofline["planned_frac_of_peak"] = roofline["planned_bytes_per_sample"] * res / avg_launch_s / 1e9 / peak
+        return {"f": f, "raw": raw_w, "st": st, "jit": jit_info, "leaf": leaf, "res": res, "passes": passes, "samples_step": samples_step,
+                "sps": sps, "ms": ms, "launches": launches, "clocks": clocks, "roofline": roofline, "t_compile": t_compile,
+                "allreduce_check": allreduce_check, "L": L, "R": R, "W": W, "es": es, "tdt": tdt, "first_sample": lo}
+
+    def e2e_host(w, be_cap):
+        """eval_graph(root, leafVal) on pinned host arrays: H2D of the leaves, kernels, D2H of the roots, synchronous."""
+        f, L, R, es, tdt = w["f"], w["L"], w["R"], w["es"], w["tdt"]
+        be = a.e2e_samples or max(1024, min(a.samples, be_cap // max(L * es, 1)))
         be = 1 << int(math.floor(math.log2(be)))
         hl = torch.empty(max(L, 1), be, dtype=tdt).pin_memory()
         hr = torch.empty(max(R, 1), be, dtype=tdt).pin_memory()
@@ -385,20 +535,48 @@ def main():
         for _ in range(2):
             f(hr_np.T, hl_np.T)
         barrier()
-        k_e2e = max(2, min(a.steps, 5))
+        k = max(2, min(a.steps, 5))
         t = time.perf_counter()
-        for _ in range(k_e2e):
-            f(hr_np.T, hl_np.T)  # eval_graph(root, leafVal): H2D, kernel, D2H, synchronous
+        for _ in range(k):
+            f(hr_np.T, hl_np.T)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t
-        if dist is not None:
-            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        out["e2e"] = {"value": be * k_e2e * world * R / dt, "unit": "graph-evals/s", "h2d_bytes_per_step": L * es * be,
-                      "d2h_bytes_per_step": R * es * be, "samples_per_step_per_gpu": be, "steps": k_e2e,
-                      "api": "Compilers.compile(graphs) -> eval_graph(root, leafVal) on pinned host arrays (fdg_eval_host)"}
+        dt = max_over_ranks(time.perf_counter() - t)
+        out = {"value": be * k * world * R / dt, "unit": "graph-evals/s", "samples_per_s": be * k * world / dt,
+               "h2d_bytes_per_step": L * es * be, "d2h_bytes_per_step": R * es * be, "samples_per_step_per_gpu": be, "steps": k,
+               "host_gbs_moved": (L + R) * es * be * k * world / dt / 1e9,
+               "api": "Compilers.compile(graphs) -> eval_graph(root, leafVal) on pinned host arrays (fdg_eval_host)"}
         del hl, hr
+        return out
+
+    # ================================ the headline workload ================================
+    w = run_workload(a.workload, a.dtype, a.samples, a.steps, a.warmup, headline=True)
+    f, st, jit_info, leaf, res, R, L, W, es = w["f"], w["st"], w["jit"], w["leaf"], w["res"], w["R"], w["L"], w["W"], w["es"]
+    raw = w["raw"]
+    out = {
+        "metric": "MC-sample graph-evals/sec", "value": w["sps"] * R, "unit": "graph-evals/s", "samples_per_s": w["sps"],
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": w["ms"] / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": a.workload, "mode": "accumulate (per-root sums on device" + (", NCCL all-reduce)" if world > 1 else ")"),
+                   "samples_per_step_per_gpu": w["samples_step"], "resident_samples": res, "passes_per_step": w["passes"],
+                   "leaves": L, "statements": st["n_inner"], "roots": R,
+                   "backend": "vm" if jit_info is None else "jit", "jit": jit_info,
+                   "arithmetic": "fma opt-in (not bit-identical)" if a.fma else "bit-exact (no contraction)", "compile_seconds": round(w["t_compile"], 2),
+                   "vm_packets": st["n_packets"], "vm_slots": st["n_slots"],
+                   "l2": f"resident inputs {L * es * res / 2 ** 30:.1f} GiB per GPU >> 126 MB L2, no flush needed; a step is "
+                         f"{w['passes']} passes over the SAME resident samples (2^26 distinct samples of this graph are 528 GB)",
+                   "leaf_values": "0.5 + U[0,1) from a counter-based generator keyed (seed 1234, leaf, GLOBAL sample index): rank r of N holds "
+                                  "samples [r S, (r + 1) S) of one stream (sharding.shard_range), so rank 0's shard is the 1-GPU set",
+                   "numa": numa},
+        "roofline": w["roofline"], "gpu_launches": int(w["launches"]), "clocks": w["clocks"],
+    }
+    if w["allreduce_check"]:
+        out["allreduce_check"] = w["allreduce_check"]
+
+    if not a.no_e2e:
+        out["e2e"] = e2e_host(w, 2 << 30)
+        if pcie:
+            out["e2e"]["pcie_pinned_h2d_gbs"], out["e2e"]["pcie_pinned_d2h_gbs"] = pcie["h2d_gbs"], pcie["d2h_gbs"]
+            out["e2e"]["pcie_probe"] = pcie["how"]
 
     # ---- e2e with the leaves generated on the device: host (K, tau) in, R sums out ----------------
     side = os.path.join(ROOT, "workloads", a.workload + ".leaves.npz")
@@ -430,10 +608,7 @@ def main():
         gen.fill_device(dv.data_ptr(), dv[gen.dim * gen.n_loops:].data_ptr(), bg, nfill, leaf.data_ptr(), res, stream)
         e1.record()
         torch.cuda.synchronize()
-        if dist is not None:
-            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
+        dt = max_over_ranks(dt)
         out["e2e_generated"] = {
             "value": bg * k_gen * world * R / dt, "unit": "graph-evals/s", "samples_per_s": bg * k_gen * world / dt,
             "h2d_bytes_per_step": rows * 8 * bg, "d2h_bytes_per_step": R * 8, "samples_per_step_per_gpu": bg, "steps": k_gen,
@@ -441,6 +616,7 @@ def main():
             "api": "fdg_eval_generated_host: host (K, tau) of example/benchmark.jl:44-53 -> leaves on device (fdg_leafgen) -> "
                    "graph kernels -> R per-root sums; leaf values overwrite the synthetic resident batch AFTER the timed region above"}
         del hv, dv
+        fill_leaves(torch, leaf, a.dtype, first_sample=w["first_sample"], seed=1234)  # the synthetic values again (parity check below)
 
     # ---- the reference's own batched design point on this GPU: the emitted torch function (compiler_python.jl) ------
     if rank == 0 and world == 1 and not a.no_torch_emitter and a.dtype == "f64":
@@ -472,11 +648,46 @@ def main():
         except Exception as ex:  # noqa: BLE001
             out["reference_torch_emitter"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
 
-    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------------
+    # ---- CPU baseline beside it (rank 0, N=1 only), and the checker on a strided subset of the timed batch ---------------
     if rank == 0 and world == 1 and not a.no_cpu:
         rate, cores, n, secs, what = cpu_reference(raw, a.dtype, a.cpu_seconds)
         out["cpu_baseline"] = {"value": rate * R, "unit": "graph-evals/s", "cores": cores, "kind": "port",
                                "sample": f"{n} samples of {a.workload} in {secs:.1f} s; {what}; sample-major leaves, OpenMP over samples"}
+        out["cpu_baseline"]["parity_check"] = parity_check(torch, w, stream)
+
+    # ---- every other BASELINE configuration, compact (each in its own CUDA-event region; the headline above is cfg4) ------
+    if not a.no_configs and a.workload == "parquet_ver4_o4" and a.dtype == "f64":
+        del leaf
+        w["leaf"] = None
+        torch.cuda.empty_cache()
+        cfgs = {}
+        for key, name, dtype, samples in (("cfg1", "parquet_sigma_o2", "f64", 1 << 16), ("cfg2", "parquet_sigma_o3", "f64", 1 << 24),
+                                         ("cfg3", "gv_ver4_o4", "f64", 1 << 26), ("cfg5", "taylor_sigma_o3", "c128", 1 << 24)):
+            wc = run_workload(name, dtype, samples, steps=3, warmup=3, headline=False)
+            rl = wc["roofline"]
+            c = {"workload": name, "dtype": dtype, "samples_per_step_per_gpu": wc["samples_step"], "samples_per_s": wc["sps"],
+                 "graph_evals_per_s": wc["sps"] * wc["R"], "ms_per_step": wc["ms"] / 3, "kernels_per_pass": (wc["jit"] or {}).get("kernels"),
+                 "frac_of_hbm_peak_algorithmic": rl["frac"], "frac_of_hbm_peak_planned_traffic": rl.get("planned_frac_of_peak"),
+                 "planned_bytes_per_sample": rl.get("planned_bytes_per_sample"), "algorithmic_bytes_per_sample": rl["algorithmic_bytes_per_sample"],
+                 "fp64_frac_executed": rl.get("fp64_frac_executed"), "cse": (wc["jit"] or {}).get("cse"), "gpu_launches": int(wc["launches"])}
+            if not a.no_e2e:
+                e = e2e_host(wc, 1 << 29)
+                c["e2e_samples_per_s"], c["e2e_graph_evals_per_s"] = e["samples_per_s"], e["value"]
+            if rank == 0 and world == 1 and not a.no_cpu:
+                try:
+                    rate, cores, n, secs, what = cpu_reference(wc["raw"], dtype, 3.0, compile_timeout=5.0)
+                    c["cpu_samples_per_s"], c["cpu_cores"] = rate, cores
+                    c["cpu_kind"] = "emitted C" if what.startswith("to_Cstr") else "array-walking port"
+                    c["parity_check"] = parity_check(torch, wc, stream)
+                except Exception as ex:  # noqa: BLE001
+                    c["cpu_samples_per_s"] = None
+                    c["cpu_note"] = f"{type(ex).__name__}"
+            cfgs[key] = c
+            del wc
+            torch.cuda.empty_cache()
+        cfgs["cfg4"] = "the headline of this line"
+        out["configs"] = cfgs
+
     if rank == 0:
         print(json.dumps(out))
     if comm is not None:

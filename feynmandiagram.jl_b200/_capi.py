@@ -61,6 +61,7 @@ EXPORTS = [
     "fdg_comm_unique_id", "fdg_comm_init", "fdg_comm_destroy", "fdg_allreduce", "fdg_jit_prepare", "fdg_jit_ptx",
     "fdg_jit_info", "fdg_leafgen_create", "fdg_leafgen_destroy", "fdg_leafgen_fill", "fdg_eval_generated_accumulate",
     "fdg_eval_generated_host", "fdg_graph_write", "fdg_compile_file", "fdg_pipeline_prepare", "fdg_pipeline_stats",
+    "fdg_probe_fp64",
 ]
 BACKEND_AUTO, BACKEND_VM, BACKEND_JIT = 0, 1, 2
 
@@ -99,6 +100,7 @@ def lib() -> C.CDLL:
     L.fdg_jit_info.argtypes = [vp, i32, i32, C.POINTER(i64), i32]
     L.fdg_pipeline_prepare.argtypes = [vp, i32, i32, i32, C.POINTER(i64), i32]
     L.fdg_pipeline_stats.argtypes = [vp, vp, C.POINTER(i64), i32]
+    L.fdg_probe_fp64.argtypes = [i32, i64, vp, vp, C.POINTER(i64)]
     L.fdg_graph_write.argtypes = [C.POINTER(GraphDesc), C.c_char_p]
     L.fdg_compile_file.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(vp)]
     L.fdg_leafgen_create.argtypes = [C.POINTER(LeafGenDesc), C.POINTER(vp)]

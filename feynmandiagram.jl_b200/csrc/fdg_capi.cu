@@ -281,6 +281,32 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
     return FDG_OK;
 }
 
+// FP64 rate of the device, measured: 8 independent chains per thread, either one DMUL and one DADD per step (what the
+// bit-exact kernels may issue: nothing is contracted) or one DFMA.  The roofline's FP64 denominator (bench.py).
+template <bool FMA>
+__global__ void __launch_bounds__(256) fdg_fp64_probe(long long iters, double *sink) {
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    const double a = 1.0000000001, c = 1e-12;
+    for (long long k = 0; k < iters; ++k) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (FMA) {
+                x[i] = __fma_rn(x[i], a, c);
+                x[i] = __fma_rn(x[i], a, c);
+            } else {
+                x[i] = __dmul_rn(x[i], a);
+                x[i] = __dadd_rn(x[i], c);
+            }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    if (s == 12345.678) sink[0] = s;  // never true: keeps the chains alive
+}
+
 // One block per SM (the launch asks for more than half of an SM's shared memory); every block reports the SM it runs on and
 // stays until all have reported, so that no SM is counted twice.
 __global__ void fdg_probe_smids(unsigned *out, unsigned *counter) {
@@ -1828,5 +1854,20 @@ int fdg_eval_generated_accumulate(fdg_handle h, fdg_leafgen_t g, const double *K
 }
 int fdg_eval_generated_host(fdg_handle h, fdg_leafgen_t g, const double *K_host, const double *T_host, int64_t ld_var, int64_t batch, double *acc_host) {
     return guarded([&] { return fdg_eval_generated_host_impl(h, g, K_host, T_host, ld_var, batch, acc_host); });
+}
+int fdg_probe_fp64(int32_t fma, int64_t iters, void *stream, double *sink_device, int64_t *ops_per_launch) {
+    return guarded([&] {
+        if (iters < 1 || !sink_device) return fail(FDG_ERR_BAD_ARG, "bad argument");
+        int dev = 0, sms = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int blocks = sms * 8;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (fma) fdg_fp64_probe<true><<<blocks, 256, 0, st>>>((long long)iters, sink_device);
+        else fdg_fp64_probe<false><<<blocks, 256, 0, st>>>((long long)iters, sink_device);
+        CUDA_TRY(cudaGetLastError());
+        if (ops_per_launch) *ops_per_launch = (int64_t)blocks * 256 * iters * 16;  // instructions x lanes (an FMA counts once)
+        return (int)FDG_OK;
+    });
 }
 }  // extern "C"

@@ -199,6 +199,11 @@ int fdg_pipeline_stats(fdg_handle h, void *stream, int64_t *out, int32_t n_out);
 int fdg_jit_ptx(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t index, const char **ptx,
                 const char **ptxas_log);
 
+/* measurement aid: launches a kernel of 8 independent FP64 chains per thread on `stream` (8 blocks of 256 threads per SM),
+ * `iters` steps of either DMUL + DADD (fma = 0: what the bit-exact kernels issue) or DFMA + DFMA (fma = 1) per chain;
+ * *ops_per_launch = FP64 instructions x lanes executed.  Timed by the caller with events: the roofline's FP64 denominator. */
+int fdg_probe_fp64(int32_t fma, int64_t iters, void *stream, double *sink_device, int64_t *ops_per_launch);
+
 /* --- leaf values computed on the device from the Monte-Carlo variables ------------------------
  * What the integrand of the reference's driver does between `compile` and `eval_graph!` for every sample
  * (example/benchmark.jl:44-81, with the per-leaf metadata of `leafstates`, src/frontend/frontends.jl:175-232):
