@@ -1276,10 +1276,25 @@ static int compile_one(JitSegment &js, bool fma, std::string &err, bool relocata
 }
 
 double jit_model_ns(const JitPlan &plan, int bytes_per_element) {
+    // Calibrated on B200 measurements of seven workloads with and without merged sub-expressions (profiles/r02_experiments/
+    // cse_ab.log): the kernels move their planned bytes at up to ~5.0 TB/s and issue FP64 instructions at up to ~13.8 T/s
+    // (75 % of the measured DMUL + DADD rate); the two overlap imperfectly (a smooth maximum, exponent 3); a spilled
+    // register costs about six instructions per 8 bytes stored or reloaded (known once the kernels are assembled).
     const double bytes = (double)(plan.leaf_loads + plan.cross_loads + plan.cross_stores) * bytes_per_element;
-    const double t_mem = bytes / (0.78 * 6555.0);                          // bytes / (GB/s) = ns
-    const double t_fp = (double)plan.fp64_instr / (0.70 * 148 * 64 * 1.7);  // instructions / (G lane-instructions/s) = ns
-    return std::max(t_mem, t_fp) + 0.01 * (double)plan.seg.size();
+    double spill = 0;
+    for (const JitSegment &sg : plan.seg) {
+        const char *p = sg.info.c_str();
+        while ((p = std::strstr(p, "bytes spill")) != nullptr) {  // "... N bytes spill stores, M bytes spill loads"
+            const char *q = p;
+            while (q > sg.info.c_str() && (q[-1] == ' ')) --q;
+            while (q > sg.info.c_str() && q[-1] >= '0' && q[-1] <= '9') --q;
+            spill += std::atof(q);
+            p += 11;
+        }
+    }
+    const double t_mem = bytes / 5000.0;                                         // bytes / (GB/s) = ns
+    const double t_fp = ((double)plan.fp64_instr + spill / 8.0 * 6.0) / 13800.0;  // instructions / (G lane-instructions/s) = ns
+    return std::cbrt(t_mem * t_mem * t_mem + t_fp * t_fp * t_fp) + 0.01 * (double)plan.seg.size();
 }
 
 int jit_assemble(const std::string &ptx, int opt_level, std::vector<char> &cubin, std::string &err) {

@@ -64,9 +64,9 @@ struct PipeOptions {
     }
 };
 
-// Modelled time of one sample on a B200, ns: the slower of the plan's memory traffic at the HBM rate such kernels reach
-// (78 % of the measured copy bandwidth) and its FP64 instructions at the rate they reach (70 % of 148 SMs x 64 lanes at
-// 1.7 GHz under the power cap), DESIGN.md section 5.  Used to choose between plans, not reported as a result.
+// Modelled time of one sample on a B200, ns: a smooth maximum of the plan's memory traffic at the rate such kernels reach and
+// of its FP64 instructions (plus the cost of spilled registers, once the kernels are assembled) at the rate they reach;
+// constants and calibration in fdg_jit.cpp.  Used to choose between plans, not reported as a result.
 double jit_model_ns(const JitPlan &plan, int bytes_per_element);
 
 // linearise the emitted function in fold order, cut it into segments of `seg_ops` operations, write their PTX

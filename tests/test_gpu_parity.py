@@ -569,14 +569,16 @@ def test_common_subexpressions_merged_same_bits(name, dtype, cse):
 
 
 def test_automatic_cse_follows_the_model():
-    """The planner keeps the merged program where its modelled time is lower (FP64-bound graphs: Taylor-AD, Parquet sigma
-    order 4) and the unmerged one where the extra values crossing kernels cost more than the saved arithmetic (the
-    memory-bound order-4 vertices)."""
+    """The planner keeps the merged program where its modelled time (traffic, FP64 instructions, registers spilled) is at
+    least 5 % lower -- measured on this hardware: Parquet sigma order 4 +9 %, Taylor-AD sigma order 4 +10 % -- and the
+    unmerged one elsewhere: the memory-bound order-4 vertices (merging makes more values cross kernels) and Taylor-AD
+    sigma order 3, where the shared values push ptxas into spilling (-9 % measured)."""
     picks = {}
-    for name, dtype in (("taylor_sigma_o3", np.complex128), ("parquet_sigma_o4", np.float64), ("parquet_ver4_o4", np.float64), ("gv_ver4_o4", np.float64)):
+    for name, dtype in (("taylor_sigma_o4", np.complex128), ("parquet_sigma_o4", np.float64), ("taylor_sigma_o3", np.complex128),
+                        ("parquet_ver4_o4", np.float64), ("gv_ver4_o4", np.float64)):
         ev = fd.compile_raw(_workload(name), dtype=dtype, backend=JIT)
         picks[name] = ev.jit_prepare(1, True)["cse"]
-    assert picks == {"taylor_sigma_o3": True, "parquet_sigma_o4": True, "parquet_ver4_o4": False, "gv_ver4_o4": False}
+    assert picks == {"taylor_sigma_o4": True, "parquet_sigma_o4": True, "taylor_sigma_o3": False, "parquet_ver4_o4": False, "gv_ver4_o4": False}
 
 
 @pytest.mark.parametrize("name", ["parquet_ver4_o4", "gv_ver4_o4"])
