@@ -1,7 +1,10 @@
 # FDGraphB200.jl -- the Julia side of the drop-in: `ccall` shim over libfdgraph.so (include/fdgraph.h).
 #
-# UNTESTED: there is no julia binary in the build image or on the GPU box (SURVEY.md D2).  The shim is kept
-# deliberately thin -- it only flattens Graph objects through the four getters the reference emitter itself uses
+# NEVER EXECUTED: there is no julia binary in the build image or on the GPU box (SURVEY.md D2).  What is checked instead:
+# the struct layouts and the call sequence of compile() / leafgen() are restated in C (tests/abi/julia_layout.c: the
+# fieldoffsets of the structs below are static-asserted against include/fdgraph.h and the calls are made in this file's
+# order), and the FDGRAPH file written by save_graph() is the format tests/test_lowering.py and tests/test_gpu_parity.py
+# read back.  The shim is kept deliberately thin -- it only flattens Graph objects through the four getters the reference emitter itself uses
 # (id / operator / subgraphs / subgraph_factors, src/backend/static.jl:106-124) and forwards pointers -- and it is
 # mirrored 1:1 by the Python ctypes binding (feynmandiagram.jl_b200/_capi.py), which IS tested against the library.
 #
@@ -41,7 +44,7 @@ struct Options
     schedule::Int32
     backend::Int32
     jit_segment::Int32
-    cse::Int32
+    cse::Int32   # 0 = automatic (the planner's model decides), 1 = always, -1 = never merge common sub-expressions
     fma::Int32   # 1 = multiplies may be fused into adds (opt-in, not bit-identical)
 end
 
@@ -150,13 +153,16 @@ function eval_graph!(ev::Evaluator, root::AbstractMatrix, leafVal::AbstractMatri
     B = size(leafVal, 1)
     size(root, 1) == B || throw(DimensionMismatch("root and leafVal must have the same number of rows (samples)"))
     (size(leafVal, 2) >= ev.n_leaves && size(root, 2) >= ev.n_roots) || throw(BoundsError())
-    if leafVal isa Array   # host matrices: fdg_eval_host does H2D / kernel / D2H
-        check(ccall((:fdg_eval_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64),
-            ev.handle, pointer(leafVal), stride(leafVal, 2), pointer(root), stride(root, 2), B))
-    else                   # CuArray: pointer() gives a CuPtr, reinterpret as the raw device address
-        check(ccall((:fdg_eval, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}),
-            ev.handle, reinterpret(Ptr{Cvoid}, pointer(leafVal)), stride(leafVal, 2), reinterpret(Ptr{Cvoid}, pointer(root)),
-            stride(root, 2), B, stream))
+    # the raw pointers handed to ccall do not keep the arrays alive: GC.@preserve does, for the duration of the call
+    GC.@preserve root leafVal begin
+        if leafVal isa Array   # host matrices: fdg_eval_host does H2D / kernel / D2H
+            check(ccall((:fdg_eval_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64),
+                ev.handle, pointer(leafVal), stride(leafVal, 2), pointer(root), stride(root, 2), B))
+        else                   # CuArray: pointer() gives a CuPtr, reinterpret as the raw device address
+            check(ccall((:fdg_eval, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}),
+                ev.handle, reinterpret(Ptr{Cvoid}, pointer(leafVal)), stride(leafVal, 2), reinterpret(Ptr{Cvoid}, pointer(root)),
+                stride(root, 2), B, stream))
+        end
     end
     return ev.last_root >= 1 ? view(root, :, ev.last_root) : nothing
 end

@@ -605,3 +605,22 @@ def test_opt_in_fma_on_the_headline_graph():
     want = O.Oracle(raw).eval(leaf)
     assert got.tobytes() != want.tobytes()
     assert np.all(np.abs(got - want) <= 1e-12 * np.abs(want).max(axis=1, keepdims=True))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_graph_file_compiled_by_the_library_evaluates_to_the_oracle(tmp_path, dtype):
+    """a graph flattened elsewhere travels as an FDGRAPH file (RawGraph.save_fdg here,
+    FDGraphB200.save_graph in Julia), the library reads the file itself (fdg_compile_file) and the program it builds
+    evaluates on the device to the oracle's bytes -- eval mode and the host entry point."""
+    raw = _workload("parquet_ver4_o3")
+    path = str(tmp_path / "g.fdgraph")
+    raw.save_fdg(path)
+    ev = fd.compile_file(path, dtype=dtype)
+    assert ev.n_leaves == 175 and ev.n_roots == 84
+    B = 3000
+    leaf = graphgen.leaf_values(12, ev.n_leaves, B, dtype=dtype, signed=True)
+    want = O.Oracle(raw).eval(leaf)
+    assert _dev_eval(ev, leaf, B).tobytes() == want.tobytes()
+    root = np.asfortranarray(np.zeros((B, ev.n_roots), dtype))
+    ev(root, np.asfortranarray(leaf.T))
+    assert np.ascontiguousarray(root.T).tobytes() == want.tobytes()

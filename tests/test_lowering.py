@@ -380,3 +380,19 @@ def test_pipeline_plan_of_the_headline_graph():
     per_pass = [(cost[p:p + 8] / blocks[p:p + 8]).max() for p in (0, 8)]
     assert sum(per_pass) / (cost.sum() / 148) < 1.08  # the slowest stage of each pass is within 8 % of a perfect split
     assert 0 < info["boundary_rows"] <= 80            # values that go from the first pass to the second
+
+
+def test_julia_shim_struct_layouts_and_call_sequence(tmp_path):
+    """The Julia shim cannot run here (no julia binary).  tests/abi/julia_layout.c asserts, at compile time, that the byte
+    offsets of the shim's structs (= Julia's fieldoffsets: natural C layout) are those of include/fdgraph.h, then makes
+    FDGraphB200.compile()'s calls in its order on the 4.5 graph of test/compiler.jl:4-15 and prints what the shim reads."""
+    import os
+    import subprocess
+
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = _capi.lib()._name
+    exe = str(tmp_path / "julia_layout")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(here, "include"), os.path.join(here, "tests", "abi", "julia_layout.c"),
+                    "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib)], check=True, capture_output=True, text=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split("\n")
+    assert out[0] == "L=2 R=1 leafmap=0,1 last_root=0 abi=1" and out[1] == "ok"
