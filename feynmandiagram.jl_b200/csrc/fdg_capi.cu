@@ -253,32 +253,45 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
         int rc = FDG_OK;
         // automatic CSE: plan the program with and without merged sub-expressions (planning is cheap, assembling is not) and
         // keep the plan whose modelled time is lower: fewer operations against more values crossing kernel boundaries
-        const fdg::Lowered *lowp = &h->low;
+        const fdg::Lowered *lowp = &h->low, *mergedp = nullptr;
         if (h->has_cse) {
-            fdg::JitPlan a, b;
-            std::string e1, e2;
+            // three ways to evaluate the same bits: as emitted; with equal sub-expressions merged everywhere (fewest
+            // operations, but the shared values travel between kernels); merged only where the copies sit close together
+            // ("scoped": fewer operations at about the traffic of the plain plan)
+            fdg::JitPlan plain, full, scoped;
+            std::string e1, e2, e3;
             const int es = h->low.dtype == FDG_C128 ? 16 : 8;
-            if (fdg::jit_plan(h->low, spt, acc, budget, wide, h->fma, a, e1) == FDG_OK &&
-                fdg::jit_plan(h->low_cse, spt, acc, budget, wide, h->fma, b, e2) == FDG_OK && fdg::jit_model_ns(b, es) < 0.95 * fdg::jit_model_ns(a, es)) {
-                // the merged program looks at least 5 % faster on paper.  More shared values also mean more registers held:
-                // assemble both and let the spills ptxas reports have their say
-                if (fdg::jit_compile(a, e1) == FDG_OK && fdg::jit_compile(b, e2) == FDG_OK) {
-                    const bool merged = fdg::jit_model_ns(b, es) < 0.95 * fdg::jit_model_ns(a, es);
-                    if (merged) lowp = &h->low_cse;
-                    fdg::JitPlan &pick = merged ? b : a;
-                    if (pick.seg.size() < 2 || pick.max_code_bytes <= 120 * 1024) {  // assembled already and within the cache budget
-                        v.plan = std::move(pick);
-                        v.plan.uses_cse = merged;
-                        v.compiled = true;
-                        *out = &v;
-                        return FDG_OK;
+            int mode = -1;  // FDG_CSE_MODE: 0 plain, 1 merged, 2 scoped (experiments); default: the model decides
+            if (const char *e = getenv("FDG_CSE_MODE")) mode = atoi(e);
+            if (fdg::jit_plan(h->low, spt, acc, budget, wide, h->fma, plain, e1) == FDG_OK &&
+                fdg::jit_plan(h->low_cse, spt, acc, budget, wide, h->fma, full, e2) == FDG_OK &&
+                fdg::jit_plan(h->low, spt, acc, budget, wide, h->fma, scoped, e3, nullptr, &h->low_cse) == FDG_OK) {
+                const double tp = fdg::jit_model_ns(plain, es), tf = fdg::jit_model_ns(full, es), ts = fdg::jit_model_ns(scoped, es);
+                fdg::JitPlan *cand = tf <= ts ? &full : &scoped;
+                if (mode == 1) cand = &full;
+                if (mode == 2) cand = &scoped;
+                if (mode != 0 && (mode > 0 || std::min(tf, ts) < 0.95 * tp)) {
+                    // at least 5 % faster on paper.  More shared values also mean more registers held: assemble both and let
+                    // the spills ptxas reports have their say
+                    if (fdg::jit_compile(plain, e1) == FDG_OK && fdg::jit_compile(*cand, e2) == FDG_OK) {
+                        const bool take = mode > 0 || fdg::jit_model_ns(*cand, es) < 0.95 * fdg::jit_model_ns(plain, es);
+                        fdg::JitPlan &pick = take ? *cand : plain;
+                        if (take && cand == &full) lowp = &h->low_cse;
+                        if (take && cand == &scoped) mergedp = &h->low_cse;
+                        if (pick.seg.size() < 2 || pick.max_code_bytes <= 120 * 1024) {  // assembled already and within the cache budget
+                            v.plan = std::move(pick);
+                            v.plan.uses_cse = take;
+                            v.compiled = true;
+                            *out = &v;
+                            return FDG_OK;
+                        }
                     }
                 }
             }
         }
         for (int attempt = 0; attempt < 3; ++attempt) {
-            rc = fdg::jit_plan(*lowp, spt, acc, budget, wide, h->fma, v.plan, err);
-            v.plan.uses_cse = lowp == &h->low_cse || h->low.cse_removed > 0;
+            rc = fdg::jit_plan(*lowp, spt, acc, budget, wide, h->fma, v.plan, err, nullptr, mergedp);
+            v.plan.uses_cse = lowp == &h->low_cse || mergedp != nullptr || h->low.cse_removed > 0;
             if (rc == FDG_OK) rc = fdg::jit_compile(v.plan, err);
             if (rc != FDG_OK || v.plan.seg.size() < 2 || v.plan.max_code_bytes <= 120 * 1024 || getenv("FDG_JIT_NO_REFIT")) break;
             const int smaller = (int)((double)budget * 112.0 * 1024.0 / (double)v.plan.max_code_bytes);

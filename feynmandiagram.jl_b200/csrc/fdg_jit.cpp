@@ -404,10 +404,18 @@ static void order_roots(const Lowered &low, std::vector<int32_t> &order) {
     }
 }
 
-static void build_ir(const Lowered &low, std::vector<IrOp> &ir) {
+static void build_ir(const Lowered &low, std::vector<IrOp> &ir, const Lowered *merged = nullptr, int scope = 0) {
     const auto &st = low.st;
     const auto &ops = low.ops;
     std::vector<int32_t> val_of(st.size(), INT32_MIN);  // value id of a materialised statement once computed
+    // scoped merging: value and position of the latest evaluation of every class of equal statements
+    const bool scoped = merged && merged->canon.size() == st.size() && scope > 0;
+    std::vector<int32_t> cls_val, cls_at;
+    if (scoped) {
+        cls_val.assign(st.size(), INT32_MIN);
+        cls_at.assign(st.size(), 0);
+    }
+    auto cls = [&](int32_t v) { return merged->canon[(size_t)v]; };
     // `x * (-1.0)` is the sign flip of x for every finite and infinite double (round-to-nearest is symmetric), so it is
     // written as a negation, which sm_100a folds into the operand modifiers of the DMUL / DADD that reads it: the
     // multiply disappears, the bits stay (NaN sign/payload is hardware-specific either way).  FDG_JIT_NEGFOLD=0 keeps it.
@@ -425,7 +433,7 @@ static void build_ir(const Lowered &low, std::vector<IrOp> &ir) {
     };
     std::vector<Frame> stack;
     std::vector<int32_t> root_order;
-    order_roots(low, root_order);
+    order_roots(scoped ? *merged : low, root_order);  // statement indices are the same in both views
     for (const int32_t root_stmt : root_order) {
         if (st[(size_t)root_stmt].op < 0) {  // root[r] = leafVal[k]
             emit(IR_ROOT, -(st[(size_t)root_stmt].leaf + 1), 0, st[(size_t)root_stmt].root, 1.0);
@@ -445,6 +453,10 @@ static void build_ir(const Lowered &low, std::vector<IrOp> &ir) {
                 }
                 if (s.root >= 0) emit(IR_ROOT, res, 0, s.root, 1.0);
                 if (s.root >= 0 || s.uses >= 2) val_of[(size_t)fr.v] = res;
+                if (scoped && res >= 0) {
+                    cls_val[(size_t)cls(fr.v)] = res;
+                    cls_at[(size_t)cls(fr.v)] = (int32_t)ir.size();
+                }
                 stack.pop_back();
                 if (!stack.empty()) {
                     stack.back().have_ret = true;
@@ -461,6 +473,9 @@ static void build_ir(const Lowered &low, std::vector<IrOp> &ir) {
                 t = -(st[(size_t)o.val].leaf + 1);
             } else if (val_of[(size_t)o.val] != INT32_MIN) {
                 t = val_of[(size_t)o.val];
+            } else if (scoped && cls_val[(size_t)cls(o.val)] != INT32_MIN && (int32_t)ir.size() - cls_at[(size_t)cls(o.val)] <= scope) {
+                t = cls_val[(size_t)cls(o.val)];  // an equal statement was evaluated a moment ago: same bits, no work
+                if (st[(size_t)o.val].uses >= 2) val_of[(size_t)o.val] = t;
             } else {
                 const int32_t child = o.val;
                 stack.push_back({child, 0, 0, false, 0});  // NB: invalidates fr
@@ -485,7 +500,7 @@ static void build_ir(const Lowered &low, std::vector<IrOp> &ir) {
 }
 
 static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt, bool acc, int seg_ops, bool wide_strides, bool fma,
-                        JitPlan &plan, std::string &err, const PipeOptions *pipe);
+                        JitPlan &plan, std::string &err, const PipeOptions *pipe, bool bulk = false);
 
 // prefix sums of the per-operation instruction estimate (pipeline form: in 1/16 instructions, stretched by the stage weights)
 static void plan_costs(const Lowered &low, const std::vector<IrOp> &ir, int spt, bool acc, const PipeOptions *pipe, std::vector<int64_t> &cost) {
@@ -522,9 +537,11 @@ static void plan_costs(const Lowered &low, const std::vector<IrOp> &ir, int spt,
 }
 
 int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strides, bool fma, JitPlan &plan, std::string &err,
-             const PipeOptions *pipe) {
+             const PipeOptions *pipe, const Lowered *merged, int scope, bool bulk) {
     std::vector<IrOp> ir;
-    build_ir(low, ir);
+    if (merged && scope <= 0) scope = (seg_ops > 0 ? seg_ops : 4000) * 2 / 3;
+    if (const char *e = getenv("FDG_CSE_SCOPE")) scope = atoi(e);
+    build_ir(low, ir, merged, scope);
     if (const char *dump = getenv("FDG_JIT_DUMP_IR")) {  // debugging aid: the fold-order IR as raw records
         if (FILE *fp = std::fopen(dump, "wb")) {
             for (const IrOp &o : ir) {
@@ -534,7 +551,7 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
             std::fclose(fp);
         }
     }
-    if (!pipe) return plan_from_ir(low, ir, spt, acc, seg_ops, wide_strides, fma, plan, err, nullptr);
+    if (!pipe) return plan_from_ir(low, ir, spt, acc, seg_ops, wide_strides, fma, plan, err, nullptr, bulk);
     // Pipeline form: the cuts follow a cost estimate per operation, but what a stage really costs is only known once its
     // code is written (input rows are charged where they are first read in the stage, roots cost a warp reduction).  So the
     // plan is made, the stages are re-weighted with (cost of the written code) / (estimate), and the cuts are placed again.
@@ -620,8 +637,12 @@ int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strid
 }
 
 static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt, bool acc, int seg_ops, bool wide_strides, bool fma,
-                        JitPlan &plan, std::string &err, const PipeOptions *pipe) {
+                        JitPlan &plan, std::string &err, const PipeOptions *pipe, bool bulk) {
     const bool cplx = low.dtype == FDG_C128;
+    if (bulk && !cplx && spt != 1) {
+        err = "the bulk form evaluates one sample per thread";
+        return FDG_ERR_BAD_ARG;
+    }
     if (pipe && !cplx && spt != 1) {
         err = "the pipeline form evaluates one sample per thread";
         return FDG_ERR_BAD_ARG;
@@ -806,7 +827,9 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
     plan.seg.resize((size_t)nseg);
     // a single accumulate kernel with few roots runs as a grid-stride loop: per-thread running sums in registers,
     // one warp reduction per root at the very end (instead of one per tile)
-    plan.persistent = !pipe && acc && nseg == 1 && low.R * W <= 32;
+    plan.persistent = !pipe && !bulk && acc && nseg == 1 && low.R * W <= 32;
+    plan.bulk = bulk;
+    int bulk_smem_max = 0;
     plan.pipeline = pipe != nullptr;
     plan.stage_start.assign(seg_start.begin(), seg_start.end());
     plan.stage_estimate.clear();
@@ -857,12 +880,19 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         const int ES = cplx ? 16 : 8 * samples_per_thread;  // bytes per thread per row
         const int G = 4;
         int NR = ring_rows > 0 ? ring_rows : (ES == 8 ? 32 : 24);
-        const int T = pipe ? pipe->threads : 128;  // threads per block
+        const int T = pipe ? pipe->threads : (bulk ? 256 : 128);  // (consumer) threads per block
         // static shared memory stops at 48 KB; the pipeline kernel asks for dynamic shared memory and may go deeper
         NR = std::max(G, std::min(NR, (pipe ? 131072 : 49152) / (T * ES)) / G * G);
-        const bool ring = ring_on && !e.persistent && n_in > 0;
-        const int sacc0 = 256 + (ring ? NR * T * ES : 0);  // pipeline form: where the running sums of the roots start
-        if (pipe && acc) {
+        // bulk form: NG groups of BG rows; a group is what one mbarrier phase covers
+        const int BG = 8, NG = 4;
+        if (bulk) NR = NG * BG;
+        const int ROWB = T * ES;  // bytes of one ring row (one input row of one tile)
+        const bool ring = (ring_on || bulk) && !e.persistent && n_in > 0;
+        const int sacc0 = 256 + (ring ? NR * T * ES : 0);  // pipeline / bulk form: where the running sums of the roots start
+        const int b_groups = (n_in + BG - 1) / BG;                                  // bulk form: groups with rows in them ...
+        const int b_groups_padded = (b_groups + 2 * NG - 1) / (2 * NG) * (2 * NG);  // ... padded so that slot and phase of a group do not depend on the tile
+        int b_wait_id = 0;
+        if ((pipe || bulk) && acc) {
             e.sacc_stride = (T + 1) * 8;
             e.sacc_cap = std::max(0, (200 * 1024 - sacc0) / e.sacc_stride);
         }
@@ -874,10 +904,33 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
             e.row_addr(o2, a, row.first == 2 ? "%rd9" : (row.first ? "%rd3" : "%rd1"), row.first == 2 ? "%rd11" : (row.first ? "%rd4" : "%rd2"), row.second);
             o2 << "\tcp.async." << (ES == 16 ? "cg" : "ca") << ".shared.global [%r12+" << (j % NR) * T * ES << "], [%rd" << a << "], " << ES << ";\n";
         };
+        // bulk form: wait until the producer's copies of group g have landed (full barrier of its slot, phase known here)
+        auto bulk_wait = [&](std::ostringstream &o2, int g) {
+            const int id = b_wait_id++;
+            o2 << "\tmov.u32 %r21, 0;\nFDG_BW" << id << ":\n"
+               << "\tmbarrier.try_wait.parity.shared::cta.b64 %p7, [fdg_ring+" << 8 * (g % NG) << "], " << ((g / NG) & 1) << ";\n"
+               << "\t@%p7 bra FDG_BG" << id << ";\n\tadd.u32 %r21, %r21, 1;\n\tsetp.lt.u32 %p7, %r21, 4194304;\n\t@%p7 bra FDG_BW" << id << ";\n"
+               << "\tbra FDG_FAIL;\nFDG_BG" << id << ":\n";
+        };
+        // ... and hand the slot back once this warp has read the group's rows (empty barrier: one arrival per consumer warp)
+        auto bulk_release = [&](std::ostringstream &o2, int g) {
+            o2 << "\t@%p3 mbarrier.arrive.shared::cta.b64 %rd31, [fdg_ring+" << 8 * (NG + g % NG) << "];\n";
+        };
         auto ring_load = [&](int kind_, int32_t row_) -> int {
             const int j = next_in++;
             (void)kind_;
             (void)row_;
+            if (bulk) {
+                const int g = j / BG;
+                if (j % BG == 0) bulk_wait(os, g);
+                const int r = e.new_val();
+                if (ES == 16)
+                    os << "\tld.shared.v2.f64 {" << e.fd(r, 0) << ", " << e.fd(r, 1) << "}, [%r12+" << (j % NR) * ROWB << "];\n";
+                else
+                    os << "\tld.shared.f64 " << e.fd(r, 0) << ", [%r12+" << (j % NR) * ROWB << "];\n";
+                if (j % BG == BG - 1 || j == n_in - 1) bulk_release(os, g);
+                return r;
+            }
             const int g = j / G;
             if (j % G == 0) os << "\tcp.async.wait_group " << std::min(NR / G - 1, n_groups - 1 - g) << ";\n";
             const int r = e.new_val();

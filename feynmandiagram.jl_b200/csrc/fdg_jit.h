@@ -27,6 +27,13 @@ struct JitPlan {
     int64_t fp64_instr = 0;      // FP64 arithmetic instructions per sample the kernels execute (folded negations are none)
     bool uses_cse = false;       // planned from the program with common sub-expressions merged
     bool persistent = false;  // single accumulate kernel run as a grid-stride loop (per-thread running sums)
+    // ---- bulk form (DESIGN.md section 4b'): persistent warp-specialised kernels.  Blocks of 384 threads, one per SM: eight
+    // consumer warps (256 samples per tile, 240 registers after setmaxnreg) run the straight-line arithmetic and read their
+    // input rows from a shared-memory ring; one producer warp (24 registers) fills the ring with cp.async.bulk row copies
+    // (2 KB per row and tile) signalled through mbarriers, following a row table.  No address arithmetic, no cp.async and
+    // no wait-group bookkeeping is left in the consumers' instruction stream.
+    bool bulk = false;
+    int bulk_smem = 0;   // dynamic shared memory of the kernels (barriers + ring + running sums of the roots)
     std::vector<JitSegment> seg;
     // ---- pipeline form: ONE kernel, one resident block per SM; the blocks of stage k run only
     // the code of segment k (it stays in that SM's instruction cache) and tiles of 32 samples flow from stage to stage
@@ -71,9 +78,14 @@ double jit_model_ns(const JitPlan &plan, int bytes_per_element);
 
 // linearise the emitted function in fold order, cut it into segments of `seg_ops` operations, write their PTX
 // wide_strides: row offsets need 64 bits (a leading dimension of 4 GiB or more)
-// pipe != nullptr: pipeline form (stage functions + entry kernel, linked by jit_compile)
+// pipe != nullptr: pipeline form (stage functions + entry kernel, linked by jit_compile).
+// merged != nullptr: SCOPED merging of common sub-expressions.  `merged` is the same program lowered with merging (its
+// `canon` says which statements are copies of which, its sharing decides the order of the roots); `low` is evaluated, but a
+// copy reads the value of its class instead of recomputing it when that value was computed at most `scope` operations
+// earlier -- close enough to sit in the same kernel, so that merging saves arithmetic without sending more values through
+// memory (scope <= 0: about two thirds of a kernel).
 int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strides, bool fma, JitPlan &plan, std::string &err,
-             const PipeOptions *pipe = nullptr);
+             const PipeOptions *pipe = nullptr, const Lowered *merged = nullptr, int scope = 0, bool bulk = false);
 // PTX text -> sm_100a cubin with the PTX compiler library (no GPU needed)
 int jit_assemble(const std::string &ptx, int opt_level, std::vector<char> &cubin, std::string &err);
 // assemble every segment with the PTX compiler library (no GPU needed), segments in parallel

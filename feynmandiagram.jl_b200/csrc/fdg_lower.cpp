@@ -236,8 +236,8 @@ void mark_live(std::vector<Stmt> &st, const std::vector<Operand> &ops) {
 // optimize!(level=1) / remove_duplicated_nodes!, src/computational_graph/optimize.jl:345-390): two statements with the
 // same operator and the same (operand, factor) sequence compute the same bits, so later copies read the first one.
 // Operand ORDER is part of the key -- the fold order defines the rounding -- so nothing is re-associated.
-int64_t eliminate_common_subexpressions(std::vector<Stmt> &st, std::vector<Operand> &ops, int64_t min_cost) {
-    std::vector<int32_t> canon(st.size());
+int64_t eliminate_common_subexpressions(std::vector<Stmt> &st, std::vector<Operand> &ops, int64_t min_cost, std::vector<int32_t> &canon) {
+    canon.assign(st.size(), 0);
     std::vector<int64_t> cost(st.size(), 0);  // operations needed to recompute the statement from leaves
     std::unordered_map<uint64_t, std::vector<int32_t>> buckets;
     buckets.reserve(st.size() * 2 + 1);
@@ -888,7 +888,7 @@ int lower(const fdg_graph_desc &g, const fdg_options &opt, Lowered &out, std::st
     if (opt.cse != 0) {
         int64_t min_cost = 2;  // everything that saves at least one operation
         if (const char *e = getenv("FDG_CSE_MIN_COST")) min_cost = atoll(e);
-        out.cse_removed = eliminate_common_subexpressions(st, ops, min_cost);
+        out.cse_removed = eliminate_common_subexpressions(st, ops, min_cost, out.canon);
         mark_live(st, ops);
     }
 

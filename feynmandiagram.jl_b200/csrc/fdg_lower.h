@@ -44,6 +44,7 @@ struct Lowered {
     // operation counts per sample: value*value, value*real-factor, value+value, multiplies inside Power
     int64_t muls_vv = 0, muls_vf = 0, adds_vv = 0, pow_muls = 0;
     int64_t cse_removed = 0;  // statements that turned out to be copies of an earlier one
+    std::vector<int32_t> canon;  // with merging: statement -> the earlier statement it is a copy of (itself otherwise)
 };
 
 // returns FDG_OK or an FDG_ERR_* code with `err` filled

@@ -112,11 +112,13 @@ def test_specialised_kernels_assemble_without_a_gpu(name, acc):
     ev = fd.compile_raw(raw, jit_segment=300)
     info = ev.jit_prepare(2, acc)
     assert info["kernels"] >= 1 and info["cubin_bytes"] > 0
+    muls = 0
     for i in range(info["kernels"]):
         ptx, log = ev.jit_ptx(2, acc, i)
         assert ".target sm_100a" in ptx and "fma" not in ptx
-        assert "mul.rn.f64" in ptx
+        muls += ptx.count("mul.rn.f64")  # (a short last kernel may hold nothing but the tail of a sum)
         assert "registers" in log
+    assert muls > 0
 
 
 @pytest.mark.parametrize("seed", range(4))
@@ -286,7 +288,7 @@ def test_planner_of_the_specialised_back_end_on_the_headline_graph(monkeypatch):
     import os
 
     raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", "parquet_ver4_o4.npz"))
-    ev = fd.compile_raw(raw, backend=2)
+    ev = fd.compile_raw(raw, backend=2, cse=False)
     info = ev.jit_prepare(1, True)
     assert info["operations"] == 94500 and not info["grid_stride"]
     assert 15 <= info["kernels"] <= 24
@@ -297,16 +299,22 @@ def test_planner_of_the_specialised_back_end_on_the_headline_graph(monkeypatch):
     assert "cp.async.ca.shared.global" in ptx and "cp.async.wait_group" in ptx and "neg.f64" in ptx and "mad.wide.u32" in ptx
     assert "fma.rn.f64" not in ptx                         # nothing is contracted
     assert "bytes spill stores" not in log or " 0 bytes spill stores" in log
+    # the automatic choice (cse=None): equal sub-expressions merged where the copies sit within one kernel of each other --
+    # a third of the arithmetic goes, the traffic does not grow
+    auto = fd.compile_raw(raw, backend=2).jit_prepare(1, True)
+    assert auto["cse"] and auto["fp64_instr"] < 0.75 * info["fp64_instr"] and auto["kernels"] < info["kernels"]
+    assert auto["leaf_loads"] + auto["cross_loads"] + auto["cross_stores"] <= info["leaf_loads"] + info["cross_loads"] + info["cross_stores"]
+    assert auto["max_code_bytes"] <= 120 * 1024
     monkeypatch.setenv("FDG_JIT_ROOT_ORDER", "0")
-    worse = fd.compile_raw(raw, backend=2).jit_prepare(1, True)
+    worse = fd.compile_raw(raw, backend=2, cse=False).jit_prepare(1, True)
     assert worse["cross_values"] > 4 * info["cross_values"]
     monkeypatch.delenv("FDG_JIT_ROOT_ORDER")
     # a budget that would overflow the 128 KB instruction cache is refitted from the machine code ptxas produced
     assert info["max_code_bytes"] <= 120 * 1024
-    big = fd.compile_raw(raw, backend=2, jit_segment=9000).jit_prepare(1, True)
+    big = fd.compile_raw(raw, backend=2, jit_segment=9000, cse=False).jit_prepare(1, True)
     assert big["max_code_bytes"] <= 120 * 1024 and big["kernels"] >= 12
     monkeypatch.setenv("FDG_JIT_NO_REFIT", "1")
-    assert fd.compile_raw(raw, backend=2, jit_segment=9000).jit_prepare(1, True)["max_code_bytes"] > 128 * 1024
+    assert fd.compile_raw(raw, backend=2, jit_segment=9000, cse=False).jit_prepare(1, True)["max_code_bytes"] > 128 * 1024
 
 
 def test_root_ordering_brings_sharing_roots_together(monkeypatch):

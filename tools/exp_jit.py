@@ -43,11 +43,13 @@ def main():
         kv = dict(x.split("=") for x in var.split(",") if x)
         for k in [k for k in os.environ if k.startswith("FDG_")]:
             os.environ.pop(k, None)
-        seg, spt, cse, fma = int(kv.pop("seg", 0)), int(kv.pop("spt", 1)), int(kv.pop("cse", 0)), int(kv.pop("fma", 0))
+        seg, spt, fma = int(kv.pop("seg", 0)), int(kv.pop("spt", 1)), int(kv.pop("fma", 0))
+        cse = kv.pop("cse", "0")
+        cse = None if cse == "auto" else bool(int(cse))  # auto: the planner decides (FDG_CSE_MODE = 0 / 1 / 2 forces plain / merged / scoped)
         os.environ.update(kv)
         os.environ.setdefault("FDG_JIT_NO_REFIT", "1")  # experiments time the budget they ask for
         try:
-            f = fd.compile_raw(raw, dtype=npdt, backend=2, jit_segment=seg, cse=bool(cse), fma=bool(fma))
+            f = fd.compile_raw(raw, dtype=npdt, backend=2, jit_segment=seg, cse=cse, fma=bool(fma))
             f.set_launch(0, spt, 0)
             t0 = time.time()
             info = f.jit_prepare(spt, True)
@@ -73,7 +75,7 @@ def main():
                     best = min(best, e0.elapsed_time(e1))
             model = (info["leaf_loads"] + info["cross_loads"] + info["cross_stores"]) * es
             print(f"{var:60s} {B / best * 1e3 / 1e6:9.2f} Msamples/s  {best:9.3f} ms  kernels={info['kernels']:3d} rows={info['cross_rows']:5d} "
-                  f"model={model / 1e3:6.1f} KB/sample  code={info['cubin_bytes'] / max(info['kernels'], 1) / 1e3:6.1f} KB/kernel  compile={tc:5.1f}s  "
+                  f"model={model / 1e3:6.1f} KB/sample fp64={info['fp64_instr']} code={info['cubin_bytes'] / max(info['kernels'], 1) / 1e3:6.1f} KB/kernel  compile={tc:5.1f}s  "
                   f"bit-equal-to-first={same}", flush=True)
             del f
         except Exception as ex:  # noqa: BLE001
