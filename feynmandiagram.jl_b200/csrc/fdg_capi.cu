@@ -207,8 +207,8 @@ int get_device_state(fdg_program *h, DeviceState **out) {
 }
 
 // ---- specialised back end ----------------------------------------------------------------------------------------
-int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = false, const std::vector<int> *groups = nullptr) {
-    int key = spt * 2 + (acc ? 1 : 0) + (wide ? 64 : 0);
+int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = false, const std::vector<int> *groups = nullptr, bool bulk = false) {
+    int key = spt * 2 + (acc ? 1 : 0) + (wide ? 64 : 0) + (bulk ? 32 : 0);
     if (groups) {
         unsigned hash = 2166136261u;
         for (const int g : *groups) hash = (hash ^ (unsigned)g) * 16777619u;
@@ -250,6 +250,10 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
         // beyond the 128 KB instruction cache runs 20-50 % slower.  If the largest kernel of a
         // multi-kernel plan comes out above 120 KB the plan is redone with a proportionally smaller budget (at most twice).
         int budget = h->jit_segment > 0 ? h->jit_segment : 4000;
+        if (bulk && h->jit_segment <= 0) {
+            budget = 4400;  // the bulk form spends one instruction per input row where the ring spends five
+            if (const char *e = getenv("FDG_JIT_BULK_BUDGET")) budget = std::max(64, atoi(e));
+        }
         int rc = FDG_OK;
         // automatic CSE: plan the program with and without merged sub-expressions (planning is cheap, assembling is not) and
         // keep the plan whose modelled time is lower: fewer operations against more values crossing kernel boundaries
@@ -263,9 +267,9 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
             const int es = h->low.dtype == FDG_C128 ? 16 : 8;
             int mode = -1;  // FDG_CSE_MODE: 0 plain, 1 merged, 2 scoped (experiments); default: the model decides
             if (const char *e = getenv("FDG_CSE_MODE")) mode = atoi(e);
-            if (fdg::jit_plan(h->low, spt, acc, budget, wide, h->fma, plain, e1) == FDG_OK &&
-                fdg::jit_plan(h->low_cse, spt, acc, budget, wide, h->fma, full, e2) == FDG_OK &&
-                fdg::jit_plan(h->low, spt, acc, budget, wide, h->fma, scoped, e3, nullptr, &h->low_cse) == FDG_OK) {
+            if (fdg::jit_plan(h->low, spt, acc, budget, wide, h->fma, plain, e1, nullptr, nullptr, 0, bulk) == FDG_OK &&
+                fdg::jit_plan(h->low_cse, spt, acc, budget, wide, h->fma, full, e2, nullptr, nullptr, 0, bulk) == FDG_OK &&
+                fdg::jit_plan(h->low, spt, acc, budget, wide, h->fma, scoped, e3, nullptr, &h->low_cse, 0, bulk) == FDG_OK) {
                 const double tp = fdg::jit_model_ns(plain, es), tf = fdg::jit_model_ns(full, es), ts = fdg::jit_model_ns(scoped, es);
                 fdg::JitPlan *cand = tf <= ts ? &full : &scoped;
                 if (mode == 1) cand = &full;
@@ -290,7 +294,7 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
             }
         }
         for (int attempt = 0; attempt < 3; ++attempt) {
-            rc = fdg::jit_plan(*lowp, spt, acc, budget, wide, h->fma, v.plan, err, nullptr, mergedp);
+            rc = fdg::jit_plan(*lowp, spt, acc, budget, wide, h->fma, v.plan, err, nullptr, mergedp, 0, bulk);
             v.plan.uses_cse = lowp == &h->low_cse || mergedp != nullptr || h->low.cse_removed > 0;
             if (rc == FDG_OK) rc = fdg::jit_compile(v.plan, err);
             if (rc != FDG_OK || v.plan.seg.size() < 2 || v.plan.max_code_bytes <= 120 * 1024 || getenv("FDG_JIT_NO_REFIT")) break;
@@ -663,8 +667,22 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
     StreamScratch &ss = ds.per_stream[stream];
     // row offsets are formed with one 32-bit multiply-add unless a leading dimension reaches 4 GiB
     const bool wide = (uint64_t)ld_leaf * (h->low.dtype == FDG_C128 ? 16 : 8) >= (1ull << 32);
-    int rc = jit_get(h, spt, acc, &v, wide);
+    // Bulk form (persistent warp-specialised kernels fed by cp.async.bulk, DESIGN.md section 4b'): for programs of several
+    // kernels on batches that give every SM a few tiles; bulk copies move whole 16-byte units from 16-byte aligned addresses.
+    // FDG_JIT_BULK = 0 never, 1 whenever the buffers allow it (tests), unset: the rule above.
+    bool bulk = false;
+    {
+        const bool cplx = h->low.dtype == FDG_C128;
+        const bool aligned = cplx || (((uintptr_t)leaf % 16 == 0) && (ld_leaf % 2 == 0));
+        const int64_t work = h->low.muls_vv + h->low.muls_vf + h->low.adds_vv + h->low.pow_muls;
+        int mode = -1;
+        if (const char *e = getenv("FDG_JIT_BULK")) mode = atoi(e);
+        const int budget = h->jit_segment > 0 ? h->jit_segment : 4000;
+        bulk = aligned && (spt == 1 || cplx) && mode != 0 && (mode > 0 || (work >= 2 * (int64_t)budget && batch >= (int64_t)256 * ds.sm_count * 4));
+    }
+    int rc = jit_get(h, spt, acc, &v, wide, nullptr, bulk);
     if (rc != FDG_OK) return rc;
+    bulk = v->plan.bulk;
     auto &kern = v->kernels[dev];
     if (kern.empty()) {
         for (auto &sg : v->plan.seg) {
@@ -673,6 +691,7 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
             v->libs[dev].push_back(lib);
             cudaKernel_t k;
             CUDA_TRY(cudaLibraryGetKernel(&k, lib, sg.name.c_str()));
+            if (bulk) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, v->plan.bulk_smem));
             kern.push_back(k);
         }
     }
@@ -681,7 +700,8 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
     const size_t es = 8 * (size_t)W;
     int T = 128;
     if (const char *e = getenv("FDG_JIT_THREADS")) T = std::max(32, std::min(128, atoi(e) / 32 * 32));
-    const int64_t per_block = (int64_t)T * spt;
+    if (bulk) T = 256;  // samples of a tile (the block has 128 more threads: the producer's warpgroup)
+    const int64_t per_block = bulk ? 256 : (int64_t)T * spt;
     // sub-batches keep the cross buffer bounded (8 GiB unless FDG_JIT_CROSS_GB says otherwise)
     int64_t sub = batch;
     if (v->plan.n_cross > 0) {
@@ -704,6 +724,7 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
     int64_t max_grid = (sub + per_block - 1) / per_block;
     if (v->plan.persistent) max_grid = std::min<int64_t>(max_grid, (int64_t)ds.sm_count * 16);
     const int64_t ld_cross = max_grid * per_block;
+    if (bulk) max_grid = std::min<int64_t>(max_grid, ds.sm_count);  // one block per SM walks the tiles
     if (v->plan.n_cross > 0) {
         const size_t need = (size_t)v->plan.n_cross * ld_cross * es;
         if (need > ss.cross_bytes) {
@@ -732,13 +753,14 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
     for (int64_t b0 = 0; b0 < batch; b0 += sub) {
         const int64_t nb = std::min<int64_t>(sub, batch - b0);
         const unsigned grid = (unsigned)std::min<int64_t>((nb + per_block - 1) / per_block, max_grid);
-        const void *p_leaf = static_cast<const char *>(leaf) + (size_t)b0 * es;
+        const void *p_leaf = static_cast<const char *>(leaf) + (size_t)b0 * es;  // (sub-batches are whole tiles: stays 16-byte aligned)
         void *p_out = acc ? out : static_cast<void *>(static_cast<char *>(root) + (size_t)b0 * es);
         void *p_cross = ss.cross;
         long long a_ld_leaf = ld_leaf, a_ld_cross = ld_cross, a_ld_root = ld_root, a_batch = nb, a_nroots = low.R * W;
         void *args[] = {(void *)&p_leaf, &a_ld_leaf, &p_cross, &a_ld_cross, &p_out, &a_ld_root, &a_batch, &a_nroots};
         for (size_t sg = 0; sg < kern.size(); ++sg) {
-            CUDA_TRY(cudaLaunchKernel((const void *)kern[sg], dim3(grid), dim3(T), args, 0, stream));
+            if (bulk) CUDA_TRY(cudaLaunchKernel((const void *)kern[sg], dim3(grid), dim3(T + 128), args, (size_t)v->plan.bulk_smem, stream));
+            else CUDA_TRY(cudaLaunchKernel((const void *)kern[sg], dim3(grid), dim3(T), args, 0, stream));
             h->launches++;
         }
         if (acc && v->plan.persistent && low.R > 0 && b0 + sub < batch) {
@@ -960,13 +982,19 @@ static int fdg_compile_file_impl(const char *path, const fdg_options *opts, fdg_
     return fdg_compile(&d, opts, out);
 }
 
+// fdg_jit_prepare / _info / _ptx look at the bulk form of the kernels when FDG_JIT_BULK >= 1 (tools, tests)
+static bool inspect_bulk() {
+    const char *e = getenv("FDG_JIT_BULK");
+    return e && atoi(e) > 0;
+}
+
 static int fdg_jit_prepare_impl(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t *n_kernels, int32_t *n_cross,
                     int64_t *cubin_bytes) {
     if (!h) return fail(FDG_ERR_BAD_ARG, "null handle");
     if (samples_per_thread != 1 && samples_per_thread != 2) return fail(FDG_ERR_BAD_ARG, "samples_per_thread must be 1 or 2");
     std::lock_guard<std::mutex> lock(h->mu);
     JitVariant *v = nullptr;
-    int rc = jit_get(h, samples_per_thread, accumulate != 0, &v);
+    int rc = jit_get(h, samples_per_thread, accumulate != 0, &v, false, nullptr, inspect_bulk());
     if (rc != FDG_OK) return rc;
     if (n_kernels) *n_kernels = (int32_t)v->plan.seg.size();
     if (n_cross) *n_cross = v->plan.n_cross;
@@ -980,7 +1008,7 @@ static int fdg_jit_prepare_impl(fdg_handle h, int32_t samples_per_thread, int32_
 static int fdg_jit_info_impl(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int64_t *out, int32_t n_out) {
     if (!h || !out || n_out < 0) return fail(FDG_ERR_BAD_ARG, "null argument");
     std::lock_guard<std::mutex> lock(h->mu);
-    auto it = h->jit.find(samples_per_thread * 2 + (accumulate ? 1 : 0));
+    auto it = h->jit.find(samples_per_thread * 2 + (accumulate ? 1 : 0) + (inspect_bulk() ? 32 : 0));
     if (it == h->jit.end() || !it->second.compiled) return fail(FDG_ERR_BAD_ARG, "variant not prepared");
     const fdg::JitPlan &pl = it->second.plan;
     int64_t ops = 0;
@@ -1048,7 +1076,7 @@ static int fdg_jit_ptx_impl(fdg_handle h, int32_t samples_per_thread, int32_t ac
                 const char **ptxas_log) {
     if (!h || !ptx) return fail(FDG_ERR_BAD_ARG, "null argument");
     std::lock_guard<std::mutex> lock(h->mu);
-    auto it = h->jit.find(samples_per_thread * 2 + (accumulate ? 1 : 0));
+    auto it = h->jit.find(samples_per_thread * 2 + (accumulate ? 1 : 0) + (inspect_bulk() ? 32 : 0));
     if (it == h->jit.end() || !it->second.compiled) return fail(FDG_ERR_BAD_ARG, "variant not prepared");
     if (index < 0 || index >= (int32_t)it->second.plan.seg.size()) return fail(FDG_ERR_BAD_ARG, "kernel index out of range");
     *ptx = it->second.plan.seg[(size_t)index].ptx.c_str();

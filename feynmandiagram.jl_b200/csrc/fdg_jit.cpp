@@ -884,7 +884,13 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         // static shared memory stops at 48 KB; the pipeline kernel asks for dynamic shared memory and may go deeper
         NR = std::max(G, std::min(NR, (pipe ? 131072 : 49152) / (T * ES)) / G * G);
         // bulk form: NG groups of BG rows; a group is what one mbarrier phase covers
-        const int BG = 8, NG = 4;
+        int BG = 16, NG = ES == 8 ? 4 : 2;  // 128 KB of rows in flight per SM; few, long groups: every wait costs the consumers code
+        if (const char *x = getenv("FDG_JIT_BULK_GROUPS")) NG = std::max(2, std::min(16, atoi(x)));
+        if (const char *x = getenv("FDG_JIT_BULK_GROUP_ROWS")) BG = std::max(1, std::min(64, atoi(x)));
+        bool bulk_guard = true;
+        if (const char *x = getenv("FDG_JIT_BULK_GUARD")) bulk_guard = atoi(x) != 0;
+        int bulk_hint = 1000000;  // ns
+        if (const char *x = getenv("FDG_JIT_BULK_HINT")) bulk_hint = std::max(0, atoi(x));
         if (bulk) NR = NG * BG;
         const int ROWB = T * ES;  // bytes of one ring row (one input row of one tile)
         const bool ring = (ring_on || bulk) && !e.persistent && n_in > 0;
@@ -894,7 +900,7 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         int b_wait_id = 0;
         if ((pipe || bulk) && acc) {
             e.sacc_stride = (T + 1) * 8;
-            e.sacc_cap = std::max(0, (200 * 1024 - sacc0) / e.sacc_stride);
+            e.sacc_cap = std::max(0, ((pipe ? 200 : 226) * 1024 - sacc0) / e.sacc_stride);
         }
         const int n_groups = (n_in + G - 1) / G;
         int next_in = 0;  // rows consumed so far
@@ -907,14 +913,22 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         // bulk form: wait until the producer's copies of group g have landed (full barrier of its slot, phase known here)
         auto bulk_wait = [&](std::ostringstream &o2, int g) {
             const int id = b_wait_id++;
+            // (the last operand is a suspend-time hint in ns: the warp sleeps in the barrier unit instead of polling)
+            if (!bulk_guard) {
+                o2 << "FDG_BW" << id << ":\n\tmbarrier.try_wait.parity.shared::cta.b64 %p7, [fdg_ring+" << 8 * (g % NG) << "], " << ((g / NG) & 1)
+                   << ", " << bulk_hint << ";\n\t@!%p7 bra FDG_BW" << id << ";\n";
+                return;
+            }
+            // guarded form: a wait that does not end within 4096 (long) polls traps instead of hanging the device
             o2 << "\tmov.u32 %r21, 0;\nFDG_BW" << id << ":\n"
-               << "\tmbarrier.try_wait.parity.shared::cta.b64 %p7, [fdg_ring+" << 8 * (g % NG) << "], " << ((g / NG) & 1) << ";\n"
-               << "\t@%p7 bra FDG_BG" << id << ";\n\tadd.u32 %r21, %r21, 1;\n\tsetp.lt.u32 %p7, %r21, 4194304;\n\t@%p7 bra FDG_BW" << id << ";\n"
-               << "\tbra FDG_FAIL;\nFDG_BG" << id << ":\n";
+               << "\tmbarrier.try_wait.parity.shared::cta.b64 %p7, [fdg_ring+" << 8 * (g % NG) << "], " << ((g / NG) & 1) << ", " << bulk_hint << ";\n"
+               << "\t@%p7 bra FDG_BG" << id << ";\n\tadd.u32 %r21, %r21, 1;\n\tsetp.lt.u32 %p7, %r21, 4096;\n\t@%p7 bra FDG_BW" << id << ";\n"
+               << "\ttrap;\nFDG_BG" << id << ":\n";
         };
-        // ... and hand the slot back once this warp has read the group's rows (empty barrier: one arrival per consumer warp)
+        // ... and hand the slot back once this warp has read the group's rows (empty barrier: one arrival per consumer
+        // warp; the warp-level barrier in front orders the other lanes' reads before lane 0's arrival)
         auto bulk_release = [&](std::ostringstream &o2, int g) {
-            o2 << "\t@%p3 mbarrier.arrive.shared::cta.b64 %rd31, [fdg_ring+" << 8 * (NG + g % NG) << "];\n";
+            o2 << "\tbar.warp.sync 0xffffffff;\n\t@%p3 mbarrier.arrive.shared::cta.b64 %rd31, [fdg_ring+" << 8 * (NG + g % NG) << "];\n";
         };
         auto ring_load = [&](int kind_, int32_t row_) -> int {
             const int j = next_in++;
@@ -1013,6 +1027,11 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
                     os << "\tst.global.f64 [%rd" << a << "], " << e.fd(r, 0) << ";\n";
             }
         }
+        if (bulk && ring)  // the padding groups: no rows, but every slot sees the same (even) number of phases per tile
+            for (int g = b_groups; g < b_groups_padded; ++g) {
+                bulk_wait(os, g);
+                bulk_release(os, g);
+            }
         const std::string body = os.str();
         const int spt_hdr = samples_per_thread;
         JitSegment &js = plan.seg[(size_t)sg];
@@ -1161,6 +1180,147 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
             }
             continue;
         }
+        if (bulk) {
+            // ---- bulk form: persistent, warp-specialised -------------------------------------------------------------------
+            // 384 threads, one block per SM.  Warps 0-7 (two warpgroups, 240 registers each after setmaxnreg) are the
+            // consumers: tile after tile of 256 samples they run the straight-line code, reading every input row out of the
+            // ring.  Warp 8 (its warpgroup shrinks to 24 registers) is the producer: it walks the row table of the kernel
+            // and copies row after row of the tile global -> shared with cp.async.bulk, eight rows per mbarrier phase.
+            // Shared memory: [0, 8 NG) full barriers, [8 NG, 16 NG) empty barriers, [256, ...) the ring, then the per-thread
+            // running sums of the roots (accumulate mode).
+            const int n_sacc = (int)e.sacc_pos.size();
+            const int smem = sacc0 + n_sacc * e.sacc_stride;
+            bulk_smem_max = std::max(bulk_smem_max, smem);
+            const int CT = T;  // consumer threads
+            p << ".extern .shared .align 128 .b8 fdg_ring[];\n";
+            if (n_in > 0) {
+                p << ".const .align 4 .u32 fdg_tab[" << n_in << "] = {";
+                for (int j = 0; j < n_in; ++j) p << (j ? ", " : "") << (((uint32_t)in_rows[(size_t)j].first << 31) | (uint32_t)in_rows[(size_t)j].second);
+                p << "};\n";
+            }
+            if (n_sacc > 0) {
+                p << ".const .align 4 .u32 fdg_rt[" << n_sacc << "] = {";
+                for (int j = 0; j < n_sacc; ++j) p << (j ? ", " : "") << e.sacc_pos[(size_t)j];
+                p << "};\n";
+            }
+            p << ".visible .entry " << js.name << "(\n"
+              << "\t.param .u64 p_leaf, .param .u64 p_ld_leaf, .param .u64 p_cross, .param .u64 p_ld_cross,\n"
+              << "\t.param .u64 p_out, .param .u64 p_ld_root, .param .u64 p_batch, .param .u64 p_nroots)\n"
+              << ".maxntid " << CT + 128 << ", 1, 1\n.minnctapersm 1\n{\n";
+            p << "\t.reg .f64 %fd<" << e.nfd + 2 << ">;\n\t.reg .b64 %rd<" << e.nrd + 1 << ">;\n\t.reg .pred %p<" << e.np + 1
+              << ">;\n\t.reg .b32 %r<" << e.nr + 1 << ">;\n";
+            // ---- common prologue: barriers, role split ----
+            p << "\tmov.u32 %r2, %tid.x;\n\tsetp.ne.u32 %p6, %r2, 0;\n\t@%p6 bra FDG_INITED;\n";
+            for (int sl = 0; sl < NG; ++sl)
+                p << "\tmbarrier.init.shared::cta.b64 [fdg_ring+" << 8 * sl << "], 4;\n"
+                  << "\tmbarrier.init.shared::cta.b64 [fdg_ring+" << 8 * (NG + sl) << "], " << CT / 32 << ";\n";
+            p << "\tfence.mbarrier_init.release.cluster;\nFDG_INITED:\n\tbar.sync 0;\n"
+              << "\tsetp.ge.u32 %p6, %r2, " << CT << ";\n\t@%p6 bra FDG_PRODUCER;\n"
+              << "\tsetmaxnreg.inc.sync.aligned.u32 240;\n";
+            // ---- consumers ----
+            // %r2 tid, %r3 lane, %r5 warp, %p3 lane 0, %r4 tile (the one value carried from tile to tile), %rd10 batch
+            p << "\tand.b32 %r3, %r2, 31;\n\tsetp.eq.u32 %p3, %r3, 0;\n\tshr.u32 %r5, %r2, 5;\n\tmov.u32 %r0, %ctaid.x;\n"
+              << "\tmov.u32 %r12, fdg_ring;\n\tmad.lo.u32 %r12, %r2, " << ES << ", %r12;\n\tadd.u32 %r12, %r12, 256;\n";
+            if (n_sacc > 0) {
+                p << "\tmov.u32 %r16, fdg_ring;\n\tmad.lo.u32 %r16, %r2, 8, %r16;\n\tadd.u32 %r16, %r16, " << sacc0 << ";\n"
+                  << "\tmov.u32 %r17, 0;\n\tmov.u32 %r18, %r16;\n\tmov.f64 %fd" << e.nfd << ", 0d0000000000000000;\n"
+                  << "FDG_ZERO:\n\tst.shared.f64 [%r18], %fd" << e.nfd << ";\n\tadd.u32 %r18, %r18, " << e.sacc_stride << ";\n"
+                  << "\tadd.u32 %r17, %r17, 1;\n\tsetp.lt.u32 %p6, %r17, " << n_sacc << ";\n\t@%p6 bra FDG_ZERO;\n";
+            }
+            p << "\tmov.u32 %r4, %r0;\n"
+              << "FDG_TILE:\n"
+              << "\tld.param.u64 %rd10, [p_batch];\n\tadd.u64 %rd8, %rd10, " << CT - 1 << ";\n\tshr.u64 %rd8, %rd8, " << (CT == 256 ? 8 : 7) << ";\n"  // tiles
+              << "\tcvt.u64.u32 %rd9, %r4;\n\tsetp.ge.u64 %p6, %rd9, %rd8;\n\t@%p6 bra FDG_DONE;\n"
+              << "\tshl.b64 %rd9, %rd9, " << (CT == 256 ? 8 : 7) << ";\n\tcvt.u64.u32 %rd8, %r2;\n\tadd.u64 %rd0, %rd9, %rd8;\n"
+              << "\tsetp.lt.s64 %p0, %rd0, %rd10;\n\tshl.b64 %rd13, %rd0, " << esh << ";\n";
+            if (n_cross > 0)
+                p << "\tld.param.u64 %rd3, [p_cross];\n\tcvta.to.global.u64 %rd3, %rd3;\n\tadd.u64 %rd3, %rd3, %rd13;\n"
+                  << "\tld.param.u64 %rd4, [p_ld_cross];\n\tshl.b64 %rd4, %rd4, " << esh << ";\n\tcvt.u32.u64 %r14, %rd4;\n";
+            p << "\tld.param.u64 %rd14, [p_out];\n\tcvta.to.global.u64 %rd14, %rd14;\n";
+            if (acc) {
+                // partial row of this warp (roots beyond the shared-memory running sums go there tile by tile)
+                p << "\tld.param.u64 %rd5, [p_nroots];\n\tmad.lo.u32 %r6, %r0, " << CT / 32 << ", %r5;\n\tcvt.u64.u32 %rd15, %r6;\n"
+                  << "\tmul.lo.u64 %rd15, %rd15, %rd5;\n\tshl.b64 %rd15, %rd15, 3;\n\tadd.u64 %rd7, %rd14, %rd15;\n";
+            } else {
+                p << "\tld.param.u64 %rd5, [p_ld_root];\n\tshl.b64 %rd5, %rd5, " << esh << ";\n\tadd.u64 %rd6, %rd14, %rd13;\n";
+            }
+            p << body;
+            p << "\tmov.u32 %r1, %nctaid.x;\n\tadd.u32 %r4, %r4, %r1;\n\tbra FDG_TILE;\nFDG_DONE:\n";
+            if (n_sacc > 0) {
+                // lane l adds up entries l, l + 32, ... over the 32 columns of its warp, in lane order, and adds the sum to the
+                // warp's row of partial sums (every entry of that row has exactly one writer; the host zeroed it)
+                p << "\tbar.warp.sync 0xffffffff;\n"
+                  << "\tld.param.u64 %rd14, [p_out];\n\tcvta.to.global.u64 %rd14, %rd14;\n\tld.param.u64 %rd5, [p_nroots];\n"
+                  << "\tmad.lo.u32 %r6, %r0, " << CT / 32 << ", %r5;\n\tcvt.u64.u32 %rd15, %r6;\n"
+                  << "\tmul.lo.u64 %rd15, %rd15, %rd5;\n\tshl.b64 %rd15, %rd15, 3;\n\tadd.u64 %rd7, %rd14, %rd15;\n"
+                  << "\tmov.u32 %r17, %r3;\n"
+                  << "FDG_RED:\n\tsetp.ge.u32 %p6, %r17, " << n_sacc << ";\n\t@%p6 bra FDG_RED_END;\n"
+                  << "\tmov.u32 %r18, fdg_ring;\n\tmad.lo.u32 %r18, %r17, " << e.sacc_stride << ", %r18;\n\tmad.lo.u32 %r18, %r5, 256, %r18;\n"
+                  << "\tmov.f64 %fd" << e.nfd << ", 0d0000000000000000;\n\tmov.u32 %r19, 0;\n"
+                  << "FDG_RED_IN:\n\tld.shared.f64 %fd" << e.nfd + 1 << ", [%r18+" << sacc0 << "];\n"
+                  << "\tadd.rn.f64 %fd" << e.nfd << ", %fd" << e.nfd << ", %fd" << e.nfd + 1 << ";\n"
+                  << "\tadd.u32 %r18, %r18, 8;\n\tadd.u32 %r19, %r19, 1;\n\tsetp.lt.u32 %p7, %r19, 32;\n\t@%p7 bra FDG_RED_IN;\n"
+                  << "\tmov.u64 %rd22, fdg_rt;\n\tmul.wide.u32 %rd23, %r17, 4;\n\tadd.u64 %rd22, %rd22, %rd23;\n\tld.const.u32 %r19, [%rd22];\n"
+                  << "\tmul.wide.u32 %rd23, %r19, 8;\n\tadd.u64 %rd23, %rd7, %rd23;\n"
+                  << "\tld.global.f64 %fd" << e.nfd + 1 << ", [%rd23];\n\tadd.rn.f64 %fd" << e.nfd << ", %fd" << e.nfd + 1 << ", %fd" << e.nfd << ";\n"
+                  << "\tst.global.f64 [%rd23], %fd" << e.nfd << ";\n"
+                  << "\tadd.u32 %r17, %r17, 32;\n\tbra FDG_RED;\n"
+                  << "FDG_RED_END:\n";
+            }
+            p << "\tret;\n";
+            // ---- producer ----
+            // All four warps of the producer's warpgroup copy: warp w takes rows w, w + 4, ... of every group, so four copies
+            // are being set up at any time (one warp alone needs ~50 cycles per copy and cannot keep the ring full).  Every
+            // value below is the same in all lanes of a warp (uniform datapath); one elected lane issues.  Warp 0 announces
+            // the bytes of the group (expect_tx) -- copies of the other warps may complete before that: the transaction count
+            // is signed and the phase cannot end before the arrival of all four warps.
+            p << "FDG_PRODUCER:\n\tsetmaxnreg.dec.sync.aligned.u32 24;\n"
+              << "\tshr.u32 %r5, %r2, 5;\n\tsub.u32 %r5, %r5, " << CT / 32 << ";\n\tsetp.eq.u32 %p3, %r5, 0;\n";
+            if (n_in > 0) {
+                const int tsh = CT == 256 ? 8 : 7;
+                p << "\tld.param.u64 %rd10, [p_batch];\n\tadd.u64 %rd8, %rd10, " << CT - 1 << ";\n\tshr.u64 %rd8, %rd8, " << tsh << ";\n"  // %rd8 tiles
+                  << "\tld.param.u64 %rd1, [p_leaf];\n\tcvta.to.global.u64 %rd1, %rd1;\n\tld.param.u64 %rd2, [p_ld_leaf];\n\tshl.b64 %rd2, %rd2, " << esh << ";\n"
+                  << "\tld.param.u64 %rd3, [p_cross];\n\tcvta.to.global.u64 %rd3, %rd3;\n\tld.param.u64 %rd4, [p_ld_cross];\n\tshl.b64 %rd4, %rd4, " << esh << ";\n"
+                  << "\tmov.u32 %r4, %ctaid.x;\n\tmov.u32 %r1, %nctaid.x;\n\tmov.u32 %r7, fdg_ring;\n"
+                  << "FDG_PTILE:\n\tcvt.u64.u32 %rd9, %r4;\n\tsetp.ge.u64 %p6, %rd9, %rd8;\n\t@%p6 bra FDG_PEND;\n"
+                  << "\tshl.b64 %rd9, %rd9, " << tsh << ";\n"                                                       // first sample of the tile
+                  << "\tsub.u64 %rd11, %rd10, %rd9;\n\tmin.u64 %rd11, %rd11, " << CT << ";\n\tcvt.u32.u64 %r8, %rd11;\n"  // valid samples
+                  << "\tshl.b32 %r8, %r8, " << esh << ";\n\tadd.u32 %r8, %r8, 15;\n\tand.b32 %r8, %r8, 0xfffffff0;\n"      // bytes per row, whole 16-byte units
+                  << "\tshl.b64 %rd9, %rd9, " << esh << ";\n"                                                       // byte offset of the tile within a row
+                  << "\tmov.u32 %r9, 0;\n\tmov.u32 %r10, 0;\n\tmov.u32 %r11, 1;\n"                               // group, its slot, parity to wait for
+                  << "FDG_PGROUP:\n"
+                  << "\tshl.b32 %r15, %r10, 3;\n\tadd.u32 %r15, %r15, %r7;\n"                                      // full barrier of the slot (+ 8 NG: empty)
+                  << "\tmul.lo.u32 %r17, %r9, " << BG << ";\n"                                                       // first row of the group
+                  << "\tsetp.ge.u32 %p5, %r17, " << n_in << ";\n"                                                    // a padding group: nothing to copy
+                  << "\tsub.u32 %r18, " << n_in << ", %r17;\n\tmin.u32 %r18, %r18, " << BG << ";\n\tselp.u32 %r18, 0, %r18, %p5;\n"  // rows in the group
+                  << "\tmul.lo.u32 %r19, %r18, %r8;\n"                                                               // bytes of the group
+                  << "\tmov.u32 %r21, 0;\n"
+                  << "FDG_PWAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 %p7, [%r15+" << 8 * NG << "], %r11, " << bulk_hint << ";\n\t@%p7 bra FDG_PGO;\n"
+                  << "\tadd.u32 %r21, %r21, 1;\n\tsetp.lt.u32 %p7, %r21, 4096;\n\t@%p7 bra FDG_PWAIT;\n\ttrap;\n"
+                  << "FDG_PGO:\n"
+                  // every producer warp arrives on the full barrier of every group, rows or not (count 4): a phase cannot end
+                  // before all four have passed their wait for it, so the parity a warp polls is never more than one phase old
+                  << "\telect.sync %r22|%p4, 0xffffffff;\n\tand.pred %p5, %p4, %p3;\n\tnot.pred %p6, %p3;\n\tand.pred %p6, %p6, %p4;\n"
+                  << "\t@%p5 mbarrier.arrive.expect_tx.shared::cta.b64 %rd31, [%r15], %r19;\n"
+                  << "\t@%p6 mbarrier.arrive.shared::cta.b64 %rd31, [%r15];\n"
+                  << "\tmov.u32 %r6, %r5;\n"                                                                         // row of the group this warp copies next
+                  << "FDG_PROW:\n\tsetp.ge.u32 %p6, %r6, %r18;\n\t@%p6 bra FDG_PNEXT;\n"
+                  << "\tadd.u32 %r20, %r17, %r6;\n\tmov.u64 %rd12, fdg_tab;\n\tmul.wide.u32 %rd13, %r20, 4;\n\tadd.u64 %rd12, %rd12, %rd13;\n\tld.const.u32 %r20, [%rd12];\n"
+                  << "\tand.b32 %r22, %r20, 0x7fffffff;\n\tcvt.u64.u32 %rd13, %r22;\n\tsetp.ge.u32 %p6, %r20, 0x80000000;\n"
+                  << "\tselp.u64 %rd14, %rd4, %rd2, %p6;\n\tselp.u64 %rd15, %rd3, %rd1, %p6;\n"
+                  << "\tmad.lo.u64 %rd15, %rd13, %rd14, %rd15;\n\tadd.u64 %rd15, %rd15, %rd9;\n"
+                  << "\tmad.lo.u32 %r23, %r10, " << BG << ", %r6;\n\tmad.lo.u32 %r23, %r23, " << ROWB << ", %r7;\n"
+                  << "\t@%p4 cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%r23+256], [%rd15], %r8, [%r15];\n"
+                  << "\tadd.u32 %r6, %r6, 4;\n\tbra FDG_PROW;\n"
+                  << "FDG_PNEXT:\n"
+                  << "\tadd.u32 %r10, %r10, 1;\n\tsetp.eq.u32 %p6, %r10, " << NG << ";\n\t@%p6 xor.b32 %r11, %r11, 1;\n\t@%p6 mov.u32 %r10, 0;\n"  // next slot; the parity flips every NG groups
+                  << "\tadd.u32 %r9, %r9, 1;\n\tsetp.lt.u32 %p6, %r9, " << b_groups_padded << ";\n\t@%p6 bra FDG_PGROUP;\n"
+                  << "\tadd.u32 %r4, %r4, %r1;\n\tbra FDG_PTILE;\n";
+            }
+            p << "FDG_PEND:\n\tret;\n}\n";
+            js.ptx = p.str();
+            continue;
+        }
         p << ".visible .entry " << js.name << "(\n"
           << "\t.param .u64 p_leaf, .param .u64 p_ld_leaf, .param .u64 p_cross, .param .u64 p_ld_cross,\n"
           << "\t.param .u64 p_out, .param .u64 p_ld_root, .param .u64 p_batch, .param .u64 p_nroots)\n"
@@ -1230,6 +1390,7 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         p << "\tret;\n}\n";
         js.ptx = p.str();
     }
+    plan.bulk_smem = bulk_smem_max;
     if (pipe) {
         const int S = nseg, spp = pipe_stages_per_pass;
         plan.n_sm = pipe->n_sm();

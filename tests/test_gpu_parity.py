@@ -371,7 +371,7 @@ def test_host_arrays_in_many_chunks_on_a_multi_kernel_program():
 
     raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", "parquet_ver4_o3.npz"))
     ev = fd.compile_raw(raw, backend=JIT, jit_segment=700)
-    assert ev.jit_prepare(1, False)["kernels"] >= 8 and ev.jit_prepare(1, False)["cross_rows"] > 0
+    assert ev.jit_prepare(1, False)["kernels"] >= 4 and ev.jit_prepare(1, False)["cross_rows"] > 0
     B = 150000  # 4 chunks of 46080 samples
     leafT = graphgen.leaf_values(11, ev.n_leaves, B, signed=True)      # (L, B)
     leafVal = np.asfortranarray(leafT.T)                                # (B, L), batch unit-stride
