@@ -486,6 +486,16 @@ def main():
             if not allreduce_check["ok"]:
                 raise SystemExit(f"fdg_allreduce disagrees with torch.distributed: {rel}")
 
+        if jit_info is not None:
+            # the plan of the variant the timed launches actually ran (the bulk form is a different plan from the ring form
+            # prepared above: other cuts, other kernel count)
+            try:
+                last = f.jit_last()
+                jit_info = {**jit_info, **last, "form": "bulk (persistent warp-specialised, cp.async.bulk + mbarrier ring)" if last["bulk"]
+                            else ("grid-stride" if last["grid_stride"] else "ring (cp.async per thread)")}
+                jit_info.pop("cubin_bytes", None)
+            except Exception:  # noqa: BLE001
+                pass
         avg_launch_s = 1e-3 * float(np.mean(kern_ms)) if kern_ms else float("nan")
         bytes_launch = st["bytes_in"] * res  # accumulate mode: sizeof(W) * L per sample
         achieved = bytes_launch / avg_launch_s / 1e9
@@ -669,7 +679,8 @@ def main():
                  "graph_evals_per_s": wc["sps"] * wc["R"], "ms_per_step": wc["ms"] / 3, "kernels_per_pass": (wc["jit"] or {}).get("kernels"),
                  "frac_of_hbm_peak_algorithmic": rl["frac"], "frac_of_hbm_peak_planned_traffic": rl.get("planned_frac_of_peak"),
                  "planned_bytes_per_sample": rl.get("planned_bytes_per_sample"), "algorithmic_bytes_per_sample": rl["algorithmic_bytes_per_sample"],
-                 "fp64_frac_executed": rl.get("fp64_frac_executed"), "cse": (wc["jit"] or {}).get("cse"), "gpu_launches": int(wc["launches"])}
+                 "fp64_frac_executed": rl.get("fp64_frac_executed"), "cse": (wc["jit"] or {}).get("cse"), "form": (wc["jit"] or {}).get("form"),
+                 "gpu_launches": int(wc["launches"])}
             if not a.no_e2e:
                 e = e2e_host(wc, 1 << 29)
                 c["e2e_samples_per_s"], c["e2e_graph_evals_per_s"] = e["samples_per_s"], e["value"]

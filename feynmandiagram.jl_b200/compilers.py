@@ -89,6 +89,10 @@ class Evaluator:
         """Generate + assemble the specialised kernels now (host only)."""
         return _capi.jit_prepare(self._h, samples_per_thread, accumulate)
 
+    def jit_last(self) -> dict:
+        """Plan of the specialised kernels the last launch of this evaluator ran (which form, kernels, traffic)."""
+        return _capi.jit_info(self._h, 0, False)
+
     def pipeline_prepare(self, accumulate: bool = True, n_sm: int = 148) -> dict:
         """Build the pipeline form of the specialised kernels for a device with ``n_sm`` SMs (host only); its plan."""
         return _capi.pipeline_prepare(self._h, accumulate, n_sm)

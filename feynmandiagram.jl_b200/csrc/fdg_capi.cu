@@ -108,6 +108,7 @@ struct fdg_program {
     int blocks_per_sm = 0;
     std::map<int, DeviceState> dev;
     std::atomic<long long> launches{0};
+    int last_jit_key = -1;  // the variant of the specialised back end the last launch ran (fdg_jit_info with samples_per_thread 0)
     std::mutex mu;
     std::mutex host_mu;  // fdg_eval_host: its staging buffers and streams belong to one caller at a time
 };
@@ -258,6 +259,7 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
         // automatic CSE: plan the program with and without merged sub-expressions (planning is cheap, assembling is not) and
         // keep the plan whose modelled time is lower: fewer operations against more values crossing kernel boundaries
         const fdg::Lowered *lowp = &h->low, *mergedp = nullptr;
+        int scoped_reach = 0;  // 0: the default reach of scoped merging (two thirds of a kernel)
         if (h->has_cse) {
             // three ways to evaluate the same bits: as emitted; with equal sub-expressions merged everywhere (fewest
             // operations, but the shared values travel between kernels); merged only where the copies sit close together
@@ -278,6 +280,16 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
                     // at least 5 % faster on paper.  More shared values also mean more registers held: assemble both and let
                     // the spills ptxas reports have their say
                     if (fdg::jit_compile(plain, e1) == FDG_OK && fdg::jit_compile(*cand, e2) == FDG_OK) {
+                        // A scoped plan that spills gets a second chance with a quarter of the reach: values merged over a
+                        // shorter distance are held in registers for a shorter time (the headline graph: 5.7 KB of spill
+                        // stores per sample at two thirds of a kernel, 1.9 KB at a quarter; 194 -> 209 M samples/s)
+                        fdg::JitPlan near;
+                        if (cand == &scoped && !getenv("FDG_CSE_SCOPE") && fdg::jit_spill_bytes(scoped) > 1024 &&
+                            fdg::jit_plan(h->low, spt, acc, budget, wide, h->fma, near, e3, nullptr, &h->low_cse, std::max(64, budget / 4), bulk) == FDG_OK &&
+                            fdg::jit_compile(near, e3) == FDG_OK && fdg::jit_model_ns(near, es) < fdg::jit_model_ns(scoped, es)) {
+                            scoped = std::move(near);
+                            scoped_reach = std::max(64, budget / 4);
+                        }
                         const bool take = mode > 0 || fdg::jit_model_ns(*cand, es) < 0.95 * fdg::jit_model_ns(plain, es);
                         fdg::JitPlan &pick = take ? *cand : plain;
                         if (take && cand == &full) lowp = &h->low_cse;
@@ -294,7 +306,7 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
             }
         }
         for (int attempt = 0; attempt < 3; ++attempt) {
-            rc = fdg::jit_plan(*lowp, spt, acc, budget, wide, h->fma, v.plan, err, nullptr, mergedp, 0, bulk);
+            rc = fdg::jit_plan(*lowp, spt, acc, budget, wide, h->fma, v.plan, err, nullptr, mergedp, scoped_reach, bulk);
             v.plan.uses_cse = lowp == &h->low_cse || mergedp != nullptr || h->low.cse_removed > 0;
             if (rc == FDG_OK) rc = fdg::jit_compile(v.plan, err);
             if (rc != FDG_OK || v.plan.seg.size() < 2 || v.plan.max_code_bytes <= 120 * 1024 || getenv("FDG_JIT_NO_REFIT")) break;
@@ -678,11 +690,14 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
         int mode = -1;
         if (const char *e = getenv("FDG_JIT_BULK")) mode = atoi(e);
         const int budget = h->jit_segment > 0 ? h->jit_segment : 4000;
-        bulk = aligned && (spt == 1 || cplx) && mode != 0 && (mode > 0 || (work >= 2 * (int64_t)budget && batch >= (int64_t)256 * ds.sm_count * 4));
+        // (ComplexF64 keeps the ring form unless asked: two registers per value make the 240-register consumers spill where
+        // the ring form's 255 do not -- Taylor-AD sigma order 4: 120 vs 113 M samples/s)
+        bulk = aligned && (spt == 1 || cplx) && mode != 0 && (mode > 0 || (!cplx && work >= 2 * (int64_t)budget && batch >= (int64_t)256 * ds.sm_count * 4));
     }
     int rc = jit_get(h, spt, acc, &v, wide, nullptr, bulk);
     if (rc != FDG_OK) return rc;
     bulk = v->plan.bulk;
+    h->last_jit_key = spt * 2 + (acc ? 1 : 0) + (wide ? 64 : 0) + (bulk ? 32 : 0);
     auto &kern = v->kernels[dev];
     if (kern.empty()) {
         for (auto &sg : v->plan.seg) {
@@ -983,9 +998,9 @@ static int fdg_compile_file_impl(const char *path, const fdg_options *opts, fdg_
 }
 
 // fdg_jit_prepare / _info / _ptx look at the bulk form of the kernels when FDG_JIT_BULK >= 1 (tools, tests)
-static bool inspect_bulk() {
+static bool inspect_bulk(const fdg_program *h, int spt) {
     const char *e = getenv("FDG_JIT_BULK");
-    return e && atoi(e) > 0;
+    return e && atoi(e) > 0 && (spt == 1 || h->low.dtype == FDG_C128);
 }
 
 static int fdg_jit_prepare_impl(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int32_t *n_kernels, int32_t *n_cross,
@@ -994,7 +1009,7 @@ static int fdg_jit_prepare_impl(fdg_handle h, int32_t samples_per_thread, int32_
     if (samples_per_thread != 1 && samples_per_thread != 2) return fail(FDG_ERR_BAD_ARG, "samples_per_thread must be 1 or 2");
     std::lock_guard<std::mutex> lock(h->mu);
     JitVariant *v = nullptr;
-    int rc = jit_get(h, samples_per_thread, accumulate != 0, &v, false, nullptr, inspect_bulk());
+    int rc = jit_get(h, samples_per_thread, accumulate != 0, &v, false, nullptr, inspect_bulk(h, samples_per_thread));
     if (rc != FDG_OK) return rc;
     if (n_kernels) *n_kernels = (int32_t)v->plan.seg.size();
     if (n_cross) *n_cross = v->plan.n_cross;
@@ -1008,15 +1023,17 @@ static int fdg_jit_prepare_impl(fdg_handle h, int32_t samples_per_thread, int32_
 static int fdg_jit_info_impl(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int64_t *out, int32_t n_out) {
     if (!h || !out || n_out < 0) return fail(FDG_ERR_BAD_ARG, "null argument");
     std::lock_guard<std::mutex> lock(h->mu);
-    auto it = h->jit.find(samples_per_thread * 2 + (accumulate ? 1 : 0) + (inspect_bulk() ? 32 : 0));
+    // samples_per_thread == 0: the variant the last launch of this handle ran
+    auto it = h->jit.find(samples_per_thread == 0 ? h->last_jit_key
+                                                  : samples_per_thread * 2 + (accumulate ? 1 : 0) + (inspect_bulk(h, samples_per_thread) ? 32 : 0));
     if (it == h->jit.end() || !it->second.compiled) return fail(FDG_ERR_BAD_ARG, "variant not prepared");
     const fdg::JitPlan &pl = it->second.plan;
     int64_t ops = 0;
     for (auto &sg : pl.seg) ops += sg.n_stmts;
-    const int64_t vals[12] = {(int64_t)pl.seg.size(), pl.n_cross, pl.n_cross_values, pl.leaf_loads, pl.cross_loads, pl.cross_stores, ops,
+    const int64_t vals[14] = {(int64_t)pl.seg.size(), pl.n_cross, pl.n_cross_values, pl.leaf_loads, pl.cross_loads, pl.cross_stores, ops,
                               pl.persistent ? 1 : 0, pl.max_code_bytes, pl.uses_cse ? 1 : 0, pl.fp64_instr,
-                              (int64_t)(1000.0 * fdg::jit_model_ns(pl, h->low.dtype == FDG_C128 ? 16 : 8))};
-    for (int32_t i = 0; i < n_out && i < 12; ++i) out[i] = vals[i];
+                              (int64_t)(1000.0 * fdg::jit_model_ns(pl, h->low.dtype == FDG_C128 ? 16 : 8)), pl.bulk ? 1 : 0, pl.bulk_smem};
+    for (int32_t i = 0; i < n_out && i < 14; ++i) out[i] = vals[i];
     return FDG_OK;
 }
 
@@ -1076,7 +1093,8 @@ static int fdg_jit_ptx_impl(fdg_handle h, int32_t samples_per_thread, int32_t ac
                 const char **ptxas_log) {
     if (!h || !ptx) return fail(FDG_ERR_BAD_ARG, "null argument");
     std::lock_guard<std::mutex> lock(h->mu);
-    auto it = h->jit.find(samples_per_thread * 2 + (accumulate ? 1 : 0) + (inspect_bulk() ? 32 : 0));
+    auto it = h->jit.find(samples_per_thread == 0 ? h->last_jit_key
+                                                  : samples_per_thread * 2 + (accumulate ? 1 : 0) + (inspect_bulk(h, samples_per_thread) ? 32 : 0));
     if (it == h->jit.end() || !it->second.compiled) return fail(FDG_ERR_BAD_ARG, "variant not prepared");
     if (index < 0 || index >= (int32_t)it->second.plan.seg.size()) return fail(FDG_ERR_BAD_ARG, "kernel index out of range");
     *ptx = it->second.plan.seg[(size_t)index].ptx.c_str();

@@ -1489,12 +1489,7 @@ static int compile_one(JitSegment &js, bool fma, std::string &err, bool relocata
     return FDG_OK;
 }
 
-double jit_model_ns(const JitPlan &plan, int bytes_per_element) {
-    // Calibrated on B200 measurements of seven workloads with and without merged sub-expressions (profiles/r02_experiments/
-    // cse_ab.log): the kernels move their planned bytes at up to ~5.0 TB/s and issue FP64 instructions at up to ~13.8 T/s
-    // (75 % of the measured DMUL + DADD rate); the two overlap imperfectly (a smooth maximum, exponent 3); a spilled
-    // register costs about six instructions per 8 bytes stored or reloaded (known once the kernels are assembled).
-    const double bytes = (double)(plan.leaf_loads + plan.cross_loads + plan.cross_stores) * bytes_per_element;
+double jit_spill_bytes(const JitPlan &plan) {
     double spill = 0;
     for (const JitSegment &sg : plan.seg) {
         const char *p = sg.info.c_str();
@@ -1506,6 +1501,19 @@ double jit_model_ns(const JitPlan &plan, int bytes_per_element) {
             p += 11;
         }
     }
+    return spill;
+}
+
+double jit_model_ns(const JitPlan &plan, int bytes_per_element) {
+    // Calibrated on B200 measurements of seven workloads with and without merged sub-expressions (profiles/r02_experiments/
+    // cse_ab.log): the kernels move their planned bytes at up to ~5.0 TB/s and issue FP64 instructions at up to ~13.8 T/s
+    // (75 % of the measured DMUL + DADD rate); the two overlap imperfectly (a smooth maximum, exponent 3).  A spilled
+    // register (known once the kernels are assembled) costs about six instructions per 8 bytes stored or reloaded, and
+    // half of the spilled bytes end up as memory traffic: local memory is cached, but 38 000 threads' worth of it competes
+    // with the streamed rows for L2 (measured on the headline graph: 1.8 KB of DRAM writes per sample beyond the plan
+    // at 5.7 KB of spill stores, profiles/r02_bulk_segments_summary.txt; scope experiments in r02_experiments/bulk_form.log).
+    const double spill = jit_spill_bytes(plan);
+    const double bytes = (double)(plan.leaf_loads + plan.cross_loads + plan.cross_stores) * bytes_per_element + 0.5 * spill;
     const double t_mem = bytes / 5000.0;                                         // bytes / (GB/s) = ns
     const double t_fp = ((double)plan.fp64_instr + spill / 8.0 * 6.0) / 13800.0;  // instructions / (G lane-instructions/s) = ns
     return std::cbrt(t_mem * t_mem * t_mem + t_fp * t_fp * t_fp) + 0.01 * (double)plan.seg.size();

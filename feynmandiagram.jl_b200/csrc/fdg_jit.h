@@ -75,6 +75,8 @@ struct PipeOptions {
 // of its FP64 instructions (plus the cost of spilled registers, once the kernels are assembled) at the rate they reach;
 // constants and calibration in fdg_jit.cpp.  Used to choose between plans, not reported as a result.
 double jit_model_ns(const JitPlan &plan, int bytes_per_element);
+// bytes of spill stores + spill loads per thread over all kernels of an assembled plan (from the ptxas logs)
+double jit_spill_bytes(const JitPlan &plan);
 
 // linearise the emitted function in fold order, cut it into segments of `seg_ops` operations, write their PTX
 // wide_strides: row offsets need 64 bits (a leading dimension of 4 GiB or more)

@@ -182,8 +182,10 @@ int fdg_jit_prepare(fdg_handle h, int32_t samples_per_thread, int32_t accumulate
  * boundary, then per sample over all kernels: leaf loads, cross loads, cross stores, operations; [7] = 1 if the
  * variant is a single grid-stride kernel; [8] = bytes of machine code of the largest kernel; [9] = 1 if the plan was made
  * from the program with common sub-expressions merged; [10] = FP64 instructions per sample the kernels execute;
- * [11] = modelled time of one sample, ps.  (leaf loads + cross loads + cross stores) x sizeof(W) is the traffic the
- * plan asks of the memory system per sample -- the figure DESIGN.md compares with ncu's dram bytes. */
+ * [11] = modelled time of one sample, ps; [12] = 1 for the bulk form (persistent warp-specialised kernels fed by
+ * cp.async.bulk), [13] = its dynamic shared memory per block.  (leaf loads + cross loads + cross stores) x sizeof(W) is
+ * the traffic the plan asks of the memory system per sample -- the figure DESIGN.md compares with ncu's dram bytes.
+ * samples_per_thread = 0 asks for the variant the last launch of this handle ran (fdg_jit_ptx likewise). */
 int fdg_jit_info(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int64_t *out, int32_t n_out);
 /* Pipeline form of the specialised back end: ONE cooperative kernel, one block per SM; the blocks
  * of stage k run only the code of segment k (resident in that SM's instruction cache) and tiles of 32 samples flow from

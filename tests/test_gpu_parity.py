@@ -578,7 +578,9 @@ def test_automatic_cse_follows_the_model():
                         ("parquet_ver4_o4", np.float64), ("gv_ver4_o4", np.float64)):
         ev = fd.compile_raw(_workload(name), dtype=dtype, backend=JIT)
         picks[name] = ev.jit_prepare(1, True)["cse"]
-    assert picks == {"taylor_sigma_o4": True, "parquet_sigma_o4": True, "taylor_sigma_o3": False, "parquet_ver4_o4": False, "gv_ver4_o4": False}
+    # (Parquet vertex4 order 4: merged only within the reach of one kernel -- "scoped" -- which saves a third of the
+    # arithmetic without more values crossing kernels)
+    assert picks == {"taylor_sigma_o4": True, "parquet_sigma_o4": True, "taylor_sigma_o3": False, "parquet_ver4_o4": True, "gv_ver4_o4": False}
 
 
 @pytest.mark.parametrize("name", ["parquet_ver4_o4", "gv_ver4_o4"])
@@ -624,3 +626,88 @@ def test_graph_file_compiled_by_the_library_evaluates_to_the_oracle(tmp_path, dt
     root = np.asfortranarray(np.zeros((B, ev.n_roots), dtype))
     ev(root, np.asfortranarray(leaf.T))
     assert np.ascontiguousarray(root.T).tobytes() == want.tobytes()
+
+
+# ---- bulk form: persistent warp-specialised kernels, rows fetched by cp.async.bulk into a ring (DESIGN.md 4b') ----------
+@pytest.mark.parametrize("name,dtype,seg", [("parquet_ver4_o3", np.float64, 700), ("parquet_ver4_o3", np.float64, 0), ("taylor_sigma_o3", np.complex128, 900),
+                                            ("gv_sigma_o5", np.float64, 500)])
+@pytest.mark.parametrize("batch,ld", [(256, 256), (1000, 1000), (1001, 1002), (4099, 4100), (77777, 77778)])
+def test_bulk_form_is_bit_exact(name, dtype, seg, batch, ld, monkeypatch):
+    """FDG_JIT_BULK=1 forces the bulk form whatever the batch: whole and ragged tiles (the copy of a ragged tile is rounded
+    up to 16 bytes, inside the row), fewer tiles than SMs and more, real and complex; every sample against the oracle."""
+    monkeypatch.setenv("FDG_JIT_BULK", "1")
+    raw = _workload(name)
+    ev = fd.compile_raw(raw, dtype=dtype, backend=JIT, jit_segment=seg)
+    leaf = graphgen.leaf_values(41, ev.n_leaves, batch, dtype=dtype, signed=True, ld=ld)
+    got = _dev_eval(ev, leaf, batch, spt=1)
+    last = ev.jit_last()
+    assert last["bulk"] and last["bulk_smem"] > 64 * 1024 and not last["grid_stride"]
+    want = O.Oracle(raw).eval(np.ascontiguousarray(leaf[:, :batch]), "emitter", root=np.full((ev.n_roots, batch), -3.0, dtype))
+    assert got.tobytes() == want.tobytes()
+    ptx, log = ev.jit_ptx(0, False, 0)
+    assert "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes" in ptx and "setmaxnreg.inc.sync.aligned.u32 240" in ptx
+    assert "mbarrier.try_wait.parity" in ptx and "cp.async.ca" not in ptx
+
+
+@pytest.mark.parametrize("name,dtype", [("parquet_ver4_o3", np.float64), ("taylor_sigma_o3", np.complex128)])
+def test_bulk_form_accumulates_over_launch_sequences(name, dtype, monkeypatch):
+    """Accumulate mode of the bulk form: per-thread running sums in shared memory, added into the warp's partial row at
+    the end of the kernel -- so several launch sequences (FDG_JIT_MAX_SUB) add up; deterministic from run to run."""
+    monkeypatch.setenv("FDG_JIT_BULK", "1")
+    raw = _workload(name)
+    W = 2 if dtype == np.complex128 else 1
+    ev = fd.compile_raw(raw, dtype=dtype, backend=JIT, jit_segment=800)
+    ev.set_launch(0, 1, 0)
+    B = 50001
+    leaf = graphgen.leaf_values(43, ev.n_leaves, B, dtype=dtype, signed=True, ld=B + 1)
+    want = O.Oracle(raw).eval(np.ascontiguousarray(leaf[:, :B]))
+    ref = want.sum(axis=1)
+    scale = np.abs(want).sum(axis=1)
+    dleaf = torch.from_numpy(leaf).cuda()
+    s = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for max_sub in (0, 0, 4096):
+        if max_sub:
+            monkeypatch.setenv("FDG_JIT_MAX_SUB", str(max_sub))
+        acc = torch.zeros(ev.n_roots * W, dtype=torch.float64, device="cuda")
+        ev.accumulate_device(dleaf.data_ptr(), B + 1, B, acc.data_ptr(), s)
+        torch.cuda.synchronize()
+        assert ev.jit_last()["bulk"]
+        a = acc.cpu().numpy()
+        outs.append(a)
+        got = a.view(np.complex128) if W == 2 else a
+        assert np.all(np.abs(got - ref) <= 1e-12 * (scale + 1e-300))
+    assert outs[0].tobytes() == outs[1].tobytes()  # same launch shape, same bits
+
+
+def test_bulk_form_is_chosen_for_big_batches_and_needs_aligned_rows(monkeypatch):
+    """Without the override the bulk form runs where it pays -- programs of several kernels on batches that give every SM a
+    few tiles -- and never on rows a bulk copy cannot address (16-byte alignment): those take the ring form.  Same bits."""
+    raw = _workload("parquet_ver4_o3")
+    ev = fd.compile_raw(raw, backend=JIT, jit_segment=700)
+    ev.set_launch(0, 1, 0)
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    B = 256 * sm * 4
+    leaf = graphgen.leaf_values(47, ev.n_leaves, B + 2, signed=True)          # (L, B + 2), rows 16-byte aligned
+    dleaf = torch.from_numpy(leaf).cuda()
+    s = torch.cuda.current_stream().cuda_stream
+    root = torch.empty(ev.n_roots, B, dtype=torch.float64, device="cuda")
+    ev.eval_device(dleaf.data_ptr(), B + 2, root.data_ptr(), B, B, s)
+    torch.cuda.synchronize()
+    assert ev.jit_last()["bulk"]
+    big = root.cpu().numpy()
+    ev.eval_device(dleaf.data_ptr(), B + 2, root.data_ptr(), B, 4096, s)            # a small batch: ring form
+    torch.cuda.synchronize()
+    assert not ev.jit_last()["bulk"]
+    assert root.cpu().numpy()[:, :4096].tobytes() == big[:, :4096].tobytes()
+    root2 = torch.empty(ev.n_roots, B, dtype=torch.float64, device="cuda")
+    ev.eval_device(dleaf.data_ptr() + 8, B + 2, root2.data_ptr(), B, B, s)          # rows start 8 bytes off a 16-byte boundary
+    torch.cuda.synchronize()
+    assert not ev.jit_last()["bulk"]
+    want = O.Oracle(raw).eval(np.ascontiguousarray(leaf[:, 1:4097]))
+    assert root2.cpu().numpy()[:, :4096].tobytes() == want.tobytes()
+    assert big[:, 1:4096].tobytes() == root2.cpu().numpy()[:, :4095].tobytes()
+    monkeypatch.setenv("FDG_JIT_BULK", "0")
+    ev.eval_device(dleaf.data_ptr(), B + 2, root2.data_ptr(), B, B, s)
+    torch.cuda.synchronize()
+    assert not ev.jit_last()["bulk"] and root2.cpu().numpy().tobytes() == big.tobytes()

@@ -121,6 +121,29 @@ def test_specialised_kernels_assemble_without_a_gpu(name, acc):
     assert muls > 0
 
 
+@pytest.mark.parametrize("name,dtype", [("parquet_ver4_o2", np.float64), ("gv_sigma_o4", np.float64), ("taylor_sigma_o2", np.complex128)])
+@pytest.mark.parametrize("acc", [False, True])
+def test_bulk_form_assembles_without_a_gpu(name, dtype, acc, monkeypatch):
+    """The bulk form of the specialised kernels (persistent blocks: consumer warps + a producer warpgroup that fills a
+    shared-memory ring with cp.async.bulk row copies, mbarrier-signalled) assembles for sm_100a on the host; nothing
+    spills, the consumers' straight-line code holds no address arithmetic for its inputs."""
+    import os
+
+    monkeypatch.setenv("FDG_JIT_BULK", "1")
+    raw = fd.RawGraph.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", name + ".npz"))
+    ev = fd.compile_raw(raw, jit_segment=300, dtype=dtype, backend=2)
+    info = ev.jit_prepare(1, acc)
+    assert info["bulk"] and info["kernels"] >= 1 and 64 * 1024 < info["bulk_smem"] <= 227 * 1024
+    for i in range(info["kernels"]):
+        ptx, log = ev.jit_ptx(1, acc, i)
+        assert ".maxntid 384" in ptx and "setmaxnreg.dec.sync.aligned.u32 24" in ptx and "setmaxnreg.inc.sync.aligned.u32 240" in ptx
+        assert "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes" in ptx and "mbarrier.arrive.expect_tx" in ptx
+        assert "cp.async.ca" not in ptx and "cp.async.cg" not in ptx and "fma" not in ptx
+        assert "Used 168 registers" in log and " 0 bytes spill stores" in log
+    monkeypatch.setenv("FDG_JIT_BULK", "0")
+    assert not ev.jit_prepare(1, acc)["bulk"]  # the ring form of the same program is a separate variant
+
+
 @pytest.mark.parametrize("seed", range(4))
 @pytest.mark.parametrize("cse,schedule", [(True, 0), (False, 1), (True, 1)])
 def test_lowering_options_do_not_change_values(seed, cse, schedule):
