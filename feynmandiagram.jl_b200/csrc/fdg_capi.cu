@@ -1455,55 +1455,87 @@ __device__ __forceinline__ double lg_green_derive(double tau, double w, double b
 // multiply-adds in the dot products, a multiply by the reciprocal instead of a division): leaf values agree to ~1e-15
 // relative (tests: <= 2e-14), which is the bar for this off-path producer (its bits are unpinned in the reference: BLAS
 // `mul!` and Lehmann's kernels); the graph evaluation on top of the leaves stays bit-exact.
-// exp(x) for x <= 0, the only arguments the propagators produce (-|w| x with x in (0, beta]).  n = round(x log2 e),
-// r = x - n ln 2 in two pieces, exp(r) as the degree-13 Taylor polynomial on |r| <= ln 2 / 2 (remainder below 1e-17
-// relative), 2^n applied as two factors so that results in the denormal range come out right.  About 25 instructions
-// against ~40 of the library's exp; error <= 2 ulp (the leaf values' bar is 2e-14 relative, tests/test_leafgen.py).
-__device__ __forceinline__ double lg_exp_neg(double x) {
-    x = fmax(x, -746.0);  // exp(-746) = 0 in double: keeps the exponent arithmetic below in range
-    const double t = rint(x * 1.4426950408889634074);
-    double r = fma(t, -6.93147180369123816490e-01, x);
-    r = fma(t, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;               // 1 / 13!
-    p = fma(p, r, 2.08767569878680989792e-09);       // 1 / 12!
-    p = fma(p, r, 2.50521083854417187751e-08);       // 1 / 11!
-    p = fma(p, r, 2.75573192239858906526e-07);       // 1 / 10!
-    p = fma(p, r, 2.75573192239858906526e-06);       // 1 / 9!
-    p = fma(p, r, 2.48015873015873015873e-05);       // 1 / 8!
-    p = fma(p, r, 1.98412698412698412698e-04);       // 1 / 7!
-    p = fma(p, r, 1.38888888888888888889e-03);       // 1 / 6!
-    p = fma(p, r, 8.33333333333333333333e-03);       // 1 / 5!
-    p = fma(p, r, 4.16666666666666666667e-02);       // 1 / 4!
-    p = fma(p, r, 1.66666666666666666667e-01);       // 1 / 3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    const int n = (int)t, h = n >> 1;  // 2^n = 2^h 2^(n - h), both factors normal for n >= -1077
-    return p * __hiloint2double((h + 1023) << 20, 0) * __hiloint2double((n - h + 1023) << 20, 0);
+// exp(x) for x <= 0 with a 32-entry table: n = round(x 32 / ln 2) = 32 m + j, r = x - n ln 2 / 32 in two pieces
+// (|r| <= ln 2 / 64), exp(x) = 2^m 2^(j/32) (1 + q(r)) with q of degree 6 (remainder 3e-18 relative).  Eleven FP64
+// instructions against the twenty-five of lg_exp_neg; error below 0.9 ulp (checked against 60-digit arithmetic over
+// [-746, 0], tools/check_exp_table.py).  `tab` = 2^(j/32), j = 0..31, in shared memory.
+__constant__ double lg_exp2_32[32] = {0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0, 0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0, 0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0, 0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0, 0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0, 0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0, 0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0, 0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};  // correctly rounded
+// (constants as constant-bank operands of the DFMAs: immediates would cost two moves each per use)
+__constant__ double lg_exp_c[10] = {46.16624130844683, 6755399441055744.0, -0.021660849364707246, -2.7791044496520866e-11,
+                                    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0};
+// results in the denormal range (x < -708): 2^m as two normal factors.  Kept out of line: the propagators almost never get there.
+__device__ __noinline__ double lg_exp_scale_slow(double p, int m) {
+    if (m < -1100) return 0.0;
+    const int h = m >> 1;
+    return p * __hiloint2double((h + 1023) << 20, 0) * __hiloint2double((m - h + 1023) << 20, 0);
+}
+__device__ __forceinline__ double lg_exp_tab(double x, const double *__restrict__ tab) {
+    const double magic = lg_exp_c[1];  // 1.5 * 2^52: the sum below holds n in its low mantissa bits
+    const double t = fma(x, lg_exp_c[0], magic);
+    const int n = __double2loint(t);
+    const double nd = t - magic;
+    double r = fma(nd, lg_exp_c[2], x);  // ln 2 / 32, upper 30 bits (n * hi is exact)
+    r = fma(nd, lg_exp_c[3], r);
+    double q = lg_exp_c[4];
+    q = fma(q, r, lg_exp_c[5]);
+    q = fma(q, r, lg_exp_c[6]);
+    q = fma(q, r, lg_exp_c[7]);
+    q = fma(q, r, lg_exp_c[8]);
+    q = fma(q, r, lg_exp_c[9]);
+    q = q * r;
+    const double tj = tab[n & 31];
+    const double p = fma(tj, q, tj);
+    const int m = n >> 5;
+    // x < -1e6 (n no longer fits the trick above) gives 0 like every x < -746
+    if (__builtin_expect(m < -1021 || x < -1.0e6, 0)) return x < -1.0e6 ? 0.0 : lg_exp_scale_slow(p, m);
+    return __hiloint2double(__double2hiint(p) + (m << 20), __double2loint(p));  // p in [1, 2): the result is normal
 }
 
-struct LgBasis {
-    int32_t nnz, leaf0, n_leaves, pad;
-    int32_t idx[FDG_LG_MAXLOOPS];
-    double coef[FDG_LG_MAXLOOPS];
+// 1 / d for d in [1, 2]: the hardware's 20-bit estimate and two Newton steps (about 1 ulp; five instructions against the
+// ~20 of a correctly rounded division)
+__device__ __forceinline__ double lg_rcp(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+}
+
+struct LgTerm {  // one non-zero coefficient of a loop-basis vector and the first row of its loop momentum in the staged variables
+    double coef;
+    int32_t off, pad;
+};
+struct alignas(16) LgBasis {
+    // leaves of this momentum by kind: order-0 propagators g0[g0_first ..), leaves whose value does not depend on the times
+    // (order-0 interactions, constants) cst[c_first ..), everything else leaves[leaf0 ..)
+    int32_t nnz, g0_first, n_g0, c_first, n_c, leaf0, n_leaves, pad;
+    LgTerm term[FDG_LG_MAXLOOPS];
 };
 struct LgLeaf {
     int32_t type, order, tau_in, tau_out, out, pad[3];
 };
-constexpr int FDG_LG_BASES_PER_BLOCK = 24;
+struct LgG0 {  // an order-0 Green's function leaf: the two times (tau_in | tau_out << 16) and the row it fills ...
+    int32_t taus, out;
+    long long off;  // ... as an element offset, out * ld_leaf (filled in per leading dimension when the table is uploaded)
+};
+struct LgCst {  // a leaf that is 1 (kind 0) or the order-0 interaction 8 pi (q^2 + lambda) (kind 1); row as an element offset
+    long long off;
+    int32_t kind, out;
+};
 
-constexpr int FDG_LG_SPT = 1;  // samples per thread (2 was measured slower: 124 vs 142 M samples/s on Parquet vertex4 order 4)
-
-template <int DIM>
+template <int DIM, int S>
 __global__ void __launch_bounds__(FDG_LG_THREADS)
-fdg_leafgen2_kernel(const LgBasis *__restrict__ bases, int n_bases, const LgLeaf *__restrict__ leaves, int n_loops, int n_tau,
-                    const double *__restrict__ K, const double *__restrict__ T, long long ld_var, long long batch, double *__restrict__ leaf,
-                    long long ld_leaf, double kF2, double beta, double lambda) {
-    constexpr int S = FDG_LG_SPT, COLS = FDG_LG_THREADS * S;
-    extern __shared__ double lg_var[];  // [(n_loops * DIM + n_tau)][COLS]
+fdg_leafgen2_kernel(const LgBasis *__restrict__ bases, int n_bases, int bases_per_block, const LgLeaf *__restrict__ leaves, const LgG0 *__restrict__ g0,
+                    const LgCst *__restrict__ cst, int n_loops, int n_tau, const double *__restrict__ K, const double *__restrict__ T, long long ld_var, long long batch,
+                    double *__restrict__ leaf, long long ld_leaf, double kF2, double beta, double lambda) {
+    constexpr int COLS = FDG_LG_THREADS * S;
+    extern __shared__ double lg_var[];  // [(n_loops * DIM + n_tau)][COLS], then the table of lg_exp_tab
     const int tid = threadIdx.x;
     const long long base = (long long)blockIdx.x * COLS;
     const int kr = n_loops * DIM;
+    double *tab = lg_var + (size_t)(kr + n_tau) * COLS;
+    if (tid < 32) tab[tid] = lg_exp2_32[tid];
     bool valid[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -1513,19 +1545,23 @@ fdg_leafgen2_kernel(const LgBasis *__restrict__ bases, int n_bases, const LgLeaf
         for (int r = 0; r < kr; ++r) lg_var[r * COLS + s * FDG_LG_THREADS + tid] = K[(long long)r * ld_var + bs];
         for (int r = 0; r < n_tau; ++r) lg_var[(kr + r) * COLS + s * FDG_LG_THREADS + tid] = T[(long long)r * ld_var + bs];
     }
-    // (every thread reads back only its own columns: no barrier needed)
+    __syncthreads();  // (the variables are read back by their own thread only; the table by everybody)
+    if (S == 1 && !valid[0]) return;  // no barrier below: threads past the end of the batch are done
+    double *const lp = leaf + base + tid;  // this thread's column of the leaf matrix
     const double *kv = lg_var + tid;
     const double *tv = lg_var + kr * COLS + tid;
-    const int b0 = blockIdx.y * FDG_LG_BASES_PER_BLOCK, b1 = min(n_bases, b0 + FDG_LG_BASES_PER_BLOCK);
+    const int b0 = blockIdx.y * bases_per_block, b1 = min(n_bases, b0 + bases_per_block);
     for (int ib = b0; ib < b1; ++ib) {
-        const LgBasis *B = bases + ib;  // read field by field (uniform loads): a local copy would be indexed through local memory
-        const int nnz = B->nnz, leaf0 = B->leaf0, n_leaves = B->n_leaves;
+        const LgBasis *B = bases + ib;  // (uniform loads, 16 bytes at a time)
+        const int4 h0 = *reinterpret_cast<const int4 *>(&B->nnz), h1 = *reinterpret_cast<const int4 *>(&B->n_c);
+        const int nnz = h0.x, g0_first = h0.y, n_g0 = h0.z, c_first = h0.w, n_c = h1.x, leaf0 = h1.y, n_leaves = h1.z;
         double kq[S][3];
 #pragma unroll
         for (int s = 0; s < S; ++s) kq[s][0] = kq[s][1] = kq[s][2] = 0.0;
         for (int n = 0; n < nnz; ++n) {
-            const double cf = B->coef[n];
-            const double *kp = kv + B->idx[n] * DIM * COLS;
+            const int4 tm = *reinterpret_cast<const int4 *>(&B->term[n]);
+            const double cf = __hiloint2double(tm.y, tm.x);
+            const double *kp = kv + tm.z * COLS;
 #pragma unroll
             for (int s = 0; s < S; ++s)
 #pragma unroll
@@ -1541,14 +1577,56 @@ fdg_leafgen2_kernel(const LgBasis *__restrict__ bases, int n_bases, const LgLeaf
             ebeta[s] = 0.0, den[s] = inv_den[s] = 1.0;
         }
         bool have_den = false;
+        if (n_g0 > 0) {
+            // ---- order-0 propagators of this momentum: green(tau, w, beta) = s exp(-|w| x) / (1 + exp(-|w| beta)), x in (0, beta],
+            //      s = sign(tau).  With st = tau sign(w):  x = st if st > 0, else st + beta -- the four cases of the reference's
+            //      formula (example/benchmark.jl:113-127), the same operands in the same operations.
+            double sw[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                ebeta[s] = lg_exp_tab(-aw[s] * beta, tab);
+                den[s] = 1.0 + ebeta[s];
+                inv_den[s] = lg_rcp(den[s]);
+                sw[s] = w[s] > 0.0 ? 1.0 : -1.0;
+            }
+            have_den = true;
+            for (int i = g0_first; i < g0_first + n_g0; ++i) {
+                const LgG0 m = g0[i];
+                const double *t_out = tv + (m.taus >> 16) * COLS, *t_in = tv + (m.taus & 0xffff) * COLS;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    double tau = t_out[s * FDG_LG_THREADS] - t_in[s * FDG_LG_THREADS];
+                    if (tau == 0.0) tau = -1e-10;
+                    const double st = __dmul_rn(tau, sw[s]);
+                    const double x = st > 0.0 ? st : st + beta;
+                    const double e = lg_exp_tab(-aw[s] * x, tab) * inv_den[s];
+                    // sign(tau) copied onto e (e >= 0)
+                    const double v = __hiloint2double(__double2hiint(e) | (__double2hiint(tau) & 0x80000000), __double2loint(e));
+                    if (S == 1 || valid[s]) lp[m.off + s * FDG_LG_THREADS] = v;
+                }
+            }
+        }
+        if (n_c > 0) {
+            // ---- leaves that do not depend on the times: 1, or the order-0 interaction 8 pi / invK with invK = 1 / (q^2 + lambda)
+            double wv[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) wv[s] = 25.132741228718345 * (q2[s] + lambda);
+            for (int i = c_first; i < c_first + n_c; ++i) {
+                const int4 m = *reinterpret_cast<const int4 *>(cst + i);
+                const long long off = ((long long)m.y << 32) | (unsigned)m.x;
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    if (S == 1 || valid[s]) lp[off + s * FDG_LG_THREADS] = m.z ? wv[s] : 1.0;
+            }
+        }
         for (int il = leaf0; il < leaf0 + n_leaves; ++il) {
             const LgLeaf m = leaves[il];
             if (m.type == 1 && !have_den) {
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    ebeta[s] = lg_exp_neg(-aw[s] * beta);
+                    ebeta[s] = lg_exp_tab(-aw[s] * beta, tab);
                     den[s] = 1.0 + ebeta[s];
-                    inv_den[s] = 1.0 / den[s];
+                    inv_den[s] = lg_rcp(den[s]);
                 }
                 have_den = true;
             }
@@ -1559,9 +1637,8 @@ fdg_leafgen2_kernel(const LgBasis *__restrict__ bases, int n_bases, const LgLeaf
                     double tau = tv[m.tau_out * COLS + s * FDG_LG_THREADS] - tv[m.tau_in * COLS + s * FDG_LG_THREADS];
                     if (m.order == 0) {
                         if (tau == 0.0) tau = -1e-10;
-                        // green(tau, w, beta) = s exp(-|w| x) / (1 + exp(-|w| beta)),  x in (0, beta], s = sign(tau)
                         const double x = tau > 0.0 ? (w[s] > 0.0 ? tau : beta - tau) : (w[s] > 0.0 ? tau + beta : -tau);
-                        const double e = lg_exp_neg(-aw[s] * x) * inv_den[s];
+                        const double e = lg_exp_tab(-aw[s] * x, tab) * inv_den[s];
                         v = tau > 0.0 ? e : -e;
                     } else {
                         v = lg_green_derive(tau, w[s], beta, ebeta[s], den[s], m.order);
@@ -1571,7 +1648,7 @@ fdg_leafgen2_kernel(const LgBasis *__restrict__ bases, int n_bases, const LgLeaf
                     const double sm = q2[s] + lambda;
                     v = m.order == 0 ? 25.132741228718345 * sm : (25.132741228718345 * sm) * lg_pow(lambda / sm, m.order);
                 }
-                if (valid[s]) leaf[(long long)m.out * ld_leaf + base + s * FDG_LG_THREADS + tid] = v;
+                if (S == 1 || valid[s]) lp[(long long)m.out * ld_leaf + s * FDG_LG_THREADS] = v;
             }
         }
     }
@@ -1583,7 +1660,10 @@ struct fdg_leafgen {
     std::vector<LeafMeta> meta;
     std::vector<LgBasis> bases;  // leaves grouped by loop-basis vector (non-zero coefficients only)
     std::vector<LgLeaf> leaves;
+    std::vector<LgG0> g0;        // the order-0 propagators, grouped like `bases`
+    std::vector<LgCst> cst;      // leaves that do not depend on the times, grouped like `bases`
     std::map<int, std::pair<LgBasis *, LgLeaf *>> d_tab;  // per device
+    std::map<std::pair<int, long long>, std::pair<LgG0 *, LgCst *>> d_g0;  // per device and leading dimension of the leaf matrix
     int n_loops = 0, dim = 3, n_tau = 0;
     double kF = 0, beta = 0, lambda = 0;
     std::map<std::pair<int, cudaStream_t>, std::pair<double *, size_t>> d_leaf;  // per device and stream: sub-batch leaf matrix of the fused path
@@ -1611,20 +1691,50 @@ int leafgen_launch(fdg_leafgen *g, const double *K, const double *T, int64_t ld_
         CUDA_TRY(cudaMemcpy(dl, g->leaves.data(), g->leaves.size() * sizeof(LgLeaf), cudaMemcpyHostToDevice));
         it = g->d_tab.emplace(dev, std::make_pair(db, dl)).first;
     }
-    const int nb = (int)g->bases.size();
-    const int64_t cols = (int64_t)FDG_LG_THREADS * FDG_LG_SPT;
-    dim3 grid((unsigned)((batch + cols - 1) / cols), (unsigned)((nb + FDG_LG_BASES_PER_BLOCK - 1) / FDG_LG_BASES_PER_BLOCK));
-    const double kF2 = g->kF * g->kF;
-    const size_t smem = (size_t)(g->n_loops * g->dim + g->n_tau) * FDG_LG_THREADS * FDG_LG_SPT * sizeof(double);
-    if (g->dim == 3) {
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(fdg_leafgen2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fdg_leafgen2_kernel<3><<<grid, FDG_LG_THREADS, smem, st>>>(it->second.first, nb, it->second.second, g->n_loops, g->n_tau, K, T, ld_var, batch,
-                                                                  leaf, ld_leaf, kF2, g->beta, g->lambda);
-    } else {
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(fdg_leafgen2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fdg_leafgen2_kernel<2><<<grid, FDG_LG_THREADS, smem, st>>>(it->second.first, nb, it->second.second, g->n_loops, g->n_tau, K, T, ld_var, batch,
-                                                                  leaf, ld_leaf, kF2, g->beta, g->lambda);
+    // the table of the order-0 propagators carries row offsets: one copy per device and leading dimension
+    auto ig = g->d_g0.find(std::make_pair(dev, (long long)ld_leaf));
+    if (ig == g->d_g0.end()) {
+        std::vector<LgG0> tab = g->g0;
+        for (LgG0 &r : tab) r.off = (long long)r.out * (long long)ld_leaf;
+        std::vector<LgCst> tc = g->cst;
+        for (LgCst &r : tc) r.off = (long long)r.out * (long long)ld_leaf;
+        LgG0 *dg = nullptr;
+        LgCst *dc = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&dg, std::max<size_t>(tab.size(), 1) * sizeof(LgG0)));
+        CUDA_TRY(cudaMalloc((void **)&dc, std::max<size_t>(tc.size(), 1) * sizeof(LgCst)));
+        CUDA_TRY(cudaMemcpy(dg, tab.data(), tab.size() * sizeof(LgG0), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dc, tc.data(), tc.size() * sizeof(LgCst), cudaMemcpyHostToDevice));
+        ig = g->d_g0.emplace(std::make_pair(dev, (long long)ld_leaf), std::make_pair(dg, dc)).first;
     }
+    const LgG0 *dg0 = ig->second.first;
+    const LgCst *dcst = ig->second.second;
+    const int nb = (int)g->bases.size();
+    // samples per thread (two share the decoding of the tables, but measure the same: 169 vs 170 M samples/s)
+    int spt = 1;
+    if (const char *e = getenv("FDG_LG_SPT")) spt = atoi(e) >= 2 ? 2 : 1;
+    const int64_t cols = (int64_t)FDG_LG_THREADS * spt;
+    // one block walks all the basis vectors of its samples: (K, T) are read once (FDG_LG_BASES_PER_BLOCK splits the walk
+    // over several blocks -- experiments)
+    int per_block = nb;
+    if (const char *e = getenv("FDG_LG_BASES_PER_BLOCK")) per_block = std::max(1, atoi(e));
+    dim3 grid((unsigned)((batch + cols - 1) / cols), (unsigned)((nb + per_block - 1) / per_block));
+    const double kF2 = g->kF * g->kF;
+    const size_t smem = ((size_t)(g->n_loops * g->dim + g->n_tau) * cols + 32) * sizeof(double);
+    auto launch = [&](auto kern) -> int {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // (experiments: giving L1 more room for the tables at the price of resident blocks only loses -- 25 % shared memory
+        // 79 M samples/s, 50 % 110 M, 100 % 174 M on Parquet vertex4 order 4: the kernel lives on the number of warps in flight)
+        int carve = -1;
+        if (const char *e = getenv("FDG_LG_CARVEOUT")) carve = atoi(e);
+        if (carve >= 0) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        kern<<<grid, FDG_LG_THREADS, smem, st>>>(it->second.first, nb, per_block, it->second.second, dg0, dcst, g->n_loops, g->n_tau, K, T, ld_var, batch, leaf,
+                                                ld_leaf, kF2, g->beta, g->lambda);
+        return FDG_OK;
+    };
+    int rc;
+    if (g->dim == 3) rc = spt == 2 ? launch(fdg_leafgen2_kernel<3, 2>) : launch(fdg_leafgen2_kernel<3, 1>);
+    else rc = spt == 2 ? launch(fdg_leafgen2_kernel<2, 2>) : launch(fdg_leafgen2_kernel<2, 1>);
+    if (rc != FDG_OK) return rc;
     CUDA_TRY(cudaGetLastError());
     return FDG_OK;
 }
@@ -1690,11 +1800,25 @@ static int fdg_leafgen_create_impl(const fdg_leafgen_desc *d, fdg_leafgen_t *out
         if (g->meta[i].basis_id >= 0)
             for (int q = 0; q < g->n_loops; ++q)
                 if (g->meta[i].basis[q] != 0.0) {
-                    B.idx[B.nnz] = q;
-                    B.coef[B.nnz] = g->meta[i].basis[q];
+                    B.term[B.nnz].off = q * g->dim;  // first of the DIM rows of loop momentum q in the staged variables
+                    B.term[B.nnz].coef = g->meta[i].basis[q];
                     B.nnz++;
                 }
+        B.g0_first = (int32_t)g->g0.size();
+        B.c_first = (int32_t)g->cst.size();
         for (size_t q = i; q < j; ++q) {
+            if (g->meta[q].type == 0 || (g->meta[q].type == 2 && g->meta[q].order == 0)) {
+                g->cst.push_back({0, g->meta[q].type == 2 ? 1 : 0, g->meta[q].out});
+                B.n_c++;
+                B.n_leaves--;
+                continue;
+            }
+            if (g->meta[q].type == 1 && g->meta[q].order == 0 && g->meta[q].tau_in < 65536 && g->meta[q].tau_out < 32768) {
+                g->g0.push_back({g->meta[q].tau_in | (g->meta[q].tau_out << 16), g->meta[q].out, 0});  // the tight loop of the kernel
+                B.n_g0++;
+                B.n_leaves--;
+                continue;
+            }
             LgLeaf lf;
             std::memset(&lf, 0, sizeof(lf));
             lf.type = g->meta[q].type, lf.order = g->meta[q].order, lf.tau_in = g->meta[q].tau_in, lf.tau_out = g->meta[q].tau_out;
@@ -1724,6 +1848,11 @@ static int fdg_leafgen_destroy_impl(fdg_leafgen_t g) {
         for (auto &kv : g->d_var) {
             cudaSetDevice(kv.first);
             cudaFree(kv.second.first);
+        }
+        for (auto &kv : g->d_g0) {
+            cudaSetDevice(kv.first.first);
+            cudaFree(kv.second.first);
+            cudaFree(kv.second.second);
         }
         cudaSetDevice(cur);
         for (int i = 0; i < 2; ++i)
@@ -1758,11 +1887,16 @@ static int fdg_eval_generated_accumulate_impl(fdg_handle h, fdg_leafgen_t g, con
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // sub-batches: the leaf matrix of a sub-batch lives in a scratch buffer of about 2 GiB (>> L2), never more
+    // sub-batches: the leaf matrix of a sub-batch lives in a scratch buffer of about 8 GiB (>> L2), never more; big sub-batches
+    // are whole waves of 256-sample tiles (one per SM) so that the persistent graph kernels end together
     const int64_t L = std::max<int64_t>(h->low.L, 1);
-    double gb = 2.0;
+    double gb = 8.0;
     if (const char *e = getenv("FDG_LEAFGEN_GB")) gb = atof(e);
     int64_t sub = std::max<int64_t>(4096, (int64_t)(gb * (double)(1 << 30)) / (8 * L)) / 1024 * 1024;
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t wave = (int64_t)256 * std::max(sms, 1);
+    if (sub >= 4 * wave) sub = sub / wave * wave;
     sub = std::min<int64_t>(sub, (batch + 1023) / 1024 * 1024);
     double *buf = nullptr;
     {
@@ -1803,7 +1937,11 @@ static int fdg_eval_generated_host_impl(fdg_handle h, fdg_leafgen_t g, const dou
     const int64_t kr = (int64_t)g->n_loops * g->dim, rows = kr + g->n_tau;
     const int64_t R = h->low.R;
     // chunks of (K, T) are copied on one stream while the previous chunk is generated and evaluated on another
-    const int64_t chunk = std::min<int64_t>(std::max<int64_t>(batch, 1), 1 << 19);
+    // (about half a million samples: thirteen whole waves of 256-sample tiles on a 148-SM device)
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t wave = (int64_t)256 * std::max(sms, 1);
+    const int64_t chunk = std::min<int64_t>(std::max<int64_t>(batch, 1), std::max<int64_t>(1, (1 << 19) / wave) * wave);
     std::lock_guard<std::mutex> host_lock(g->host_mu);
     double *d_var = nullptr;
     cudaStream_t s_copy = nullptr, s_run = nullptr;
