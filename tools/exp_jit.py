@@ -73,9 +73,14 @@ def main():
                 torch.cuda.synchronize()
                 if r:
                     best = min(best, e0.elapsed_time(e1))
+            try:
+                last = f.jit_last()  # the plan of the variant the timed launches ran (the bulk form has its own)
+                info = {**info, **last, "cubin_bytes": last["max_code_bytes"] * last["kernels"]}
+            except Exception:  # noqa: BLE001
+                pass
             model = (info["leaf_loads"] + info["cross_loads"] + info["cross_stores"]) * es
             print(f"{var:60s} {B / best * 1e3 / 1e6:9.2f} Msamples/s  {best:9.3f} ms  kernels={info['kernels']:3d} rows={info['cross_rows']:5d} "
-                  f"model={model / 1e3:6.1f} KB/sample fp64={info['fp64_instr']} code={info['cubin_bytes'] / max(info['kernels'], 1) / 1e3:6.1f} KB/kernel  compile={tc:5.1f}s  "
+                  f"model={model / 1e3:6.1f} KB/sample fp64={info['fp64_instr']} code<={info['max_code_bytes'] / 1e3:6.1f} KB/kernel {'bulk' if info.get('bulk') else 'ring'}  compile={tc:5.1f}s  "
                   f"bit-equal-to-first={same}", flush=True)
             del f
         except Exception as ex:  # noqa: BLE001
