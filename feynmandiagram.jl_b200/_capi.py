@@ -222,12 +222,12 @@ def jit_prepare(h, samples_per_thread: int = 2, accumulate: bool = False) -> dic
 
 def jit_info(h, samples_per_thread: int = 0, accumulate: bool = False) -> dict:
     """Counters of a prepared variant; samples_per_thread = 0: of the variant the last launch ran."""
-    out = (C.c_int64 * 14)()
-    check(lib().fdg_jit_info(h, samples_per_thread, int(accumulate), out, 14))
+    out = (C.c_int64 * 15)()
+    check(lib().fdg_jit_info(h, samples_per_thread, int(accumulate), out, 15))
     return {"kernels": int(out[0]), "cross_rows": int(out[1]), "cross_values": int(out[2]),
             "leaf_loads": int(out[3]), "cross_loads": int(out[4]), "cross_stores": int(out[5]), "operations": int(out[6]),
             "grid_stride": bool(out[7]), "max_code_bytes": int(out[8]), "cse": bool(out[9]), "fp64_instr": int(out[10]),
-            "model_ns": out[11] / 1000.0, "bulk": bool(out[12]), "bulk_smem": int(out[13])}
+            "model_ns": out[11] / 1000.0, "bulk": bool(out[12]), "bulk_smem": int(out[13]), "refetch_loads": int(out[14])}
 
 
 def pipeline_prepare(h, accumulate: bool = True, n_sm: int = 148) -> dict:

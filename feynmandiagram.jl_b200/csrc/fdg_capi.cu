@@ -1030,10 +1030,10 @@ static int fdg_jit_info_impl(fdg_handle h, int32_t samples_per_thread, int32_t a
     const fdg::JitPlan &pl = it->second.plan;
     int64_t ops = 0;
     for (auto &sg : pl.seg) ops += sg.n_stmts;
-    const int64_t vals[14] = {(int64_t)pl.seg.size(), pl.n_cross, pl.n_cross_values, pl.leaf_loads, pl.cross_loads, pl.cross_stores, ops,
+    const int64_t vals[15] = {(int64_t)pl.seg.size(), pl.n_cross, pl.n_cross_values, pl.leaf_loads, pl.cross_loads, pl.cross_stores, ops,
                               pl.persistent ? 1 : 0, pl.max_code_bytes, pl.uses_cse ? 1 : 0, pl.fp64_instr,
-                              (int64_t)(1000.0 * fdg::jit_model_ns(pl, h->low.dtype == FDG_C128 ? 16 : 8)), pl.bulk ? 1 : 0, pl.bulk_smem};
-    for (int32_t i = 0; i < n_out && i < 14; ++i) out[i] = vals[i];
+                              (int64_t)(1000.0 * fdg::jit_model_ns(pl, h->low.dtype == FDG_C128 ? 16 : 8)), pl.bulk ? 1 : 0, pl.bulk_smem, pl.refetch_loads};
+    for (int32_t i = 0; i < n_out && i < 15; ++i) out[i] = vals[i];
     return FDG_OK;
 }
 

@@ -661,6 +661,9 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
     if (seg_ops <= 0) seg_ops = 4000;
     bool ring_on = true;
     int ring_rows = 0;
+    // bulk form: a row is fetched again when its next use is more than a third of a kernel away (see `reload_gap` below)
+    int64_t reload_gap = bulk ? seg_ops / 3 : 0;
+    if (const char *rg = getenv("FDG_JIT_RELOAD_GAP")) reload_gap = atoll(rg);
     if (const char *rg = getenv("FDG_JIT_RING")) ring_on = atoi(rg) != 0;
     if (const char *rr = getenv("FDG_JIT_RING_ROWS")) ring_rows = atoi(rr);
     const size_t nops = ir.size();
@@ -852,26 +855,36 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         std::unordered_map<int32_t, int32_t> cross_reg;    // register of a cross value loaded in this segment
         // ---- input rows (leaves, cross values) in order of first use ------------------------------------------------
         std::vector<std::pair<int, int32_t>> in_rows;  // (0 leaf / 1 cross, row)
+        // A row whose next use lies more than `reload_gap` operations after the previous one is fetched AGAIN instead of
+        // being held in a register all that time: at the widest point of a kernel of the headline graph ~150 values are
+        // live and 60-95 of them are leaves waiting for their next use, which is what made ptxas spill.  The second copy
+        // comes out of L2, where the same SM put it microseconds ago (ncu: +1 % DRAM reads for +17 % rows fetched; spill
+        // stores 3.5 KB -> 0.7 KB per sample; 199 -> 213 M samples/s).  0 = every row is fetched once per kernel.
         {
-            std::vector<uint8_t> seen_leaf((size_t)low.L, 0);
-            std::unordered_map<int32_t, int> seen_cross;
-            auto note = [&](int32_t a) {
+            std::vector<int64_t> seen_leaf((size_t)low.L, -1);  // position of the latest use
+            std::unordered_map<int32_t, int64_t> seen_cross;
+            auto note = [&](int32_t a, int64_t at) {
                 if (a < 0) {
-                    if (!seen_leaf[(size_t)(-a - 1)]) {
-                        seen_leaf[(size_t)(-a - 1)] = 1;
-                        in_rows.emplace_back(0, -a - 1);
+                    int64_t &last = seen_leaf[(size_t)(-a - 1)];
+                    if (last < 0 || (reload_gap > 0 && at - last > reload_gap)) in_rows.emplace_back(0, -a - 1);
+                    last = at;
+                } else if ((size_t)a < lo) {
+                    auto it = seen_cross.find(a);
+                    if (it == seen_cross.end() || (reload_gap > 0 && at - it->second > reload_gap)) {
+                        if (bcross[(size_t)a] >= 0) in_rows.emplace_back(2, bcross[(size_t)a]);
+                        else in_rows.emplace_back(1, cross[(size_t)a]);
                     }
-                } else if ((size_t)a < lo && !seen_cross.count(a)) {
-                    seen_cross.emplace(a, 1);
-                    if (bcross[(size_t)a] >= 0) in_rows.emplace_back(2, bcross[(size_t)a]);
-                    else in_rows.emplace_back(1, cross[(size_t)a]);
+                    seen_cross[a] = at;
                 }
             };
             for (size_t i = lo; i < hi; ++i) {
-                note(ir[i].a);
-                if (is_binary(ir[i])) note(ir[i].b);
+                note(ir[i].a, (int64_t)i);
+                if (is_binary(ir[i])) note(ir[i].b, (int64_t)i);
             }
         }
+        std::vector<int64_t> leaf_last((size_t)low.L, -1);
+        std::unordered_map<int32_t, int64_t> cross_last;
+        int64_t cur = 0;  // the operation being written
         // The ring: every thread streams its own element of each input row global -> shared with cp.async (LDGSTS),
         // `ring_rows` rows ahead of the row the arithmetic is reading, in the order the straight-line code first needs
         // them.  A copy in flight holds no register and no scoreboard entry, so the depth of the memory pipeline no
@@ -964,23 +977,31 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         auto operand = [&](int32_t a) -> int {
             if (a < 0) {
                 const int32_t k = -a - 1;
-                if (leaf_reg[(size_t)k] < 0) {
+                if (leaf_reg[(size_t)k] < 0 || (reload_gap > 0 && cur - leaf_last[(size_t)k] > reload_gap)) {
+                    if (leaf_reg[(size_t)k] < 0) plan.leaf_loads++;
+                    else plan.refetch_loads++;
                     leaf_reg[(size_t)k] = ring ? ring_load(0, k) : e.load("ld.global.nc", "%rd1", "%rd2", k);
-                    plan.leaf_loads++;
                 }
+                leaf_last[(size_t)k] = cur;
                 return leaf_reg[(size_t)k];
             }
             if ((size_t)a >= lo) return reg_of[(size_t)a - lo];
             auto it = cross_reg.find(a);
-            if (it != cross_reg.end()) return it->second;
+            if (it != cross_reg.end() && !(reload_gap > 0 && cur - cross_last[a] > reload_gap)) {
+                cross_last[a] = cur;
+                return it->second;
+            }
             const int r = ring ? ring_load(1, cross[(size_t)a])
                                : (bcross[(size_t)a] >= 0 ? e.load("ld.global", "%rd9", "%rd11", bcross[(size_t)a]) : e.load("ld.global", "%rd3", "%rd4", cross[(size_t)a]));
-            plan.cross_loads++;
-            cross_reg.emplace(a, r);
+            if (it == cross_reg.end()) plan.cross_loads++;
+            else plan.refetch_loads++;
+            cross_reg[a] = r;
+            cross_last[a] = cur;
             return r;
         };
         for (size_t i = lo; i < hi; ++i) {
             const IrOp &o = ir[i];
+            cur = (int64_t)i;
             int r = -1;
             switch (o.kind) {
                 case IR_MUL:
@@ -1513,7 +1534,9 @@ double jit_model_ns(const JitPlan &plan, int bytes_per_element) {
     // with the streamed rows for L2 (measured on the headline graph: 1.8 KB of DRAM writes per sample beyond the plan
     // at 5.7 KB of spill stores, profiles/r02_bulk_segments_summary.txt; scope experiments in r02_experiments/bulk_form.log).
     const double spill = jit_spill_bytes(plan);
-    const double bytes = (double)(plan.leaf_loads + plan.cross_loads + plan.cross_stores) * bytes_per_element + 0.5 * spill;
+    // (rows fetched a second time within a kernel come out of L2 -- measured: +1 % of DRAM reads for +17 % of rows -- and
+    // are charged a sixth of a DRAM row)
+    const double bytes = ((double)(plan.leaf_loads + plan.cross_loads + plan.cross_stores) + (double)plan.refetch_loads / 6.0) * bytes_per_element + 0.5 * spill;
     const double t_mem = bytes / 5000.0;                                         // bytes / (GB/s) = ns
     const double t_fp = ((double)plan.fp64_instr + spill / 8.0 * 6.0) / 13800.0;  // instructions / (G lane-instructions/s) = ns
     return std::cbrt(t_mem * t_mem * t_mem + t_fp * t_fp * t_fp) + 0.01 * (double)plan.seg.size();

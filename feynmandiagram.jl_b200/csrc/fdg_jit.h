@@ -24,6 +24,7 @@ struct JitPlan {
     int32_t n_cross_values = 0;  // values that cross a kernel boundary
     int64_t leaf_loads = 0, cross_loads = 0, cross_stores = 0;  // global loads / stores per sample over all kernels
     int64_t max_code_bytes = 0;  // machine code of the largest kernel (the instruction cache holds 128 KB)
+    int64_t refetch_loads = 0;   // rows fetched a second time within a kernel (served by L2; not in leaf_loads / cross_loads)
     int64_t fp64_instr = 0;      // FP64 arithmetic instructions per sample the kernels execute (folded negations are none)
     bool uses_cse = false;       // planned from the program with common sub-expressions merged
     bool persistent = false;  // single accumulate kernel run as a grid-stride loop (per-thread running sums)

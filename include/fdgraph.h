@@ -183,7 +183,8 @@ int fdg_jit_prepare(fdg_handle h, int32_t samples_per_thread, int32_t accumulate
  * variant is a single grid-stride kernel; [8] = bytes of machine code of the largest kernel; [9] = 1 if the plan was made
  * from the program with common sub-expressions merged; [10] = FP64 instructions per sample the kernels execute;
  * [11] = modelled time of one sample, ps; [12] = 1 for the bulk form (persistent warp-specialised kernels fed by
- * cp.async.bulk), [13] = its dynamic shared memory per block.  (leaf loads + cross loads + cross stores) x sizeof(W) is
+ * cp.async.bulk), [13] = its dynamic shared memory per block, [14] = rows fetched a second time within a kernel
+ * (served by L2, not counted in the loads above).  (leaf loads + cross loads + cross stores) x sizeof(W) is
  * the traffic the plan asks of the memory system per sample -- the figure DESIGN.md compares with ncu's dram bytes.
  * samples_per_thread = 0 asks for the variant the last launch of this handle ran (fdg_jit_ptx likewise). */
 int fdg_jit_info(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int64_t *out, int32_t n_out);
