@@ -682,20 +682,27 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
     // Bulk form (persistent warp-specialised kernels fed by cp.async.bulk, DESIGN.md section 4b'): for programs of several
     // kernels on batches that give every SM a few tiles; bulk copies move whole 16-byte units from 16-byte aligned addresses.
     // FDG_JIT_BULK = 0 never, 1 whenever the buffers allow it (tests), unset: the rule above.
-    bool bulk = false;
+    bool bulk = false, bulk_forced = false;
     {
         const bool cplx = h->low.dtype == FDG_C128;
         const bool aligned = cplx || (((uintptr_t)leaf % 16 == 0) && (ld_leaf % 2 == 0));
-        const int64_t work = h->low.muls_vv + h->low.muls_vf + h->low.adds_vv + h->low.pow_muls;
+        const int64_t work = (h->low.muls_vv + h->low.muls_vf + h->low.adds_vv + h->low.pow_muls) * (cplx ? 4 : 1);  // ~instructions
         int mode = -1;
         if (const char *e = getenv("FDG_JIT_BULK")) mode = atoi(e);
         const int budget = h->jit_segment > 0 ? h->jit_segment : 4000;
-        // (ComplexF64 keeps the ring form unless asked: two registers per value make the 240-register consumers spill where
-        // the ring form's 255 do not -- Taylor-AD sigma order 4: 120 vs 113 M samples/s)
-        bulk = aligned && (spt == 1 || cplx) && mode != 0 && (mode > 0 || (!cplx && work >= 2 * (int64_t)budget && batch >= (int64_t)256 * ds.sm_count * 4));
+        bulk = aligned && (spt == 1 || cplx) && mode != 0 && (mode > 0 || (work >= 2 * (int64_t)budget && batch >= (int64_t)256 * ds.sm_count * 4));
+        bulk_forced = mode > 0;
     }
     int rc = jit_get(h, spt, acc, &v, wide, nullptr, bulk);
     if (rc != FDG_OK) return rc;
+    if (bulk && !bulk_forced && h->low.dtype == FDG_C128 && fdg::jit_spill_bytes(v->plan) > 4096) {
+        // ComplexF64 has two registers per value: where the 240-register consumers of the bulk form spill, the ring form's
+        // 255 registers do better (Taylor-AD sigma order 4: 14 KB of spill stores per sample, 114 vs 129 M samples/s);
+        // where they do not, the bulk form wins here too (Taylor-AD sigma order 3: 1.84e9 vs 1.66e9)
+        bulk = false;
+        rc = jit_get(h, spt, acc, &v, wide, nullptr, false);
+        if (rc != FDG_OK) return rc;
+    }
     bulk = v->plan.bulk;
     h->last_jit_key = spt * 2 + (acc ? 1 : 0) + (wide ? 64 : 0) + (bulk ? 32 : 0);
     auto &kern = v->kernels[dev];
