@@ -1532,7 +1532,7 @@ struct LgCst {  // a leaf that is 1 (kind 0) or the order-0 interaction 8 pi (q^
 };
 
 template <int DIM, int S>
-__global__ void __launch_bounds__(FDG_LG_THREADS)
+__global__ void __launch_bounds__(FDG_LG_THREADS, S == 1 ? 7 : 4)
 fdg_leafgen2_kernel(const LgBasis *__restrict__ bases, int n_bases, int bases_per_block, const LgLeaf *__restrict__ leaves, const LgG0 *__restrict__ g0,
                     const LgCst *__restrict__ cst, int n_loops, int n_tau, const double *__restrict__ K, const double *__restrict__ T, long long ld_var, long long batch,
                     double *__restrict__ leaf, long long ld_leaf, double kF2, double beta, double lambda) {
@@ -1558,10 +1558,16 @@ fdg_leafgen2_kernel(const LgBasis *__restrict__ bases, int n_bases, int bases_pe
     const double *kv = lg_var + tid;
     const double *tv = lg_var + kr * COLS + tid;
     const int b0 = blockIdx.y * bases_per_block, b1 = min(n_bases, b0 + bases_per_block);
+    // The tables are read one record ahead (every table ends with a spare record): a record's load is in flight while the
+    // previous one is being worked on -- the kernel is bound by the latency of exactly these loads.
+    int4 nh0 = *reinterpret_cast<const int4 *>(&bases[b0].nnz), nh1 = *reinterpret_cast<const int4 *>(&bases[b0].n_c);
     for (int ib = b0; ib < b1; ++ib) {
         const LgBasis *B = bases + ib;  // (uniform loads, 16 bytes at a time)
-        const int4 h0 = *reinterpret_cast<const int4 *>(&B->nnz), h1 = *reinterpret_cast<const int4 *>(&B->n_c);
+        const int4 h0 = nh0, h1 = nh1;
+        nh0 = *reinterpret_cast<const int4 *>(&B[1].nnz), nh1 = *reinterpret_cast<const int4 *>(&B[1].n_c);
         const int nnz = h0.x, g0_first = h0.y, n_g0 = h0.z, c_first = h0.w, n_c = h1.x, leaf0 = h1.y, n_leaves = h1.z;
+        LgG0 mg = g0[g0_first];                                              // first records of this momentum's lists
+        int4 mc = *reinterpret_cast<const int4 *>(cst + c_first);
         double kq[S][3];
 #pragma unroll
         for (int s = 0; s < S; ++s) kq[s][0] = kq[s][1] = kq[s][2] = 0.0;
@@ -1598,7 +1604,8 @@ fdg_leafgen2_kernel(const LgBasis *__restrict__ bases, int n_bases, int bases_pe
             }
             have_den = true;
             for (int i = g0_first; i < g0_first + n_g0; ++i) {
-                const LgG0 m = g0[i];
+                const LgG0 m = mg;
+                mg = g0[i + 1];
                 const double *t_out = tv + (m.taus >> 16) * COLS, *t_in = tv + (m.taus & 0xffff) * COLS;
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
@@ -1619,7 +1626,8 @@ fdg_leafgen2_kernel(const LgBasis *__restrict__ bases, int n_bases, int bases_pe
 #pragma unroll
             for (int s = 0; s < S; ++s) wv[s] = 25.132741228718345 * (q2[s] + lambda);
             for (int i = c_first; i < c_first + n_c; ++i) {
-                const int4 m = *reinterpret_cast<const int4 *>(cst + i);
+                const int4 m = mc;
+                mc = *reinterpret_cast<const int4 *>(cst + i + 1);
                 const long long off = ((long long)m.y << 32) | (unsigned)m.x;
 #pragma unroll
                 for (int s = 0; s < S; ++s)
@@ -1692,7 +1700,8 @@ int leafgen_launch(fdg_leafgen *g, const double *K, const double *T, int64_t ld_
     if (it == g->d_tab.end()) {
         LgBasis *db = nullptr;
         LgLeaf *dl = nullptr;
-        CUDA_TRY(cudaMalloc((void **)&db, g->bases.size() * sizeof(LgBasis)));
+        CUDA_TRY(cudaMalloc((void **)&db, (g->bases.size() + 1) * sizeof(LgBasis)));  // (+ 1: the kernel reads one record ahead)
+        CUDA_TRY(cudaMemset(db, 0, (g->bases.size() + 1) * sizeof(LgBasis)));
         CUDA_TRY(cudaMalloc((void **)&dl, g->leaves.size() * sizeof(LgLeaf)));
         CUDA_TRY(cudaMemcpy(db, g->bases.data(), g->bases.size() * sizeof(LgBasis), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(dl, g->leaves.data(), g->leaves.size() * sizeof(LgLeaf), cudaMemcpyHostToDevice));
@@ -1707,8 +1716,10 @@ int leafgen_launch(fdg_leafgen *g, const double *K, const double *T, int64_t ld_
         for (LgCst &r : tc) r.off = (long long)r.out * (long long)ld_leaf;
         LgG0 *dg = nullptr;
         LgCst *dc = nullptr;
-        CUDA_TRY(cudaMalloc((void **)&dg, std::max<size_t>(tab.size(), 1) * sizeof(LgG0)));
-        CUDA_TRY(cudaMalloc((void **)&dc, std::max<size_t>(tc.size(), 1) * sizeof(LgCst)));
+        CUDA_TRY(cudaMalloc((void **)&dg, (tab.size() + 1) * sizeof(LgG0)));
+        CUDA_TRY(cudaMalloc((void **)&dc, (tc.size() + 1) * sizeof(LgCst)));
+        CUDA_TRY(cudaMemset(dg, 0, (tab.size() + 1) * sizeof(LgG0)));
+        CUDA_TRY(cudaMemset(dc, 0, (tc.size() + 1) * sizeof(LgCst)));
         CUDA_TRY(cudaMemcpy(dg, tab.data(), tab.size() * sizeof(LgG0), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(dc, tc.data(), tc.size() * sizeof(LgCst), cudaMemcpyHostToDevice));
         ig = g->d_g0.emplace(std::make_pair(dev, (long long)ld_leaf), std::make_pair(dg, dc)).first;
