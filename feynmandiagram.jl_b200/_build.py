@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfdgraph.so")
-SOURCES = ["fdg_capi.cu", "fdg_lower.cpp", "fdg_jit.cpp"]
+SOURCES = ["fdg_capi.cu", "fdg_lower.cpp", "fdg_jit.cpp", "fdg_lgjit.cpp"]
 HEADERS = ["fdg_vm.cuh", "fdg_isa.h", "fdg_lower.h", "fdg_jit.h", os.path.join("..", "..", "include", "fdgraph.h")]
 
 NVCC_FLAGS = [

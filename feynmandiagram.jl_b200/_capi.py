@@ -61,7 +61,7 @@ EXPORTS = [
     "fdg_comm_unique_id", "fdg_comm_init", "fdg_comm_destroy", "fdg_allreduce", "fdg_jit_prepare", "fdg_jit_ptx",
     "fdg_jit_info", "fdg_leafgen_create", "fdg_leafgen_destroy", "fdg_leafgen_fill", "fdg_eval_generated_accumulate",
     "fdg_eval_generated_host", "fdg_graph_write", "fdg_compile_file", "fdg_pipeline_prepare", "fdg_pipeline_stats",
-    "fdg_probe_fp64",
+    "fdg_probe_fp64", "fdg_leafgen_jit_prepare",
 ]
 BACKEND_AUTO, BACKEND_VM, BACKEND_JIT = 0, 1, 2
 
@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
     L.fdg_compile_file.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(vp)]
     L.fdg_leafgen_create.argtypes = [C.POINTER(LeafGenDesc), C.POINTER(vp)]
     L.fdg_leafgen_destroy.argtypes = [vp]
+    L.fdg_leafgen_jit_prepare.argtypes = [vp, i32, i32, C.POINTER(i64), i32, C.POINTER(C.c_char_p)]
     L.fdg_leafgen_fill.argtypes = [vp, vp, vp, i64, i64, vp, i64, vp]
     L.fdg_eval_generated_accumulate.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp]
     L.fdg_eval_generated_host.argtypes = [vp, vp, vp, vp, i64, i64, vp]
@@ -260,3 +261,13 @@ def jit_ptx(h, samples_per_thread: int, accumulate: bool, index: int):
     p, log = C.c_char_p(), C.c_char_p()
     check(lib().fdg_jit_ptx(h, samples_per_thread, int(accumulate), index, C.byref(p), C.byref(log)))
     return p.value.decode(), (log.value or b"").decode()
+
+
+def leafgen_jit_prepare(g, wide: bool = False, index: int = -1):
+    """Builds + assembles the specialised leaf-generation kernels (host only); counters and, for index >= 0, the PTX."""
+    out = (C.c_int64 * 5)()
+    ptx = C.c_char_p()
+    check(lib().fdg_leafgen_jit_prepare(g, int(wide), max(index, 0), out, 5, C.byref(ptx) if index >= 0 else None))
+    info = {"kernels": int(out[0]), "code_bytes": int(out[1]), "instructions": int(out[2]), "leaves_covered": int(out[3]),
+            "max_code_bytes": int(out[4])}
+    return (info, ptx.value.decode()) if index >= 0 else info

@@ -275,6 +275,10 @@ class LeafGenerator:
         """rows of the (K, T) input per sample: dim * n_loops + n_tau"""
         return self.dim * self.n_loops + self.n_tau
 
+    def jit_prepare(self, wide: bool = False, index: int = -1):
+        """The kernels specialised for this graph's leaves, built and assembled now (host only): counters [, PTX of one]."""
+        return _capi.leafgen_jit_prepare(self._g, wide, index)
+
     def fill_device(self, K_ptr: int, T_ptr: int, ld_var: int, batch: int, leaf_ptr: int, ld_leaf: int, stream: int = 0) -> None:
         """K[(j * dim + c) * ld_var + b], T[t * ld_var + b] -> leaf[l * ld_leaf + b] (device pointers)."""
         _capi.check(_capi.lib().fdg_leafgen_fill(self._g, K_ptr, T_ptr, ld_var, batch, leaf_ptr, ld_leaf, stream))

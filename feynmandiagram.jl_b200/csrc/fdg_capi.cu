@@ -10,6 +10,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -1677,6 +1678,14 @@ struct fdg_leafgen {
     std::vector<LgLeaf> leaves;
     std::vector<LgG0> g0;        // the order-0 propagators, grouped like `bases`
     std::vector<LgCst> cst;      // leaves that do not depend on the times, grouped like `bases`
+    // the generator specialised for this graph (fdg_lgjit.cpp): what it covers, its kernels per (device, wide offsets), and the
+    // tables of the leaves it does not cover (counter-term orders >= 1), which the table-driven kernel then fills
+    std::vector<fdg::LgJitBasis> jit_bases;
+    std::vector<LgBasis> rest_bases;
+    std::map<std::pair<int, int>, std::vector<cudaKernel_t>> jit_kernels;
+    std::map<std::pair<int, int>, std::vector<cudaLibrary_t>> jit_libs;
+    std::map<int, LgBasis *> d_rest;
+    bool jit_failed = false;
     std::map<int, std::pair<LgBasis *, LgLeaf *>> d_tab;  // per device
     std::map<std::pair<int, long long>, std::pair<LgG0 *, LgCst *>> d_g0;  // per device and leading dimension of the leaf matrix
     int n_loops = 0, dim = 3, n_tau = 0;
@@ -1690,6 +1699,23 @@ struct fdg_leafgen {
 };
 
 namespace {
+// PTX of the generator specialised for this graph, assembled for sm_100a (host only)
+int lg_jit_assemble(fdg_leafgen *g, bool wide, std::vector<fdg::JitSegment> &segs, std::string &err) {
+    int budget = 0;
+    if (const char *e = getenv("FDG_LG_JIT_BUDGET")) budget = atoi(e);
+    int rc = fdg::lgjit_build(g->jit_bases, g->n_loops, g->dim, g->n_tau, g->kF * g->kF, g->beta, g->lambda, wide, budget, segs, err);
+    if (rc != FDG_OK) return rc;
+    std::vector<std::string> errs(segs.size());
+    std::vector<int> rcs(segs.size(), FDG_OK);
+    std::vector<std::thread> th;
+    for (size_t q = 0; q < segs.size(); ++q)
+        th.emplace_back([&, q] { rcs[q] = fdg::jit_assemble(segs[q].ptx, 3, segs[q].cubin, errs[q]); });
+    for (auto &t : th) t.join();
+    for (size_t q = 0; q < segs.size(); ++q)
+        if (rcs[q] != FDG_OK) rc = rcs[q], err = errs[q];
+    return rc;
+}
+
 int leafgen_launch(fdg_leafgen *g, const double *K, const double *T, int64_t ld_var, int64_t batch, double *leaf,
                    int64_t ld_leaf, cudaStream_t st) {
     int dev = 0;
@@ -1726,7 +1752,54 @@ int leafgen_launch(fdg_leafgen *g, const double *K, const double *T, int64_t ld_
     }
     const LgG0 *dg0 = ig->second.first;
     const LgCst *dcst = ig->second.second;
-    const int nb = (int)g->bases.size();
+    // ---- the generator specialised for this graph, where it can be built; the table-driven kernel below then only fills the
+    //      leaves it does not cover
+    bool use_jit = !g->jit_failed;
+    if (const char *e = getenv("FDG_LG_JIT")) use_jit = use_jit && atoi(e) != 0;
+    const LgBasis *d_bases = it->second.first;
+    int nb = (int)g->bases.size();
+    if (use_jit) {
+        const int wide = (uint64_t)ld_leaf * 8 >= (1ull << 32) ? 1 : 0;
+        auto jk = g->jit_kernels.find(std::make_pair(dev, wide));
+        if (jk == g->jit_kernels.end()) {
+            std::vector<fdg::JitSegment> segs;
+            std::string err;
+            int rc = lg_jit_assemble(g, wide != 0, segs, err);
+            if (rc != FDG_OK) {
+                g->jit_failed = true;  // (e.g. no PTX compiler library): the table-driven kernel does everything
+                use_jit = false;
+                if (getenv("FDG_LG_JIT_VERBOSE")) std::fprintf(stderr, "fdg_leafgen: specialised generator not built: %s\n", err.c_str());
+            } else {
+                std::vector<cudaKernel_t> ks;
+                for (auto &sg : segs) {
+                    cudaLibrary_t lib;
+                    CUDA_TRY(cudaLibraryLoadData(&lib, sg.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+                    g->jit_libs[std::make_pair(dev, wide)].push_back(lib);
+                    cudaKernel_t k;
+                    CUDA_TRY(cudaLibraryGetKernel(&k, lib, sg.name.c_str()));
+                    ks.push_back(k);
+                }
+                jk = g->jit_kernels.emplace(std::make_pair(dev, wide), std::move(ks)).first;
+            }
+        }
+        if (use_jit) {
+            const unsigned grid1 = (unsigned)((batch + 127) / 128);
+            long long a_ld_var = ld_var, a_batch = batch, a_ld_leaf = ld_leaf;
+            void *args[] = {(void *)&K, (void *)&T, &a_ld_var, &a_batch, (void *)&leaf, &a_ld_leaf};
+            for (const cudaKernel_t k : jk->second) CUDA_TRY(cudaLaunchKernel((const void *)k, dim3(grid1), dim3(128), args, 0, st));
+            if (g->rest_bases.empty()) return FDG_OK;
+            auto ir = g->d_rest.find(dev);
+            if (ir == g->d_rest.end()) {
+                LgBasis *db = nullptr;
+                CUDA_TRY(cudaMalloc((void **)&db, (g->rest_bases.size() + 1) * sizeof(LgBasis)));
+                CUDA_TRY(cudaMemset(db, 0, (g->rest_bases.size() + 1) * sizeof(LgBasis)));
+                CUDA_TRY(cudaMemcpy(db, g->rest_bases.data(), g->rest_bases.size() * sizeof(LgBasis), cudaMemcpyHostToDevice));
+                ir = g->d_rest.emplace(dev, db).first;
+            }
+            d_bases = ir->second;
+            nb = (int)g->rest_bases.size();
+        }
+    }
     // samples per thread (two share the decoding of the tables, but measure the same: 169 vs 170 M samples/s)
     int spt = 1;
     if (const char *e = getenv("FDG_LG_SPT")) spt = atoi(e) >= 2 ? 2 : 1;
@@ -1745,7 +1818,7 @@ int leafgen_launch(fdg_leafgen *g, const double *K, const double *T, int64_t ld_
         int carve = -1;
         if (const char *e = getenv("FDG_LG_CARVEOUT")) carve = atoi(e);
         if (carve >= 0) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-        kern<<<grid, FDG_LG_THREADS, smem, st>>>(it->second.first, nb, per_block, it->second.second, dg0, dcst, g->n_loops, g->n_tau, K, T, ld_var, batch, leaf,
+        kern<<<grid, FDG_LG_THREADS, smem, st>>>(d_bases, nb, per_block, it->second.second, dg0, dcst, g->n_loops, g->n_tau, K, T, ld_var, batch, leaf,
                                                 ld_leaf, kF2, g->beta, g->lambda);
         return FDG_OK;
     };
@@ -1844,9 +1917,50 @@ static int fdg_leafgen_create_impl(const fdg_leafgen_desc *d, fdg_leafgen_t *out
             g->leaves.push_back(lf);
         }
         g->bases.push_back(B);
+        {
+            fdg::LgJitBasis J;
+            J.nnz = B.nnz;
+            for (int q = 0; q < B.nnz; ++q) J.idx[q] = B.term[q].off / std::max(g->dim, 1), J.coef[q] = B.term[q].coef;
+            for (int q = 0; q < B.n_g0; ++q) {
+                const LgG0 &r = g->g0[(size_t)(B.g0_first + q)];
+                J.g0.push_back({r.taus & 0xffff, r.taus >> 16, r.out});
+            }
+            for (int q = 0; q < B.n_c; ++q) {
+                const LgCst &r = g->cst[(size_t)(B.c_first + q)];
+                (r.kind ? J.w0_out : J.one_out).push_back(r.out);
+            }
+            g->jit_bases.push_back(std::move(J));
+            if (B.n_leaves > 0) {
+                LgBasis Rb = B;
+                Rb.n_g0 = Rb.n_c = 0;
+                g->rest_bases.push_back(Rb);
+            }
+        }
         i = j;
     }
     *out = g;
+    return FDG_OK;
+}
+
+static int fdg_leafgen_jit_prepare_impl(fdg_leafgen_t g, int32_t wide, int32_t index, int64_t *out, int32_t n_out, const char **ptx) {
+    if (!g || n_out < 0 || (!out && n_out > 0)) return fail(FDG_ERR_BAD_ARG, "bad argument");
+    std::lock_guard<std::mutex> lock(g->mu);
+    static thread_local std::string keep;
+    std::vector<fdg::JitSegment> segs;
+    std::string err;
+    int rc = lg_jit_assemble(g, wide != 0, segs, err);
+    if (rc != FDG_OK) return fail(rc, err);
+    int64_t code = 0, lines = 0, biggest = 0;
+    for (auto &sg : segs) code += (int64_t)sg.cubin.size(), lines += sg.n_stmts, biggest = std::max<int64_t>(biggest, (int64_t)sg.cubin.size());
+    int64_t covered = 0;
+    for (auto &b : g->jit_bases) covered += (int64_t)(b.g0.size() + b.w0_out.size() + b.one_out.size());
+    const int64_t vals[5] = {(int64_t)segs.size(), code, lines, covered, biggest};
+    for (int32_t i = 0; i < n_out && i < 5; ++i) out[i] = vals[i];
+    if (ptx) {
+        if (index < 0 || index >= (int32_t)segs.size()) return fail(FDG_ERR_BAD_ARG, "kernel index out of range");
+        keep = segs[(size_t)index].ptx;
+        *ptx = keep.c_str();
+    }
     return FDG_OK;
 }
 
@@ -1866,6 +1980,14 @@ static int fdg_leafgen_destroy_impl(fdg_leafgen_t g) {
         for (auto &kv : g->d_var) {
             cudaSetDevice(kv.first);
             cudaFree(kv.second.first);
+        }
+        for (auto &kv : g->d_rest) {
+            cudaSetDevice(kv.first);
+            cudaFree(kv.second);
+        }
+        for (auto &kv : g->jit_libs) {
+            cudaSetDevice(kv.first.first);
+            for (auto lib : kv.second) cudaLibraryUnload(lib);
         }
         for (auto &kv : g->d_g0) {
             cudaSetDevice(kv.first.first);
@@ -2071,6 +2193,9 @@ int fdg_allreduce(fdg_comm_t c, double *acc, int64_t n, void *stream) {
 }
 int fdg_leafgen_create(const fdg_leafgen_desc *d, fdg_leafgen_t *out) {
     return guarded([&] { return fdg_leafgen_create_impl(d, out); });
+}
+int fdg_leafgen_jit_prepare(fdg_leafgen_t g, int32_t wide, int32_t index, int64_t *out, int32_t n_out, const char **ptx) {
+    return guarded([&] { return fdg_leafgen_jit_prepare_impl(g, wide, index, out, n_out, ptx); });
 }
 int fdg_leafgen_destroy(fdg_leafgen_t g) {
     return guarded([&] { return fdg_leafgen_destroy_impl(g); });

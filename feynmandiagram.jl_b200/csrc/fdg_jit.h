@@ -89,6 +89,23 @@ double jit_spill_bytes(const JitPlan &plan);
 // memory (scope <= 0: about two thirds of a kernel).
 int jit_plan(const Lowered &low, int spt, bool acc, int seg_ops, bool wide_strides, bool fma, JitPlan &plan, std::string &err,
              const PipeOptions *pipe = nullptr, const Lowered *merged = nullptr, int scope = 0, bool bulk = false);
+// ---- leaf generator specialised per graph (fdg_lgjit.cpp) ----
+struct LgJitBasis {  // the leaves that carry one loop-basis vector (momentum)
+    struct G0 {
+        int32_t tau_in, tau_out, out;
+    };
+    int32_t nnz = 0;
+    int32_t idx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double coef[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<G0> g0;            // order-0 Green's functions: times and row of the leaf matrix
+    std::vector<int32_t> w0_out;   // order-0 interactions: rows
+    std::vector<int32_t> one_out;  // constant leaves (value 1): rows
+};
+// straight-line PTX kernels (fdg_lg0, fdg_lg1, ...) that fill the rows of the leaves above for one sample per thread;
+// params of every kernel: K, T, ld_var, batch, leaf, ld_leaf.  wide: ld_leaf * 8 does not fit 32 bits.
+int lgjit_build(const std::vector<LgJitBasis> &bases, int n_loops, int dim, int n_tau, double kF2, double beta, double lambda, bool wide,
+                int budget, std::vector<JitSegment> &out, std::string &err);
+
 // PTX text -> sm_100a cubin with the PTX compiler library (no GPU needed)
 int jit_assemble(const std::string &ptx, int opt_level, std::vector<char> &cubin, std::string &err);
 // assemble every segment with the PTX compiler library (no GPU needed), segments in parallel

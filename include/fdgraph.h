@@ -237,6 +237,12 @@ typedef struct fdg_leafgen_desc {
 typedef struct fdg_leafgen *fdg_leafgen_t;
 int fdg_leafgen_create(const fdg_leafgen_desc *desc, fdg_leafgen_t *out);
 int fdg_leafgen_destroy(fdg_leafgen_t g);
+/* The order-0 propagators, order-0 interactions and constant leaves are filled by kernels written for the graph at hand
+ * (straight-line PTX, loop-basis coefficients / time indices / rows as immediates), the counter-term leaves by a
+ * table-driven kernel.  This builds and assembles the specialised kernels now (host only, no GPU needed) and reports
+ * out[0..n_out): kernels, bytes of machine code, instructions written, leaves covered, bytes of the largest kernel;
+ * `ptx` (optional) receives the text of kernel `index`.  wide: the variant for ld_leaf * 8 >= 4 GiB. */
+int fdg_leafgen_jit_prepare(fdg_leafgen_t g, int32_t wide, int32_t index, int64_t *out, int32_t n_out, const char **ptx);
 /* device pointers, batch-major like everything else: component c of loop momentum j of sample b at
  * K[(j * dim + c) * ld_var + b], time t at T[t * ld_var + b]; writes leaf[l * ld_leaf + b]. */
 int fdg_leafgen_fill(fdg_leafgen_t g, const double *K, const double *T, int64_t ld_var, int64_t batch, double *leaf,

@@ -275,12 +275,18 @@ def test_large_batch_properties():
     assert root[:, idx].cpu().numpy().tobytes() == want.tobytes()
 
 
-def test_leading_dimension_of_4_gib_and_more():
+@pytest.mark.parametrize("bulk", [False, True])
+def test_leading_dimension_of_4_gib_and_more(bulk, monkeypatch):
     """Row offsets are one 32-bit multiply-add in the specialised kernels; a leaf matrix whose leading dimension
-    reaches 4 GiB takes the 64-bit variant.  Only the first `batch` columns of each row are touched."""
+    reaches 4 GiB takes the 64-bit variant (the bulk form's producer always forms 64-bit addresses; its consumers' cross
+    stores switch).  Only the first `batch` columns of each row are touched."""
     roots = graphgen.random_dag(91, n_leaves=3, n_inner=12, n_roots=2)
     raw, _ = fd.flatten(roots)
-    ev = fd.compile_raw(raw, backend=JIT)
+    if bulk:
+        monkeypatch.setenv("FDG_JIT_BULK", "1")
+    ev = fd.compile_raw(raw, backend=JIT, jit_segment=6 if bulk else 0)
+    if bulk:
+        ev.set_launch(0, 1, 0)
     batch, ld = 2050, (1 << 29) + 16
     host = graphgen.leaf_values(3, ev.n_leaves, batch, signed=True)
     leaf = torch.empty(ev.n_leaves, ld, dtype=torch.float64, device="cuda")
@@ -289,6 +295,9 @@ def test_leading_dimension_of_4_gib_and_more():
     ev.eval_device(leaf.data_ptr(), ld, root.data_ptr(), batch, batch, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert root.cpu().numpy().tobytes() == O.Oracle(raw).eval(host).tobytes()
+    if bulk:
+        last = ev.jit_last()
+        assert last["bulk"] and last["kernels"] >= 2 and last["cross_rows"] > 0
 
 
 @pytest.mark.parametrize("name,dtype,log2_batch", [("parquet_sigma_o3", np.float64, 24), ("parquet_ver4_o4", np.float64, 20),
