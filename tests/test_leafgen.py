@@ -189,3 +189,53 @@ def test_generated_sub_batches_and_ragged_sizes(monkeypatch):
     leaf = leafgen.leaf_values(meta, K, T, KF, BETA, LAM)
     ref = O.Oracle(raw).eval(leaf)
     assert (np.abs(acc - ref.sum(axis=1)) <= 1e-11 * (np.abs(ref).sum(axis=1) + 1e-300)).all()
+
+
+def test_specialised_generator_assembles_without_a_gpu():
+    """The kernels written for a graph's leaves (csrc/fdg_lgjit.cpp) assemble for sm_100a on the host, cover every order-0
+    leaf, stay inside the instruction cache, and hold the graph's data as immediates (no table is read)."""
+    for name, n_cov in (("parquet_ver4_o4", 984), ("parquet_sigma_o3", 27), ("taylor_sigma_o3", 27)):
+        _, meta = _load(name)
+        gen = fd.LeafGenerator(meta, kF=KF, beta=BETA, lam=LAM)
+        info, ptx = gen.jit_prepare(False, 0)
+        assert info["leaves_covered"] == n_cov and info["kernels"] >= 1 and info["max_code_bytes"] < 120 * 1024
+        assert ".target sm_100a" in ptx and "rcp.approx.ftz.f64" in ptx and "copysign.f64" in ptx and "mad.wide.u32" in ptx
+        assert "ld.global.nc.f64 %fk" in ptx and "ld.global.nc.f64 %ft" in ptx  # the sample's variables, once, into registers
+        wide, ptxw = gen.jit_prepare(True, 0)
+        assert wide["kernels"] == info["kernels"] and "mad.lo.u64 %rd8, %rd7" in ptxw
+    gen = fd.LeafGenerator(_load("parquet_ver4_o4")[1], kF=KF, beta=BETA, lam=LAM)
+    assert gen.jit_prepare()["kernels"] >= 8  # ~40 momenta per kernel
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["parquet_ver4_o4", "gv_ver4_o3", "taylor_sigma_o3"])
+def test_specialised_and_table_driven_generators_agree(name, monkeypatch):
+    """FDG_LG_JIT=0 runs the table-driven kernel on every leaf; the default runs the kernels specialised for the graph
+    (and the table-driven one on the counter-term leaves only).  Same formulas, same order of operations: the leaves agree
+    to rounding (the specialised exp flushes results below 2^-1022 to zero), on whole and ragged blocks."""
+    torch = pytest.importorskip("torch")
+    raw, meta = _load(name)
+    B = 5000 + 77
+    K, T = _variables(meta, B, seed=11)
+    gen = fd.LeafGenerator(meta, kF=KF, beta=BETA, lam=LAM)
+    dK = torch.from_numpy(K.transpose(1, 0, 2).reshape(-1, B).copy()).cuda()
+    dT = torch.from_numpy(T).cuda()
+    s = torch.cuda.current_stream().cuda_stream
+    out = []
+    for jit in ("1", "0"):
+        monkeypatch.setenv("FDG_LG_JIT", jit)
+        leaf = torch.full((gen.n_leaves, B + 3), -7.0, dtype=torch.float64, device="cuda")
+        gen.fill_device(dK.data_ptr(), dT.data_ptr(), B, B, leaf.data_ptr(), B + 3, s)
+        torch.cuda.synchronize()
+        got = leaf.cpu().numpy()
+        assert (got[:, B:] == -7.0).all()  # nothing written past the batch
+        out.append(got[:, :B])
+    want = leafgen.leaf_values(meta, K, T, KF, BETA, LAM)
+    derived = (meta["leaf_order"].sum(axis=1) > 0)[:, None]
+    assert (out[0][derived[:, 0]] == out[1][derived[:, 0]]).all()          # counter-term leaves: the same kernel either way
+    plain = ~derived[:, 0]
+    assert (np.abs(out[0][plain] - out[1][plain]) <= 4e-16 * np.abs(out[1][plain]) + 1e-300).all()
+    # against the numpy restatement: exp(a) carries the rounding of its argument, |a| eps relative, and |a| = |w| x is
+    # |log| of the leaf (order-4 momenta reach |a| > 100, where one rounding of a dot product is already 2e-14 of the value)
+    w = np.abs(want[plain])
+    assert (np.abs(out[0][plain] - want[plain]) <= (2e-14 + 4e-16 * np.abs(np.log(w + 1e-300))) * w + 1e-300).all()
