@@ -11,8 +11,12 @@
 //     roots ordered so that few values are live across a cut, each cut placed where the fewest are; a value defined
 //     in one kernel and read in a later one travels through a per-launch "cross" buffer laid out [row][thread]
 //     (coalesced), rows reused once their last reader has run;
-//   * inputs (leaf rows of the batch-major leaf matrix, cross rows) are streamed global -> shared by cp.async, a ring
-//     of 32 rows ahead of the arithmetic with compile-time wait counts; x * (-1.0) is a folded negation;
+//   * inputs (leaf rows of the batch-major leaf matrix, cross rows) are streamed global -> shared: per thread by
+//     cp.async, a ring of 32 rows ahead of the arithmetic with compile-time wait counts ("ring form"), or -- big
+//     batches -- per block by cp.async.bulk from a producer warpgroup into an mbarrier-signalled ring that persistent
+//     consumer warps read ("bulk form", DESIGN.md section 4b'); x * (-1.0) is a folded negation;
+//   * equal sub-expressions are merged where the copies sit within one kernel (scoped merging); in the bulk form rows
+//     whose next use is far away are fetched again (from L2) instead of being held in registers;
 //   * roots are stored per sample (eval) or shuffle-reduced per warp into per-warp partial sums (accumulate);
 //     a single small accumulate kernel runs as a grid-stride loop with per-thread running sums.
 // Every one of these decisions is bit-neutral: each statement keeps its own left fold.

@@ -30,13 +30,13 @@ struct JitPlan {
     bool persistent = false;  // single accumulate kernel run as a grid-stride loop (per-thread running sums)
     // ---- bulk form (DESIGN.md section 4b'): persistent warp-specialised kernels.  Blocks of 384 threads, one per SM: eight
     // consumer warps (256 samples per tile, 240 registers after setmaxnreg) run the straight-line arithmetic and read their
-    // input rows from a shared-memory ring; one producer warp (24 registers) fills the ring with cp.async.bulk row copies
-    // (2 KB per row and tile) signalled through mbarriers, following a row table.  No address arithmetic, no cp.async and
-    // no wait-group bookkeeping is left in the consumers' instruction stream.
+    // input rows from a shared-memory ring; the four warps of a producer warpgroup (24 registers) fill the ring with
+    // cp.async.bulk row copies (2 KB per row and tile) signalled through mbarriers, following a row table.  No address
+    // arithmetic, no cp.async and no wait-group bookkeeping is left in the consumers' instruction stream.
     bool bulk = false;
     int bulk_smem = 0;   // dynamic shared memory of the kernels (barriers + ring + running sums of the roots)
     std::vector<JitSegment> seg;
-    // ---- pipeline form (DESIGN.md section 4c): ONE kernel, one resident block per SM; the blocks of stage k run only
+    // ---- pipeline form (DESIGN.md section 4d): ONE kernel, one resident block per SM; the blocks of stage k run only
     // the code of segment k (it stays in that SM's instruction cache) and tiles of 32 samples flow from stage to stage
     // through L2: cross rows live in a ring of `window` tile slots, progress[tile] counts the stages a tile has passed.
     bool pipeline = false;

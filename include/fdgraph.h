@@ -188,7 +188,7 @@ int fdg_jit_prepare(fdg_handle h, int32_t samples_per_thread, int32_t accumulate
  * the traffic the plan asks of the memory system per sample -- the figure DESIGN.md compares with ncu's dram bytes.
  * samples_per_thread = 0 asks for the variant the last launch of this handle ran (fdg_jit_ptx likewise). */
 int fdg_jit_info(fdg_handle h, int32_t samples_per_thread, int32_t accumulate, int64_t *out, int32_t n_out);
-/* Pipeline form of the specialised back end (DESIGN.md section 4c): ONE cooperative kernel, one block per SM; the blocks
+/* Pipeline form of the specialised back end (DESIGN.md section 4d): ONE cooperative kernel, one block per SM; the blocks
  * of stage k run only the code of segment k (resident in that SM's instruction cache) and tiles of 32 samples flow from
  * stage to stage through L2.  fdg_pipeline_prepare builds it for a device with n_sm SMs (host only, no GPU needed) and
  * answers a query: what = 0: stages, cross rows, cross values, then per sample leaf loads, cross loads, cross stores,
