@@ -907,6 +907,8 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         if (const char *x = getenv("FDG_JIT_BULK_GROUP_ROWS")) BG = std::max(1, std::min(64, atoi(x)));
         bool bulk_guard = true;
         if (const char *x = getenv("FDG_JIT_BULK_GUARD")) bulk_guard = atoi(x) != 0;
+        int bulk_prefetch = 0;  // groups ahead of the ring that are prefetched into L2 (experiment)
+        if (const char *x = getenv("FDG_JIT_BULK_PREFETCH")) bulk_prefetch = std::max(0, atoi(x));
         int bulk_hint = 1000000;  // ns
         if (const char *x = getenv("FDG_JIT_BULK_HINT")) bulk_hint = std::max(0, atoi(x));
         if (bulk) NR = NG * BG;
@@ -1336,8 +1338,17 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
                   << "\tselp.u64 %rd14, %rd4, %rd2, %p6;\n\tselp.u64 %rd15, %rd3, %rd1, %p6;\n"
                   << "\tmad.lo.u64 %rd15, %rd13, %rd14, %rd15;\n\tadd.u64 %rd15, %rd15, %rd9;\n"
                   << "\tmad.lo.u32 %r23, %r10, " << BG << ", %r6;\n\tmad.lo.u32 %r23, %r23, " << ROWB << ", %r7;\n"
-                  << "\t@%p4 cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%r23+256], [%rd15], %r8, [%r15];\n"
-                  << "\tadd.u32 %r6, %r6, 4;\n\tbra FDG_PROW;\n"
+                  << "\t@%p4 cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%r23+256], [%rd15], %r8, [%r15];\n";
+                if (bulk_prefetch > 0)
+                    // ... and the row `bulk_prefetch` groups further down the table is asked into L2 now: DRAM keeps working
+                    // through the arithmetic-heavy stretches of the code, when the ring is full
+                    p << "\tadd.u32 %r20, %r17, %r6;\n\tadd.u32 %r20, %r20, " << bulk_prefetch * BG << ";\n\tsetp.ge.u32 %p6, %r20, " << n_in << ";\n\t@%p6 bra FDG_PNOPF;\n"
+                      << "\tmov.u64 %rd12, fdg_tab;\n\tmul.wide.u32 %rd13, %r20, 4;\n\tadd.u64 %rd12, %rd12, %rd13;\n\tld.const.u32 %r20, [%rd12];\n"
+                      << "\tand.b32 %r22, %r20, 0x7fffffff;\n\tcvt.u64.u32 %rd13, %r22;\n\tsetp.ge.u32 %p6, %r20, 0x80000000;\n"
+                      << "\tselp.u64 %rd14, %rd4, %rd2, %p6;\n\tselp.u64 %rd15, %rd3, %rd1, %p6;\n"
+                      << "\tmad.lo.u64 %rd15, %rd13, %rd14, %rd15;\n\tadd.u64 %rd15, %rd15, %rd9;\n"
+                      << "\t@%p4 cp.async.bulk.prefetch.L2.global [%rd15], %r8;\nFDG_PNOPF:\n";
+                p << "\tadd.u32 %r6, %r6, 4;\n\tbra FDG_PROW;\n"
                   << "FDG_PNEXT:\n"
                   << "\tadd.u32 %r10, %r10, 1;\n\tsetp.eq.u32 %p6, %r10, " << NG << ";\n\t@%p6 xor.b32 %r11, %r11, 1;\n\t@%p6 mov.u32 %r10, 0;\n"  // next slot; the parity flips every NG groups
                   << "\tadd.u32 %r9, %r9, 1;\n\tsetp.lt.u32 %p6, %r9, " << b_groups_padded << ";\n\t@%p6 bra FDG_PGROUP;\n"
