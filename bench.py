@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--backend", type=int, default=0, help="0 auto (specialised kernels, VM fallback), 1 VM, 2 JIT")
     ap.add_argument("--jit-segment", type=int, default=0)
     ap.add_argument("--samples", type=int, default=1 << 26, help="samples per step per GPU")
-    ap.add_argument("--resident-gb", type=float, default=48.0)
+    ap.add_argument("--resident-gb", type=float, default=64.0, help="device memory for the resident leaf matrix of the timed batch (GiB)")
     ap.add_argument("--e2e-samples", type=int, default=0, help="samples per e2e step (0 = about 2 GiB of leaves)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline leg")
     ap.add_argument("--dtype", default="f64", choices=["f64", "c128"])
