@@ -681,7 +681,8 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
     // row offsets are formed with one 32-bit multiply-add unless a leading dimension reaches 4 GiB
     const bool wide = (uint64_t)ld_leaf * (h->low.dtype == FDG_C128 ? 16 : 8) >= (1ull << 32);
     // Bulk form (persistent warp-specialised kernels fed by cp.async.bulk, DESIGN.md section 4b'): for programs of several
-    // kernels on batches that give every SM a few tiles; bulk copies move whole 16-byte units from 16-byte aligned addresses.
+    // kernels on batches that give every SM at least eight tiles (a launch of these kernels costs ~10 us: at four tiles per SM
+    // the ring form is still ahead, 168 vs 162 M samples/s on the headline graph); bulk copies move whole 16-byte units from 16-byte aligned addresses.
     // FDG_JIT_BULK = 0 never, 1 whenever the buffers allow it (tests), unset: the rule above.
     bool bulk = false, bulk_forced = false;
     {
@@ -691,7 +692,7 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
         int mode = -1;
         if (const char *e = getenv("FDG_JIT_BULK")) mode = atoi(e);
         const int budget = h->jit_segment > 0 ? h->jit_segment : 4000;
-        bulk = aligned && (spt == 1 || cplx) && mode != 0 && (mode > 0 || (work >= 2 * (int64_t)budget && batch >= (int64_t)256 * ds.sm_count * 4));
+        bulk = aligned && (spt == 1 || cplx) && mode != 0 && (mode > 0 || (work >= 2 * (int64_t)budget && batch >= (int64_t)256 * ds.sm_count * 8));
         bulk_forced = mode > 0;
     }
     int rc = jit_get(h, spt, acc, &v, wide, nullptr, bulk);

@@ -696,7 +696,7 @@ def test_bulk_form_is_chosen_for_big_batches_and_needs_aligned_rows(monkeypatch)
     ev = fd.compile_raw(raw, backend=JIT, jit_segment=700)
     ev.set_launch(0, 1, 0)
     sm = torch.cuda.get_device_properties(0).multi_processor_count
-    B = 256 * sm * 4
+    B = 256 * sm * 8
     leaf = graphgen.leaf_values(47, ev.n_leaves, B + 2, signed=True)          # (L, B + 2), rows 16-byte aligned
     dleaf = torch.from_numpy(leaf).cuda()
     s = torch.cuda.current_stream().cuda_stream
