@@ -911,7 +911,16 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         if (const char *x = getenv("FDG_JIT_BULK_PREFETCH")) bulk_prefetch = std::max(0, atoi(x));
         int bulk_hint = 1000000;  // ns
         if (const char *x = getenv("FDG_JIT_BULK_HINT")) bulk_hint = std::max(0, atoi(x));
-        if (bulk) NR = NG * BG;
+        if (bulk) {
+            // deeper ring where the kernel's running sums leave room for it (experiment: FDG_JIT_BULK_GROUPS_MAX)
+            if (const char *x = getenv("FDG_JIT_BULK_GROUPS_MAX")) {
+                int n_roots_here = 0;
+                for (size_t i = lo; i < hi; ++i) n_roots_here += ir[i].kind == IR_ROOT ? (cplx ? 2 : 1) : 0;
+                const int room = 226 * 1024 - 256 - (acc ? n_roots_here * (T + 1) * 8 : 0);
+                NG = std::max(NG, std::min(atoi(x), room / (BG * T * ES)));
+            }
+            NR = NG * BG;
+        }
         const int ROWB = T * ES;  // bytes of one ring row (one input row of one tile)
         const bool ring = (ring_on || bulk) && !e.persistent && n_in > 0;
         const int sacc0 = 256 + (ring ? NR * T * ES : 0);  // pipeline / bulk form: where the running sums of the roots start
