@@ -906,7 +906,8 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         if (const char *x = getenv("FDG_JIT_BULK_GROUPS")) NG = std::max(2, std::min(16, atoi(x)));
         if (const char *x = getenv("FDG_JIT_BULK_GROUP_ROWS")) BG = std::max(1, std::min(64, atoi(x)));
         bool bulk_guard = true;
-        if (const char *x = getenv("FDG_JIT_BULK_GUARD")) bulk_guard = atoi(x) != 0;
+        int bulk_guard_mode = 1;
+        if (const char *x = getenv("FDG_JIT_BULK_GUARD")) bulk_guard = atoi(x) != 0, bulk_guard_mode = atoi(x);
         int bulk_prefetch = 0;  // groups ahead of the ring that are prefetched into L2 (experiment)
         if (const char *x = getenv("FDG_JIT_BULK_PREFETCH")) bulk_prefetch = std::max(0, atoi(x));
         int bulk_hint = 1000000;  // ns
@@ -943,6 +944,11 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         auto bulk_wait = [&](std::ostringstream &o2, int g) {
             const int id = b_wait_id++;
             // (the last operand is a suspend-time hint in ns: the warp sleeps in the barrier unit instead of polling)
+            if (bulk_guard_mode == 2) {  // experiment: unguarded, but sleeping between polls
+                o2 << "FDG_BW" << id << ":\n\tmbarrier.try_wait.parity.shared::cta.b64 %p7, [fdg_ring+" << 8 * (g % NG) << "], " << ((g / NG) & 1)
+                   << ", " << bulk_hint << ";\n\t@%p7 bra FDG_BG" << id << ";\n\tnanosleep.u32 40;\n\tbra FDG_BW" << id << ";\nFDG_BG" << id << ":\n";
+                return;
+            }
             if (!bulk_guard) {
                 o2 << "FDG_BW" << id << ":\n\tmbarrier.try_wait.parity.shared::cta.b64 %p7, [fdg_ring+" << 8 * (g % NG) << "], " << ((g / NG) & 1)
                    << ", " << bulk_hint << ";\n\t@!%p7 bra FDG_BW" << id << ";\n";
