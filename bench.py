@@ -523,6 +523,9 @@ def main():
             if jit_info is not None:
                 roofline["fp64_instr_executed_per_sample"] = jit_info["fp64_instr"]
                 roofline["fp64_frac_executed"] = jit_info["fp64_instr"] * res / avg_launch_s / 1e9 / fp64["dmul_dadd_gops"]
+                roofline["fp64_note"] = ("fp64_frac_algorithmic counts the operations of the REFERENCE function (flops_per_sample); the kernels "
+                                         "execute fewer (x * -1 folded into the reader, equal sub-expressions merged within a kernel): "
+                                         "fp64_frac_executed is the fraction of the measured DMUL+DADD rate the hardware actually runs at")
         if traffic:
             roofline["traffic_gbs"] = traffic / avg_launch_s / 1e9
             roofline["traffic_frac_of_peak"] = traffic / avg_launch_s / 1e9 / peak
