@@ -19,6 +19,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 #include <sstream>
@@ -99,6 +100,8 @@ int lgjit_build(const std::vector<LgJitBasis> &bases, int n_loops, int dim, int 
         err = "dim must be 2 or 3";
         return FDG_ERR_UNSUPPORTED;
     }
+    int maxnreg = 0;  // registers per thread (0: ptxas decides -- 150-170, three blocks per SM)
+    if (const char *e = getenv("FDG_LG_JIT_MAXNREG")) maxnreg = atoi(e);
     if (budget <= 0) budget = 4400;  // lines of PTX per kernel: ~100 KB of machine code, inside the instruction cache
     // 2^(j/32), correctly rounded
     static const char *tab[32] = {
@@ -197,7 +200,7 @@ int lgjit_build(const std::vector<LgJitBasis> &bases, int n_loops, int dim, int 
         for (int j = 0; j < 32; ++j) p << (j ? ", " : "") << "0x" << tab[j];
         p << "};\n.visible .entry " << js.name
           << "(\n\t.param .u64 p_K, .param .u64 p_T, .param .u64 p_ld_var, .param .u64 p_batch, .param .u64 p_leaf, .param .u64 p_ld_leaf)\n"
-          << ".maxntid 128, 1, 1\n{\n\t.shared .align 8 .b8 lgtab[256];\n"
+          << ".maxntid 128, 1, 1\n" << (maxnreg > 0 ? ".maxnreg " + std::to_string(maxnreg) + "\n" : std::string()) << "{\n\t.shared .align 8 .b8 lgtab[256];\n"
           << "\t.reg .f64 %fd<" << g.nfd + 2 << ">;\n\t.reg .f64 %fk<" << n_loops * dim + 1 << ">;\n\t.reg .f64 %ft<" << n_tau + 1 << ">;\n"
           << "\t.reg .b64 %rd<12>;\n\t.reg .b32 %r<12>;\n\t.reg .pred %p<8>;\n"
           // the table of 2^(j/32) into shared memory
