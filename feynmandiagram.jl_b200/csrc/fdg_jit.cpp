@@ -289,6 +289,13 @@ enum { IR_MUL = 0, IR_ADD = 1, IR_SCALE = 2, IR_POW = 3, IR_ROOT = 4, IR_NEG = 5
 // time configuration, which puts roots that share sub-vertices far apart (Parquet vertex4 order 4: 1800 values live).
 // Greedy: next comes the root whose cone retires the most already-computed shared values and opens the fewest new
 // ones; ties by emitter order.  (Same graph: <= 190 values live, cross traffic 4x smaller.)
+static thread_local double g_root_leaf_w = 0.0;
+static thread_local long g_root_leaf_window = 4;
+void jit_set_root_leaf_bias(double w, long window) {
+    g_root_leaf_w = w;
+    g_root_leaf_window = window;
+}
+
 static void order_roots(const Lowered &low, std::vector<int32_t> &order) {
     const auto &st = low.st;
     const auto &ops = low.ops;
@@ -347,6 +354,17 @@ static void order_roots(const Lowered &low, std::vector<int32_t> &order) {
     }
     std::vector<uint8_t> computed(n, 0), taken(R, 0);
     std::vector<int32_t> in_cone(n, -1);
+    // Leaf bias: a root is also charged w for every leaf its new statements read that none of the roots taken in the last
+    // `window` steps has read -- with a small w a tie-break between roots that retire equally many shared values, which
+    // brings roots over the same leaves into the same kernel.  The effect on the planned traffic is a few per cent and not
+    // monotone in w, so the caller tries a few (w, window) pairs and keeps the plan the model likes best (jit_set_root_leaf_bias;
+    // FDG_JIT_ROOT_LEAF_WEIGHT / _WINDOW force one).
+    double leaf_w = g_root_leaf_w;
+    long leaf_window = g_root_leaf_window;
+    if (const char *e = getenv("FDG_JIT_ROOT_LEAF_WEIGHT")) leaf_w = atof(e);
+    if (const char *e = getenv("FDG_JIT_ROOT_LEAF_WINDOW")) leaf_window = atol(e);
+    std::vector<long> leaf_step((size_t)low.L, -1000000);
+    std::vector<int32_t> leaf_seen((size_t)low.L, -1);
     order.clear();
     std::vector<size_t> cand;
     size_t next_emitter = 0;
@@ -392,7 +410,25 @@ static void order_roots(const Lowered &low, std::vector<int32_t> &order) {
                         }
                 }
             }
-            const long score = kills - creates;
+            long score = kills - creates;
+            if (leaf_w > 0.0) {
+                long cold = 0;
+                for (const int32_t v : cone[r]) {
+                    if (computed[(size_t)v]) continue;
+                    const Stmt &sv = st[(size_t)v];
+                    for (int32_t i = 0; i < sv.count; ++i) {
+                        const int32_t c = ops[(size_t)(sv.first + i)].val;
+                        if (st[(size_t)c].op >= 0) continue;
+                        const int32_t lf = st[(size_t)c].leaf;
+                        if (leaf_seen[(size_t)lf] == (int32_t)(step * R + r) % 2000000000) continue;
+                        leaf_seen[(size_t)lf] = (int32_t)(step * R + r) % 2000000000;
+                        if ((long)step - leaf_step[(size_t)lf] > leaf_window) ++cold;
+                    }
+                }
+                score = (long)(1000.0 * (double)score - 1000.0 * leaf_w * (double)cold);
+            } else {
+                score *= 1000;
+            }
             if (score > best_score) {
                 best_score = score;
                 best = r;
@@ -400,6 +436,15 @@ static void order_roots(const Lowered &low, std::vector<int32_t> &order) {
         }
         taken[best] = 1;
         order.push_back(roots[best]);
+        if (leaf_w > 0.0)
+            for (const int32_t v : cone[best]) {
+                if (computed[(size_t)v]) continue;
+                const Stmt &sv = st[(size_t)v];
+                for (int32_t i = 0; i < sv.count; ++i) {
+                    const int32_t c = ops[(size_t)(sv.first + i)].val;
+                    if (st[(size_t)c].op < 0) leaf_step[(size_t)st[(size_t)c].leaf] = (long)step;
+                }
+            }
         for (const int32_t v : cone[best]) {
             if (shortlist && !computed[(size_t)v])
                 for (const int32_t r2 : roots_of[(size_t)v]) warm[(size_t)r2]++;

@@ -106,6 +106,9 @@ struct LgJitBasis {  // the leaves that carry one loop-basis vector (momentum)
 int lgjit_build(const std::vector<LgJitBasis> &bases, int n_loops, int dim, int n_tau, double kF2, double beta, double lambda, bool wide,
                 int budget, std::vector<JitSegment> &out, std::string &err);
 
+// bias of the root ordering towards roots over recently read leaves, for the plans made by this thread from now on
+// (0 = none; see order_roots)
+void jit_set_root_leaf_bias(double w, long window);
 // PTX text -> sm_100a cubin with the PTX compiler library (no GPU needed)
 int jit_assemble(const std::string &ptx, int opt_level, std::vector<char> &cubin, std::string &err);
 // assemble every segment with the PTX compiler library (no GPU needed), segments in parallel
