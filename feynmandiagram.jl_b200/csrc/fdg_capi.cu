@@ -263,34 +263,34 @@ int jit_get(fdg_program *h, int spt, bool acc, JitVariant **out, bool wide = fal
         const fdg::Lowered *lowp = &h->low, *mergedp = nullptr;
         int scoped_reach = 0;  // 0: the default reach of scoped merging (two thirds of a kernel)
         // Last step, once the variant is chosen and assembled: the root order with a leaf bias (see order_roots) is tried on
-        // paper for two weights; a plan that moves at least 1.5 % fewer rows is assembled and kept if it does not spill more
+        // paper for a few weights; a plan that moves at least 1.5 % fewer rows is assembled and kept if it does not spill more
         // (headline graph: 3186 -> 3072 rows per sample, 212 -> 217 M samples/s)
         auto refine_root_order = [&]() {
             const int64_t work = (h->low.muls_vv + h->low.muls_vf + h->low.adds_vv + h->low.pow_muls) * (h->low.dtype == FDG_C128 ? 4 : 1);
             if (h->low.R < 3 || v.plan.seg.size() < 2 || work < 2 * (int64_t)budget || getenv("FDG_JIT_ROOT_LEAF_WEIGHT")) return;
             auto rows = [](const fdg::JitPlan &p) { return (double)(p.leaf_loads + p.cross_loads + p.cross_stores) + (double)p.refetch_loads / 6.0; };
-            const double ws[2] = {0.02, 0.1};
-            const long wins[2] = {2, 8};
-            fdg::JitPlan best;
-            double best_rows = rows(v.plan) * 0.985;
-            bool found = false;
-            for (int i = 0; i < 2; ++i) {
+            const double ws[4] = {0.02, 0.03, 0.02, 0.1};
+            const long wins[4] = {1, 1, 2, 8};
+            std::vector<fdg::JitPlan> cands;
+            const double limit = rows(v.plan) * 0.985;
+            for (int i = 0; i < 4; ++i) {
                 fdg::jit_set_root_leaf_bias(ws[i], wins[i]);
                 fdg::JitPlan trial;
                 std::string e0;
                 if (fdg::jit_plan(*lowp, spt, acc, budget, wide, h->fma, trial, e0, nullptr, mergedp, scoped_reach, bulk) == FDG_OK &&
-                    trial.seg.size() <= v.plan.seg.size() && rows(trial) < best_rows) {
-                    best_rows = rows(trial);
-                    best = std::move(trial);
-                    found = true;
-                }
+                    trial.seg.size() <= v.plan.seg.size() && rows(trial) < limit)
+                    cands.push_back(std::move(trial));
             }
             fdg::jit_set_root_leaf_bias(0.0, 4);
-            std::string e1;
-            if (found && fdg::jit_compile(best, e1) == FDG_OK && best.max_code_bytes <= 120 * 1024 &&
-                fdg::jit_spill_bytes(best) <= fdg::jit_spill_bytes(v.plan) + 512) {
-                best.uses_cse = v.plan.uses_cse;
-                v.plan = std::move(best);
+            std::sort(cands.begin(), cands.end(), [&](const fdg::JitPlan &a, const fdg::JitPlan &b) { return rows(a) < rows(b); });
+            for (size_t i = 0; i < cands.size() && i < 2; ++i) {  // (assembling is what costs time: the best two at most)
+                std::string e1;
+                if (fdg::jit_compile(cands[i], e1) == FDG_OK && cands[i].max_code_bytes <= 120 * 1024 &&
+                    fdg::jit_spill_bytes(cands[i]) <= fdg::jit_spill_bytes(v.plan) + 512) {
+                    cands[i].uses_cse = v.plan.uses_cse;
+                    v.plan = std::move(cands[i]);
+                    break;
+                }
             }
         };
         if (h->has_cse) {
