@@ -1304,7 +1304,7 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
                   << "\tmbarrier.init.shared::cta.b64 [fdg_ring+" << 8 * (NG + sl) << "], " << CT / 32 << ";\n";
             p << "\tfence.mbarrier_init.release.cluster;\nFDG_INITED:\n\tbar.sync 0;\n"
               << "\tsetp.ge.u32 %p6, %r2, " << CT << ";\n\t@%p6 bra FDG_PRODUCER;\n"
-              << "\tsetmaxnreg.inc.sync.aligned.u32 240;\n";
+              << "\tsetmaxnreg.inc.sync.aligned.u32 " << (getenv("FDG_JIT_BULK_CREGS") ? atoi(getenv("FDG_JIT_BULK_CREGS")) : 240) << ";\n";
             // ---- consumers ----
             // %r2 tid, %r3 lane, %r5 warp, %p3 lane 0, %r4 tile (the one value carried from tile to tile), %rd10 batch
             p << "\tand.b32 %r3, %r2, 31;\n\tsetp.eq.u32 %p3, %r3, 0;\n\tshr.u32 %r5, %r2, 5;\n\tmov.u32 %r0, %ctaid.x;\n"

@@ -1,10 +1,12 @@
-"""Restated Parquet front end (4-point vertex, self-energy, Green's function).  TEST / WORKLOAD INFRASTRUCTURE.
+"""Restated Parquet front end (4-point vertex, self-energy, Green's function, 3-point vertex, polarisation).
+TEST / WORKLOAD INFRASTRUCTURE.
 
 Producer of the evaluator's input for BASELINE.json's Parquet configurations -- not part of the hot path.
 
 Reference: src/frontend/parquet/parquet.jl:102-122 (DiagPara), :60-92 (Interaction, ParquetBlocks),
            common.jl:28-130 (partitions, tau / loop index bookkeeping), operation.jl:1-106 (mergeby),
-           operation.jl:108-182 (update_extKT!), filter.jl:30-64, vertex4.jl:27-485, green.jl:21-115, sigma.jl:20-137.
+           operation.jl:108-182 (update_extKT!), filter.jl:30-64, vertex4.jl:27-485, green.jl:21-115, sigma.jl:20-137,
+           vertex3.jl:20-123, polarization.jl:16-135.
 
 Known, documented deviations from a Julia run (they permute operands inside merged Sum nodes or root columns,
 never the set of terms): `orderedPartition` iterates a Julia `Set` of permutations and `bubble!` iterates a Julia
@@ -778,3 +780,145 @@ def sigma(para: DiagPara, ext_k=None, subdiagram=False, name="Σ", blocks: Optio
                          getid=lambda g: SigmaId(para, g[0]["type"], k=ext_k, t=g[0]["extT"]))
     assert all(r["extT"][0] == para.firstTauIdx for r in sigmadf)
     return sigmadf
+
+
+# ---------------------------------------------------------------------------------------------------------
+# vertex3.jl / polarization.jl
+# ---------------------------------------------------------------------------------------------------------
+
+
+def _approx_vec(a, b) -> bool:
+    """isapprox of two real vectors (norm(a - b) <= sqrt(eps) * max(norm(a), norm(b)))."""
+    if len(a) != len(b):
+        return False
+    d = sum((x - y) ** 2 for x, y in zip(a, b)) ** 0.5
+    return d <= 1.4901161193847656e-08 * max(sum(x * x for x in a) ** 0.5, sum(y * y for y in b) ** 0.5)
+
+
+def _union_filter(first, flt):
+    return tuple(dict.fromkeys([first] + list(flt)))
+
+
+def vertex3(para: DiagPara, ext_k=None, subdiagram=False, name="Γ3", channels=(PHr, PHEr, PPr, Alli),
+            blocks: Optional[ParquetBlocks] = None) -> List[dict]:
+    """vertex3.jl:20-123 -> rows {response, extT, diagram, hash}.  extT = (bosonic, fermionic in, fermionic out)."""
+    blocks = blocks or ParquetBlocks()
+    if ext_k is None:
+        ext_k = [get_k(para.totalLoopNum, 1), get_k(para.totalLoopNum, 2)]
+    assert para.type == Ver3Diag
+    assert para.innerLoopNum >= 1, "Only generates vertex corrections with more than one internal loops."
+    for k in ext_k:
+        assert len(k) >= para.totalLoopNum
+    q = [float(x) for x in ext_k[0][: para.totalLoopNum]]
+    k_in = [float(x) for x in ext_k[1][: para.totalLoopNum]]
+    k_out = _vsub(k_in, q)
+    assert not _approx_vec(q, k_in) and not _approx_vec(q, k_out), "The bosonic q cann't be same as the fermionic k."
+    legs = [q, k_in, k_out]
+    if Proper in para.filter and (len(para.transferLoop) != len(q) or not _approx_vec(para.transferLoop, q)):
+        para = para.reconstruct(transferLoop=tuple(q))  # vertex3.jl:114-123
+    t0 = para.firstTauIdx
+    rows: List[dict] = []
+    K = [0.0] * len(q)
+    loop_idx = para.firstLoopIdx
+    K[loop_idx - 1] = 1.0
+    leg_k = [k_in, k_out, K, _vadd(K, q)]
+    for part in ordered_partition(para.innerLoopNum - 1, 3, 0):
+        o_ver4, o_gin, o_gout = part
+        idx, max_loop = find_first_loop_idx(part, loop_idx + 1)
+        assert max_loop <= para.totalLoopNum
+        ver4_loop, gin_loop, gout_loop = idx
+        ver4_t0 = para.firstTauIdx + 1 if para.hasTau else para.firstTauIdx
+        idx, max_tau = find_first_tau_idx(part, [Ver4Diag, GreenDiag, GreenDiag], ver4_t0, para.interactionTauNum)
+        assert max_tau <= para.totalTauNum
+        ver4_tau, gin_tau, gout_tau = idx
+        if not (is_valid_g(para.filter, o_gin) and is_valid_g(para.filter, o_gout)):
+            continue
+        para_gin = para.reconstruct(type=GreenDiag, innerLoopNum=o_gin, firstLoopIdx=gin_loop, firstTauIdx=gin_tau)
+        para_gout = para.reconstruct(type=GreenDiag, innerLoopNum=o_gout, firstLoopIdx=gout_loop, firstTauIdx=gout_tau)
+        para_ver4 = para.reconstruct(type=Ver4Diag, innerLoopNum=o_ver4, firstLoopIdx=ver4_loop, firstTauIdx=ver4_tau)
+        ver4 = vertex4(para_ver4, leg_k, True, channels=channels, blocks=blocks)
+        if not ver4:
+            continue
+        if para.hasTau:
+            assert all(r["extT"][INL] == ver4_t0 for r in ver4), "The TinL of the inner Γ4 must be firstTauIdx+1"
+        df = [dict(r, extT=(t0, r["extT"][INL], r["extT"][OUTL]), GinT=(t0, r["extT"][INR]), GoutT=(r["extT"][OUTR], t0))
+              for r in ver4]
+        for v4 in mergeby_df(df, ["response", "GinT", "GoutT", "extT"], operator=Sum()):
+            response = v4["response"]
+            assert response in (UpUp, UpDown)
+            gin = green(para_gin, K, v4["GinT"], True, name="Gin", blocks=blocks)
+            gout = green(para_gout, _vadd(K, q), v4["GoutT"], True, name="Gout", blocks=blocks)
+            diag = Graph([gin, gout, v4["diagram"]], properties=Ver3Id(para, response, k=legs, t=v4["extT"]),
+                         operator=Prod(), name=name)
+            rows.append(dict(response=response, extT=v4["extT"], diagram=diag))
+    if rows:
+        rows = mergeby_df(rows, ["response", "extT"], name=name,
+                          getid=lambda g: Ver3Id(para, g[0]["response"], k=legs, t=g[0]["extT"]))
+    return rows
+
+
+def polarization(para: DiagPara, ext_k=None, subdiagram=False, name="Π", blocks: Optional[ParquetBlocks] = None) -> List[dict]:
+    """polarization.jl:16-135 -> rows {response, extT, diagram, hash}; every row has extT = (firstTauIdx, firstTauIdx + 1)."""
+    blocks = blocks or ParquetBlocks()
+    if ext_k is None:
+        ext_k = get_k(para.totalLoopNum, 1)
+    assert para.type == PolarDiag and para.innerLoopNum >= 1
+    assert len(ext_k) >= para.totalLoopNum
+    q_full = [float(x) for x in ext_k]
+    if Proper not in para.filter or len(para.transferLoop) != len(q_full) or _approx_vec(para.transferLoop, q_full):
+        # polarization.jl:129-135, condition as written there (a transfer loop EQUAL to q is replaced by q as well)
+        para = para.reconstruct(transferLoop=tuple(q_full), filter=_union_filter(Proper, para.filter))
+    q = q_full[: para.totalLoopNum]
+    K = [0.0] * len(q)
+    loop_idx = para.firstLoopIdx
+    K[loop_idx - 1] = 1.0
+    assert not _approx_vec(K, q)
+    t0 = para.firstTauIdx
+    ext_t = (t0, t0 + 1) if para.hasTau else (t0, t0)
+    leg_k = [q, K, _vsub(K, q)]
+    rows: List[dict] = []
+    for part in ordered_partition(para.innerLoopNum - 1, 3, 0):
+        o_ver3, o_gin, o_gout = part
+        idx, max_loop = find_first_loop_idx(part, loop_idx + 1)
+        assert max_loop <= para.totalLoopNum
+        ver3_loop, gin_loop, gout_loop = idx
+        if not (is_valid_g(para.filter, o_gin) and is_valid_g(para.filter, o_gout)):
+            continue
+        if o_ver3 == 0:  # Π0 = G G
+            gt0 = ext_t[1] + 1 if para.hasTau else ext_t[0]
+            idx, max_tau = find_first_tau_idx([o_gin, o_gout], [GreenDiag, GreenDiag], gt0, para.interactionTauNum)
+            assert max_tau <= para.totalTauNum
+            gin_tau, gout_tau = idx
+            para_gin = para.reconstruct(type=GreenDiag, innerLoopNum=o_gin, firstLoopIdx=gin_loop, firstTauIdx=gin_tau)
+            para_gout = para.reconstruct(type=GreenDiag, innerLoopNum=o_gout, firstLoopIdx=gout_loop, firstTauIdx=gout_tau)
+            gin = green(para_gin, K, (ext_t[0], ext_t[1]), True, name="Gin")
+            gout = green(para_gout, _vsub(K, q), (ext_t[1], ext_t[0]), True, name="Gout")
+            sign = -1.0 if para.isFermi else 1.0
+            diag = Graph([gin, gout], properties=PolarId(para, UpUp, k=q, t=ext_t), operator=Prod(), name=name, factor=sign)
+            rows.append(dict(response=UpUp, extT=ext_t, diagram=diag))
+            continue
+        idx, max_tau = find_first_tau_idx(part, [Ver3Diag, GreenDiag, GreenDiag], ext_t[1], para.interactionTauNum)
+        assert max_tau <= para.totalTauNum
+        ver3_tau, gin_tau, gout_tau = idx
+        para_gin = para.reconstruct(type=GreenDiag, innerLoopNum=o_gin, firstLoopIdx=gin_loop, firstTauIdx=gin_tau)
+        para_gout = para.reconstruct(type=GreenDiag, innerLoopNum=o_gout, firstLoopIdx=gout_loop, firstTauIdx=gout_tau)
+        para_ver3 = para.reconstruct(type=Ver3Diag, innerLoopNum=o_ver3, firstLoopIdx=ver3_loop, firstTauIdx=ver3_tau)
+        ver3 = vertex3(para_ver3, leg_k, True, blocks=blocks)
+        if not ver3:
+            continue
+        if para.hasTau:
+            assert all(r["extT"][0] == ext_t[1] for r in ver3), "The bosonic T must be firstTauIdx+1 if hasTau"
+            assert all(r["extT"][1] == ver3[0]["extT"][1] for r in ver3), "The TinL must be firstTauIdx+2 if hasTau"
+        df = [dict(r, extT=ext_t, GinT=(ext_t[0], r["extT"][1]), GoutT=(r["extT"][2], ext_t[0])) for r in ver3]
+        for v3 in mergeby_df(df, ["response", "GinT", "GoutT", "extT"], operator=Sum()):
+            response = v3["response"]
+            assert response in (UpUp, UpDown)
+            gin = green(para_gin, K, v3["GinT"], True, name="Gin", blocks=blocks)
+            gout = green(para_gout, _vsub(K, q), v3["GoutT"], True, name="Gout", blocks=blocks)
+            diag = Graph([gin, gout, v3["diagram"]], properties=PolarId(para, response, k=q, t=v3["extT"]),
+                         operator=Prod(), name=name)
+            rows.append(dict(response=response, extT=v3["extT"], diagram=diag))
+    if rows:
+        rows = mergeby_df(rows, ["response", "extT"], name=name,
+                          getid=lambda g: PolarId(para, g[0]["response"], k=q, t=ext_t))
+    return rows

@@ -11,8 +11,11 @@ workload is their output, so their known answers belong in the suite:
     for a hand-built graph (test/computational_graph.jl:471-491);
   * the hand-built diagram of test/front_end.jl:221-310 and its Taylor coefficients, closed forms (-2+spin) f {1, 2, 2}.
 
-Not restated (no BASELINE configuration needs them): Parquet.vertex3 and Parquet.polarization, hence no Gamma3 /
-polarisation counts (test/front_end.jl:701-825)."""
+  * the 3-point vertex and the polarisation (vertex3.jl, polarization.jl; no BASELINE configuration needs them, they
+    are here for their counts, test/front_end.jl:701-825 with diagram_count.jl:23-36, :73-123): Gamma3 in the G^2 v
+    expansion, loops 1-3 = 1, 4+3s, 27+31s+5s^2; polarisation in the G^2 v expansion, loops 1-4 = s x Gamma3(loops-1);
+    in the g^2 v expansion without Fock sub-diagrams, loops 1-4 = 2, 2, 32, 326 (up-up + up-down) and 2, 2, 28, 274
+    (up-up alone)."""
 import math
 
 import numpy as np
@@ -25,7 +28,7 @@ from oracle.frontend import optimize as opt
 from oracle.frontend import parquet as pq
 from oracle.frontend import taylor
 from oracle.frontend.ids import (Alli, BareGreenId, BareInteractionId, ChargeCharge, Dynamic, GenericId, Girreducible, Instant,
-                                 NoFock, NoHartree, PHEr, PHr, PPr, UpDown, UpUp)
+                                 NoFock, NoHartree, PHEr, PHr, PPr, Proper, UpDown, UpUp)
 
 
 def _eval(graphs, leaf_value=lambda leaf: 1.0):
@@ -78,6 +81,74 @@ def test_sigma_diagram_counts(loops):
     raw, _ = fd.flatten(merged)
     orc = O.Oracle(raw)
     assert orc.eval(np.ones((orc.n_leaves, 1)), "eval")[0, 0] == w
+
+
+def count_ver3_G2v(loops, spin):  # benchmark/diagram_count.jl:23-36
+    return {0: 1, 1: 1, 2: 4 + 3 * spin, 3: 27 + 31 * spin + 5 * spin ** 2}[loops]
+
+
+def _gamma3(loops, flt):
+    # getGamma3, test/front_end.jl:702-729
+    fd.uidreset()
+    pq._ver4I.clear()
+    para = pq.DiagPara(type=pq.Ver3Diag, innerLoopNum=loops, isFermi=False, hasTau=True, filter=flt,
+                       interaction=(pq.Interaction(ChargeCharge, Instant),))
+    q, k_in = [0.0] * para.totalLoopNum, [0.0] * para.totalLoopNum
+    q[0], k_in[1] = 1.0, 1.0
+    return para, pq.vertex3(para, [q, k_in])
+
+
+@pytest.mark.parametrize("loops", [1, 2, 3])
+def test_vertex3_diagram_counts(loops):
+    # test/front_end.jl:732-750
+    para, rows = _gamma3(loops, (NoHartree, Girreducible, Proper))
+    assert all(r["extT"][0] == para.firstTauIdx and r["extT"][1] == para.firstTauIdx + 1 for r in rows)
+    merged = pq.mergeby_df(rows, [])
+    assert len(merged) == 1
+    (w,) = _eval([merged[0]["diagram"]])
+    assert w * (-1) ** loops == pytest.approx(count_ver3_G2v(loops, para.spin), rel=0, abs=1e-9)
+    assert [1, 10, 109][loops - 1] == count_ver3_G2v(loops, 2)
+    raw, _ = fd.flatten([merged[0]["diagram"]])
+    orc = O.Oracle(raw)
+    assert orc.eval(np.ones((orc.n_leaves, 1)), "eval")[0, 0] == w
+
+
+def _polar(loops, flt):
+    # getPolar, test/front_end.jl:759-781
+    fd.uidreset()
+    pq._ver4I.clear()
+    para = pq.DiagPara(type=pq.PolarDiag, innerLoopNum=loops, isFermi=False, hasTau=True, filter=flt,
+                       interaction=(pq.Interaction(ChargeCharge, Instant),))
+    q = [0.0] * para.totalLoopNum
+    q[0] = 1.0
+    return para, pq.polarization(para, q)
+
+
+@pytest.mark.parametrize("loops", [1, 2, 3, 4])
+def test_polarization_diagram_counts(loops):
+    # test/front_end.jl:783-825
+    spin = 2
+    sign = (-1) ** (loops - 1)
+    para, rows = _polar(loops, (NoHartree, Girreducible))  # G^2 v expansion
+    assert all(r["extT"] == (para.firstTauIdx, para.firstTauIdx + 1) for r in rows)
+    (w,) = _eval([pq.mergeby_df(rows, [])[0]["diagram"]])
+    assert w * spin * sign == pytest.approx(spin * count_ver3_G2v(loops - 1, spin), rel=0, abs=1e-9)
+    para, rows = _polar(loops, (NoHartree, NoFock))  # g^2 v expansion, up-up + up-down and up-up alone
+    total = pq.mergeby_df(rows, [])[0]["diagram"]
+    w, upup = _eval([total, rows[0]["diagram"]])
+    assert rows[0]["response"] == UpUp
+    assert w * spin * sign == pytest.approx([2, 2, 32, 326][loops - 1], rel=0, abs=1e-9)
+    assert upup * spin * sign == pytest.approx([2, 2, 28, 274][loops - 1], rel=0, abs=1e-9)
+    raw, _ = fd.flatten([total])
+    orc = O.Oracle(raw)
+    assert orc.eval(np.ones((orc.n_leaves, 1)), "eval")[0, 0] == w
+
+
+def test_polarization_with_an_explicit_proper_filter():
+    # test/front_end.jl:784: the builder accepts a filter that already holds Proper
+    from oracle.frontend.ids import Proper
+    para, rows = _polar(1, (Proper, NoHartree, NoFock))
+    assert len(rows) == 1 and not rows[0]["diagram"].subgraphs[0].subgraphs  # Pi0 = G G, two bare propagators
 
 
 def test_which_green_functions_and_self_energies_a_filter_allows():
@@ -246,7 +317,16 @@ def test_committed_workloads_are_what_the_front_ends_build():
         raw, _ = fd.flatten(graphs)
         ref = fd.RawGraph.load(os.path.join(here, "workloads", f"parquet_ver4_o{order}.npz"))
         assert all(np.array_equal(getattr(raw, k), getattr(ref, k)) for k in raw.__dataclass_fields__)
-    for name in ("parquet_ver4_o4", "gv_ver4_o4", "parquet_sigma_o3", "taylor_sigma_o3"):
+    for order, name, build in ((3, "parquet_ver3_o3", lambda o: pq.vertex3(pq.DiagPara(type=pq.Ver3Diag, innerLoopNum=o))),
+                               (4, "parquet_polar_o4", lambda o: pq.polarization(pq.DiagPara(type=pq.PolarDiag, innerLoopNum=o)))):
+        fd.uidreset()
+        pq._ver4I.clear()
+        graphs = [r["diagram"] for r in build(order)]
+        opt.optimize(graphs)
+        raw, _ = fd.flatten(graphs)
+        ref = fd.RawGraph.load(os.path.join(here, "workloads", name + ".npz"))
+        assert all(np.array_equal(getattr(raw, k), getattr(ref, k)) for k in raw.__dataclass_fields__)
+    for name in ("parquet_ver4_o4", "gv_ver4_o4", "parquet_sigma_o3", "taylor_sigma_o3", "parquet_ver3_o4", "parquet_polar_o5"):
         raw = fd.RawGraph.load(os.path.join(here, "workloads", name + ".npz"))
         orc = O.Oracle(raw)
         ones = orc.eval(np.ones((orc.n_leaves, 1)))[:, 0]

@@ -133,7 +133,8 @@ def test_term_blocks_every_operand_count(term_len):
 
 
 @pytest.mark.parametrize("name", ["gv_sigma_o3", "gv_ver4_o2", "gv_ver4_o3", "gv_sigma_o5", "parquet_sigma_o2", "parquet_sigma_o3",
-                                  "parquet_sigma_o4", "parquet_ver4_o3", "taylor_sigma_o3"])
+                                  "parquet_sigma_o4", "parquet_ver4_o3", "taylor_sigma_o3", "parquet_ver3_o3", "parquet_ver3_o4",
+                                  "parquet_polar_o4", "parquet_polar_o5"])
 @pytest.mark.parametrize("spt,backend", [(2, VM), (4, VM), (1, JIT), (2, JIT)])
 def test_real_workload_graphs(name, spt, backend):
     import os

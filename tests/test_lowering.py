@@ -81,7 +81,8 @@ def test_term_blocks_every_operand_count(term_len):
         assert cnt["terms"] == 2 * 70
 
 
-@pytest.mark.parametrize("name", ["gv_sigma_o2", "gv_sigma_o3", "gv_sigma_o4", "gv_ver4_o1", "gv_ver4_o2", "gv_ver4_o3", "gv_ver4I_o3"])
+@pytest.mark.parametrize("name", ["gv_sigma_o2", "gv_sigma_o3", "gv_sigma_o4", "gv_ver4_o1", "gv_ver4_o2", "gv_ver4_o3", "gv_ver4I_o3",
+                                  "parquet_ver3_o2", "parquet_ver3_o3", "parquet_polar_o3", "parquet_polar_o4"])
 def test_real_workload_graphs(name):
     import json
     import os

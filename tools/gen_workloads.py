@@ -62,6 +62,28 @@ def taylor_workloads(manifest):
              manifest, optimize=False)
 
 
+def ver3_polar_workloads(manifest):
+    """The other two Parquet front ends (vertex3.jl, polarization.jl) with their default parameters + optimize!, as
+    parity cases of the evaluator: not BASELINE configurations, their all-leaves-one values are the diagram counts
+    of test/front_end.jl:701-825 up to the spin / sign conventions written there."""
+    from oracle.frontend import parquet as pq
+
+    def ver3(order):
+        pq._ver4I.clear()
+        return [r["diagram"] for r in pq.vertex3(pq.DiagPara(type=pq.Ver3Diag, innerLoopNum=order))]
+
+    def polar(order):
+        pq._ver4I.clear()
+        return [r["diagram"] for r in pq.polarization(pq.DiagPara(type=pq.PolarDiag, innerLoopNum=order))]
+
+    for order in (2, 3, 4):
+        emit(f"parquet_ver3_o{order}", lambda o=order: ver3(o),
+             f"Parquet.vertex3(DiagPara(type=Ver3Diag, innerLoopNum={order})) + optimize!  (src/frontend/parquet/vertex3.jl:20-112)", manifest)
+    for order in (3, 4, 5):
+        emit(f"parquet_polar_o{order}", lambda o=order: polar(o),
+             f"Parquet.polarization(DiagPara(type=PolarDiag, innerLoopNum={order})) + optimize!  (src/frontend/parquet/polarization.jl:16-127)", manifest)
+
+
 def leaf_sidecars():
     """workloads/<name>.leaves.npz: the `leafstates` metadata (frontends.jl:175-232) of a workload's leaves, in leafVal
     order, for the on-device leaf generation (N1).  The graphs are rebuilt and must flatten to the committed arrays."""
@@ -116,6 +138,13 @@ def main():
         with open(os.path.join(OUT, "MANIFEST.json"), "w") as fh:
             json.dump(manifest, fh, indent=1, sort_keys=True)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "ver3polar":  # add / refresh the vertex3 / polarization workloads only
+        with open(os.path.join(OUT, "MANIFEST.json")) as fh:
+            manifest = json.load(fh)
+        ver3_polar_workloads(manifest)
+        with open(os.path.join(OUT, "MANIFEST.json"), "w") as fh:
+            json.dump(manifest, fh, indent=1, sort_keys=True)
+        return
     manifest = {}
     for order in (2, 3, 4, 5, 6):
         emit(f"gv_sigma_o{order}", lambda o=order: gv.diagsGV("sigma", o),
@@ -145,6 +174,7 @@ def main():
              f"Parquet.vertex4(DiagPara(type=Ver4Diag, innerLoopNum={order})) + optimize!  (example/benchmark.jl:13,23-25)",
              manifest)
     taylor_workloads(manifest)
+    ver3_polar_workloads(manifest)
     with open(os.path.join(OUT, "MANIFEST.json"), "w") as fh:
         json.dump(manifest, fh, indent=1, sort_keys=True)
     leaf_sidecars()
