@@ -783,6 +783,9 @@ int jit_launch(fdg_program *h, DeviceState &ds, int dev, int spt, bool acc, cons
     if (v->plan.persistent) max_grid = std::min<int64_t>(max_grid, (int64_t)ds.sm_count * 16);
     const int64_t ld_cross = max_grid * per_block;
     if (bulk) max_grid = std::min<int64_t>(max_grid, ds.sm_count);  // one block per SM walks the tiles
+    if (bulk) {  // experiment (tools/exp_lanes.py): fewer blocks than SMs, so that launch sequences on two streams share the device
+        if (const char *e = getenv("FDG_JIT_BULK_GRID")) max_grid = std::max<int64_t>(1, std::min<int64_t>(max_grid, atoll(e)));
+    }
     if (v->plan.n_cross > 0) {
         const size_t need = (size_t)v->plan.n_cross * ld_cross * es;
         if (need > ss.cross_bytes) {
