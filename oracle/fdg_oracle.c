@@ -23,9 +23,9 @@
  *
  * Parity status: pinned against the reference's own known-answer tests: tests/test_oracle_kat.py holds
  * test/compiler.jl:4-15 (4.5), test/computational_graph.jl:874-887 (26, 27, 702), the derivative known answers
- * of test/computational_graph.jl:930-1071 (through the restated Taylor expansion, not the reference's graph-level
- * AD) and test/taylor.jl:42-56, :96-112; tests/test_frontends.py holds the diagram counts and filters of
- * test/front_end.jl:186-219, :398-443, :446-598, :600-700, :221-310.  Power{N>=4}, ComplexF64 and random-leaf values through the compiled path have no pinned
+ * of test/computational_graph.jl:930-1071 (through the restated graph-level AD, oracle/frontend/ad.py, and again
+ * through the restated Taylor expansion) and test/taylor.jl:42-56, :96-112; tests/test_frontends.py holds the
+ * diagram counts and filters of test/front_end.jl:186-219, :398-443, :446-598, :600-825, :221-310.  Power{N>=4}, ComplexF64 and random-leaf values through the compiled path have no pinned
  * numbers in the reference ("parity unpinned" for those sub-cases; covered by emitter-vs-interpreter-
  * vs-exact-rational self-consistency).
  */

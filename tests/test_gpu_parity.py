@@ -721,3 +721,22 @@ def test_bulk_form_is_chosen_for_big_batches_and_needs_aligned_rows(monkeypatch)
     ev.eval_device(dleaf.data_ptr(), B + 2, root2.data_ptr(), B, B, s)
     torch.cuda.synchronize()
     assert not ev.jit_last()["bulk"] and root2.cpu().numpy().tobytes() == big.tobytes()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("loops,orders", [(2, (2, 1)), (3, (1, 1))])
+def test_derivative_graphs_of_a_self_energy(loops, orders, backend):
+    """Another producer of evaluator inputs: the reference's graph-level AD (build_derivative_graph,
+    operation.jl:478-543, restated in oracle/frontend/ad.py and pinned on the reference's known answers in the CPU suite)
+    applied to the Parquet self-energy; every derivative graph of every root is a root of the compiled program, the dual
+    leaves are ordinary leaves.  Device bytes == oracle bytes."""
+    from oracle.frontend import ad, parquet as pq
+
+    fd.uidreset()
+    pq._ver4I.clear()
+    graphs = [r["diagram"] for r in pq.sigma(pq.DiagPara(type=pq.SigmaDiag, innerLoopNum=loops))]
+    dual = ad.build_derivative_graph(graphs, orders)
+    root_ids = {g.id for g in graphs}
+    roots = list(graphs) + [d for (nid, _), d in sorted(dual.items(), key=lambda kv: (kv[0][0], kv[0][1])) if nid in root_ids]
+    assert len(roots) == len(graphs) * (1 + sum(orders))
+    _parity(roots, batch=3000, backend=backend)

@@ -428,3 +428,18 @@ def test_julia_shim_struct_layouts_and_call_sequence(tmp_path):
                     "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib)], check=True, capture_output=True, text=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split("\n")
     assert out[0] == "L=2 R=1 leafmap=0,1 last_root=0 abi=1" and out[1] == "ok"
+
+
+def test_derivative_graphs_lower_and_evaluate():
+    """Graphs made by the restated graph-level AD (oracle/frontend/ad.py; operation.jl:478-543) go through the lowering
+    like any other: placeholders filled in place, sums of product-rule terms, dual leaves as ordinary leaves."""
+    from oracle.frontend import ad, parquet as pq
+
+    fd.uidreset()
+    pq._ver4I.clear()
+    graphs = [r["diagram"] for r in pq.sigma(pq.DiagPara(type=pq.SigmaDiag, innerLoopNum=2))]
+    dual = ad.build_derivative_graph(graphs, (2, 1))
+    root_ids = {g.id for g in graphs}
+    roots = list(graphs) + [d for (nid, _), d in sorted(dual.items(), key=lambda kv: (kv[0][0], kv[0][1])) if nid in root_ids]
+    ev, _ = _check(roots)
+    assert ev.n_roots == 8

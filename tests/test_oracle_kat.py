@@ -195,7 +195,7 @@ def test_taylor_workload_checksums():
 def test_derivative_known_answers_through_the_taylor_series():
     """reference test/computational_graph.jl:930-1071 (`forwardAD_root!`, `build_derivative_graph`): explicit leaf vectors
     -> 120 / 5 / 1, 570 / 3 / 1, 120 / 2 / 0, 300, 3840, 480, 1002, 426, 90, 0, 5568, 1003, 3708, 1638, 234.  The
-    reference's graph-level AD is not restated; the same numbers are pinned on the restated Taylor-series expansion, which
+    reference's graph-level AD is restated and pinned further down; here the same numbers are pinned on the restated Taylor-series expansion, which
     is what the Taylor-AD workloads (BASELINE config 5) are made with: the derivative of order n is n! times the Taylor
     coefficient, a leaf's own first derivative is the seed of the test's leaf vector and its higher derivatives are 0."""
     import math
@@ -255,3 +255,131 @@ def test_derivative_known_answers_through_the_taylor_series():
     assert [derivative(s1, o, leaf) for o in ((1, 0, 0), (2, 0, 0), (3, 0, 0), (3, 1, 0))] == [1002.0, 426.0, 90.0, 0.0]
     assert [derivative(s0, o, leaf) for o in ((1, 0, 0), (2, 0, 0), (3, 0, 0), (3, 1, 0), (3, 2, 0))] == [5568.0, 3708.0, 1638.0, 234.0, 0.0]
     assert [derivative(s0r, o, leaf) for o in ((1, 0, 0), (2, 0, 0), (3, 0, 0), (3, 1, 0), (3, 2, 0))] == [1003.0, 426.0, 90.0, 0.0, 0.0]
+
+
+def _eval_by_id(graph, leafmap, leaf):
+    """Graphs.eval!(g, leafmap, leaf) (eval.jl:15-39) on Graph objects: a node without subgraphs reads leaf[leafmap[id]]."""
+    import math
+
+    import fdgraph_b200 as fd
+
+    val = {}
+    for node in fd.graph.post_order_unique([graph]):
+        if not node.subgraphs:
+            val[id(node)] = leaf[leafmap[node.id] - 1]
+            continue
+        terms = [val[id(s)] * f for s, f in zip(node.subgraphs, node.subgraph_factors)]
+        if isinstance(node.operator, fd.Sum):
+            val[id(node)] = sum(terms)
+        elif isinstance(node.operator, fd.Prod):
+            val[id(node)] = math.prod(terms)
+        else:
+            val[id(node)] = terms[0] ** node.operator.N
+    return val[id(graph)]
+
+
+def _compiled_by_id(graphs, leafmap, leaf):
+    """The same values through flatten + the C oracle in emitter order (what Compilers.compile would evaluate)."""
+    import fdgraph_b200 as fd
+
+    raw, nodes = fd.flatten(list(graphs))
+    orc = O.Oracle(raw)
+    vec = np.array([[leaf[leafmap[nodes[i].id] - 1]] for i in orc.leaf_nodes], dtype=np.float64).reshape(orc.n_leaves, 1)
+    return [float(x) for x in orc.eval(vec)[:, 0]]
+
+
+def test_forwardAD_root_known_answers():
+    """reference test/computational_graph.jl:930-987, with the restated forwardAD_root! (oracle/frontend/ad.py)."""
+    import fdgraph_b200 as fd
+    from oracle.frontend import ad
+
+    fd.uidreset()
+    g1, g2 = fd.Graph([]), fd.Graph([])
+    g3 = fd.Graph([], factor=2.0)
+    F3 = g1 + g2
+    F2 = fd.graph.linear_combination([g1, g3, F3], [2, 1, 3])
+    F1 = fd.Graph([g1, F2, F3], operator=fd.Prod(), subgraph_factors=[3.0, 1.0, 1.0])
+    k = (True,)
+    kg1, kg2, kg3 = (g1.id, k), (g2.id, k), (g3.eldest().id, k)
+    kF1, kF2, kF3 = (F1.id, k), (F2.id, k), (F3.id, k)
+    dual = ad.forwardAD_root([F1])
+    assert dual[kF3].subgraphs == [dual[kg1], dual[kg2]]
+    assert dual[kF2].subgraphs == [dual[kg1], dual[kg3], dual[kF3]]
+    assert all(d.name != ad.UNDEFINED for d in dual.values())
+    leafmap = {g1.id: 1, g2.id: 2, g3.eldest().id: 3, dual[kg1].id: 4, dual[kg2].id: 5, dual[kg3].id: 6}
+    for leaf, want in (([1.0, 1.0, 1.0, 1.0, 0.0, 0.0], (120.0, 5.0, 1.0)), ([5.0, -1.0, 2.0, 0.0, 1.0, 0.0], (570.0, 3.0, 1.0)),
+                       ([5.0, -1.0, 2.0, 0.0, 0.0, 1.0], (120.0, 2.0, 0.0))):
+        assert tuple(_eval_by_id(dual[key], leafmap, leaf) for key in (kF1, kF2, kF3)) == want
+        assert tuple(_compiled_by_id([dual[kF1], dual[kF2], dual[kF3]], leafmap, leaf)) == want
+    F0 = F1 * F3
+    kF0 = (F0.id, k)
+    dual1 = ad.forwardAD_root([F0])
+    leafmap.update({dual1[kg1].id: 4, dual1[kg2].id: 5, dual1[kg3].id: 6})
+    assert _eval_by_id(dual1[kF0], leafmap, [1.0, 1.0, 1.0, 1.0, 0.0, 0.0]) == 300.0
+    assert _eval_by_id(dual1[kF0], leafmap, [5.0, -1.0, 2.0, 0.0, 1.0, 0.0]) == 3840.0
+    leaf = [5.0, -1.0, 2.0, 0.0, 0.0, 1.0]
+    assert _eval_by_id(dual1[kF0], leafmap, leaf) == 480.0
+    F0_r1 = F1 + F3
+    dual2 = ad.forwardAD_root([F0, F0_r1])
+    leafmap.update({dual2[kg1].id: 4, dual2[kg2].id: 5, dual2[kg3].id: 6})
+    assert _eval_by_id(dual2[kF0], leafmap, leaf) == 480.0
+    assert _eval_by_id(dual2[(F0_r1.id, k)], leafmap, leaf) == 120.0
+    assert _compiled_by_id([dual2[kF0], dual2[(F0_r1.id, k)]], leafmap, leaf) == [480.0, 120.0]
+
+
+def test_build_derivative_graph_known_answers():
+    """reference test/computational_graph.jl:988-1071: orders (3, 2, 2), before and after burn_from_targetleaves!."""
+    import itertools
+
+    import fdgraph_b200 as fd
+    from oracle.frontend import ad
+
+    fd.uidreset()
+    g1, g2 = fd.Graph([]), fd.Graph([])
+    g3 = fd.Graph([], factor=2.0)
+    l3 = g3.eldest()
+    F3 = g1 + g2
+    F2 = fd.graph.linear_combination([g1, g3, F3], [2, 1, 3])
+    F1 = fd.Graph([g1, F2, F3], operator=fd.Prod(), subgraph_factors=[3.0, 1.0, 1.0])
+    orders = (3, 2, 2)
+    leaf = [5.0, -1.0, 2.0, 1.0, 1.0, 1.0, 0.0]
+
+    def leafmap_of(dual):
+        leafmap = {g1.id: 1, g2.id: 2, l3.id: 3, dual[(g1.id, (1, 0, 0))].id: 4, dual[(g2.id, (0, 1, 0))].id: 5,
+                   dual[(l3.id, (0, 0, 1))].id: 6}
+        burn = []
+        for order in itertools.product(*[range(o + 1) for o in orders]):
+            if order == (0, 0, 0):
+                continue
+            for g in (g1, g2, l3):
+                if dual[(g.id, order)].id not in leafmap:
+                    leafmap[dual[(g.id, order)].id] = 7
+                    burn.append(dual[(g.id, order)].id)
+        return leafmap, burn
+
+    dual = ad.build_derivative_graph(F1, orders)
+    leafmap, burn = leafmap_of(dual)
+    keys = [(F1.id, o) for o in ((1, 0, 0), (2, 0, 0), (3, 0, 0), (3, 1, 0))]
+    want = [1002.0, 426.0, 90.0, 0.0]
+    assert [_eval_by_id(dual[key], leafmap, leaf) for key in keys] == want
+    assert _compiled_by_id([dual[key] for key in keys], leafmap, leaf) == want
+    c0 = ad.burn_from_targetleaves([dual[key] for key in keys], burn)
+    if c0 is not None:
+        leafmap[c0] = 7
+    assert [_eval_by_id(dual[key], leafmap, leaf) for key in keys] == want
+    # a vector of graphs
+    F0 = F1 * F3
+    F0_r1 = F1 + F3
+    dual = ad.build_derivative_graph([F0, F0_r1], orders)
+    leafmap, burn = leafmap_of(dual)
+    olist = ((1, 0, 0), (2, 0, 0), (3, 0, 0), (3, 1, 0), (3, 2, 0))
+    want0, want1 = [5568.0, 3708.0, 1638.0, 234.0, 0.0], [1003.0, 426.0, 90.0, 0.0, 0.0]
+    assert [_eval_by_id(dual[(F0.id, o)], leafmap, leaf) for o in olist] == want0
+    assert [_eval_by_id(dual[(F0_r1.id, o)], leafmap, leaf) for o in olist] == want1
+    roots = [dual[(F0.id, o)] for o in olist] + [dual[(F0_r1.id, o)] for o in olist]
+    assert _compiled_by_id(roots, leafmap, leaf) == want0 + want1
+    c0 = ad.burn_from_targetleaves(roots, burn)
+    if c0 is not None:
+        leafmap[c0] = 7
+    assert [_eval_by_id(dual[(F0.id, o)], leafmap, leaf) for o in olist] == want0
+    assert [_eval_by_id(dual[(F0_r1.id, o)], leafmap, leaf) for o in olist] == want1
