@@ -251,6 +251,31 @@ def test_optimize_on_a_hand_built_graph():
     assert len([n for n in fd.graph.post_order_unique([h]) if not n.subgraphs]) <= 2
 
 
+def test_optimize_reaches_the_expected_graph_of_the_reference_test():
+    """test/computational_graph.jl:471-491 and :676-695 with their own graph and expected result
+    _h = 2 (-28 g1 + 3 g1') + 3 g1': the chains 2 * 3 * 5 are flattened into factors, the two leaves stay apart (the
+    reference tells them apart by a user operator, here by their properties), equal sub-graphs are merged."""
+    fd.uidreset()
+    g1 = Graph([])
+    g2 = 2 * g1
+    g3 = Graph([g2], subgraph_factors=[3], operator=Prod())
+    g4 = Graph([g3], subgraph_factors=[5], operator=Prod())
+    g5 = Graph([], factor=3.0, properties=BareGreenId(k=[1.0], t=(1, 2)))
+    h0 = Graph([g1, g4, g5], subgraph_factors=[2, -1, 1])
+    h1 = Graph([h0], operator=Prod(), subgraph_factors=[2])
+    h = Graph([h1, g5])
+    g1p = g5.eldest()
+    values = {g1.id: 0.7391, g1p.id: -1.1875}
+    before = _eval([h], lambda leaf: values[leaf.id])[0]
+    assert before == pytest.approx(2 * (-28 * values[g1.id] + 3 * values[g1p.id]) + 3 * values[g1p.id], rel=1e-15)
+    (o,) = opt.optimize([h])
+    assert isinstance(o.operator, Sum) and o.subgraph_factors == [2.0, 3.0] and len(o.subgraphs) == 2
+    inner, leaf = o.subgraphs
+    assert isinstance(inner.operator, Sum) and inner.subgraph_factors == [-28.0, 3.0]
+    assert [s.id for s in inner.subgraphs] == [g1.id, g1p.id] and leaf is inner.subgraphs[1] and not leaf.subgraphs
+    assert _eval([o], lambda leaf: values[leaf.id])[0] == pytest.approx(before, rel=1e-15)
+
+
 def _getdiagram(spin=2.0, D=3, Nk=4, Nt=2):
     """test/front_end.jl:221-263 (the direct part of a two-bubble diagram)."""
     fd.uidreset()
