@@ -955,6 +955,8 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
         if (const char *x = getenv("FDG_JIT_BULK_GUARD")) bulk_guard = atoi(x) != 0, bulk_guard_mode = atoi(x);
         int bulk_prefetch = 0;  // groups ahead of the ring that are prefetched into L2 (experiment)
         if (const char *x = getenv("FDG_JIT_BULK_PREFETCH")) bulk_prefetch = std::max(0, atoi(x));
+        int bulk_psleep = 0;  // ns a producer warp sleeps after a failed poll of an empty-slot barrier (experiment)
+        if (const char *x = getenv("FDG_JIT_BULK_PSLEEP")) bulk_psleep = std::max(0, atoi(x));
         int bulk_hint = 1000000;  // ns
         if (const char *x = getenv("FDG_JIT_BULK_HINT")) bulk_hint = std::max(0, atoi(x));
         if (bulk) {
@@ -1384,7 +1386,8 @@ static int plan_from_ir(const Lowered &low, const std::vector<IrOp> &ir, int spt
                   << "\tmul.lo.u32 %r19, %r18, %r8;\n"                                                               // bytes of the group
                   << "\tmov.u32 %r21, 0;\n"
                   << "FDG_PWAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 %p7, [%r15+" << 8 * NG << "], %r11, " << bulk_hint << ";\n\t@%p7 bra FDG_PGO;\n"
-                  << "\tadd.u32 %r21, %r21, 1;\n\tsetp.lt.u32 %p7, %r21, 4096;\n\t@%p7 bra FDG_PWAIT;\n\ttrap;\n"
+                  << (bulk_psleep > 0 ? "\tnanosleep.u32 " + std::to_string(bulk_psleep) + ";\n" : std::string())  // experiment: idle producers poll less often
+                  << "\tadd.u32 %r21, %r21, 1;\n\tsetp.lt.u32 %p7, %r21, " << (bulk_psleep > 0 ? 1u << 22 : 4096u) << ";\n\t@%p7 bra FDG_PWAIT;\n\ttrap;\n"
                   << "FDG_PGO:\n"
                   // every producer warp arrives on the full barrier of every group, rows or not (count 4): a phase cannot end
                   // before all four have passed their wait for it, so the parity a warp polls is never more than one phase old
