@@ -205,13 +205,55 @@ def remove_all_zero_valued_subgraphs(graphs: Sequence[Graph]) -> Sequence[Graph]
     return graphs
 
 
+def remove_duplicated_nodes(root: Graph) -> Graph:
+    """optimize.jl:345-390 (the method optimize!(level > 0) calls on Graph(graphs)): top-down, a node equivalent
+    (isequiv modulo id / name / weight: same operator, orders, properties and the same MULTISET of (subgraph, factor)
+    pairs) to one already kept is replaced by it in its parent; the search over the kept nodes is by structural hash here
+    instead of the reference's scan of all of them."""
+    unique: Dict[int, Graph] = {}
+    buckets: Dict[int, List[Graph]] = {}
+    hv: Dict[int, int] = {}
+    for n in post_order_unique([root]):
+        hv[id(n)] = _node_hash(n, hv, with_name=False)
+
+    def process(node: Graph) -> Graph:
+        # (explicit stack: the graphs are deeper than Python's recursion limit likes)
+        result: Dict[int, Graph] = {}
+        stack = [(node, 0)]
+        while stack:
+            n, i = stack.pop()
+            if i == 0:
+                if n.id in unique:
+                    result[id(n)] = unique[n.id]
+                    continue
+                rep = next((g for g in buckets.get(hv[id(n)], ()) if isequiv(n, g, "id", "name", "weight")), None)
+                if rep is not None:
+                    result[id(n)] = rep
+                    continue
+            if i > 0:
+                n.subgraphs[i - 1] = result[id(n.subgraphs[i - 1])]
+            if i < len(n.subgraphs):
+                stack.append((n, i + 1))
+                stack.append((n.subgraphs[i], 0))
+                continue
+            unique[n.id] = n
+            buckets.setdefault(hv[id(n)], []).append(n)
+            result[id(n)] = n
+        return result[id(node)]
+
+    process(root)
+    return root
+
+
 def optimize(graphs: Sequence[Graph], level: int = 0) -> Sequence[Graph]:
-    """`optimize!(graphs)` (optimize.jl:16-36), level 0 -- the level every example and test of the reference uses."""
+    """`optimize!(graphs)` (optimize.jl:16-36).  Level 0 is what every example and front-end test of the reference uses;
+    level > 0 merges equivalent inner nodes too (remove_duplicated_nodes! on a root above the graphs)."""
     if not graphs:
         return graphs
     if level > 0:
-        raise NotImplementedError("optimize!(level>0) (remove_duplicated_nodes!) is not restated")
-    remove_duplicated_leaves(graphs)
+        remove_duplicated_nodes(Graph(list(graphs)))
+    else:
+        remove_duplicated_leaves(graphs)
     flatten_all_chains(graphs)
     merge_all_linear_combinations(graphs)
     remove_all_zero_valued_subgraphs(graphs)

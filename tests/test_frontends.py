@@ -251,6 +251,40 @@ def test_optimize_on_a_hand_built_graph():
     assert len([n for n in fd.graph.post_order_unique([h]) if not n.subgraphs]) <= 2
 
 
+@pytest.mark.parametrize("order", [2, 3])
+def test_optimize_level_one_merges_equivalent_nodes_and_keeps_the_values(order):
+    """optimize!(level = 1) = remove_duplicated_nodes! (optimize.jl:16-36, :345-390) on the Parquet 4-point vertex: the
+    values do not move, fewer nodes are left than at level 0's start, and the product's own merging of common
+    sub-expressions (fdg_options.cse, arithmetic only: it ignores the diagram ids the reference's isequiv compares, and
+    keeps operand order, which isequiv does not) lands in the same region -- order 3: 4659 statements, 3072 after the
+    reference's pass over the level-0 graph, 2843 after the product's."""
+    def build():
+        fd.uidreset()
+        pq._ver4I.clear()
+        return [r["diagram"] for r in pq.vertex4(pq.DiagPara(type=pq.Ver4Diag, innerLoopNum=order))]
+
+    g = build()
+    want, ones = _eval(g, _leaf_by_content), _eval(g)
+    n_start = len(fd.graph.post_order_unique(g))
+    opt.optimize(g, level=1)
+    assert _eval(g, _leaf_by_content) == pytest.approx(want, rel=1e-12) and _eval(g) == pytest.approx(ones, rel=0, abs=1e-9)
+    assert len(fd.graph.post_order_unique(g)) < n_start / 3
+    # the same pass over the graph optimize!(level = 0) leaves, beside the product's merging of that graph
+    g0 = build()
+    opt.optimize(g0, level=0)
+    raw0, _ = fd.flatten(g0)
+    n0 = O.Oracle(raw0).n_stmts
+    merged_by_product = n0 - fd.compile_raw(raw0, cse=True).stats["cse_removed"]
+    want0 = _eval(g0, _leaf_by_content)
+    opt.remove_duplicated_nodes(Graph(list(g0)))
+    assert _eval(g0, _leaf_by_content) == pytest.approx(want0, rel=1e-12)
+    n1 = O.Oracle(fd.flatten(g0)[0]).n_stmts
+    assert n1 < n0 and merged_by_product < n0
+    assert abs(merged_by_product - n1) < 0.1 * n0
+    if order == 3:
+        assert (n0, n1, merged_by_product) == (4659, 3072, 2843)
+
+
 def test_optimize_reaches_the_expected_graph_of_the_reference_test():
     """test/computational_graph.jl:471-491 and :676-695 with their own graph and expected result
     _h = 2 (-28 g1 + 3 g1') + 3 g1': the chains 2 * 3 * 5 are flattened into factors, the two leaves stay apart (the
