@@ -1,4 +1,5 @@
-"""Restated graph-level automatic differentiation (forwardAD_root!, build_derivative_graph, burn_from_targetleaves!).
+"""Restated graph-level automatic differentiation (forwardAD_root!, build_derivative_graph, burn_from_targetleaves!; at the
+end of the file the older forwardAD / node_derivative / backAD).
 TEST / WORKLOAD INFRASTRUCTURE -- a producer of evaluator inputs (derivative graphs are compiled and evaluated like any
 other graph), not part of the hot path.
 
@@ -7,7 +8,7 @@ Reference: src/computational_graph/operation.jl:331-338 (insert_dualDict! is not
            src/computational_graph/optimize.jl:405-456 (burn_from_targetleaves!),
            src/computational_graph/abstractgraph.jl:14 (decrement_power).
 
-Pinned on the reference's own known answers (test/computational_graph.jl:930-1071) in tests/test_oracle_kat.py.
+Pinned on the reference's own known answers (test/computational_graph.jl:887-1071) in tests/test_oracle_kat.py.
 
 `dual` maps (node id, key) to the derivative graph of that node; key is a tuple of N booleans in forwardAD_root! (one
 true entry: the variable differentiated) and a tuple of N orders in build_derivative_graph.  A node whose derivative is
@@ -190,3 +191,178 @@ def burn_from_targetleaves(graphs: Sequence[Graph], targetleaves_id: Sequence[in
             has_c0 = True
             g.id, g.operator, g.weight = c1.id, Unitary(), 0.0
     return c1.id if has_c0 else None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the older derivative builders: operation.jl:12-44 (linear_combination_number_with_graph), :53-122 (forwardAD),
+# :130-147 (all_parent), :161-224 (node_derivative), :226-281 (recursive_backAD!, backAD).  A derivative is a Graph or
+# a plain number (`Union{F, Graph}` in the reference); None stands for the reference's `nothing`.
+# Known answers: test/computational_graph.jl:901-928.
+# ---------------------------------------------------------------------------------------------------------
+
+
+def _is_number(x) -> bool:
+    return isinstance(x, (int, float))
+
+
+def _times(a, b):
+    """`*` of the reference between numbers and graphs (graph.jl:136-163, :403-415)."""
+    if _is_number(a) and _is_number(b):
+        return a * b
+    if _is_number(b):
+        return a * b          # Graph.__mul__(number)
+    return a * b if not _is_number(a) else b * a  # graph * graph, or number * graph -> Graph.__mul__(number)
+
+
+def linear_combination_number_with_graph(g: list, coeff: Optional[list] = None):
+    if coeff is None:
+        coeff = [1.0] * len(g)
+    assert len(g) == len(coeff)
+    subgraphs, subcoeff, subnumber = [], [], None
+    for child, c in zip(g, coeff):
+        if _is_number(child):
+            subnumber = child * c if subnumber is None else subnumber + child * c
+        else:
+            assert isinstance(child, Graph), "The type of subgraphs in derivative is incorrect!"
+            subgraphs.append(child)
+            subcoeff.append(c)
+    if subgraphs:
+        if subnumber is not None:
+            subgraphs.append(constant_graph(float(subnumber)))
+            subcoeff.append(1.0)
+        return linear_combination(subgraphs, subcoeff)
+    return subnumber
+
+
+def forwardAD(diag: Graph, ID: int):
+    """d diag / d (the leaf with id ID), forward propagation (operation.jl:53-122)."""
+    from fdgraph_b200.graph import post_order_unique
+
+    dual: Dict[int, object] = {}
+    rootid = -1
+    for d in post_order_unique([diag]):
+        rootid = d.id
+        if d.id in dual:
+            continue
+        if not d.subgraphs:
+            if d.id == ID:
+                dual[d.id] = 1.0
+            continue
+        op = d.operator
+        if isinstance(op, Sum):
+            children, coeff = [], []
+            for sub, f in zip(d.subgraphs, d.subgraph_factors):
+                if sub.id in dual:
+                    children.append(dual[sub.id])
+                    coeff.append(f)
+            dum = linear_combination_number_with_graph(children, coeff)
+            if dum is not None:
+                dual[d.id] = dum
+        elif isinstance(op, Prod):
+            factor, children = 1.0, []
+            for si, sub in enumerate(d.subgraphs):
+                if sub.id not in dual:
+                    continue
+                factor *= d.subgraph_factors[si]
+                child = dual[sub.id]
+                for sj, other in enumerate(d.subgraphs):
+                    if si != sj:
+                        child = _times(child, other)
+                children.append(child)
+            dum = linear_combination_number_with_graph(children)
+            if dum is not None:
+                dual[d.id] = _times(factor, dum)
+        elif isinstance(op, Power):
+            if d.eldest().id not in dual:
+                continue
+            children = [Graph(d.subgraphs, subgraph_factors=[float(op.N)], operator=_decrement_power(op))]
+            child = dual[d.eldest().id]
+            children.append(constant_graph(float(child)) if _is_number(child) else child)
+            dual[d.id] = Graph(children, subgraph_factors=[d.subgraph_factors[0], 1.0], operator=Prod())
+        else:
+            raise NotImplementedError("not implemented!")
+    if not dual:
+        return 0.0
+    return dual.get(rootid)  # (the reference indexes dual[rootid]: a KeyError there when the root does not depend on ID)
+
+
+def node_derivative(g1: Graph, g2: Graph):
+    """The LOCAL derivative d g1 / d g2 (only g1's own subgraphs are looked at), operation.jl:161-224."""
+    import copy
+
+    if not g1.subgraphs:
+        return None
+    op = g1.operator
+    if isinstance(op, Sum):
+        hits = [f for s, f in zip(g1.subgraphs, g1.subgraph_factors) if s.id == g2.id]
+        return float(sum(hits)) if hits else None
+    if isinstance(op, Prod):
+        count, subgraphs, factors, factor = 0, [], [], None
+        for s, f in zip(g1.subgraphs, g1.subgraph_factors):
+            if s.id == g2.id:
+                count += 1
+                if count == 1:
+                    factor = f          # the first g2 is the one removed
+                    continue
+            subgraphs.append(s)
+            factors.append(f)
+        if count == 0:
+            return None
+        if not subgraphs:
+            return factor
+        factors[0] *= count * factor
+        g = copy.copy(g1)               # deepcopy in the reference; the subgraphs are replaced right away
+        g.subgraphs, g.subgraph_factors = subgraphs, factors
+        return g
+    if isinstance(op, Power):
+        if g1.eldest().id == g2.id:
+            return Graph(g1.subgraphs, subgraph_factors=[f * op.N for f in g1.subgraph_factors], operator=_decrement_power(op))
+        return None
+    return None
+
+
+def all_parent(diag: Graph) -> Dict[int, List[Graph]]:
+    from fdgraph_b200.graph import post_order_unique
+
+    nodes = post_order_unique([diag])
+    result: Dict[int, List[Graph]] = {}
+    for d in nodes:
+        if d.id in result:
+            continue
+        parents, seen = [], set()
+        for g in nodes:
+            if g.id not in seen and any(s.id == d.id for s in g.subgraphs):
+                parents.append(g)
+                seen.add(g.id)
+        result[d.id] = parents
+    return result
+
+
+def backAD(diag: Graph) -> Dict[Tuple[int, int], Graph]:
+    """(root id, leaf id) -> d root / d leaf for every non-constant leaf, backward propagation (operation.jl:226-281)."""
+    dual: Dict[int, object] = {}
+    result: Dict[Tuple[int, int], Graph] = {}
+    parents = all_parent(diag)
+
+    def back(node: Graph):
+        if node.id not in dual:
+            if not parents[node.id]:
+                dual[node.id] = 1.0
+            else:
+                terms = []
+                for parent in parents[node.id]:
+                    parent_ad = back(parent)
+                    d_node = node_derivative(parent, node)
+                    if d_node is not None and parent_ad is not None:
+                        terms.append(_times(d_node, parent_ad))
+                dual[node.id] = linear_combination_number_with_graph(terms)
+        if not node.subgraphs:
+            v = dual[node.id]
+            result[(diag.id, node.id)] = constant_graph(float(v)) if _is_number(v) else v
+        return dual[node.id]
+
+    for leaf in _leaves(diag):
+        if isinstance(leaf.operator, Unitary) or leaf.id in dual:
+            continue
+        back(leaf)
+    return result

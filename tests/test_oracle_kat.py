@@ -383,3 +383,45 @@ def test_build_derivative_graph_known_answers():
         leafmap[c0] = 7
     assert [_eval_by_id(dual[(F0.id, o)], leafmap, leaf) for o in olist] == want0
     assert [_eval_by_id(dual[(F0_r1.id, o)], leafmap, leaf) for o in olist] == want1
+
+
+def test_node_derivative_forwardAD_and_backAD_known_answers():
+    """reference test/computational_graph.jl:887-928 (testsets "node_derivative" and "Eval"), every leaf = 1."""
+    import fdgraph_b200 as fd
+    from oracle.frontend import ad
+
+    def ev(x):  # eval!(::Number) = the number; eval!(graph) with all leaves one; eval!(nothing) does not exist: None
+        if x is None or isinstance(x, (int, float)):
+            return x
+        ids = {n.id for n in fd.graph.post_order_unique([x]) if not n.subgraphs}
+        return _eval_by_id(x, {i: 1 for i in ids}, [1.0])
+
+    fd.uidreset()
+    g1, g2 = fd.Graph([]), fd.Graph([])
+    g3 = fd.Graph([], factor=2.0)
+    G3 = g1
+    G4 = 4 * g1 * g1
+    G5 = 4 * (2 * G3 + 3 * G4)
+    G6 = (2 * g1 + 3 * g2) * (4 * g1 + g3) * g1
+    G7 = (3 * g1 + 4 * g2 + 5 * g3) * 3 * g1
+    F1 = g1 * g1
+    F2 = (3 * g1) * (4 * g1)
+    F3 = (2 * g1 * g2) * (3 * g1)
+    F4 = (2 * g1 + 3 * g2) + g1
+    assert ev(ad.node_derivative(F1, g1)) == 2
+    assert ev(ad.node_derivative(F2, g1)) == 24
+    assert ev(ad.node_derivative(F1, g2)) is None
+    assert ev(ad.node_derivative(F3, g1)) == 6  # local: only the children of the root count
+    assert ev(ad.node_derivative(F4, g1)) == 1
+    assert ev(ad.forwardAD(G3, g1.id)) == 1
+    assert ev(ad.forwardAD(G4, g1.id)) == 8
+    assert ev(ad.forwardAD(G5, g1.id)) == 104
+    assert ev(ad.forwardAD(G6, g1.id)) == 62
+    assert ev(ad.forwardAD(G6, g2.id)) == 18
+    assert ev(ad.forwardAD(ad.forwardAD(G6, g1.id), g2.id)) == 30
+    assert ev(ad.forwardAD(G6, g3.id)) == 0
+    for G in (G3, G4, G5, G6, G7):
+        back = ad.backAD(G)
+        assert back
+        for (_, leaf_id), value_back in back.items():
+            assert ev(value_back) == ev(ad.forwardAD(G, leaf_id))
