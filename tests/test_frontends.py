@@ -5,6 +5,8 @@ workload is their output, so their known answers belong in the suite:
   * closed-form diagram counts, all leaves = 1 (test/front_end.jl:600-656 with
     src/frontend/parquet/benchmark/diagram_count.jl:53-66): Sigma in the G^2 v expansion, loops 1-4 = 1, 1+s, 4+5s+s^2,
     27+40s+14s^2+s^3;
+  * leaf identity of interactions (equal-time rule), parameter equality, ordered partitions, first loop / time indices
+    (test/front_end.jl:70-102, :126-183);
   * which Green's functions / self-energies a filter allows (test/front_end.jl:186-219, :660-700);
   * the RPA chain of the 4-point vertex, +-2^3 2^4 (test/front_end.jl:398-443);
   * value invariance under optimize! for the 4-point vertex, loops 1-3, every channel (test/front_end.jl:446-598) and
@@ -149,6 +151,39 @@ def test_polarization_with_an_explicit_proper_filter():
     from oracle.frontend.ids import Proper
     para, rows = _polar(1, (Proper, NoHartree, NoFock))
     assert len(rows) == 1 and not rows[0]["diagram"].subgraphs[0].subgraphs  # Pi0 = G G, two bare propagators
+
+
+@pytest.mark.parametrize("kind", [Instant, Dynamic])
+def test_interaction_ids_equal_time_rule(kind):
+    # test/front_end.jl:70-102 (diagram_id.jl:49-69): leaf identity of interactions -- equal-time labels are interchangeable
+    a = BareInteractionId(UpUp, kind, k=[1.0, 1.0], t=(1, 1))
+    b = BareInteractionId(UpUp, kind, k=[1.0, 1.0], t=(1, 1))
+    c = BareInteractionId(UpUp, kind, k=[2.0, 2.0], t=(2, 2))
+    d = BareInteractionId(UpUp, kind, k=[1.0, 1.0], t=(2, 2))
+    e = BareInteractionId(UpUp, kind, k=[1.0, 1.0], t=(1, 2))
+    f = BareInteractionId(UpUp, kind, k=[1.0, 1.0], t=(1, 2))
+    assert a == b and a != c and a == d and a != e and e == f
+    assert hash(a) == hash(d) and opt._prop_key(a) == opt._prop_key(d)  # what remove_duplicated_leaves compares
+
+
+def test_parameters_partitions_and_first_indices():
+    # test/front_end.jl:126-147 "Parameter"
+    p, q, a = (pq.DiagPara(type=pq.Ver4Diag, innerLoopNum=n) for n in (1, 2, 2))
+    assert p.key() != q.key() and q.key() == a.key()
+    assert a.key() != a.reconstruct(transferLoop=[0.0, 0.0, 0.0]).key()
+    assert a.key() != a.reconstruct(interaction=[]).key()
+    assert a.reconstruct(type=pq.SigmaDiag).key() != pq.DiagPara(type=pq.SigmaDiag, innerLoopNum=2).key()
+    # :149-157 "Partition"
+    assert set(pq.ordered_partition(5, 2)) == {(4, 1), (1, 4), (2, 3), (3, 2)}
+    assert set(pq.ordered_partition(3, 2, 0)) == {(3, 0), (0, 3), (1, 2), (2, 1)}
+    # :159-183 "FindFirstIdx"
+    for partition, first, expected in (([1, 1, 2, 1], 1, [1, 2, 3, 5]), ([1, 1, 2, 1], 0, [0, 1, 2, 4]), ([1, 0, 2, 0], 1, [1, 2, 2, 4]),
+                                       ([1], 1, [1])):
+        idx, total = pq.find_first_loop_idx(partition, first)
+        assert idx == expected and total == sum(partition) + first - 1
+    kinds = [pq.Ver4Diag, pq.GreenDiag, pq.Ver4Diag, pq.GreenDiag]
+    for partition, first, expected in (([1, 1, 2, 1], 1, [1, 3, 4, 7]), ([1, 1, 2, 1], 0, [0, 2, 3, 6]), ([1, 0, 2, 0], 1, [1, 3, 3, 6])):
+        assert pq.find_first_tau_idx(partition, kinds, first, 1)[0] == expected
 
 
 def test_which_green_functions_and_self_energies_a_filter_allows():
